@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE — records golden vectors from the UNMODIFIED reference env.
+
+Run in the build container only (needs `/root/reference`):
+
+    python oracle/make_golden.py            # rewrites tests/golden/*
+
+It executes `/root/reference/merging_gym/envs/merging_env.py` and
+`/root/reference/scripts/helper.py` as they are, with the third-party imports that
+are missing from the image replaced by `oracle/ref_shims/` (see its README), and
+stores what `reset()` / `step()` return:
+
+* `config1_pve_trace.npz`  BASELINE.json configs[0]: pve, one env, 10 000 steps,
+  actions `np.random.default_rng(0).integers(5)`, manual reset on done.
+* `pvp_trace.npz`          same protocol, two players, rng seed 1, 6 000 steps.
+* `pvp_vec16_trace.npz`    16 envs x 640 steps, pvp, per-env manual reset replayed with
+  the gym-0.20 vector convention (a finished env returns its reset observation),
+  the fixture the CUDA kernel is compared with directly.
+* `kat.json`               known-answer episodes for scripted action pairs
+  (SURVEY.md §8c): steps, winner, collision, returns, final positions, last obs.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle.ref_loader import load_reference_env, quiet  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _f(v):
+    return np.asarray(v, dtype=np.float64)
+
+
+def trace(env, pvp, seed, steps):
+    rng = np.random.default_rng(seed)
+    acts = np.zeros((steps, 2), np.uint8)
+    obs = np.zeros((steps, 10)); rew = np.zeros((steps, 2))
+    done = np.zeros(steps, bool); col = np.zeros(steps, bool)
+    win = np.zeros(steps, np.uint8)
+    ret = np.zeros((steps, 2))
+    reset_obs = _f(env.reset())
+    with quiet():
+        for t in range(steps):
+            a1 = int(rng.integers(5))
+            a2 = int(rng.integers(5)) if pvp else None
+            acts[t] = (a1, a2 if pvp else 0)
+            o, r, d, info = env.step(a1, a2)
+            obs[t], rew[t], done[t], col[t] = _f(o), _f(r), d, info["collision"]
+            win[t] = env.winner or 0
+            ret[t] = (env.r1_accumulate, env.r2_accumulate)
+            if d:
+                env.reset()
+    return dict(actions=acts, obs=obs, rewards=rew, done=done, collision=col, winner=win,
+                returns=ret, reset_obs=reset_obs, pvp=np.array(pvp), seed=np.array(seed))
+
+
+def vec_trace(env, n_envs, steps, seed):
+    rng = np.random.default_rng(seed)
+    acts = rng.integers(0, 5, size=(steps, n_envs, 2)).astype(np.uint8)
+    obs = np.zeros((steps, n_envs, 10)); term = np.zeros((steps, n_envs, 10))
+    rew = np.zeros((steps, n_envs, 2))
+    done = np.zeros((steps, n_envs), bool); col = np.zeros((steps, n_envs), bool)
+    win = np.zeros((steps, n_envs), np.uint8)
+    eplen = np.zeros((steps, n_envs), np.int32); epret = np.zeros((steps, n_envs, 2))
+    with quiet():
+        for e in range(n_envs):
+            env.reset()
+            n = 0
+            for t in range(steps):
+                o, r, d, info = env.step(int(acts[t, e, 0]), int(acts[t, e, 1]))
+                n += 1
+                rew[t, e], done[t, e], col[t, e] = _f(r), d, info["collision"]
+                win[t, e] = env.winner or 0
+                term[t, e] = _f(o)
+                if d:
+                    eplen[t, e] = n
+                    epret[t, e] = (env.r1_accumulate, env.r2_accumulate)
+                    o = env.reset()
+                    n = 0
+                obs[t, e] = _f(o)
+    return dict(actions=acts, obs=obs, step_obs=term, rewards=rew, done=done, collision=col,
+                winner=win, ep_len=eplen, ep_ret=epret)
+
+
+def kat(env, script1, script2, max_steps=2700):
+    """script_i: constant int, None, or a list cycled over steps."""
+    def act(s, t):
+        if s is None or isinstance(s, int):
+            return s
+        return s[t % len(s)]
+    env.reset()
+    with quiet():
+        for t in range(max_steps):
+            o, r, d, info = env.step(act(script1, t), act(script2, t))
+            if d:
+                break
+    return dict(a1=script1, a2=script2, steps=t + 1, winner=env.winner, collision=info["collision"],
+                R1=float(env.r1_accumulate), R2=float(env.r2_accumulate),
+                pos1=float(env.state1['pos']), pos2=float(env.state2['pos']),
+                vel1=float(env.state1['vel']), vel2=float(env.state2['vel']),
+                time_stamp=float(env.time_stamp),
+                last_obs=[float(v) for v in o], last_rewards=[float(v) for v in r])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    env = load_reference_env()
+    np.savez_compressed(os.path.join(OUT, "config1_pve_trace.npz"), **trace(env, False, 0, 10000))
+    np.savez_compressed(os.path.join(OUT, "pvp_trace.npz"), **trace(env, True, 1, 6000))
+    np.savez_compressed(os.path.join(OUT, "pvp_vec16_trace.npz"), **vec_trace(env, 16, 640, 2))
+    scripts = [(2, None), (2, 2), (3, None), (4, None), (1, None), (0, None), (0, 0), (4, 0),
+               (4, 4), (3, 1), (1, 3), (4, 3), (3, 4), ([0, 4], 2), (0, 4), (2, 3), (3, 2),
+               ([4, 4, 0], [0, 4, 4]), (1, 1), (3, 3)]
+    kats = [kat(env, a, b) for a, b in scripts]
+    kats.append(dict(reset_obs=[float(v) for v in env.reset()]))
+    with open(os.path.join(OUT, "kat.json"), "w") as f:
+        json.dump(kats, f, indent=1)
+    for k in kats[:-1]:
+        print(k["a1"], k["a2"], k["steps"], k["winner"], k["collision"], k["R1"], k["R2"], k["pos1"], k["pos2"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1 @@
+"""no-op stand-in; never called on the hot path."""
