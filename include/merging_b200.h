@@ -1,0 +1,171 @@
+/*
+ * merging_b200.h — C ABI of libmerging_b200.so: the batched, device-resident replacement for
+ * the reset()/step() hot path of merging-gym's MergeEnv on NVIDIA B200 (sm_100a).
+ *
+ * The reference has no native layer: the path is pure Python
+ * (/root/reference/merging_gym/envs/merging_env.py + scripts/helper.py).  Every entry point
+ * below therefore cites the *Python* interface it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Plain C types only.  All array pointers are CUDA device pointers unless the parameter
+ *    name starts with `h_` (host memory).  Array pointers must be 16-byte aligned.
+ *  - The library never allocates or frees memory and keeps no global state except the
+ *    per-thread last-error string.  The caller (PyTorch on the Python side) owns every buffer.
+ *  - Launches are asynchronous on the caller's stream (`stream` is a cudaStream_t passed as
+ *    void*; NULL = legacy default stream).  No entry point synchronises unless documented.
+ *    All device entry points are CUDA-graph capturable.
+ *  - Return value: 0 on success, negative MgStatus for argument errors, positive cudaError_t
+ *    for CUDA runtime errors.  `mg_last_error()` returns a description.
+ *  - There is no CPU fallback anywhere in this library.
+ */
+#ifndef MERGING_B200_H
+#define MERGING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MG_API __declspec(dllexport)
+#else
+#define MG_API __attribute__((visibility("default")))
+#endif
+
+#define MG_ABI_VERSION 1
+#define MG_OBS_DIM 10      /* merging_env.py:75,118-132 */
+#define MG_NUM_ACTIONS 5   /* merging_env.py:101-102   */
+
+typedef enum MgStatus {
+    MG_OK = 0,
+    MG_ERR_NULL_POINTER = -1,
+    MG_ERR_BAD_SIZE = -2,
+    MG_ERR_ALIGNMENT = -3,
+    MG_ERR_BAD_FLAGS = -4,
+    MG_ERR_BAD_DTYPE = -5
+} MgStatus;
+
+/* Action element types accepted by mg_step (`action_dict[action]`, merging_env.py:101,147). */
+typedef enum MgActionDtype { MG_ACT_U8 = 0, MG_ACT_I32 = 1, MG_ACT_I64 = 2 } MgActionDtype;
+
+/* mg_step / mg_rollout flags */
+#define MG_FLAG_AUTO_RESET 0x1u /* gym-0.20 SyncVectorEnv convention: a finished env is reset in
+                                   the same call and returns its reset observation           */
+
+/* info byte, one per env per step (merging_env.py:144,187 `info["collision"]`, :164-181
+ * `self.winner`, :142 time limit, :143/:171/:181/:184 `self.done`). */
+#define MG_INFO_COLLISION 0x01u
+#define MG_INFO_WINNER_SHIFT 1 /* bits 1-2: winner after this step, 0 = None */
+#define MG_INFO_WINNER_MASK 0x06u
+#define MG_INFO_TIMEOUT 0x08u
+#define MG_INFO_DONE 0x10u
+#define MG_INFO_BAD_ACTION 0x80u /* action outside 0..4 (reference raises KeyError); it was clamped */
+
+/* meta word, one uint32 per env */
+#define MG_META_STEPS_MASK 0x0FFFu /* steps since reset, saturating at 4095 (time limit = 2501) */
+#define MG_META_WINNER_SHIFT 12    /* bits 12-13 */
+#define MG_META_DONE 0x4000u       /* sticky done (only ever set when auto-reset is off)        */
+
+/* Env state, structure-of-arrays, one element per env.  Replaces `self.state1/state2`
+ * (pos, vel; merging_env.py:216-217), `self.r1_accumulate/r2_accumulate` (:191-192,223-224),
+ * and `self.time_stamp / self.winner / self.done` (:211-213) packed in `meta`.
+ * float64 on purpose: `pos > 950`, `pos >= 950` and trunc(x), trunc(y) are discontinuous in the
+ * state, and the reference carries float64. */
+typedef struct MgState {
+    double *pos1, *vel1, *pos2, *vel2; /* [n] */
+    double *ret1, *ret2;               /* [n] episode-return accumulators */
+    uint32_t *meta;                    /* [n] */
+} MgState;
+
+/* Per-step outputs (the tuple `obs, rewards, done, info` of merging_env.py:195). */
+typedef struct MgOut {
+    float *obs;       /* [n,10] row-major; merging_env.py:122-131 order                          */
+    float *rew;       /* [n,2]  (reward1, reward2), merging_env.py:189                           */
+    uint8_t *done;    /* [n]    0/1                                                              */
+    uint8_t *info;    /* [n]    MG_INFO_* bit-field                                              */
+    float *term_obs;  /* [n,10] or NULL: written ONLY for envs that finished in this step        */
+    float *ep_ret;    /* [n,2]  or NULL: finished episode's (r1_accumulate, r2_accumulate), ditto */
+    int32_t *ep_len;  /* [n]    or NULL: finished episode's length in steps, ditto               */
+} MgOut;
+
+/* Reward shaping, run-time because the reference's shipped runs varied it
+ * (`show_reward()`, merging_env.py:115-116; test_params/dqn directory names). */
+typedef struct MgRewards {
+    double r_first;      /* RFirst      = 2.0    merging_env.py:28 */
+    double r_second;     /* RSecond     = 1.0    merging_env.py:29 */
+    double r_collision;  /* RCollision  = -10    merging_env.py:30 */
+    double vel_penalty;  /* vel_penalty = 0.001  merging_env.py:31 */
+    double time_penalty; /* time_penalty = 0     merging_env.py:32 */
+} MgRewards;
+
+/* Geometry / timing constants compiled into the kernels (merging_env.py:22-46,101,142). */
+typedef struct MgConstants {
+    double R, H, W, dT, start_point, end_point, prediction_t, init_vel, action_dv;
+    int32_t vehicle_w, vehicle_h, max_steps /* first step count with time_stamp > 500: 2501 */;
+    int32_t num_actions, obs_dim, stats_rows, stats_cols;
+    double return_fixed_point_scale; /* 2^24: stats columns 8,9 hold llrint(return * scale) */
+} MgConstants;
+
+/* Episode statistics: int64 [MG_STATS_ROWS][MG_STATS_COLS] partial sums, accumulated with
+ * integer atomics (order-independent, hence deterministic and world-size invariant).  Sum over
+ * rows to get totals.  Replaces the hand-kept counters of scripts/main.py:203-227. */
+#define MG_STATS_ROWS 1024
+#define MG_STATS_COLS 16
+enum {
+    MG_ST_EPISODES = 0, MG_ST_COLLISIONS, MG_ST_WINS_P1, MG_ST_WINS_P2, MG_ST_TIMEOUTS,
+    MG_ST_MERGES_OK /* done && !collision && !timeout */, MG_ST_SUM_LENGTH, MG_ST_BAD_ACTIONS,
+    MG_ST_SUM_RET1_FX, MG_ST_SUM_RET2_FX /* fixed point, scale 2^24 */
+};
+
+MG_API int mg_version(void);
+MG_API const char *mg_last_error(void);
+MG_API int mg_get_constants(MgConstants *out);
+MG_API int mg_default_rewards(MgRewards *out); /* merging_env.py:28-32 / show_reward() :115-116 */
+
+/* MergeEnv.reset()  (merging_env.py:208-230) for every env, or only where mask[i] != 0.
+ * Writes the state and, if obs != NULL, obs[n,10] for ALL envs (masked-out rows get their
+ * current observation, i.e. `observe()`, merging_env.py:118-132). */
+MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask_or_null, float *obs_or_null,
+                    void *stream);
+
+/* MergeEnv.step(action1, action2)  (merging_env.py:138-195) for n envs in one fused launch:
+ * kinematics of both cars incl. the mpc_1d controller (scripts/helper.py:152-191), lon2coord,
+ * observe, rewards / winner / done, is_collided, return accumulation, optional auto-reset,
+ * episode statistics.  a2 == NULL is `action2=None` (pve, merging_env.py:152).
+ * stats may be NULL. */
+MG_API int mg_step(const MgState *state, int64_t n, const void *a1, const void *a2_or_null,
+                   int act_dtype, const MgRewards *rewards, const MgOut *out,
+                   int64_t *stats_or_null, uint32_t flags, void *stream);
+
+/* Synthetic uniform-random discrete actions (the scripts' `env.action_space.sample()`,
+ * scripts/main.py:26), counter-based: Philox4x32-10, key = seed, counter = (global env id, step).
+ * a2 may be NULL. */
+MG_API int mg_sample_actions(uint8_t *a1, uint8_t *a2_or_null, int64_t n, uint64_t seed,
+                             uint64_t env_id_base, uint64_t step, void *stream);
+
+/* k_steps consecutive steps per launch with in-kernel Philox actions (same stream of actions as
+ * mg_sample_actions at steps step0 .. step0+k-1); state stays in registers between steps.
+ * `out` arrays are time-major: obs[k,n,10], rew[k,n,2], done[k,n], info[k,n]; any of them may be
+ * NULL to skip that output; term_obs/ep_ret/ep_len are [n] "last finished episode" buffers.
+ * actions_out_or_null: uint8 [k,n,2].  pvp != 0 selects two-player mode. */
+MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, uint64_t env_id_base,
+                      uint64_t step0, int32_t k_steps, const MgRewards *rewards, const MgOut *out,
+                      uint8_t *actions_out_or_null, int64_t *stats_or_null, uint32_t flags,
+                      void *stream);
+
+/* Host-buffer convenience path (the drop-in for callers that keep Python/NumPy data on the
+ * host, like the reference scripts): copies h_a1/h_a2 (uint8[n]) to the device scratch actions
+ * d_a1/d_a2, runs mg_step, copies obs/rew/done/info back into the h_out arrays and SYNCHRONISES
+ * the stream.  Optional members of h_out may be NULL.  Pinned host memory is recommended. */
+MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
+                        const uint8_t *h_a2_or_null, uint8_t *d_a1, uint8_t *d_a2,
+                        const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out,
+                        int64_t *stats_or_null, uint32_t flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERGING_B200_H */

@@ -1,0 +1,282 @@
+// merge_device.cuh — per-env device arithmetic of the fused merging-gym step (sm_100a).
+//
+// One env lives in one thread's registers.  Everything that decides a *discrete* outcome
+// (pos > 950, pos >= 950, trunc(x), trunc(y), step count) is computed in float64 with the
+// reference's evaluation order and explicit round-to-nearest intrinsics, so no FMA contraction
+// can change a rounding the reference performs (merging_env.py:147-154, 48-58).  Outputs are
+// cast to float32 at the very end.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/merging_b200.h"
+
+namespace mg {
+
+// ---- compile-time constants (merging_env.py:22-46, 101, 142) --------------------------------
+constexpr double kR = 30000.0;
+constexpr double kH = 1000.0;
+constexpr double kW = 300.0;
+constexpr double kHalfW = kW / 2;                 // W/2 = 150.0
+constexpr double kDT = 0.2;
+constexpr double kStart = 50.0;                   // START_POINT
+constexpr double kEnd = 950.0;                    // END_POINT = H - 50
+constexpr double kPredT = 3.0;                    // prediction_t
+constexpr double kInitVel = 20.0;
+constexpr double kActionDv = 10.0;                // action_dict = {a: 10*a}
+constexpr int kVehicleW = 4, kVehicleH = 8;
+constexpr int kMaxSteps = 2501;                   // first n with fl64 sum_{1..n} 0.2 > 500 (tests/test_oracle_golden.py)
+constexpr double kInvR = 1.0 / kR;                // RN(1/30000), folded by the host compiler
+constexpr double kInvPredT = 1.0 / kPredT;        // RN(1/3)
+constexpr double kAngle0 = 0x1.10f7317226afdp-5;  // np.arctan2(1000, 30000) = 0.033320995878247196
+constexpr double kRetScale = 16777216.0;          // 2^24 fixed point for the return statistics
+
+// Reset observation, merging_env.py:208-230 -> observe() at pos=50, vel=20 (float64 values from
+// the oracle; y2 - y1 = -30.057386826127185).  tests assert mg_reset's computed obs equals these.
+constexpr float kResetDy = -30.057386826127185f;
+constexpr float kResetRemaining = 900.0f;
+
+// ---- x / d for a compile-time divisor, bit-identical to IEEE division -----------------------
+// q = RN(x*y), r = x - d*q (exact in one FMA), q' = RN(q + r*y)  with y = RN(1/d)
+// (Markstein's correction).  oracle/merge_oracle.c::mgo_check_div and tests/test_arith.py
+// confirm q' == x/d bit for bit for d = 3 and d = 30000 over the ranges the env reaches.
+__device__ __forceinline__ double div_const(double x, double d, double y) {
+    const double q = __dmul_rn(x, y);
+    const double r = __fma_rn(-d, q, x);
+    return __fma_rn(r, y, q);
+}
+
+// ---- sin & cos on the lane-angle range ------------------------------------------------------
+// angle = atan2(H,R) - lon/R lies in [-0.64, 0.034] for any state reachable before the time
+// limit (lon <= 50 + 8*2501), so no range reduction is needed: fdlibm's k_sin/k_cos minimax
+// polynomials for |x| <= pi/4 (error < 2^-58) evaluated with FMAs.  Outside |x| <= 0.78 (only
+// reachable when a caller keeps stepping a finished env without auto-reset) fall back to the
+// CUDA library sincos.  Both stay within 1 ulp of glibc, which the reference's np.sin/np.cos use.
+__device__ __forceinline__ void sincos_lane(double x, double &s, double &c) {
+    if (fabs(x) > 0.78) {   // cold path, warp-uniformly false in normal operation
+        sincos(x, &s, &c);
+        return;
+    }
+    const double z = x * x;
+    const double w = z * z;
+    // sin
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double rs = fma(z, fma(z, S4, S3), S2) + z * w * fma(z, S6, S5);
+    const double v = z * x;
+    s = fma(v, fma(z, rs, S1), x);
+    // cos
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double rc = z * fma(z, fma(z, C3, C2), C1) + (w * w) * fma(z, fma(z, C6, C5), C4);
+    const double hz = 0.5 * z;
+    const double ww = 1.0 - hz;
+    c = ww + (((1.0 - ww) - hz) + z * rc);
+}
+
+// lon2coord (merging_env.py:48-58).  sign = +1 for "ego" (player 1), -1 for "opponent".
+__device__ __forceinline__ void lon2coord(double lon, double sign, double &x, double &y) {
+    const double angle = __dsub_rn(kAngle0, div_const(lon, kR, kInvR));
+    double s, c;
+    sincos_lane(angle, s, c);
+    x = __dmul_rn(kR, s);
+    const double d = __dsub_rn(kR, __dmul_rn(kR, c));
+    y = __fma_rn(sign, d, kHalfW);   // W/2 +/- d : sign*d is exact, one rounding like the reference
+}
+
+// ---- Philox4x32-10 (Salmon et al. SC'11) ----------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                              uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// actions of global env `env_id` at rollout step `step`: a_p = (u32_p * 5) >> 32
+__device__ __forceinline__ void philox_actions(uint64_t seed, uint64_t env_id, uint64_t step,
+                                               int &a1, int &a2) {
+    uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32);
+    uint32_t c2 = (uint32_t)step, c3 = (uint32_t)(step >> 32);
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    a1 = (int)__umulhi(c0, 5u);
+    a2 = (int)__umulhi(c1, 5u);
+}
+
+// ---- one env, one step ----------------------------------------------------------------------
+struct EnvRegs {
+    double p1, v1, p2, v2;   // state1/state2 pos, vel
+    double R1, R2;           // r1_accumulate, r2_accumulate
+    uint32_t meta;           // steps | winner << 12 | done << 14
+};
+
+struct StepResult {
+    float obs[MG_OBS_DIM];   // observation of the stepped state (terminal obs if the env finished)
+    float r1, r2;
+    uint32_t info;           // MG_INFO_* bits
+    uint32_t steps;          // episode length after this step
+    bool done;               // done flag returned for this step
+    bool finished;           // done became true in this step (0 -> 1 transition)
+};
+
+__device__ __forceinline__ void reset_regs(EnvRegs &e) {   // merging_env.py:208-230
+    e.p1 = kStart; e.v1 = kInitVel; e.p2 = kStart; e.v2 = kInitVel;
+    e.R1 = 0.0; e.R2 = 0.0; e.meta = 0u;
+}
+
+__device__ __forceinline__ void observe(const EnvRegs &e, float *obs) {   // merging_env.py:118-132
+    double x1, y1, x2, y2;
+    lon2coord(e.p1, 1.0, x1, y1);
+    lon2coord(e.p2, -1.0, x2, y2);
+    const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1), dv = __dsub_rn(e.v2, e.v1);
+    obs[0] = (float)dx;  obs[1] = (float)dy;  obs[2] = (float)dv;
+    obs[3] = (float)__dsub_rn(kEnd, e.p1);  obs[4] = (float)e.v1;
+    obs[5] = (float)-dx; obs[6] = (float)-dy; obs[7] = (float)-dv;   // a-b == -(b-a) exactly
+    obs[8] = (float)__dsub_rn(kEnd, e.p2);  obs[9] = (float)e.v2;
+}
+
+// merging_env.py:138-195 for one env.  a1/a2 already validated into 0..4 (bad -> info bit).
+// PVP=false: `action2 is None` -> acc2 = 0 (merging_env.py:152).
+template <bool PVP>
+__device__ __forceinline__ void env_step(EnvRegs &e, int a1, int a2, bool bad_action,
+                                         const MgRewards &rw, StepResult &out) {
+    // :141-143  time_stamp += dT; > 500 first holds at step 2501 -> integer step counter
+    uint32_t steps = e.meta & MG_META_STEPS_MASK;
+    steps = min(steps + 1u, (uint32_t)MG_META_STEPS_MASK);
+    const bool was_done = (e.meta & MG_META_DONE) != 0u;
+    const bool timeout = steps >= (uint32_t)kMaxSteps;
+    bool done = was_done | timeout;
+    uint32_t winner = (e.meta >> MG_META_WINNER_SHIFT) & 3u;
+
+    // :147-150  player 1: acc = mpc_1d(...) == (vt - v)/3 ; vel = max(0, vel + acc*dT) ; pos += vel*dT
+    {
+        const double vt = kActionDv * (double)a1;
+        const double acc = div_const(__dsub_rn(vt, e.v1), kPredT, kInvPredT);
+        const double v = __dadd_rn(e.v1, __dmul_rn(acc, kDT));
+        e.v1 = (v > 0.0) ? v : 0.0;
+        e.p1 = __dadd_rn(e.p1, __dmul_rn(e.v1, kDT));
+    }
+    // :152-154  player 2
+    if (PVP) {
+        const double vt = kActionDv * (double)a2;
+        const double acc = div_const(__dsub_rn(vt, e.v2), kPredT, kInvPredT);
+        const double v = __dadd_rn(e.v2, __dmul_rn(acc, kDT));
+        e.v2 = (v > 0.0) ? v : 0.0;
+    } else {
+        e.v2 = (e.v2 > 0.0) ? e.v2 : 0.0;          // max(0, vel + 0*dT)
+    }
+    e.p2 = __dadd_rn(e.p2, __dmul_rn(e.v2, kDT));
+
+    // :156, :118-132, :48-58  geometry once (the reference recomputes it in is_collided)
+    double x1, y1, x2, y2;
+    lon2coord(e.p1, 1.0, x1, y1);
+    lon2coord(e.p2, -1.0, x2, y2);
+    {
+        const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1), dv = __dsub_rn(e.v2, e.v1);
+        out.obs[0] = (float)dx;  out.obs[1] = (float)dy;  out.obs[2] = (float)dv;
+        out.obs[3] = (float)__dsub_rn(kEnd, e.p1);  out.obs[4] = (float)e.v1;
+        out.obs[5] = (float)-dx; out.obs[6] = (float)-dy; out.obs[7] = (float)-dv;
+        out.obs[8] = (float)__dsub_rn(kEnd, e.p2);  out.obs[9] = (float)e.v2;
+    }
+
+    // :158-159  reward_i = -time_penalty - vel_penalty*|v_i - 20|
+    double r1 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v1, 20.0))));
+    double r2 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v2, 20.0))));
+
+    // :163-171  player 1 crosses with strict '>' and is evaluated first
+    if (e.p1 > kEnd) {
+        if (winner == 0u)      { winner = 1u; r1 = __dadd_rn(r1, rw.r_first); }
+        else if (winner == 1u) { r1 = 0.0; }
+        else                   { r1 = __dadd_rn(r1, rw.r_second); done = true; }
+    }
+    // :173-181  player 2 crosses with '>='
+    if (e.p2 >= kEnd) {
+        if (winner == 0u)      { winner = 2u; r2 = __dadd_rn(r2, rw.r_first); }
+        else if (winner == 2u) { r2 = 0.0; }
+        else                   { r2 = __dadd_rn(r2, rw.r_second); done = true; }
+    }
+    // :183-187, :198-206, :232-239  integer pygame Rects (C truncation) 4 wide (lateral, y) x 8
+    // long (longitudinal, x); closed rectangles intersect iff both projections overlap.
+    const int ty1 = __double2int_rz(y1), ty2 = __double2int_rz(y2);
+    const int tx1 = __double2int_rz(x1), tx2 = __double2int_rz(x2);
+    const bool collided = (abs(ty1 - ty2) <= kVehicleW) & (abs(tx1 - tx2) <= kVehicleH);
+    if (collided) {
+        done = true;
+        r1 = __dadd_rn(r1, rw.r_collision);
+        r2 = __dadd_rn(r2, rw.r_collision);
+    }
+    // :191-192
+    e.R1 = __dadd_rn(e.R1, r1);
+    e.R2 = __dadd_rn(e.R2, r2);
+    e.meta = steps | (winner << MG_META_WINNER_SHIFT) | (done ? MG_META_DONE : 0u);
+
+    out.r1 = (float)r1;
+    out.r2 = (float)r2;
+    out.steps = steps;
+    out.done = done;
+    out.finished = done & !was_done;
+    out.info = (collided ? MG_INFO_COLLISION : 0u) | (winner << MG_INFO_WINNER_SHIFT) |
+               (timeout ? MG_INFO_TIMEOUT : 0u) | (done ? MG_INFO_DONE : 0u) |
+               (bad_action ? MG_INFO_BAD_ACTION : 0u);
+}
+
+// ---- per-thread episode statistics, packed so that one warp reduction covers several ---------
+struct StatAcc {
+    uint32_t a = 0;   // episodes | collisions<<8 | wins_p1<<16 | wins_p2<<24   (<= 128 each per warp)
+    uint32_t b = 0;   // timeouts | merges_ok<<8 | bad_actions<<16
+    uint32_t len = 0; // sum of finished episode lengths
+    long long fx1 = 0, fx2 = 0;   // sum of finished returns, fixed point 2^24
+
+    __device__ __forceinline__ void add(const StepResult &r, double R1, double R2) {
+        if (r.info & MG_INFO_BAD_ACTION) b += 1u << 16;
+        if (r.finished) {
+            const uint32_t col = r.info & MG_INFO_COLLISION;
+            const uint32_t w = (r.info & MG_INFO_WINNER_MASK) >> MG_INFO_WINNER_SHIFT;
+            const uint32_t to = (r.info & MG_INFO_TIMEOUT) ? 1u : 0u;
+            a += 1u | (col << 8) | ((w == 1u) << 16) | ((w == 2u) << 24);
+            b += to | (((col == 0u) & (to == 0u)) << 8);
+            len += r.steps;
+            fx1 += __double2ll_rn(R1 * kRetScale);
+            fx2 += __double2ll_rn(R2 * kRetScale);
+        }
+    }
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v, unsigned mask) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
+// Warp-aggregate with ballot / REDUX, then one lane issues <= 10 integer atomics into the
+// block's statistics row.  Integer adds commute, so totals are bit-reproducible.
+__device__ __forceinline__ void flush_stats(const StatAcc &st, unsigned long long *stats_row,
+                                            unsigned mask, int lane) {
+    if (__ballot_sync(mask, (st.a | st.b) != 0u) == 0u) return;   // nothing happened in this warp
+    const uint32_t a = __reduce_add_sync(mask, st.a);
+    const uint32_t b = __reduce_add_sync(mask, st.b);
+    const uint32_t len = __reduce_add_sync(mask, st.len);
+    const long long fx1 = warp_sum_ll(st.fx1, mask);
+    const long long fx2 = warp_sum_ll(st.fx2, mask);
+    if (lane == 0) {
+        auto add = [&](int col, unsigned long long v) { if (v) atomicAdd(stats_row + col, v); };
+        add(MG_ST_EPISODES, a & 0xFFu);
+        add(MG_ST_COLLISIONS, (a >> 8) & 0xFFu);
+        add(MG_ST_WINS_P1, (a >> 16) & 0xFFu);
+        add(MG_ST_WINS_P2, (a >> 24) & 0xFFu);
+        add(MG_ST_TIMEOUTS, b & 0xFFu);
+        add(MG_ST_MERGES_OK, (b >> 8) & 0xFFu);
+        add(MG_ST_BAD_ACTIONS, (b >> 16) & 0xFFu);
+        add(MG_ST_SUM_LENGTH, len);
+        add(MG_ST_SUM_RET1_FX, (unsigned long long)fx1);
+        add(MG_ST_SUM_RET2_FX, (unsigned long long)fx2);
+    }
+}
+
+}  // namespace mg

@@ -1,0 +1,503 @@
+// merge_kernels.cu — fused CUDA kernels (sm_100a) + the C ABI of libmerging_b200.so.
+//
+// Data layout in HBM: env state is structure-of-arrays
+//   pos1, vel1, pos2, vel2, ret1, ret2 : float64[n]     meta : uint32[n]
+// one thread owns EPT consecutive envs, so every state access is a 128-bit (EPT=2) coalesced
+// vector load/store.  Outputs follow the gym-shaped API: obs[n,10] f32 (40-byte rows, staged
+// through shared memory per warp so the global stores are linear 128-bit), rew[n,2] f32,
+// done[n] u8, info[n] u8.
+//
+// Algorithmic HBM traffic per env-step, pvp + uint8 actions + auto-reset:
+//   read  6*8 (state) + 4 (meta) + 2 (actions)            =  54 B
+//   write 6*8 + 4 (state) + 40 (obs) + 8 (rew) + 1 + 1    = 102 B        total 156 B
+#include <cstdio>
+#include <cstring>
+
+#include "merge_device.cuh"
+
+namespace mg {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+
+// ---- 128-bit helpers ---------------------------------------------------------------------------
+template <int EPT>
+__device__ __forceinline__ void load_f64(const double *__restrict__ p, int64_t i, double (&v)[EPT]) {
+    static_assert(EPT % 2 == 0, "EPT must be even");
+#pragma unroll
+    for (int k = 0; k < EPT / 2; ++k) {
+        const double2 t = *reinterpret_cast<const double2 *>(p + i + 2 * k);
+        v[2 * k] = t.x; v[2 * k + 1] = t.y;
+    }
+}
+template <int EPT>
+__device__ __forceinline__ void store_f64(double *__restrict__ p, int64_t i, const double (&v)[EPT]) {
+#pragma unroll
+    for (int k = 0; k < EPT / 2; ++k)
+        *reinterpret_cast<double2 *>(p + i + 2 * k) = make_double2(v[2 * k], v[2 * k + 1]);
+}
+
+template <typename ActT>
+__device__ __forceinline__ int load_action(const ActT *p, int64_t i) { return (int)p[i]; }
+
+// validate into 0..4 (the reference raises KeyError from action_dict[a], merging_env.py:147)
+__device__ __forceinline__ int clamp_action(long long a, bool &bad) {
+    if (a < 0 || a >= MG_NUM_ACTIONS) { bad = true; a = a < 0 ? 0 : MG_NUM_ACTIONS - 1; }
+    return (int)a;
+}
+
+// Scatter the optional "finished episode" outputs (rare: ~0.5 % of envs per step).
+__device__ __forceinline__ void write_episode_outputs(const MgOut &o, int64_t e, const StepResult &r,
+                                                      double R1, double R2) {
+    if (o.term_obs) {
+        float *t = o.term_obs + e * MG_OBS_DIM;
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM; ++k) t[k] = r.obs[k];
+    }
+    if (o.ep_ret) { o.ep_ret[2 * e] = (float)R1; o.ep_ret[2 * e + 1] = (float)R2; }
+    if (o.ep_len) o.ep_len[e] = (int32_t)r.steps;
+}
+
+__device__ __forceinline__ void reset_obs(float *obs) {
+    obs[0] = 0.f; obs[1] = kResetDy; obs[2] = 0.f; obs[3] = kResetRemaining; obs[4] = (float)kInitVel;
+    obs[5] = 0.f; obs[6] = -kResetDy; obs[7] = 0.f; obs[8] = kResetRemaining; obs[9] = (float)kInitVel;
+}
+
+// =================================================================================================
+// merge_step_kernel: one MergeEnv.step() for n envs.
+//   grid = ceil(n / (kBlock*EPT)), block = 256.  A warp owns 32*EPT consecutive envs.
+//   Full warps take the vector path; the (at most one) ragged warp takes the scalar path.
+// =================================================================================================
+template <int EPT, typename ActT, bool PVP>
+__global__ void __launch_bounds__(kBlock)
+merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
+                  const ActT *__restrict__ a2g, const int64_t n, const MgRewards rw,
+                  const uint32_t flags, unsigned long long *__restrict__ stats) {
+    __shared__ __align__(16) float stage[kWarps][32 * EPT * MG_OBS_DIM];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
+    if (warp_base >= n) return;
+    const bool full = warp_base + 32 * EPT <= n;
+    const int64_t e0 = warp_base + (int64_t)lane * EPT;
+    const bool auto_reset = (flags & MG_FLAG_AUTO_RESET) != 0u;
+
+    EnvRegs env[EPT];
+    int act1[EPT], act2[EPT];
+    bool bad[EPT];
+    bool valid[EPT];
+
+    // ---------------- loads ----------------
+    if (full) {
+        double p1[EPT], v1[EPT], p2[EPT], v2[EPT], R1[EPT], R2[EPT];
+        load_f64<EPT>(s.pos1, e0, p1); load_f64<EPT>(s.vel1, e0, v1);
+        load_f64<EPT>(s.pos2, e0, p2); load_f64<EPT>(s.vel2, e0, v2);
+        load_f64<EPT>(s.ret1, e0, R1); load_f64<EPT>(s.ret2, e0, R2);
+        uint32_t m[EPT];
+        if constexpr (EPT == 2) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(s.meta + e0);
+            m[0] = t.x; m[1] = t.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPT / 4; ++k) {
+                const uint4 t = *reinterpret_cast<const uint4 *>(s.meta + e0 + 4 * k);
+                m[4 * k] = t.x; m[4 * k + 1] = t.y; m[4 * k + 2] = t.z; m[4 * k + 3] = t.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            env[j] = EnvRegs{p1[j], v1[j], p2[j], v2[j], R1[j], R2[j], m[j]};
+            valid[j] = true;
+            bad[j] = false;
+            act1[j] = clamp_action((long long)load_action(a1g, e0 + j), bad[j]);
+            act2[j] = PVP ? clamp_action((long long)load_action(a2g, e0 + j), bad[j]) : 0;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int64_t e = e0 + j;
+            valid[j] = e < n;
+            bad[j] = false;
+            if (valid[j]) {
+                env[j] = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], s.ret1[e], s.ret2[e], s.meta[e]};
+                act1[j] = clamp_action((long long)a1g[e], bad[j]);
+                act2[j] = PVP ? clamp_action((long long)a2g[e], bad[j]) : 0;
+            } else {
+                reset_regs(env[j]);
+                act1[j] = act2[j] = 2;
+            }
+        }
+    }
+
+    // ---------------- compute + outputs ----------------
+    StatAcc st;
+    float rew[2 * EPT];
+    uint8_t done8[EPT], info8[EPT];
+    float *my_stage = &stage[warp][lane * EPT * MG_OBS_DIM];
+
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        StepResult r;
+        env_step<PVP>(env[j], act1[j], act2[j], bad[j], rw, r);
+        rew[2 * j] = r.r1; rew[2 * j + 1] = r.r2;
+        done8[j] = r.done ? 1 : 0;
+        info8[j] = (uint8_t)r.info;
+        if (valid[j]) {
+            if (stats) st.add(r, env[j].R1, env[j].R2);
+            if (r.finished) write_episode_outputs(o, e0 + j, r, env[j].R1, env[j].R2);
+        }
+        if (r.done && auto_reset) {          // gym-0.20 vector convention: return the reset obs
+            reset_regs(env[j]);
+            reset_obs(r.obs);
+        }
+        if (full) {
+#pragma unroll
+            for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = r.obs[k];
+        } else if (valid[j]) {
+            float *row = o.obs + (e0 + j) * MG_OBS_DIM;
+#pragma unroll
+            for (int k = 0; k < MG_OBS_DIM; ++k) row[k] = r.obs[k];
+        }
+    }
+
+    // ---------------- stores ----------------
+    if (full) {
+        double t[EPT];
+#define MG_ST(field, arr)                                   \
+        _Pragma("unroll") for (int j = 0; j < EPT; ++j) t[j] = env[j].field; \
+        store_f64<EPT>(arr, e0, t);
+        MG_ST(p1, s.pos1) MG_ST(v1, s.vel1) MG_ST(p2, s.pos2) MG_ST(v2, s.vel2)
+        MG_ST(R1, s.ret1) MG_ST(R2, s.ret2)
+#undef MG_ST
+        if constexpr (EPT == 2) {
+            *reinterpret_cast<uint2 *>(s.meta + e0) = make_uint2(env[0].meta, env[1].meta);
+            __stcs(reinterpret_cast<float4 *>(o.rew + 2 * e0), make_float4(rew[0], rew[1], rew[2], rew[3]));
+            __stcs(reinterpret_cast<uchar2 *>(o.done + e0), make_uchar2(done8[0], done8[1]));
+            __stcs(reinterpret_cast<uchar2 *>(o.info + e0), make_uchar2(info8[0], info8[1]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPT / 4; ++k) {
+                *reinterpret_cast<uint4 *>(s.meta + e0 + 4 * k) =
+                    make_uint4(env[4 * k].meta, env[4 * k + 1].meta, env[4 * k + 2].meta, env[4 * k + 3].meta);
+                __stcs(reinterpret_cast<uchar4 *>(o.done + e0 + 4 * k),
+                       make_uchar4(done8[4 * k], done8[4 * k + 1], done8[4 * k + 2], done8[4 * k + 3]));
+                __stcs(reinterpret_cast<uchar4 *>(o.info + e0 + 4 * k),
+                       make_uchar4(info8[4 * k], info8[4 * k + 1], info8[4 * k + 2], info8[4 * k + 3]));
+            }
+#pragma unroll
+            for (int k = 0; k < EPT / 2; ++k)
+                __stcs(reinterpret_cast<float4 *>(o.rew + 2 * e0 + 4 * k),
+                       make_float4(rew[4 * k], rew[4 * k + 1], rew[4 * k + 2], rew[4 * k + 3]));
+        }
+        // obs rows of this warp are one contiguous, 16-byte aligned span of 32*EPT*40 bytes
+        __syncwarp();
+        const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
+        float4 *dst = reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM);
+        constexpr int kVec = 32 * EPT * MG_OBS_DIM / 4;   // float4 per warp
+#pragma unroll
+        for (int k = 0; k < kVec / 32; ++k) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int64_t e = e0 + j;
+            if (!valid[j]) continue;
+            s.pos1[e] = env[j].p1; s.vel1[e] = env[j].v1; s.pos2[e] = env[j].p2; s.vel2[e] = env[j].v2;
+            s.ret1[e] = env[j].R1; s.ret2[e] = env[j].R2; s.meta[e] = env[j].meta;
+            o.rew[2 * e] = rew[2 * j]; o.rew[2 * e + 1] = rew[2 * j + 1];
+            o.done[e] = done8[j]; o.info[e] = info8[j];
+        }
+    }
+
+    if (stats) flush_stats(st, stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS, 0xFFFFFFFFu, lane);
+}
+
+// =================================================================================================
+// merge_rollout_kernel: k consecutive steps with in-kernel Philox actions; state stays in
+// registers, outputs are time-major.  One env per thread element, EPT=2 vector state I/O.
+// =================================================================================================
+template <bool PVP>
+__global__ void __launch_bounds__(kBlock)
+merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actions_out, const int64_t n,
+                     const uint64_t seed, const uint64_t env_id_base, const uint64_t step0,
+                     const int k_steps, const MgRewards rw, const uint32_t flags,
+                     unsigned long long *__restrict__ stats) {
+    constexpr int EPT = 2;
+    __shared__ __align__(16) float stage[kWarps][32 * EPT * MG_OBS_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
+    if (warp_base >= n) return;
+    const bool full = warp_base + 32 * EPT <= n;
+    const int64_t e0 = warp_base + (int64_t)lane * EPT;
+    const bool auto_reset = (flags & MG_FLAG_AUTO_RESET) != 0u;
+
+    EnvRegs env[EPT];
+    bool valid[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const int64_t e = e0 + j;
+        valid[j] = e < n;
+        if (valid[j]) env[j] = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], s.ret1[e], s.ret2[e], s.meta[e]};
+        else reset_regs(env[j]);
+    }
+    unsigned long long *stats_row = stats ? stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS : nullptr;
+    float *my_stage = &stage[warp][lane * EPT * MG_OBS_DIM];
+
+    for (int t = 0; t < k_steps; ++t) {
+        StatAcc st;
+        const int64_t toff = (int64_t)t * n;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int64_t e = e0 + j;
+            int a1, a2;
+            philox_actions(seed, env_id_base + (uint64_t)e, step0 + (uint64_t)t, a1, a2);
+            StepResult r;
+            env_step<PVP>(env[j], a1, a2, false, rw, r);
+            if (valid[j]) {
+                if (stats) st.add(r, env[j].R1, env[j].R2);
+                if (r.finished) write_episode_outputs(o, e, r, env[j].R1, env[j].R2);
+            }
+            if (r.done && auto_reset) { reset_regs(env[j]); reset_obs(r.obs); }
+            if (valid[j]) {
+                if (o.rew) __stcs(reinterpret_cast<float2 *>(o.rew + 2 * (toff + e)), make_float2(r.r1, r.r2));
+                if (o.done) __stcs(o.done + toff + e, (uint8_t)(r.done ? 1 : 0));
+                if (o.info) __stcs(o.info + toff + e, (uint8_t)r.info);
+                if (actions_out) __stcs(reinterpret_cast<uchar2 *>(actions_out + 2 * (toff + e)),
+                                        make_uchar2((uint8_t)a1, (uint8_t)(PVP ? a2 : 0)));
+            }
+            if (o.obs) {
+                if (full) {
+#pragma unroll
+                    for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = r.obs[k];
+                } else if (valid[j]) {
+                    float *row = o.obs + (toff + e) * MG_OBS_DIM;
+#pragma unroll
+                    for (int k = 0; k < MG_OBS_DIM; ++k) row[k] = r.obs[k];
+                }
+            }
+        }
+        if (o.obs && full) {
+            __syncwarp();
+            const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
+            float4 *dst = reinterpret_cast<float4 *>(o.obs + (toff + warp_base) * MG_OBS_DIM);
+#pragma unroll
+            for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+            __syncwarp();
+        }
+        if (stats) flush_stats(st, stats_row, 0xFFFFFFFFu, lane);
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const int64_t e = e0 + j;
+        if (!valid[j]) continue;
+        s.pos1[e] = env[j].p1; s.vel1[e] = env[j].v1; s.pos2[e] = env[j].p2; s.vel2[e] = env[j].v2;
+        s.ret1[e] = env[j].R1; s.ret2[e] = env[j].R2; s.meta[e] = env[j].meta;
+    }
+}
+
+// =================================================================================================
+// merge_reset_kernel: MergeEnv.reset() (+ observe()) — one env per thread.
+// =================================================================================================
+__global__ void __launch_bounds__(kBlock)
+merge_reset_kernel(const MgState s, const int64_t n, const uint8_t *__restrict__ mask, float *__restrict__ obs) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= n) return;
+    EnvRegs r;
+    if (!mask || mask[e]) {
+        reset_regs(r);
+        s.pos1[e] = r.p1; s.vel1[e] = r.v1; s.pos2[e] = r.p2; s.vel2[e] = r.v2;
+        s.ret1[e] = 0.0; s.ret2[e] = 0.0; s.meta[e] = 0u;
+    } else {
+        r = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], 0.0, 0.0, 0u};
+    }
+    if (obs) {
+        float ob[MG_OBS_DIM];
+        observe(r, ob);
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM; ++k) obs[e * MG_OBS_DIM + k] = ob[k];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+sample_actions_kernel(uint8_t *__restrict__ a1, uint8_t *__restrict__ a2, const int64_t n,
+                      const uint64_t seed, const uint64_t env_id_base, const uint64_t step) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= n) return;
+    int x1, x2;
+    philox_actions(seed, env_id_base + (uint64_t)e, step, x1, x2);
+    a1[e] = (uint8_t)x1;
+    if (a2) a2[e] = (uint8_t)x2;
+}
+
+}  // namespace mg
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof g_err, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_state(const MgState *s) {
+    if (!s) return fail(MG_ERR_NULL_POINTER, "state is NULL");
+    const void *ptrs[] = {s->pos1, s->vel1, s->pos2, s->vel2, s->ret1, s->ret2, s->meta};
+    for (const void *p : ptrs) {
+        if (!p) return fail(MG_ERR_NULL_POINTER, "a state array pointer is NULL");
+        if (!aligned16(p)) return fail(MG_ERR_ALIGNMENT, "state arrays must be 16-byte aligned");
+    }
+    return MG_OK;
+}
+int check_out(const MgOut *o, bool all_required) {
+    if (!o) return fail(MG_ERR_NULL_POINTER, "out is NULL");
+    if (all_required && (!o->obs || !o->rew || !o->done || !o->info))
+        return fail(MG_ERR_NULL_POINTER, "out.obs/rew/done/info must be non-NULL");
+    const void *ptrs[] = {o->obs, o->rew, o->done, o->info, o->term_obs, o->ep_ret, o->ep_len};
+    for (const void *p : ptrs)
+        if (p && !aligned16(p)) return fail(MG_ERR_ALIGNMENT, "output arrays must be 16-byte aligned");
+    return MG_OK;
+}
+const MgRewards kDefaultRewards = {2.0, 1.0, -10.0, 0.001, 0.0};
+
+template <typename ActT>
+cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const void *a2, int64_t n,
+                        const MgRewards &rw, uint32_t flags, int64_t *stats, cudaStream_t st) {
+    constexpr int EPT = 2;
+    const int64_t per_block = (int64_t)mg::kBlock * EPT;
+    const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
+    auto *stp = reinterpret_cast<unsigned long long *>(stats);
+    if (a2)
+        mg::merge_step_kernel<EPT, ActT, true><<<grid, mg::kBlock, 0, st>>>(
+            s, o, (const ActT *)a1, (const ActT *)a2, n, rw, flags, stp);
+    else
+        mg::merge_step_kernel<EPT, ActT, false><<<grid, mg::kBlock, 0, st>>>(
+            s, o, (const ActT *)a1, nullptr, n, rw, flags, stp);
+    return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" {
+
+MG_API int mg_version(void) { return MG_ABI_VERSION; }
+MG_API const char *mg_last_error(void) { return g_err; }
+
+MG_API int mg_get_constants(MgConstants *c) {
+    if (!c) return fail(MG_ERR_NULL_POINTER, "out is NULL");
+    c->R = mg::kR; c->H = mg::kH; c->W = mg::kW; c->dT = mg::kDT;
+    c->start_point = mg::kStart; c->end_point = mg::kEnd; c->prediction_t = mg::kPredT;
+    c->init_vel = mg::kInitVel; c->action_dv = mg::kActionDv;
+    c->vehicle_w = mg::kVehicleW; c->vehicle_h = mg::kVehicleH; c->max_steps = mg::kMaxSteps;
+    c->num_actions = MG_NUM_ACTIONS; c->obs_dim = MG_OBS_DIM;
+    c->stats_rows = MG_STATS_ROWS; c->stats_cols = MG_STATS_COLS;
+    c->return_fixed_point_scale = mg::kRetScale;
+    return MG_OK;
+}
+
+MG_API int mg_default_rewards(MgRewards *r) {
+    if (!r) return fail(MG_ERR_NULL_POINTER, "out is NULL");
+    *r = kDefaultRewards;
+    return MG_OK;
+}
+
+MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask, float *obs, void *stream) {
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (n == 0) return MG_OK;
+    if (int rc = check_state(state)) return rc;
+    const unsigned grid = (unsigned)((n + mg::kBlock - 1) / mg::kBlock);
+    mg::merge_reset_kernel<<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(*state, n, mask, obs);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_reset launch");
+    return MG_OK;
+}
+
+MG_API int mg_step(const MgState *state, int64_t n, const void *a1, const void *a2, int act_dtype,
+                   const MgRewards *rewards, const MgOut *out, int64_t *stats, uint32_t flags,
+                   void *stream) {
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (flags & ~MG_FLAG_AUTO_RESET) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (act_dtype < MG_ACT_U8 || act_dtype > MG_ACT_I64)
+        return fail(MG_ERR_BAD_DTYPE, "act_dtype must be MG_ACT_U8, MG_ACT_I32 or MG_ACT_I64");
+    if (n == 0) return MG_OK;
+    if (int rc = check_state(state)) return rc;
+    if (int rc = check_out(out, true)) return rc;
+    if (!a1) return fail(MG_ERR_NULL_POINTER, "a1 is NULL");
+    const MgRewards rw = rewards ? *rewards : kDefaultRewards;
+    cudaError_t e;
+    switch (act_dtype) {
+        case MG_ACT_U8:  e = launch_step<uint8_t>(*state, *out, a1, a2, n, rw, flags, stats, (cudaStream_t)stream); break;
+        case MG_ACT_I32: e = launch_step<int32_t>(*state, *out, a1, a2, n, rw, flags, stats, (cudaStream_t)stream); break;
+        case MG_ACT_I64: e = launch_step<int64_t>(*state, *out, a1, a2, n, rw, flags, stats, (cudaStream_t)stream); break;
+        default: return fail(MG_ERR_BAD_DTYPE, "act_dtype must be MG_ACT_U8, MG_ACT_I32 or MG_ACT_I64");
+    }
+    if (e) return cuda_fail(e, "mg_step launch");
+    return MG_OK;
+}
+
+MG_API int mg_sample_actions(uint8_t *a1, uint8_t *a2, int64_t n, uint64_t seed, uint64_t env_id_base,
+                             uint64_t step, void *stream) {
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (n == 0) return MG_OK;
+    if (!a1) return fail(MG_ERR_NULL_POINTER, "a1 is NULL");
+    const unsigned grid = (unsigned)((n + mg::kBlock - 1) / mg::kBlock);
+    mg::sample_actions_kernel<<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(a1, a2, n, seed, env_id_base, step);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_sample_actions launch");
+    return MG_OK;
+}
+
+MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, uint64_t env_id_base,
+                      uint64_t step0, int32_t k_steps, const MgRewards *rewards, const MgOut *out,
+                      uint8_t *actions_out, int64_t *stats, uint32_t flags, void *stream) {
+    if (n < 0 || k_steps < 0) return fail(MG_ERR_BAD_SIZE, "n < 0 or k_steps < 0");
+    if (flags & ~MG_FLAG_AUTO_RESET) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (n == 0 || k_steps == 0) return MG_OK;
+    if (int rc = check_state(state)) return rc;
+    if (int rc = check_out(out, false)) return rc;
+    const MgRewards rw = rewards ? *rewards : kDefaultRewards;
+    const int64_t per_block = (int64_t)mg::kBlock * 2;
+    const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
+    auto *stp = reinterpret_cast<unsigned long long *>(stats);
+    if (pvp)
+        mg::merge_rollout_kernel<true><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(
+            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, stp);
+    else
+        mg::merge_rollout_kernel<false><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(
+            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, stp);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_rollout launch");
+    return MG_OK;
+}
+
+MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, const uint8_t *h_a2,
+                        uint8_t *d_a1, uint8_t *d_a2, const MgRewards *rewards, const MgOut *d_out,
+                        const MgOut *h_out, int64_t *stats, uint32_t flags, void *stream) {
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (n == 0) return MG_OK;
+    if (!h_a1 || !d_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "h_a1, d_a1, d_out or h_out is NULL");
+    if (h_a2 && !d_a2) return fail(MG_ERR_NULL_POINTER, "h_a2 given without d_a2 scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (n > 0) {
+        if ((e = cudaMemcpyAsync(d_a1, h_a1, (size_t)n, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a1");
+        if (h_a2 && (e = cudaMemcpyAsync(d_a2, h_a2, (size_t)n, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a2");
+    }
+    if (int rc = mg_step(state, n, d_a1, h_a2 ? d_a2 : nullptr, MG_ACT_U8, rewards, d_out, stats, flags, stream)) return rc;
+    if (n > 0) {
+        const size_t N = (size_t)n;
+        if (h_out->obs && (e = cudaMemcpyAsync(h_out->obs, d_out->obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H obs");
+        if (h_out->rew && (e = cudaMemcpyAsync(h_out->rew, d_out->rew, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H rew");
+        if (h_out->done && (e = cudaMemcpyAsync(h_out->done, d_out->done, N, cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H done");
+        if (h_out->info && (e = cudaMemcpyAsync(h_out->info, d_out->info, N, cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H info");
+        if (h_out->term_obs && d_out->term_obs && (e = cudaMemcpyAsync(h_out->term_obs, d_out->term_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H term_obs");
+        if (h_out->ep_ret && d_out->ep_ret && (e = cudaMemcpyAsync(h_out->ep_ret, d_out->ep_ret, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H ep_ret");
+        if (h_out->ep_len && d_out->ep_len && (e = cudaMemcpyAsync(h_out->ep_len, d_out->ep_len, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H ep_len");
+    }
+    if ((e = cudaStreamSynchronize(st))) return cuda_fail(e, "mg_step_host sync");
+    return MG_OK;
+}
+
+}  // extern "C"

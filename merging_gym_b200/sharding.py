@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing: one process per GPU, one independent shard of envs per rank.
+
+The path has no exchange step — envs never interact — so ranks share nothing on the data
+path.  The only collective is the optional SUM all-reduce of the 16-element int64 episode
+statistics vector (NCCL over NVLink on GPUs, gloo in the CPU tests).  Because the statistics are
+integers (returns in 2^24 fixed point) the reduced result is identical for every world size.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from ._native import STAT_NAMES
+
+
+def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous split of global env ids [0, total) -> (first id, count) of `rank`.
+
+    The first `total % world` ranks get one extra env; ids are global so that Philox action
+    streams (key = seed, counter = (global env id, step)) do not depend on the sharding.
+    """
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    q, r = divmod(int(total_envs), int(world_size))
+    base = rank * q + min(rank, r)
+    return base, q + (1 if rank < r else 0)
+
+
+def dist_env() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1 process per GPU)."""
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def init_distributed(backend: str | None = None) -> Tuple[int, int, int]:
+    """Initialise torch.distributed from env:// if WORLD_SIZE > 1.  NCCL when CUDA is present."""
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, local_rank, world
+
+
+def all_reduce_stats(stats: torch.Tensor, async_op: bool = False):
+    """SUM the int64 statistics vector over all ranks (no-op without an initialised group)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return stats
+    stats = stats.contiguous()
+    work = dist.all_reduce(stats, op=dist.ReduceOp.SUM, async_op=async_op)
+    return (stats, work) if async_op else stats
+
+
+def stats_to_dict(totals: np.ndarray, ret_scale: float) -> dict:
+    """int64 totals -> named dict with derived rates (what scripts/main.py:203-227 tracks by hand)."""
+    t = [int(v) for v in np.asarray(totals).reshape(-1)[:len(STAT_NAMES)]]
+    d = dict(zip(STAT_NAMES, t))
+    d["sum_return1"] = d.pop("sum_return1_fx") / ret_scale
+    d["sum_return2"] = d.pop("sum_return2_fx") / ret_scale
+    ep = max(d["episodes"], 1)
+    d["collision_rate"] = d["collisions"] / ep
+    d["merge_success_rate"] = d["merges_ok"] / ep
+    d["win_rate_p1"] = d["wins_p1"] / ep
+    d["win_rate_p2"] = d["wins_p2"] / ep
+    d["mean_length"] = d["sum_length"] / ep
+    d["mean_return1"] = d["sum_return1"] / ep
+    d["mean_return2"] = d["sum_return2"] / ep
+    return d

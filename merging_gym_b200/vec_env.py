@@ -1,0 +1,412 @@
+"""`MergeVecEnv` — gym-0.20-style vectorised front end of the fused CUDA env step.
+
+Host-side mirror of the reference's `MergeEnv` interface (merging_gym/envs/merging_env.py:72-230)
+for N independent env instances that live entirely in GPU memory:
+
+    reference (one env, Python floats)                 this class (N envs, device tensors)
+    ------------------------------------------------   ---------------------------------------------
+    env.reset() -> list[10]                  (:208)    reset() -> obs f32[N,10]
+    env.step(a1, a2|None) -> obs, [r1,r2],   (:138)    step(a1[N], a2[N]|None) -> obs f32[N,10],
+                             done, {"collision"}                 rewards f32[N,2], done bool[N], info
+    env.winner / r1_accumulate / r2_accumulate         .winner u8[N] / .r1_accumulate f64[N] / ...
+    env.action_space.n == 5, observation_space (10,)   single_action_space / single_observation_space
+    env.show_reward()                        (:115)    show_reward()
+
+All tensors are owned by PyTorch (caching allocator, streams, CUDA graphs just work); the
+kernels come from libmerging_b200.so through the C ABI (include/merging_b200.h) and are launched
+on the current torch stream.  Nothing here synchronises with the host unless stated.  There is
+no CPU path: constructing the env without CUDA raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Mapping
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .spaces import Box, Discrete, MultiDiscrete, merge_action_space, merge_observation_space
+
+ACTION_SEED_DEFAULT = 0x5EED
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class StepInfo(Mapping):
+    """Lazy `info` of one vector step: device tensors decoded from the info byte on access.
+
+    Keys: "collision" bool[N] (merging_env.py:144,187), "winner" u8[N] (0 = None; :164-181),
+    "timeout" bool[N] (:142), "bad_action" bool[N], "flags" u8[N] (raw MG_INFO_* bits), and — when
+    the env keeps them — "terminal_observation" f32[N,10], "episode_return" f32[N,2],
+    "episode_length" i32[N]; these three hold, per env, the values of the most recently finished
+    episode and are meaningful where `done` is (or has been) set.
+    """
+
+    _KEYS = ("collision", "winner", "timeout", "bad_action", "flags")
+
+    def __init__(self, flags: torch.Tensor, extras: dict):
+        self._flags = flags
+        self._extras = extras
+
+    def __getitem__(self, k):
+        f = self._flags
+        if k == "flags":
+            return f
+        if k == "collision":
+            return (f & nat.INFO_COLLISION).bool()
+        if k == "winner":
+            return (f & nat.INFO_WINNER_MASK) >> nat.INFO_WINNER_SHIFT
+        if k == "timeout":
+            return (f & nat.INFO_TIMEOUT).bool()
+        if k == "bad_action":
+            return (f & nat.INFO_BAD_ACTION).bool()
+        return self._extras[k]
+
+    def __iter__(self):
+        yield from self._KEYS
+        yield from self._extras
+
+    def __len__(self):
+        return len(self._KEYS) + len(self._extras)
+
+
+class MergeVecEnv:
+    """N device-resident merging envs stepped by one fused kernel launch.
+
+    Parameters
+    ----------
+    num_envs      number of env instances on this device (this rank's shard).
+    mode          "pvp" (two action vectors) or "pve" (`action2=None`: player 2 keeps its speed,
+                  merging_env.py:152).  Only selects the default for `sample_actions`/`rollout`;
+                  `step(a1, None)` is always pve and `step(a1, a2)` always pvp, like the reference.
+    auto_reset    True: gym-0.20 `SyncVectorEnv` convention (finished env is reset inside `step`
+                  and returns its reset observation).  False: the reference's sticky `done`.
+    seed, env_id_base   Philox key and first *global* env id of this shard; trajectories of
+                  synthetic rollouts depend only on (seed, global env id, step), never on sharding.
+    out_slots     number of output buffer sets rotated over steps (a rollout ring, [T,N,...]).
+    episode_info  keep terminal_observation / episode_return / episode_length buffers.
+    track_stats   accumulate episode statistics on the device (see `stats()`).
+    rewards       dict overriding RFirst/RSecond/RCollision/vel_penalty/time_penalty (:28-32).
+    """
+
+    def __init__(self, num_envs: int, mode: str = "pvp", device="cuda", auto_reset: bool = True,
+                 seed: int = ACTION_SEED_DEFAULT, env_id_base: int = 0, out_slots: int = 1,
+                 episode_info: bool = True, track_stats: bool = True, rewards: Optional[dict] = None,
+                 validate_actions: bool = False):
+        if mode not in ("pvp", "pve"):
+            raise ValueError("mode must be 'pvp' or 'pve'")
+        if num_envs < 0 or out_slots < 1:
+            raise ValueError("num_envs must be >= 0 and out_slots >= 1")
+        self._lib = nat.load()                       # raises if the CUDA library is not built
+        if not torch.cuda.is_available():
+            raise nat.NativeError("merging_gym_b200 needs a CUDA device (no CPU fallback exists)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nat.NativeError(f"device must be a CUDA device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = n = int(num_envs)
+        self.mode, self.auto_reset = mode, bool(auto_reset)
+        self.philox_seed, self.env_id_base = int(seed), int(env_id_base)
+        self.validate_actions = bool(validate_actions)
+        self.out_slots = int(out_slots)
+        self._slot = 0
+        self.step_count = 0                          # Philox step counter for sample_actions/rollout
+        self.closed = False
+
+        self._rw = nat.default_rewards()
+        for k, v in (rewards or {}).items():
+            if not hasattr(self._rw, k):
+                raise KeyError(f"unknown reward parameter {k!r}")
+            setattr(self._rw, k, float(v))
+        self.constants = nat.constants()
+
+        dev = self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.pos1 = torch.empty(n, **f64); self.vel1 = torch.empty(n, **f64)
+        self.pos2 = torch.empty(n, **f64); self.vel2 = torch.empty(n, **f64)
+        self.ret1 = torch.zeros(n, **f64); self.ret2 = torch.zeros(n, **f64)
+        self.meta = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._state = nat.MgState(*[t.data_ptr() for t in
+                                    (self.pos1, self.vel1, self.pos2, self.vel2, self.ret1, self.ret2, self.meta)])
+        K = self.out_slots
+        n_pad = (n + 15) // 16 * 16                  # keeps every slot's base pointer 16-byte aligned
+        self.obs_buf = torch.zeros(K, n_pad, nat.OBS_DIM, dtype=torch.float32, device=dev)[:, :n]
+        self.rew_buf = torch.zeros(K, n_pad, 2, dtype=torch.float32, device=dev)[:, :n]
+        self.done_buf = torch.zeros(K, n_pad, dtype=torch.uint8, device=dev)[:, :n]
+        self.info_buf = torch.zeros(K, n_pad, dtype=torch.uint8, device=dev)[:, :n]
+        self._extras = {}
+        if episode_info:
+            self.terminal_obs = torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, device=dev)
+            self.episode_return = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+            self.episode_length = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._extras = {"terminal_observation": self.terminal_obs,
+                            "episode_return": self.episode_return,
+                            "episode_length": self.episode_length}
+        else:
+            self.terminal_obs = self.episode_return = self.episode_length = None
+        self._outs = [nat.MgOut(self.obs_buf[k].data_ptr(), self.rew_buf[k].data_ptr(),
+                                self.done_buf[k].data_ptr(), self.info_buf[k].data_ptr(),
+                                *[None if t is None else t.data_ptr() for t in
+                                  (self.terminal_obs, self.episode_return, self.episode_length)])
+                      for k in range(K)]
+        self.stats_buf = (torch.zeros(nat.STATS_ROWS, nat.STATS_COLS, dtype=torch.int64, device=dev)
+                          if track_stats else None)
+        self.act1 = torch.zeros(n, dtype=torch.uint8, device=dev)     # sample_actions / step_host scratch
+        self.act2 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._host = None
+        self._pending = None
+
+        self.single_observation_space: Box = merge_observation_space()
+        self.single_action_space: Discrete = merge_action_space()
+        self.observation_space = Box(np.tile(self.single_observation_space.low, (n, 1)),
+                                     np.tile(self.single_observation_space.high, (n, 1)), dtype=np.float16)
+        self.action_space = MultiDiscrete(np.full(n, nat.NUM_ACTIONS))
+        self.reset()
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _flags(self):
+        return nat.FLAG_AUTO_RESET if self.auto_reset else 0
+
+    def _as_action(self, a, name):
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a))
+        if a.dtype not in (torch.uint8, torch.int32, torch.int64):
+            if a.dtype in (torch.int8, torch.int16, torch.bool):
+                a = a.to(torch.int32)
+            else:
+                raise TypeError(f"{name}: actions must be integer, got {a.dtype}")
+        if a.device != self.device:
+            a = a.to(self.device, non_blocking=True)
+        a = a.reshape(-1)
+        if a.numel() != self.num_envs:
+            raise ValueError(f"{name}: expected {self.num_envs} actions, got {a.numel()}")
+        if not a.is_contiguous():
+            a = a.contiguous()
+        if self.validate_actions and a.numel():
+            # the reference raises KeyError from action_dict[action] (merging_env.py:101,147)
+            lo, hi = int(a.min()), int(a.max())            # host sync: debug option only
+            if lo < 0 or hi >= nat.NUM_ACTIONS:
+                raise KeyError(lo if lo < 0 else hi)
+        return a
+
+    _ACT_DTYPE = {torch.uint8: nat.ACT_U8, torch.int32: nat.ACT_I32, torch.int64: nat.ACT_I64}
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`MergeEnv.reset()` (merging_env.py:208-230) for all envs, or where `mask` is set.
+
+        Returns obs f32[N,10] (current slot).  Deterministic start: pos=50, vel=20 for both cars.
+        """
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).reshape(-1).to(torch.uint8).contiguous()
+            if m.numel() != self.num_envs:
+                raise ValueError("mask must have num_envs elements")
+        obs = self.obs_buf[self._slot]
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_reset(C.byref(self._state), self.num_envs, _ptr(m), _ptr(obs),
+                                         self._stream()), "mg_reset")
+        return obs
+
+    def step_async(self, a1, a2=None) -> None:
+        a1 = self._as_action(a1, "action1")
+        if a2 is not None:
+            a2 = self._as_action(a2, "action2")
+            if a2.dtype != a1.dtype:
+                a2 = a2.to(a1.dtype)
+        self._slot = (self._slot + 1) % self.out_slots
+        k = self._slot
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_step(C.byref(self._state), self.num_envs, _ptr(a1), _ptr(a2),
+                                        self._ACT_DTYPE[a1.dtype], C.byref(self._rw),
+                                        C.byref(self._outs[k]), _ptr(self.stats_buf), self._flags(),
+                                        self._stream()), "mg_step")
+        self._pending = k
+
+    def step_wait(self):
+        k = self._pending
+        if k is None:
+            raise RuntimeError("step_wait() called without step_async()")
+        self._pending = None
+        return (self.obs_buf[k], self.rew_buf[k], self.done_buf[k].view(torch.bool),
+                StepInfo(self.info_buf[k], self._extras))
+
+    def step(self, a1, a2=None):
+        """`MergeEnv.step(action1, action2=None)` (merging_env.py:138-195) for all envs.
+
+        a1, a2: integer tensors/arrays of N actions in 0..4 (uint8, int32 or int64; device tensors
+        are used in place).  Returns (obs f32[N,10], rewards f32[N,2], done bool[N], info) — device
+        tensors that alias this env's output slot; they are overwritten `out_slots` steps later.
+        """
+        self.step_async(a1, a2)
+        return self.step_wait()
+
+    def close(self):
+        self.closed = True
+
+    def seed(self, seed=None):
+        """Sets the Philox key of the synthetic action stream (the env itself has no randomness)."""
+        if seed is not None:
+            self.philox_seed = int(seed)
+        return [seed]
+
+    def show_reward(self):
+        """merging_env.py:115-116."""
+        r = self._rw
+        return r.r_first, r.r_second, r.r_collision, r.vel_penalty
+
+    # ------------------------------------------------------------------ reference attributes
+    @property
+    def winner(self) -> torch.Tensor:
+        """u8[N]: 0 = None, 1, 2 (merging_env.py:212)."""
+        return ((self.meta >> nat.META_WINNER_SHIFT) & 3).to(torch.uint8)
+
+    @property
+    def steps(self) -> torch.Tensor:
+        """i32[N] steps since reset (time_stamp / dT, merging_env.py:141)."""
+        return self.meta & nat.META_STEPS_MASK
+
+    @property
+    def done(self) -> torch.Tensor:
+        return (self.meta & nat.META_DONE).bool()
+
+    @property
+    def r1_accumulate(self) -> torch.Tensor:
+        return self.ret1
+
+    @property
+    def r2_accumulate(self) -> torch.Tensor:
+        return self.ret2
+
+    @staticmethod
+    def opponent_view(obs: torch.Tensor) -> torch.Tensor:
+        """`state[5:] + state[:5]` — the observation from player 2's seat (scripts/main.py:199)."""
+        return torch.cat([obs[..., 5:], obs[..., :5]], dim=-1)
+
+    # ------------------------------------------------------------------ synthetic actions / rollouts
+    def sample_actions(self, step: Optional[int] = None):
+        """Uniform-random actions for this shard at rollout step `step` (default: internal counter).
+
+        Counter-based Philox4x32-10: key = seed, counter = (global env id, step).  Returns the
+        internal uint8 device buffers (a1, a2); a2 is None in pve mode.
+        """
+        if step is None:
+            step = self.step_count
+            self.step_count += 1
+        a2 = self.act2 if self.mode == "pvp" else None
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_sample_actions(_ptr(self.act1), _ptr(a2), self.num_envs, self.philox_seed,
+                                                  self.env_id_base, int(step), self._stream()),
+                      "mg_sample_actions")
+        return self.act1, a2
+
+    def rollout(self, k_steps: int, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None,
+                done: Optional[torch.Tensor] = None, info: Optional[torch.Tensor] = None,
+                actions: Optional[torch.Tensor] = None, step0: Optional[int] = None):
+        """`k_steps` random-action steps in ONE launch (state stays in registers between steps).
+
+        Time-major output tensors are optional: obs f32[k,N,10], rew f32[k,N,2], done u8[k,N],
+        info u8[k,N], actions u8[k,N,2].  The action stream equals `sample_actions` at steps
+        step0..step0+k-1, so `rollout(k)` and k x (`sample_actions` + `step`) give identical results.
+        """
+        n, k = self.num_envs, int(k_steps)
+        if step0 is None:
+            step0 = self.step_count
+            self.step_count += k
+
+        def chk(t, shape, dtype, name):
+            if t is None:
+                return None
+            if tuple(t.shape) != shape or t.dtype != dtype or t.device != self.device or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {shape} on {self.device}")
+            return t
+        chk(obs, (k, n, nat.OBS_DIM), torch.float32, "obs"); chk(rew, (k, n, 2), torch.float32, "rew")
+        chk(done, (k, n), torch.uint8, "done"); chk(info, (k, n), torch.uint8, "info")
+        chk(actions, (k, n, 2), torch.uint8, "actions")
+        out = nat.MgOut(*[None if t is None else t.data_ptr() for t in
+                          (obs, rew, done, info, self.terminal_obs, self.episode_return, self.episode_length)])
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_rollout(C.byref(self._state), n, int(self.mode == "pvp"), self.philox_seed,
+                                           self.env_id_base, int(step0), k, C.byref(self._rw),
+                                           C.byref(out), _ptr(actions), _ptr(self.stats_buf),
+                                           self._flags(), self._stream()), "mg_rollout")
+
+    # ------------------------------------------------------------------ host-buffer path
+    def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None):
+        """Drop-in for host-resident callers: uint8 NumPy actions in, NumPy outputs out.
+
+        One `mg_step_host` call = H2D of the actions, the fused step, D2H of obs/rew/done/info into
+        pinned host buffers, stream synchronise.  Returns (obs, rewards, done, info_flags) as NumPy
+        views of those pinned buffers (overwritten by the next call).
+        """
+        n = self.num_envs
+        if self._host is None:
+            pin = dict(pin_memory=True)
+            self._host = dict(a1=torch.zeros(n, dtype=torch.uint8, **pin), a2=torch.zeros(n, dtype=torch.uint8, **pin),
+                              obs=torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, **pin),
+                              rew=torch.zeros(n, 2, dtype=torch.float32, **pin),
+                              done=torch.zeros(n, dtype=torch.uint8, **pin),
+                              info=torch.zeros(n, dtype=torch.uint8, **pin))
+            h = self._host
+            self._host_out = nat.MgOut(h["obs"].data_ptr(), h["rew"].data_ptr(), h["done"].data_ptr(),
+                                       h["info"].data_ptr(), None, None, None)
+        h = self._host
+        h["a1"].numpy()[:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
+        if a2 is not None:
+            h["a2"].numpy()[:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
+        self._slot = (self._slot + 1) % self.out_slots
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_step_host(C.byref(self._state), n, _ptr(h["a1"]),
+                                             _ptr(h["a2"]) if a2 is not None else None,
+                                             _ptr(self.act1), _ptr(self.act2), C.byref(self._rw),
+                                             C.byref(self._outs[self._slot]), C.byref(self._host_out),
+                                             _ptr(self.stats_buf), self._flags(), self._stream()),
+                      "mg_step_host")
+        return h["obs"].numpy(), h["rew"].numpy(), h["done"].numpy().view(np.bool_), h["info"].numpy()
+
+    # ------------------------------------------------------------------ statistics
+    def stats_tensor(self) -> torch.Tensor:
+        """int64[16] device totals (sum of the per-block partial rows); no host sync."""
+        if self.stats_buf is None:
+            raise RuntimeError("track_stats=False")
+        return self.stats_buf.sum(dim=0)
+
+    def stats(self, reduce: bool = False, reset: bool = False) -> dict:
+        """Episode statistics as a dict (host sync).  `reduce=True` sums over all ranks first."""
+        from .sharding import all_reduce_stats, stats_to_dict
+        t = self.stats_tensor()
+        if reduce:
+            t = all_reduce_stats(t)
+        d = stats_to_dict(t.cpu().numpy(), self.constants.return_fixed_point_scale)
+        if reset:
+            self.stats_buf.zero_()
+        return d
+
+    # ------------------------------------------------------------------ checkpoint
+    _STATE_KEYS = ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta")
+
+    def state_dict(self) -> dict:
+        d = {k: getattr(self, k).clone() for k in self._STATE_KEYS}
+        d["step_count"] = self.step_count
+        if self.stats_buf is not None:
+            d["stats"] = self.stats_buf.clone()
+        return d
+
+    def load_state_dict(self, d: dict) -> None:
+        for k in self._STATE_KEYS:
+            getattr(self, k).copy_(d[k])
+        self.step_count = int(d.get("step_count", 0))
+        if self.stats_buf is not None and "stats" in d:
+            self.stats_buf.copy_(d["stats"])
+
+    def __repr__(self):
+        return (f"MergeVecEnv(num_envs={self.num_envs}, mode={self.mode!r}, device={self.device}, "
+                f"auto_reset={self.auto_reset})")

@@ -134,7 +134,7 @@ static inline uint8_t step_row(const MgoState *s, int64_t i, int a1, int a2, int
                              (bad ? INFO_BAD_ACTION : 0));
     if (bad) st[ST_BAD_ACTIONS] += 1;
 
-    if (done && auto_reset) {
+    if (done && !s->done[i]) {   /* done became true in this step (always so under auto-reset) */
         if (term_obs) memcpy(term_obs, o, sizeof o);
         if (ep_ret) { ep_ret[0] = R1; ep_ret[1] = R2; }
         if (ep_len) *ep_len = s->steps[i];
@@ -142,6 +142,8 @@ static inline uint8_t step_row(const MgoState *s, int64_t i, int a1, int a2, int
         st[ST_WINS_P2] += (w == 2); st[ST_TIMEOUTS] += timeout;
         st[ST_MERGES_OK] += (!col && !timeout); st[ST_SUM_LENGTH] += s->steps[i];
         sumret[0] += R1; sumret[1] += R2;
+    }
+    if (done && auto_reset) {
         reset_row(s, i);
         observe(s->pos1[i], s->vel1[i], s->pos2[i], s->vel2[i], obs);
     } else {

@@ -292,6 +292,7 @@ class RefVecEnv:
         self.time_stamp += dT
         self.steps += 1
         timeout = self.time_stamp > TIME_LIMIT
+        prev_done = self.done.copy()
         done = self.done | timeout
 
         vt1 = (10 * a1).astype(np.float64)
@@ -346,8 +347,9 @@ class RefVecEnv:
         rewards = np.stack([r1, r2], axis=1)
         done_out = done.copy()
 
-        if self.auto_reset and done.any():
-            m = done_out                      # a copy: _reset_rows clears self.done in place
+        fin = done_out & ~prev_done           # done became true in this step (always so under auto-reset)
+        if fin.any():
+            m = fin
             self.terminal_obs[m] = obs[m]
             self.ep_ret[m, 0] = self.ret1[m]; self.ep_ret[m, 1] = self.ret2[m]
             self.ep_len[m] = self.steps[m]
@@ -361,6 +363,8 @@ class RefVecEnv:
             st["sum_length"] += int(self.steps[m].sum())
             st["sum_return1"] += float(self.ret1[m].sum())
             st["sum_return2"] += float(self.ret2[m].sum())
+        if self.auto_reset and done_out.any():
+            m = done_out                      # a copy: _reset_rows clears self.done in place
             self._reset_rows(m)
             obs = obs.copy()
             obs[m] = self.observe()[m]

@@ -1,0 +1,108 @@
+"""The C-ABI shared library: it loads, exports every symbol include/merging_b200.h declares,
+agrees with the Python binding on struct layouts and constants, and rejects bad arguments
+without touching a GPU.  (No compute calls here — those are the `-m gpu` tests.)"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from merging_gym_b200 import _native as nat
+from merging_gym_b200 import build as mgbuild
+from merging_gym_b200._paths import INCLUDE_DIR, LIB_PATH
+from oracle import merge_oracle as mo
+
+HEADER = os.path.join(INCLUDE_DIR, "merging_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    mgbuild.build()
+    return nat.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"MG_API\s+[\w\s\*]+?\b(mg_\w+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    assert declared_symbols() == sorted([
+        "mg_version", "mg_last_error", "mg_get_constants", "mg_default_rewards", "mg_reset",
+        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host"])
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH], text=True)
+    exported = set(re.findall(r"\bT (mg_\w+)", out))
+    assert exported == set(declared_symbols())       # nothing else leaks (visibility=hidden)
+
+
+def test_library_is_sm100a_native():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_version_and_constants(lib):
+    assert lib.mg_version() == nat.MG_ABI_VERSION
+    c = nat.constants()
+    assert (c.R, c.H, c.W, c.dT) == (mo.R, mo.H, mo.W, mo.dT)
+    assert (c.start_point, c.end_point, c.prediction_t) == (mo.START_POINT, mo.END_POINT, mo.prediction_t)
+    assert (c.vehicle_w, c.vehicle_h, c.max_steps) == (mo.VEHICLE_W, mo.VEHICLE_H, 2501)
+    assert (c.num_actions, c.obs_dim) == (mo.NUM_ACTIONS, mo.OBS_DIM)
+    assert (c.stats_rows, c.stats_cols) == (nat.STATS_ROWS, nat.STATS_COLS)
+    assert c.return_fixed_point_scale == 2.0 ** 24
+    r = nat.default_rewards()
+    assert (r.r_first, r.r_second, r.r_collision, r.vel_penalty, r.time_penalty) == \
+        (mo.RFirst, mo.RSecond, mo.RCollision, mo.vel_penalty, mo.time_penalty)
+
+
+def test_header_macros_match_binding():
+    src = open(HEADER).read()
+    def macro(name):
+        return int(re.search(rf"#define {name} (0x[0-9A-Fa-f]+|\d+)", src).group(1), 0)
+    assert macro("MG_ABI_VERSION") == nat.MG_ABI_VERSION
+    assert macro("MG_OBS_DIM") == nat.OBS_DIM and macro("MG_NUM_ACTIONS") == nat.NUM_ACTIONS
+    assert macro("MG_STATS_ROWS") == nat.STATS_ROWS and macro("MG_STATS_COLS") == nat.STATS_COLS
+    for n, v in [("MG_INFO_COLLISION", nat.INFO_COLLISION), ("MG_INFO_TIMEOUT", nat.INFO_TIMEOUT),
+                 ("MG_INFO_DONE", nat.INFO_DONE), ("MG_INFO_BAD_ACTION", nat.INFO_BAD_ACTION),
+                 ("MG_INFO_WINNER_MASK", nat.INFO_WINNER_MASK), ("MG_META_DONE", nat.META_DONE),
+                 ("MG_META_STEPS_MASK", nat.META_STEPS_MASK), ("MG_FLAG_AUTO_RESET", nat.FLAG_AUTO_RESET)]:
+        assert macro(n) == v, n
+    # and with the oracle's copy of the info bits
+    assert (nat.INFO_COLLISION, nat.INFO_TIMEOUT, nat.INFO_DONE, nat.INFO_BAD_ACTION) == \
+        (mo.INFO_COLLISION, mo.INFO_TIMEOUT, mo.INFO_DONE, mo.INFO_BAD_ACTION)
+
+
+def test_struct_sizes():
+    assert C.sizeof(nat.MgState) == 7 * 8 and C.sizeof(nat.MgOut) == 7 * 8
+    assert C.sizeof(nat.MgRewards) == 5 * 8
+    assert C.sizeof(nat.MgConstants) == 9 * 8 + 7 * 4 + 4 + 8      # 4 bytes padding before the double
+
+
+def test_argument_errors_without_gpu(lib):
+    st, out, rw = nat.MgState(), nat.MgOut(), nat.default_rewards()
+    assert lib.mg_step(C.byref(st), -1, None, None, 0, C.byref(rw), C.byref(out), None, 0, None) == -2
+    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0x80, None) == -4
+    assert lib.mg_step(C.byref(st), 8, None, None, 7, C.byref(rw), C.byref(out), None, 0, None) == -5
+    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, None) == -1
+    assert b"NULL" in lib.mg_last_error()
+    st = nat.MgState(*([0x1008] * 7))                                # not 16-byte aligned
+    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, None) == -3
+    assert lib.mg_reset(None, 8, None, None, None) == -1
+    assert lib.mg_get_constants(None) == -1
+    # n == 0 is a no-op that needs no device
+    assert lib.mg_step(C.byref(nat.MgState()), 0, None, None, 0, None, C.byref(out), None, 1, None) == 0
+    assert lib.mg_reset(C.byref(nat.MgState()), 0, None, None, None) == 0
+    assert lib.mg_rollout(C.byref(nat.MgState()), 0, 1, 0, 0, 0, 4, None, C.byref(out), None, None, 1, None) == 0
+    assert lib.mg_sample_actions(None, None, 0, 0, 0, 0, None) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setenv("MERGING_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(nat, "_lib", None)
+    with pytest.raises(nat.NativeError, match="no CPU or PyTorch fallback"):
+        nat.load()

@@ -1,0 +1,360 @@
+"""Parity of the CUDA path (through the C ABI, via MergeVecEnv/ctypes) with the CPU oracle.
+
+Bar (BASELINE.json north_star): done / collision / winner / timeout flags and step counts
+bit-exact; observations, rewards and returns within 1e-5 relative, in the form
+|d| <= 1e-5 * max(|ref|, 1e-3)  (SURVEY.md §8d config 2).  The float64 state (pos, vel, returns)
+is additionally required to be BIT-IDENTICAL to the oracle's, which is what makes the flags exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import merge_oracle as mo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import merging_gym_b200
+    return merging_gym_b200
+
+
+def assert_step_equal(out, ref, t=None, state=None):
+    obs, rew, done, info = out
+    robs, rrew, rdone, rinfo = ref
+    flags = info["flags"].cpu().numpy() if not isinstance(info, np.ndarray) else info
+    assert np.array_equal(done.cpu().numpy() if hasattr(done, "cpu") else done, rdone), f"done differs at step {t}"
+    assert np.array_equal(flags, rinfo), f"info flags differ at step {t}"
+    e = rel_err(obs.cpu().numpy() if hasattr(obs, "cpu") else obs, robs).max()
+    assert e <= TOL, f"obs rel err {e} at step {t}"
+    e = rel_err(rew.cpu().numpy() if hasattr(rew, "cpu") else rew, rrew).max()
+    assert e <= TOL, f"reward rel err {e} at step {t}"
+
+
+def assert_state_bit_exact(env, ref):
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2"):
+        a = getattr(env, k).cpu().numpy()
+        assert np.array_equal(a, getattr(ref, k)), f"state {k} is not bit-identical"
+    assert np.array_equal(env.steps.cpu().numpy(), np.minimum(ref.steps, 4095))
+    assert np.array_equal(env.winner.cpu().numpy(), ref.winner)
+
+
+def test_reset_observation(mg):
+    env = mg.MergeVecEnv(130)
+    obs = env.reset().cpu().numpy()
+    ref = mo.RefVecEnv(130).reset()
+    assert rel_err(obs, ref).max() <= 1e-7
+    assert obs[0].tolist() == np.float32(ref[0]).tolist()       # fp32 cast of the fp64 oracle value
+    assert obs[0, 1] == np.float32(-30.057386826127185)
+
+
+@pytest.mark.parametrize("pvp", [True, False])
+def test_config2_trajectory_parity_4096(mg, pvp):
+    """BASELINE.json configs[1]: 4096 envs, random discrete actions, 640 steps, auto-reset."""
+    N, T = 4096, 640
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    acts = torch.randint(0, 5, (T, N, 2), dtype=torch.uint8, device="cuda", generator=g)
+    acts_h = acts.cpu().numpy()
+    env = mg.MergeVecEnv(N, mode="pvp" if pvp else "pve")
+    ref = mo.RefVecEnv(N, pvp=pvp)
+    n_done = 0
+    for t in range(T):
+        out = env.step(acts[t, :, 0], acts[t, :, 1] if pvp else None)
+        r = ref.step(acts_h[t, :, 0], acts_h[t, :, 1] if pvp else None)
+        assert_step_equal(out, r, t)
+        m = r[2]
+        if m.any():
+            n_done += int(m.sum())
+            info = out[3]
+            assert rel_err(info["terminal_observation"].cpu().numpy()[m], ref.terminal_obs[m]).max() <= TOL
+            assert np.array_equal(info["episode_length"].cpu().numpy()[m], ref.ep_len[m])
+            assert rel_err(info["episode_return"].cpu().numpy()[m], ref.ep_ret[m]).max() <= TOL
+    assert n_done > 2 * N
+    assert_state_bit_exact(env, ref)
+    s, rs = env.stats(), ref.stats
+    for k in ("episodes", "collisions", "wins_p1", "wins_p2", "timeouts", "merges_ok", "sum_length", "bad_actions"):
+        assert s[k] == rs[k], k
+    assert s["episodes"] == n_done
+    assert abs(s["sum_return1"] - rs["sum_return1"]) <= 1e-6 * n_done
+    assert abs(s["sum_return2"] - rs["sum_return2"]) <= 1e-6 * n_done
+
+
+def test_golden_vec16_from_reference_file(mg):
+    """Kernel vs the trajectory recorded from the unmodified reference file (16 envs x 640)."""
+    tr = dict(np.load(os.path.join(GOLDEN, "pvp_vec16_trace.npz")))
+    T, N = tr["done"].shape
+    env = mg.MergeVecEnv(N)
+    acts = torch.from_numpy(tr["actions"]).cuda()
+    for t in range(T):
+        obs, rew, done, info = env.step(acts[t, :, 0], acts[t, :, 1])
+        assert np.array_equal(done.cpu().numpy(), tr["done"][t]), t
+        assert np.array_equal(info["collision"].cpu().numpy(), tr["collision"][t]), t
+        assert np.array_equal(info["winner"].cpu().numpy(), tr["winner"][t]), t
+        assert rel_err(obs.cpu().numpy(), tr["obs"][t]).max() <= TOL, t
+        assert rel_err(rew.cpu().numpy(), tr["rewards"][t]).max() <= TOL, t
+        m = tr["done"][t]
+        if m.any():
+            assert np.array_equal(info["episode_length"].cpu().numpy()[m], tr["ep_len"][t][m])
+            assert rel_err(info["episode_return"].cpu().numpy()[m], tr["ep_ret"][t][m]).max() <= TOL
+            assert rel_err(info["terminal_observation"].cpu().numpy()[m], tr["step_obs"][t][m]).max() <= TOL
+
+
+def test_known_answer_episodes_sticky_done(mg):
+    """All scripted KAT episodes side by side in one launch, auto_reset off, run to 2600 steps
+    (covers the 2501-step time limit, '>=' vs '>', truncation vs rounding, winner-keeps-driving)."""
+    kats = json.load(open(os.path.join(GOLDEN, "kat.json")))[:-1]
+    kats = [k for k in kats if k["a2"] is not None]              # pvp scripts in this launch
+    N, T = len(kats), 2600
+
+    def act(s, t):
+        return s if isinstance(s, int) else s[t % len(s)]
+    env = mg.MergeVecEnv(N, auto_reset=False)
+    ref = mo.RefVecEnv(N, pvp=True, auto_reset=False)
+    first_done = np.full(N, -1)
+    snap = {}
+    for t in range(T):
+        a1 = np.array([act(k["a1"], t) for k in kats], np.uint8)
+        a2 = np.array([act(k["a2"], t) for k in kats], np.uint8)
+        out = env.step(a1, a2)
+        assert_step_equal(out, ref.step(a1, a2), t)
+        d = out[2].cpu().numpy()
+        for e in np.nonzero(d & (first_done < 0))[0]:
+            first_done[e] = t + 1
+            snap[e] = (int(env.winner[e]), bool(out[3]["collision"][e]), float(env.ret1[e]), float(env.ret2[e]),
+                       float(env.pos1[e]), float(env.pos2[e]))
+    assert_state_bit_exact(env, ref)
+    for e, k in enumerate(kats):
+        w, col, R1, R2, p1, p2 = snap[e]
+        assert first_done[e] == k["steps"], k
+        assert (w or None) == k["winner"] and col == k["collision"], k
+        assert rel_err([R1, R2, p1, p2], [k["R1"], k["R2"], k["pos1"], k["pos2"]]).max() <= 1e-9, k
+
+
+def test_known_answer_episodes_pve(mg):
+    kats = json.load(open(os.path.join(GOLDEN, "kat.json")))[:-1]
+    kats = [k for k in kats if k["a2"] is None]
+    N = len(kats)
+    env = mg.MergeVecEnv(N, mode="pve", auto_reset=False)
+    ref = mo.RefVecEnv(N, pvp=False, auto_reset=False)
+    first_done = np.full(N, -1)
+    for t in range(2600):
+        a1 = np.array([k["a1"] for k in kats], np.uint8)
+        out = env.step(a1, None)
+        assert_step_equal(out, ref.step(a1, None), t)
+        d = out[2].cpu().numpy()
+        first_done[d & (first_done < 0)] = t + 1
+    assert first_done.tolist() == [k["steps"] for k in kats]
+    assert_state_bit_exact(env, ref)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 63, 64, 65, 127, 511, 513, 1000])
+def test_ragged_sizes(mg, n):
+    """Sizes that are not a multiple of the 64-env warp tile take the scalar tail path."""
+    rng = np.random.default_rng(n)
+    env = mg.MergeVecEnv(n)
+    ref = mo.RefVecEnv(n)
+    for t in range(260):
+        a = rng.integers(0, 5, (n, 2)).astype(np.uint8)
+        assert_step_equal(env.step(a[:, 0], a[:, 1]), ref.step(a[:, 0], a[:, 1]), t)
+    assert_state_bit_exact(env, ref)
+    assert env.stats()["episodes"] == ref.stats["episodes"]
+
+
+def test_empty_env(mg):
+    env = mg.MergeVecEnv(0)
+    obs, rew, done, info = env.step(torch.zeros(0, dtype=torch.uint8), torch.zeros(0, dtype=torch.uint8))
+    assert obs.shape == (0, 10) and rew.shape == (0, 2) and done.shape == (0,)
+    assert env.stats()["episodes"] == 0
+
+
+def test_action_dtypes_and_bad_actions(mg):
+    n = 300
+    rng = np.random.default_rng(0)
+    envs = [mg.MergeVecEnv(n) for _ in range(3)]
+    ref = mo.RefVecEnv(n)
+    for t in range(50):
+        a = rng.integers(0, 5, (n, 2))
+        if t == 10:
+            a[5, 0] = 7; a[6, 1] = -1; a[7, 0] = 5            # KeyError in the reference
+        outs = [envs[0].step(torch.tensor(a[:, 0], dtype=torch.int64).cuda(), torch.tensor(a[:, 1], dtype=torch.int64).cuda()),
+                envs[1].step(torch.tensor(a[:, 0], dtype=torch.int32).cuda(), torch.tensor(a[:, 1], dtype=torch.int32).cuda()),
+                envs[2].step(np.clip(a[:, 0], 0, 255).astype(np.uint8), (a[:, 1] % 256).astype(np.uint8))]
+        r = ref.step(a[:, 0], a[:, 1])
+        for o in outs:
+            assert_step_equal(o, r, t)
+        if t == 10:
+            bad = outs[0][3]["bad_action"].cpu().numpy()
+            assert bad[5] and bad[6] and bad[7] and bad.sum() == 3
+    assert envs[0].stats()["bad_actions"] == 3
+    v = mg.MergeVecEnv(4, validate_actions=True)
+    with pytest.raises(KeyError):
+        v.step(np.array([0, 1, 9, 2]), np.array([0, 0, 0, 0]))
+    with pytest.raises(ValueError):
+        v.step(np.zeros(3, np.uint8), np.zeros(3, np.uint8))
+    with pytest.raises(TypeError):
+        v.step(np.zeros(4, np.float32), np.zeros(4, np.float32))
+
+
+def test_sample_actions_bit_exact(mg):
+    for seed, base in [(0x5EED, 0), (2 ** 40 + 17, 2 ** 33 + 5)]:
+        env = mg.MergeVecEnv(5000, seed=seed, env_id_base=base)
+        for step in (0, 1, 2 ** 35 + 1):
+            a1, a2 = env.sample_actions(step)
+            r1, r2 = mo.philox_actions(5000, seed, base, step)
+            assert np.array_equal(a1.cpu().numpy(), r1) and np.array_equal(a2.cpu().numpy(), r2)
+
+
+@pytest.mark.parametrize("pvp,n", [(True, 4096), (False, 1000), (True, 77)])
+def test_rollout_equals_stepwise_and_oracle(mg, pvp, n):
+    K, mode = 300, "pvp" if pvp else "pve"
+    a = mg.MergeVecEnv(n, mode=mode, seed=99, env_id_base=12345)
+    b = mg.MergeVecEnv(n, mode=mode, seed=99, env_id_base=12345)
+    ref = mo.RefVecEnv(n, pvp=pvp)
+    obs = torch.empty(K, n, 10, device="cuda"); rew = torch.empty(K, n, 2, device="cuda")
+    done = torch.empty(K, n, dtype=torch.uint8, device="cuda"); info = torch.empty(K, n, dtype=torch.uint8, device="cuda")
+    acts = torch.empty(K, n, 2, dtype=torch.uint8, device="cuda")
+    a.rollout(K, obs=obs, rew=rew, done=done, info=info, actions=acts)
+    for t in range(K):
+        a1, a2 = b.sample_actions()
+        assert torch.equal(acts[t, :, 0], a1)
+        o, r, d, i = b.step(a1, a2)
+        assert torch.equal(o, obs[t]) and torch.equal(r, rew[t])
+        assert torch.equal(d.view(torch.uint8), done[t]) and torch.equal(i["flags"], info[t])
+        r1, r2 = mo.philox_actions(n, 99, 12345, t)
+        assert_step_equal((o, r, d, i), ref.step(r1, r2 if pvp else None), t)
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert_state_bit_exact(a, ref)
+    assert a.stats() == b.stats()
+    assert a.stats()["episodes"] == ref.stats["episodes"]
+    # outputs are optional
+    c = mg.MergeVecEnv(n, mode=mode, seed=99, env_id_base=12345)
+    c.rollout(K)
+    assert torch.equal(c.pos1, a.pos1) and c.stats() == a.stats()
+
+
+def test_sticky_done_parity(mg):
+    n = 512
+    rng = np.random.default_rng(3)
+    env = mg.MergeVecEnv(n, auto_reset=False)
+    ref = mo.RefVecEnv(n, auto_reset=False)
+    for t in range(400):
+        a = rng.integers(0, 5, (n, 2)).astype(np.uint8)
+        assert_step_equal(env.step(a[:, 0], a[:, 1]), ref.step(a[:, 0], a[:, 1]), t)
+    assert bool(env.done.all())
+    assert env.stats()["episodes"] == n == ref.stats["episodes"]
+    # masked manual reset (the reference's caller-side `env.reset()` after done, main.py:190)
+    mask = torch.zeros(n, dtype=torch.bool); mask[::3] = True
+    obs = env.reset(mask).cpu().numpy()
+    robs = ref.reset(mask.numpy())
+    assert rel_err(obs, robs).max() <= TOL
+    assert_state_bit_exact(env, ref)
+    assert env.done.cpu().numpy().tolist() == (~mask.numpy()).tolist()
+
+
+def test_custom_rewards(mg):
+    rw = dict(r_first=5.0, r_second=0.5, r_collision=-3.0, vel_penalty=0.01, time_penalty=0.002)
+    n = 256
+    env = mg.MergeVecEnv(n, rewards=rw)
+    assert env.show_reward() == (5.0, 0.5, -3.0, 0.01)
+    old = (mo.RFirst, mo.RSecond, mo.RCollision, mo.vel_penalty, mo.time_penalty)
+    try:
+        mo.RFirst, mo.RSecond, mo.RCollision, mo.vel_penalty, mo.time_penalty = 5.0, 0.5, -3.0, 0.01, 0.002
+        ref = mo.RefVecEnv(n)
+        rng = np.random.default_rng(8)
+        for t in range(300):
+            a = rng.integers(0, 5, (n, 2)).astype(np.uint8)
+            assert_step_equal(env.step(a[:, 0], a[:, 1]), ref.step(a[:, 0], a[:, 1]), t)
+    finally:
+        mo.RFirst, mo.RSecond, mo.RCollision, mo.vel_penalty, mo.time_penalty = old
+
+
+def test_out_slots_ring_and_state_dict(mg):
+    n = 128
+    env = mg.MergeVecEnv(n, out_slots=3)
+    a1, a2 = env.sample_actions()
+    o1 = env.step(a1, a2)[0]
+    ck = env.state_dict()
+    a1, a2 = env.sample_actions()
+    o2 = env.step(a1, a2)[0]
+    assert o1.data_ptr() != o2.data_ptr() and not torch.equal(o1, o2)
+    keep = o2.clone(); st = env.stats()
+    env.load_state_dict(ck)
+    a1, a2 = env.sample_actions()
+    assert torch.equal(env.step(a1, a2)[0], keep) and env.stats() == st
+
+
+def test_cuda_graph_replay_matches_eager(mg):
+    n, K = 2048, 40
+    a = mg.MergeVecEnv(n, seed=5); b = mg.MergeVecEnv(n, seed=5)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        a1, a2 = a.sample_actions(0); a.step(a1, a2)          # warm-up outside capture
+        a.load_state_dict(mg.MergeVecEnv(n, seed=5).state_dict())
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        for t in range(K):
+            a1, a2 = a.sample_actions(t)
+            out = a.step(a1, a2)
+    g.replay()
+    for t in range(K):
+        a1, a2 = b.sample_actions(t)
+        ref = b.step(a1, a2)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], ref[0]) and torch.equal(a.pos1, b.pos1) and torch.equal(a.meta, b.meta)
+
+
+def test_step_host_matches_device_path(mg):
+    n = 1000
+    rng = np.random.default_rng(4)
+    a = mg.MergeVecEnv(n); b = mg.MergeVecEnv(n)
+    for t in range(120):
+        act = rng.integers(0, 5, (n, 2)).astype(np.uint8)
+        ho, hr, hd, hi = a.step_host(act[:, 0], act[:, 1])
+        o, r, d, i = b.step(act[:, 0], act[:, 1])
+        assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy())
+        assert np.array_equal(hd, d.cpu().numpy()) and np.array_equal(hi, i["flags"].cpu().numpy())
+    ho, *_ = a.step_host(act[:, 0], None)                       # pve through the host path
+    o, *_ = b.step(act[:, 0], None)
+    assert np.array_equal(ho, o.cpu().numpy())
+
+
+def test_scalar_reference_interface(mg):
+    """`gym.make("merging_env-v0")`-style use, as scripts/main.py:190-218 drives it."""
+    env = mg.make("merging_env-v0")
+    assert env.action_space.n == 5 and env.observation_space.shape[0] == 10
+    assert env.show_reward() == (2.0, 1.0, -10, 0.001)
+    ref = mo.RefEnv()
+    obs = env.reset()
+    assert isinstance(obs, list) and len(obs) == 10 and rel_err(obs, ref.reset()).max() <= TOL
+    n = 0
+    while True:
+        n += 1
+        o, r, d, info = env.step(2, 2)
+        o2, r2, d2, info2 = ref.step(2, 2)
+        assert d == d2 and info == info2 and rel_err(o, o2).max() <= TOL and rel_err(r, r2).max() <= TOL
+        if d:
+            break
+    assert n == 151 and env.winner is None and info == {"collision": True}
+    assert env.r1_accumulate == -10.0 and env.state1["pos"] == 654.0
+    env.reset()
+    for t in range(225):
+        o, r, d, info = env.step(3)                              # pve: action2=None
+    assert d and env.winner == 1 and env.state2["pos"] == 950.0 and env.r2_accumulate == 1.0
+    with pytest.raises(KeyError):
+        env.step(5)
+    assert state_swap_ok(o)
+
+
+def state_swap_ok(o):
+    import merging_gym_b200 as m
+    v = m.MergeVecEnv.opponent_view(torch.tensor([o]))[0].tolist()
+    return v == o[5:] + o[:5]

@@ -1,0 +1,83 @@
+"""Size-independent properties at BASELINE.json's full sizes (1M envs), where the oracle would
+take too long to compare every step: determinism, shard invariance (global env ids), statistics
+consistency, and agreement of a sub-sample with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import merge_oracle as mo
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+N = 1 << 20
+K = 256
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import merging_gym_b200
+    return merging_gym_b200
+
+
+@pytest.fixture(scope="module")
+def full_run(mg):
+    env = mg.MergeVecEnv(N, seed=0x5EED)
+    done_count = torch.zeros((), dtype=torch.int64, device="cuda")
+    for t in range(K):
+        a1, a2 = env.sample_actions()
+        _, _, done, _ = env.step(a1, a2)
+        done_count += done.sum()
+    torch.cuda.synchronize()
+    return env, int(done_count)
+
+
+def test_statistics_are_consistent(full_run):
+    env, done_count = full_run
+    s = env.stats()
+    assert s["episodes"] == done_count > 0
+    assert s["collisions"] + s["merges_ok"] + s["timeouts"] >= s["episodes"]
+    assert s["merges_ok"] == s["episodes"] - s["collisions"]          # no timeouts within 256 steps
+    assert s["timeouts"] == 0 and s["bad_actions"] == 0
+    assert s["wins_p1"] + s["wins_p2"] <= s["episodes"]
+    # SURVEY.md §6 [probe]: random pvp play -> mean length ~210, collision rate ~0.367
+    assert 195 < s["mean_length"] < 225 and 0.33 < s["collision_rate"] < 0.40
+    assert abs(s["win_rate_p1"] - s["win_rate_p2"]) < 0.01
+
+
+def test_deterministic_and_rollout_equivalent(mg, full_run):
+    env, _ = full_run
+    other = mg.MergeVecEnv(N, seed=0x5EED)
+    other.rollout(K)                                   # fused K-step launch, same Philox stream
+    torch.cuda.synchronize()
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta"):
+        assert torch.equal(getattr(env, k), getattr(other, k)), k
+    assert env.stats() == other.stats()
+
+
+def test_shard_invariance(mg, full_run):
+    """Two half-size shards with global env-id bases reproduce the single-shard run bit for bit
+    (what makes the multi-GPU statistics world-size invariant)."""
+    env, _ = full_run
+    halves = [mg.MergeVecEnv(N // 2, seed=0x5EED, env_id_base=b) for b in (0, N // 2)]
+    for h in halves:
+        h.rollout(K)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([h.pos1 for h in halves]), env.pos1)
+    assert torch.equal(torch.cat([h.ret2 for h in halves]), env.ret2)
+    tot = halves[0].stats_tensor() + halves[1].stats_tensor()
+    assert torch.equal(tot, env.stats_tensor())
+
+
+def test_subsample_matches_oracle(mg):
+    """Envs [base, base+512) of the 1M-env Philox stream against the oracle, every step."""
+    base, n = 777_216, 512
+    env = mg.MergeVecEnv(n, seed=0x5EED, env_id_base=base)
+    ref = mo.RefVecEnv(n)
+    for t in range(K):
+        a1, a2 = env.sample_actions()
+        obs, rew, done, info = env.step(a1, a2)
+        r1, r2 = mo.philox_actions(n, 0x5EED, base, t)
+        robs, rrew, rdone, rinfo = ref.step(r1, r2)
+        assert np.array_equal(done.cpu().numpy(), rdone) and np.array_equal(info["flags"].cpu().numpy(), rinfo)
+        assert rel_err(obs.cpu().numpy(), robs).max() <= 1e-5 and rel_err(rew.cpu().numpy(), rrew).max() <= 1e-5
+    assert np.array_equal(env.pos1.cpu().numpy(), ref.pos1)
