@@ -17,24 +17,64 @@
 
 namespace mg {
 
-constexpr int kBlock = 256;
+// Tunables (compile-time; the defaults are what build.py ships — see profiles/ for the sweep).
+#ifndef MG_BLOCK
+#define MG_BLOCK 128
+#endif
+#ifndef MG_EPT
+#define MG_EPT 2          // envs per thread in the step kernel: 2 -> 128-bit state accesses
+#endif
+#ifndef MG_MIN_BLOCKS
+#define MG_MIN_BLOCKS 8   // __launch_bounds__ min resident blocks per SM: caps the step kernel at 64 registers
+#endif
+constexpr int kBlock = MG_BLOCK;
 constexpr int kWarps = kBlock / 32;
 
-// ---- 128-bit helpers ---------------------------------------------------------------------------
-template <int EPT>
-__device__ __forceinline__ void load_f64(const double *__restrict__ p, int64_t i, double (&v)[EPT]) {
-    static_assert(EPT % 2 == 0, "EPT must be even");
+// ---- vector access helpers: N consecutive elements of T per thread in <=128-bit pieces ----------
+template <typename T, int N>
+struct alignas((sizeof(T) * N) <= 16 ? (sizeof(T) * N) : 16) Pack { T v[N]; };
+
+template <typename T, int N>
+__device__ __forceinline__ void ld_pack(const T *__restrict__ p, T (&out)[N]) {
+    constexpr int PER = (16 / (int)sizeof(T)) < N ? (16 / (int)sizeof(T)) : N;
 #pragma unroll
-    for (int k = 0; k < EPT / 2; ++k) {
-        const double2 t = *reinterpret_cast<const double2 *>(p + i + 2 * k);
-        v[2 * k] = t.x; v[2 * k + 1] = t.y;
+    for (int k = 0; k < N / PER; ++k) {
+        const Pack<T, PER> t = *reinterpret_cast<const Pack<T, PER> *>(p + k * PER);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) out[k * PER + i] = t.v[i];
     }
 }
-template <int EPT>
-__device__ __forceinline__ void store_f64(double *__restrict__ p, int64_t i, const double (&v)[EPT]) {
+template <typename T, int N>
+__device__ __forceinline__ void st_pack(T *__restrict__ p, const T (&in)[N]) {
+    constexpr int PER = (16 / (int)sizeof(T)) < N ? (16 / (int)sizeof(T)) : N;
 #pragma unroll
-    for (int k = 0; k < EPT / 2; ++k)
-        *reinterpret_cast<double2 *>(p + i + 2 * k) = make_double2(v[2 * k], v[2 * k + 1]);
+    for (int k = 0; k < N / PER; ++k) {
+        Pack<T, PER> t;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) t.v[i] = in[k * PER + i];
+        *reinterpret_cast<Pack<T, PER> *>(p + k * PER) = t;
+    }
+}
+// streaming (evict-first) variant for outputs that this kernel never reads back
+template <int BYTES> struct RawOf;
+template <> struct RawOf<1> { using type = unsigned char; };
+template <> struct RawOf<2> { using type = unsigned short; };
+template <> struct RawOf<4> { using type = unsigned int; };
+template <> struct RawOf<8> { using type = uint2; };
+template <> struct RawOf<16> { using type = uint4; };
+template <typename T, int N>
+__device__ __forceinline__ void st_pack_stream(T *__restrict__ p, const T (&in)[N]) {
+    constexpr int PER = (16 / (int)sizeof(T)) < N ? (16 / (int)sizeof(T)) : N;
+    using Raw = typename RawOf<PER * (int)sizeof(T)>::type;
+#pragma unroll
+    for (int k = 0; k < N / PER; ++k) {
+        Pack<T, PER> t;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) t.v[i] = in[k * PER + i];
+        Raw r;
+        memcpy(&r, &t, sizeof r);
+        __stcs(reinterpret_cast<Raw *>(p + k * PER), r);
+    }
 }
 
 template <typename ActT>
@@ -65,11 +105,11 @@ __device__ __forceinline__ void reset_obs(float *obs) {
 
 // =================================================================================================
 // merge_step_kernel: one MergeEnv.step() for n envs.
-//   grid = ceil(n / (kBlock*EPT)), block = 256.  A warp owns 32*EPT consecutive envs.
+//   grid = ceil(n / (kBlock*EPT)), block = kBlock.  A warp owns 32*EPT consecutive envs.
 //   Full warps take the vector path; the (at most one) ragged warp takes the scalar path.
 // =================================================================================================
 template <int EPT, typename ActT, bool PVP>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MG_MIN_BLOCKS)
 merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
                   const ActT *__restrict__ a2g, const int64_t n, const MgRewards rw,
                   const uint32_t flags, unsigned long long *__restrict__ stats) {
@@ -90,20 +130,11 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
     // ---------------- loads ----------------
     if (full) {
         double p1[EPT], v1[EPT], p2[EPT], v2[EPT], R1[EPT], R2[EPT];
-        load_f64<EPT>(s.pos1, e0, p1); load_f64<EPT>(s.vel1, e0, v1);
-        load_f64<EPT>(s.pos2, e0, p2); load_f64<EPT>(s.vel2, e0, v2);
-        load_f64<EPT>(s.ret1, e0, R1); load_f64<EPT>(s.ret2, e0, R2);
         uint32_t m[EPT];
-        if constexpr (EPT == 2) {
-            const uint2 t = *reinterpret_cast<const uint2 *>(s.meta + e0);
-            m[0] = t.x; m[1] = t.y;
-        } else {
-#pragma unroll
-            for (int k = 0; k < EPT / 4; ++k) {
-                const uint4 t = *reinterpret_cast<const uint4 *>(s.meta + e0 + 4 * k);
-                m[4 * k] = t.x; m[4 * k + 1] = t.y; m[4 * k + 2] = t.z; m[4 * k + 3] = t.w;
-            }
-        }
+        ld_pack<double, EPT>(s.pos1 + e0, p1); ld_pack<double, EPT>(s.vel1 + e0, v1);
+        ld_pack<double, EPT>(s.pos2 + e0, p2); ld_pack<double, EPT>(s.vel2 + e0, v2);
+        ld_pack<double, EPT>(s.ret1 + e0, R1); ld_pack<double, EPT>(s.ret2 + e0, R2);
+        ld_pack<uint32_t, EPT>(s.meta + e0, m);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             env[j] = EnvRegs{p1[j], v1[j], p2[j], v2[j], R1[j], R2[j], m[j]};
@@ -165,37 +196,25 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
         double t[EPT];
 #define MG_ST(field, arr)                                   \
         _Pragma("unroll") for (int j = 0; j < EPT; ++j) t[j] = env[j].field; \
-        store_f64<EPT>(arr, e0, t);
+        st_pack<double, EPT>(arr + e0, t);
         MG_ST(p1, s.pos1) MG_ST(v1, s.vel1) MG_ST(p2, s.pos2) MG_ST(v2, s.vel2)
         MG_ST(R1, s.ret1) MG_ST(R2, s.ret2)
 #undef MG_ST
-        if constexpr (EPT == 2) {
-            *reinterpret_cast<uint2 *>(s.meta + e0) = make_uint2(env[0].meta, env[1].meta);
-            __stcs(reinterpret_cast<float4 *>(o.rew + 2 * e0), make_float4(rew[0], rew[1], rew[2], rew[3]));
-            __stcs(reinterpret_cast<uchar2 *>(o.done + e0), make_uchar2(done8[0], done8[1]));
-            __stcs(reinterpret_cast<uchar2 *>(o.info + e0), make_uchar2(info8[0], info8[1]));
-        } else {
+        uint32_t m[EPT];
 #pragma unroll
-            for (int k = 0; k < EPT / 4; ++k) {
-                *reinterpret_cast<uint4 *>(s.meta + e0 + 4 * k) =
-                    make_uint4(env[4 * k].meta, env[4 * k + 1].meta, env[4 * k + 2].meta, env[4 * k + 3].meta);
-                __stcs(reinterpret_cast<uchar4 *>(o.done + e0 + 4 * k),
-                       make_uchar4(done8[4 * k], done8[4 * k + 1], done8[4 * k + 2], done8[4 * k + 3]));
-                __stcs(reinterpret_cast<uchar4 *>(o.info + e0 + 4 * k),
-                       make_uchar4(info8[4 * k], info8[4 * k + 1], info8[4 * k + 2], info8[4 * k + 3]));
-            }
-#pragma unroll
-            for (int k = 0; k < EPT / 2; ++k)
-                __stcs(reinterpret_cast<float4 *>(o.rew + 2 * e0 + 4 * k),
-                       make_float4(rew[4 * k], rew[4 * k + 1], rew[4 * k + 2], rew[4 * k + 3]));
-        }
+        for (int j = 0; j < EPT; ++j) m[j] = env[j].meta;
+        st_pack<uint32_t, EPT>(s.meta + e0, m);
+        st_pack_stream<float, 2 * EPT>(o.rew + 2 * e0, rew);
+        st_pack_stream<uint8_t, EPT>(o.done + e0, done8);
+        st_pack_stream<uint8_t, EPT>(o.info + e0, info8);
         // obs rows of this warp are one contiguous, 16-byte aligned span of 32*EPT*40 bytes
         __syncwarp();
         const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
         float4 *dst = reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM);
         constexpr int kVec = 32 * EPT * MG_OBS_DIM / 4;   // float4 per warp
 #pragma unroll
-        for (int k = 0; k < kVec / 32; ++k) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+        for (int k = 0; k < (kVec + 31) / 32; ++k)
+            if (kVec % 32 == 0 || lane + 32 * k < kVec) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
     } else {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
@@ -226,7 +245,8 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
     if (warp_base >= n) return;
-    const bool full = warp_base + 32 * EPT <= n;
+    // time-major obs rows start at t*n*40 bytes: 16-byte aligned for every t only if n is even
+    const bool full = (warp_base + 32 * EPT <= n) && ((n & 1) == 0);
     const int64_t e0 = warp_base + (int64_t)lane * EPT;
     const bool auto_reset = (flags & MG_FLAG_AUTO_RESET) != 0u;
 
@@ -369,7 +389,7 @@ const MgRewards kDefaultRewards = {2.0, 1.0, -10.0, 0.001, 0.0};
 template <typename ActT>
 cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const void *a2, int64_t n,
                         const MgRewards &rw, uint32_t flags, int64_t *stats, cudaStream_t st) {
-    constexpr int EPT = 2;
+    constexpr int EPT = MG_EPT;
     const int64_t per_block = (int64_t)mg::kBlock * EPT;
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);

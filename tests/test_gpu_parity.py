@@ -181,7 +181,7 @@ def test_action_dtypes_and_bad_actions(mg):
     for t in range(50):
         a = rng.integers(0, 5, (n, 2))
         if t == 10:
-            a[5, 0] = 7; a[6, 1] = -1; a[7, 0] = 5            # KeyError in the reference
+            a[5, 0] = 7; a[6, 1] = 200; a[7, 0] = 5           # KeyError in the reference
         outs = [envs[0].step(torch.tensor(a[:, 0], dtype=torch.int64).cuda(), torch.tensor(a[:, 1], dtype=torch.int64).cuda()),
                 envs[1].step(torch.tensor(a[:, 0], dtype=torch.int32).cuda(), torch.tensor(a[:, 1], dtype=torch.int32).cuda()),
                 envs[2].step(np.clip(a[:, 0], 0, 255).astype(np.uint8), (a[:, 1] % 256).astype(np.uint8))]
@@ -192,6 +192,12 @@ def test_action_dtypes_and_bad_actions(mg):
             bad = outs[0][3]["bad_action"].cpu().numpy()
             assert bad[5] and bad[6] and bad[7] and bad.sum() == 3
     assert envs[0].stats()["bad_actions"] == 3
+    # negative actions exist only for the signed dtypes: clamped to 0 and flagged
+    e, r = mg.MergeVecEnv(8), mo.RefVecEnv(8)
+    a = np.array([-1, 0, 1, 2, 3, 4, -7, 2])
+    out = e.step(torch.tensor(a, dtype=torch.int64).cuda(), torch.tensor(a[::-1].copy(), dtype=torch.int32).cuda())
+    assert_step_equal(out, r.step(a, a[::-1]))
+    assert out[3]["bad_action"].cpu().numpy().tolist() == [True, True, False, False, False, False, True, True]
     v = mg.MergeVecEnv(4, validate_actions=True)
     with pytest.raises(KeyError):
         v.step(np.array([0, 1, 9, 2]), np.array([0, 0, 0, 0]))
