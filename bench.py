@@ -6,11 +6,13 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is ONE `mg_step` launch advancing every env of the rank's shard by one dT with external
-uint8 actions (pvp, auto-reset): BASELINE.json configs[2], 2^20 envs per GPU.  Actions are
-pre-generated on the device (Philox, global env ids) and cycled, so inputs are HBM-resident.
-Outputs go to a ring of `--slots` output sets, so the per-step working set (state 54.5 MB +
-ring) exceeds the 126 MB L2 and no explicit flush is needed.  Timed with CUDA events on the
-launching (current torch) stream, barrier + synchronize on both sides, max over ranks.
+uint8 actions (pvp, auto-reset): BASELINE.json configs[2], 2^20 envs per launch per GPU.
+Actions are pre-generated on the device (Philox, global env ids), so inputs are HBM-resident.
+L2 rule: one shard's inputs (56.6 MB) would fit the 126 MB L2, so the timed region steps
+`--shards` (4) independent 2^20-env shards round-robin — inputs larger than L2, no flush — and
+every launch reads its state from HBM.  The in-place single-shard figure is reported separately as
+`l2_warm`.  Timed with CUDA events on the launching (current torch) stream, barrier +
+synchronize on both sides, max over ranks.
 
 Extra objects in the JSON line: `roofline` (HBM, algorithmic bytes = 156 B/env-step, see
 DESIGN.md), `cpu_baseline` (the C port of the oracle on this box's host cores, rank 0, N=1),
