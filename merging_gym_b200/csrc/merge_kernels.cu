@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "abi_common.h"
 #include "merge_device.cuh"
 
 namespace mg {
@@ -354,17 +355,9 @@ sample_actions_kernel(uint8_t *__restrict__ a1, uint8_t *__restrict__ a2, const 
 // C ABI
 // =================================================================================================
 namespace {
-thread_local char g_err[512] = "";
-
-int fail(int code, const char *msg) {
-    snprintf(g_err, sizeof g_err, "%s", msg);
-    return code;
-}
-int cuda_fail(cudaError_t e, const char *where) {
-    snprintf(g_err, sizeof g_err, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
-    return (int)e;
-}
-bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+using mg_abi::aligned16;
+using mg_abi::cuda_fail;
+using mg_abi::fail;
 
 int check_state(const MgState *s) {
     if (!s) return fail(MG_ERR_NULL_POINTER, "state is NULL");
@@ -406,7 +399,7 @@ cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const 
 extern "C" {
 
 MG_API int mg_version(void) { return MG_ABI_VERSION; }
-MG_API const char *mg_last_error(void) { return g_err; }
+MG_API const char *mg_last_error(void) { return mg_abi::g_err; }
 
 MG_API int mg_get_constants(MgConstants *c) {
     if (!c) return fail(MG_ERR_NULL_POINTER, "out is NULL");

@@ -1,0 +1,232 @@
+// mlp_kernels.cu — fused Q-network forward + arg-max for policy-in-the-loop rollouts (sm_100a).
+//
+// The reference's Q-networks are all `Net(in, out)`: Linear(in,200)-ReLU-Linear(200,100)-ReLU-
+// Linear(100,out) with in in {10, 11}, out in {5, 3} (scripts/main.py:30-47, scripts/hdqn.py:38-55),
+// evaluated in fp32 and followed by `torch.max(q, 1)[1]` (main.py:104-105).  One launch here does the
+// whole thing for N envs: obs rows in, uint8 actions out, nothing but 41 B/env touches HBM.
+//
+// fp32 FFMA on purpose: the reference computes in fp32 and the arg-max must not flip on near ties,
+// so no tf32/bf16 tensor-core path (45 kFLOP/env: ~250 us for 2^18 envs at FFMA rates).
+//
+// Tiling (persistent CTAs, one per SM, 256 threads, tile = 256 envs):
+//   layer 1  thread t owns env t of the tile: h1[k][t] = relu(b1[k] + sum_i x[t][i] W1t[i][k]) for the
+//            50 k's of the current K-chunk, written K-major to shared memory;
+//   layer 2  thread t = (eg = t/4, ng = t%4) owns a 4-env x 25-neuron register tile (100 FFMA per k
+//            against 1 + 7 LDS.128): acc[e][j] += h1[k][4 eg + e] * W2t[k][25 ng + j];
+//   layer 3  each thread reduces its 25 neurons into 4 x OUT partial Q-values, the 4 ng-lanes of an
+//            env group are adjacent lanes -> two shuffle-xor steps; lane ng==0 adds b3, takes the
+//            first maximum and stores 4 actions with one 32-bit store.
+// Shared memory: W2t padded to [200][4][28] (89.6 KB), h1 chunk [50][256] (51.2 KB), W1t, W3, biases,
+// x tile [256][IN] -> ~158 KB, so one CTA per SM.
+#include <cstring>
+
+#include "abi_common.h"
+
+namespace mgmlp {
+
+constexpr int H1 = 200, H2 = 100;
+constexpr int TM = 256;            // envs per tile == threads per block
+constexpr int KC = 50;             // K-chunk of layer 2 (h1 rows resident in smem)
+constexpr int NG = 4, NJ = 25;     // neuron groups x neurons per group
+constexpr int NJP = 28;            // padded group width (16-byte aligned rows)
+constexpr int MAX_IN = 12, MAX_OUT = 8;
+
+template <int IN, int OUT>
+struct Smem {
+    float w2[H1][NG][NJP];         // 89 600 B
+    float h1[KC][TM];              // 51 200 B
+    float w1[IN][H1];
+    float x[TM][IN | 1];           // odd row stride keeps the per-thread row reads conflict-free
+    float w3[OUT][H2];
+    float b1[H1], b2[H2], b3[MAX_OUT];
+};
+
+template <int IN, int OUT>
+__global__ void __launch_bounds__(TM, 1)
+mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
+               const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2t,
+               const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
+               uint8_t *__restrict__ act, float *__restrict__ q_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<IN, OUT> &S = *reinterpret_cast<Smem<IN, OUT> *>(smem_raw);
+    const int t = threadIdx.x;
+
+    // ---- weights -> shared memory, once per (persistent) CTA -----------------------------------
+    for (int i = t; i < H1 * H2; i += TM) {
+        const int k = i / H2, j = i - k * H2;
+        S.w2[k][j / NJ][j % NJ] = w2t[i];
+    }
+    for (int i = t; i < H1 * NG * (NJP - NJ); i += TM) {
+        const int k = i / (NG * (NJP - NJ)), r = i - k * (NG * (NJP - NJ));
+        S.w2[k][r / (NJP - NJ)][NJ + r % (NJP - NJ)] = 0.f;
+    }
+    for (int i = t; i < IN * H1; i += TM) (&S.w1[0][0])[i] = w1t[i];
+    for (int i = t; i < OUT * H2; i += TM) (&S.w3[0][0])[i] = w3[i];
+    for (int i = t; i < H1; i += TM) S.b1[i] = b1[i];
+    for (int i = t; i < H2; i += TM) S.b2[i] = b2[i];
+    if (t < OUT) S.b3[t] = b3[t];
+
+    const int ng = t & 3, eg = t >> 2;
+    const int64_t n_tiles = (n + TM - 1) / TM;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * TM;
+        __syncthreads();                       // previous tile done with S.x / S.h1; weights visible
+        // ---- x tile: [goal] + obs rows, coalesced ------------------------------------------------
+        {
+            const int64_t rows = min((int64_t)TM, n - base);
+            const int64_t total = rows * obs_dim;
+            const float *src = obs + base * obs_dim;
+            const int off = IN - obs_dim;      // 1 when a goal column is prepended (hdqn.py:291)
+            for (int64_t i = t; i < (int64_t)TM * obs_dim; i += TM) {
+                const int r = (int)(i / obs_dim), c = (int)(i - (int64_t)r * obs_dim);
+                S.x[r][off + c] = i < total ? __ldg(src + i) : 0.f;
+            }
+            if (off) S.x[t][0] = (base + t < n) ? (float)goal[base + t] : 0.f;
+        }
+        __syncthreads();
+        float xr[IN];
+#pragma unroll
+        for (int i = 0; i < IN; ++i) xr[i] = S.x[t][i];
+
+        float acc[4][NJ];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[e][j] = 0.f;
+
+        for (int k0 = 0; k0 < H1; k0 += KC) {
+            // ---- layer 1 for rows k0 .. k0+KC of h1 (thread = env) -------------------------------
+            if (k0) __syncthreads();           // everyone finished reading the previous chunk
+#pragma unroll 2
+            for (int kk = 0; kk < KC; kk += 2) {
+                float h0 = S.b1[k0 + kk], h1v = S.b1[k0 + kk + 1];
+#pragma unroll
+                for (int i = 0; i < IN; ++i) {
+                    const float2 w = *reinterpret_cast<const float2 *>(&S.w1[i][k0 + kk]);
+                    h0 = fmaf(xr[i], w.x, h0);
+                    h1v = fmaf(xr[i], w.y, h1v);
+                }
+                S.h1[kk][t] = fmaxf(h0, 0.f);
+                S.h1[kk + 1][t] = fmaxf(h1v, 0.f);
+            }
+            __syncthreads();
+            // ---- layer 2 partial sums over this chunk (4 envs x 25 neurons per thread) ------------
+#pragma unroll 2
+            for (int kk = 0; kk < KC; ++kk) {
+                const float4 a = *reinterpret_cast<const float4 *>(&S.h1[kk][4 * eg]);
+                const float4 *bp = reinterpret_cast<const float4 *>(&S.w2[k0 + kk][ng][0]);
+                float b[NJP];
+#pragma unroll
+                for (int v = 0; v < NJP / 4; ++v) {
+                    const float4 q = bp[v];
+                    b[4 * v] = q.x; b[4 * v + 1] = q.y; b[4 * v + 2] = q.z; b[4 * v + 3] = q.w;
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+                    acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+                    acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+                    acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+                }
+            }
+        }
+        // ---- layer 3 + arg-max ---------------------------------------------------------------------
+        float q[4][OUT];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) q[e][o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float bias = S.b2[ng * NJ + j];
+            float w[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) w[o] = S.w3[o][ng * NJ + j];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float h = fmaxf(acc[e][j] + bias, 0.f);
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) q[e][o] = fmaf(h, w[o], q[e][o]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) {
+                float v = q[e][o];
+                v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+                v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+                q[e][o] = v + S.b3[o];
+            }
+        if (ng == 0) {
+            const int64_t e0 = base + 4 * eg;
+            uint8_t a4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int best = 0;
+                float bv = q[e][0];
+#pragma unroll
+                for (int o = 1; o < OUT; ++o)
+                    if (q[e][o] > bv) { bv = q[e][o]; best = o; }   // first maximum, like torch.max
+                a4[e] = (uint8_t)best;
+            }
+            if (e0 + 4 <= n) {
+                uchar4 v = make_uchar4(a4[0], a4[1], a4[2], a4[3]);
+                *reinterpret_cast<uchar4 *>(act + e0) = v;
+            } else {
+                for (int e = 0; e < 4; ++e)
+                    if (e0 + e < n) act[e0 + e] = a4[e];
+            }
+            if (q_out) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (e0 + e < n)
+#pragma unroll
+                        for (int o = 0; o < OUT; ++o) q_out[(e0 + e) * OUT + o] = q[e][o];
+            }
+        }
+    }
+}
+
+template <int IN, int OUT>
+cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t,
+                   const float *b1, const float *w2t, const float *b2, const float *w3, const float *b3,
+                   uint8_t *act, float *q_out, cudaStream_t st) {
+    auto kern = mlp_act_kernel<IN, OUT>;
+    const size_t smem = sizeof(Smem<IN, OUT>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (n + TM - 1) / TM;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    kern<<<grid, TM, smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2t, b2, w3, b3, act, q_out);
+    return cudaGetLastError();
+}
+
+}  // namespace mgmlp
+
+extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
+                                 int32_t out_dim, const float *w1t, const float *b1, const float *w2t,
+                                 const float *b2, const float *w3, const float *b3, uint8_t *actions,
+                                 float *q_out_or_null, void *stream) {
+    using namespace mg_abi;
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
+    if (!((in_dim == 10 || in_dim == 11) && (out_dim == 5 || out_dim == 3)))
+        return fail(MG_ERR_BAD_SIZE, "mg_mlp_act supports Net(10|11, 5|3) (main.py:30-47, hdqn.py:38-55)");
+    if (n == 0) return MG_OK;
+    if (!obs || !w1t || !b1 || !w2t || !b2 || !w3 || !b3 || !actions)
+        return fail(MG_ERR_NULL_POINTER, "mg_mlp_act: NULL pointer");
+    if (!aligned16(actions)) return fail(MG_ERR_ALIGNMENT, "actions must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+#define MG_MLP_CASE(I, O) \
+    if (in_dim == I && out_dim == O) e = mgmlp::launch<I, O>(obs, goal_or_null, n, obs_dim, w1t, b1, w2t, b2, w3, b3, actions, q_out_or_null, st); else
+    MG_MLP_CASE(10, 5) MG_MLP_CASE(10, 3) MG_MLP_CASE(11, 5) MG_MLP_CASE(11, 3) e = cudaErrorInvalidValue;
+#undef MG_MLP_CASE
+    if (e) return cuda_fail(e, "mg_mlp_act launch");
+    return MG_OK;
+}

@@ -1,0 +1,159 @@
+"""Policy-in-the-loop: the reference's Q-networks evaluated for N envs on the
+device, emitting actions that `MergeVecEnv.step` consumes with no host round-trip.
+
+Reference pieces mirrored here
+  * `Net` 10 -> 200 -> 100 -> 5 (scripts/main.py:30-47) and `Net(num_inputs, num_outputs)`
+    (scripts/hdqn.py:38-55; Goal_DQN 10 -> 3, HDQN controller 11 -> 5 on `[goal] + state`).
+  * greedy action `torch.max(action_value, 1)[1]` (main.py:104-105, hdqn.py:86-87, 170-171).
+  * the scripts' exploration rule `np.random.randn() <= EPISILO` with EPISILO = 0.7, i.e. greedy
+    with probability Phi(0.7) ~ 0.758 (main.py:103, hdqn.py:84, 168) — note it is NOT epsilon-greedy.
+  * `goal_status` (hdqn.py:223-236) and the opponent view `state[5:] + state[:5]` (main.py:199).
+
+`backend="fused"` runs the hand-written CUDA kernel `mg_mlp_act` (one launch: three layers,
+bias, ReLU, arg-max, fp32 FFMA); `backend="torch"` is the plain PyTorch fp32 reference of the same
+op (cuBLAS), kept for the numerics tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+EPISILO = 0.7          # scripts/main.py:16, hdqn.py:20
+HIDDEN1, HIDDEN2 = 200, 100
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class MLPPolicy:
+    """`Net`: Linear(in,200) - ReLU - Linear(200,100) - ReLU - Linear(100,out), batched arg-max."""
+
+    def __init__(self, in_dim: int = 10, out_dim: int = 5, device="cuda", state_dict: Optional[dict] = None,
+                 seed: Optional[int] = None, backend: str = "fused"):
+        if backend not in ("fused", "torch"):
+            raise ValueError("backend must be 'fused' or 'torch'")
+        self.in_dim, self.out_dim, self.backend = int(in_dim), int(out_dim), backend
+        self.device = torch.device(device)
+        if state_dict is None:
+            # the reference's init: weights uniform_(0,1), biases nn.Linear default (main.py:34-39)
+            g = torch.Generator().manual_seed(0 if seed is None else seed)
+            def lin(i, o):
+                w = torch.rand(o, i, generator=g)
+                b = (torch.rand(o, generator=g) * 2 - 1) / np.sqrt(i)
+                return w, b
+            w1, b1 = lin(in_dim, HIDDEN1); w2, b2 = lin(HIDDEN1, HIDDEN2); w3, b3 = lin(HIDDEN2, out_dim)
+            state_dict = {"fc1.weight": w1, "fc1.bias": b1, "fc2.weight": w2, "fc2.bias": b2,
+                          "out.weight": w3, "out.bias": b3}
+        self.load_state_dict(state_dict)
+
+    # -- weights ---------------------------------------------------------------------------------
+    def load_state_dict(self, sd: dict) -> None:
+        def get(k):
+            return torch.as_tensor(np.asarray(sd[k]) if not isinstance(sd[k], torch.Tensor) else sd[k]) \
+                .to(device=self.device, dtype=torch.float32).contiguous()
+        self.w1, self.b1 = get("fc1.weight"), get("fc1.bias")
+        self.w2, self.b2 = get("fc2.weight"), get("fc2.bias")
+        self.w3, self.b3 = get("out.weight"), get("out.bias")
+        if tuple(self.w1.shape) != (HIDDEN1, self.in_dim) or tuple(self.w2.shape) != (HIDDEN2, HIDDEN1) \
+                or tuple(self.w3.shape) != (self.out_dim, HIDDEN2):
+            raise ValueError("state_dict does not match Net(%d, %d)" % (self.in_dim, self.out_dim))
+        # K-major copies for the fused kernel (built once)
+        self.w1_t = self.w1.t().contiguous(); self.w2_t = self.w2.t().contiguous()
+
+    def state_dict(self) -> dict:
+        return {"fc1.weight": self.w1, "fc1.bias": self.b1, "fc2.weight": self.w2, "fc2.bias": self.b2,
+                "out.weight": self.w3, "out.bias": self.b3}
+
+    @classmethod
+    def load(cls, path: str, in_dim: int = 10, out_dim: int = 5, **kw):
+        """Load a reference checkpoint (`eval.pth`, a plain state_dict; main.py:85-87)."""
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        return cls(in_dim, out_dim, state_dict=sd, **kw)
+
+    # -- forward ---------------------------------------------------------------------------------
+    def _inputs(self, obs: torch.Tensor, goal: Optional[torch.Tensor]):
+        if goal is None:
+            if obs.shape[-1] != self.in_dim:
+                raise ValueError(f"expected obs[..., {self.in_dim}]")
+            return obs
+        # hdqn.py:291 `[goal] + state`
+        return torch.cat([goal.to(torch.float32).unsqueeze(-1), obs], dim=-1)
+
+    def q_values_torch(self, obs: torch.Tensor, goal: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = self._inputs(obs, goal)
+        h = torch.relu(torch.addmm(self.b1, x, self.w1.t()))
+        h = torch.relu(torch.addmm(self.b2, h, self.w2.t()))
+        return torch.addmm(self.b3, h, self.w3.t())
+
+    def act(self, obs: torch.Tensor, goal: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Greedy actions uint8[N] = argmax_a Q(obs)[a] (first maximum wins, as torch.max does)."""
+        n = obs.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        if self.backend == "torch":
+            q = self.q_values_torch(obs, goal)
+            if q_out is not None:
+                q_out.copy_(q)
+            out.copy_(q.argmax(dim=1))
+            return out
+        lib = nat.load()
+        if not (obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous()):
+            raise ValueError("obs must be a contiguous float32 CUDA tensor")
+        obs_dim = obs.shape[1]
+        if obs_dim + (0 if goal is None else 1) != self.in_dim:
+            raise ValueError("obs/goal widths do not match the network input")
+        if goal is not None and not (goal.dtype == torch.uint8 and goal.is_contiguous()):
+            raise ValueError("goal must be a contiguous uint8 tensor")
+        with torch.cuda.device(self.device):
+            nat.check(lib.mg_mlp_act(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
+                                     _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_t), _ptr(self.b2),
+                                     _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out),
+                                     C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                      "mg_mlp_act")
+        return out
+
+    __call__ = act
+
+
+def explore(greedy: torch.Tensor, num_actions: int, generator: Optional[torch.Generator] = None,
+            threshold: float = EPISILO) -> torch.Tensor:
+    """The scripts' exploration rule, batched: keep the greedy action where randn() <= 0.7, else a
+    uniform random action (main.py:103-110).  Device-side, no host sync."""
+    n, dev = greedy.shape[0], greedy.device
+    keep = torch.randn(n, device=dev, generator=generator) <= threshold
+    rnd = torch.randint(0, num_actions, (n,), device=dev, generator=generator, dtype=torch.int64).to(greedy.dtype)
+    return torch.where(keep, greedy, rnd)
+
+
+def goal_status(obs: torch.Tensor) -> torch.Tensor:
+    """hdqn.py:223-236 for a batch: 0 if dx1 < -0.5*v2, 1 if dx1 < 0.5*v2, else 2  (uint8[N])."""
+    dx1, v2 = obs[:, 0], obs[:, 9]
+    return torch.where(dx1 < -0.5 * v2, 0, torch.where(dx1 < 0.5 * v2, 1, 2)).to(torch.uint8)
+
+
+class HDQNPolicy:
+    """Two-level h-DQN acting greedily: the meta-controller `Net(10,3)` picks a goal and the
+    controller `Net(11,5)` acts on `[goal] + state` (hdqn.py:58-139, 142-221).  In the reference's
+    loop the goal is re-chosen from the new state after every env step (hdqn.py:303), so acting
+    greedily is `ctrl([meta(state)] + state)` at every step."""
+
+    def __init__(self, device="cuda", meta_state: Optional[dict] = None, ctrl_state: Optional[dict] = None,
+                 seed: int = 0, backend: str = "fused"):
+        self.meta = MLPPolicy(10, 3, device, meta_state, seed, backend)
+        self.ctrl = MLPPolicy(11, 5, device, ctrl_state, seed + 1, backend)
+        self.goal: Optional[torch.Tensor] = None
+
+    def act(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.goal is None or self.goal.shape[0] != obs.shape[0]:
+            self.goal = torch.empty(obs.shape[0], dtype=torch.uint8, device=obs.device)
+        self.meta.act(obs, out=self.goal)                       # hdqn.py:283,303  choose_goal
+        return self.ctrl.act(obs, goal=self.goal, out=out)      # hdqn.py:291-292  [goal] + state
+
+    __call__ = act

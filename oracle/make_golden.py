@@ -18,6 +18,8 @@ stores what `reset()` / `step()` return:
   the fixture the CUDA kernel is compared with directly.
 * `kat.json`               known-answer episodes for scripted action pairs
   (SURVEY.md §8c): steps, winner, collision, returns, final positions, last obs.
+* `dqn_policies.npz`       (`--policies`) weights of two shipped DQN checkpoints and their greedy
+  episodes against the L0 opponent in the reference env (policy-in-the-loop).
 """
 import json
 import os
@@ -124,5 +126,54 @@ def main():
         print(k["a1"], k["a2"], k["steps"], k["winner"], k["collision"], k["R1"], k["R2"], k["pos1"], k["pos2"])
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--policies" not in sys.argv:
     main()
+
+
+# ------------------------------------------------------------------------------------------------
+# Policy-in-the-loop fixtures: the reference's shipped DQN checkpoints
+# (test_params/dqn/*/eval.pth; Net = 10 -> 200 -> 100 -> 5, scripts/main.py:30-47) played greedily
+# against the constant-speed "L0" opponent (action2=None, main.py:196-197) in the unmodified env.
+def policy_fixtures():
+    import glob
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    class Net(nn.Module):                      # same layer names as main.py:30-47 so state_dicts load
+        def __init__(self):
+            super().__init__()
+            self.fc1 = nn.Linear(10, 200); self.fc2 = nn.Linear(200, 100); self.out = nn.Linear(100, 5)
+
+        def forward(self, x):
+            return self.out(F.relu(self.fc2(F.relu(self.fc1(x)))))
+
+    env = load_reference_env()
+    out = {}
+    root = os.path.join(os.environ.get("MERGING_GYM_REFERENCE", "/root/reference"), "test_params", "dqn")
+    for tag, prefix in (("L1_1445", "2022--03--31 14:45:59"), ("L0_2037", "2022--03--31 20:37:39")):
+        d = [p for p in sorted(glob.glob(os.path.join(root, "*"))) if os.path.basename(p).startswith(prefix)][0]
+        sd = torch.load(os.path.join(d, "eval.pth"), map_location="cpu", weights_only=True)
+        net = Net(); net.load_state_dict(sd); net.eval()
+        for k, v in sd.items():
+            out[f"{tag}/{k}"] = v.numpy().astype(np.float32)
+        state = env.reset()
+        acts, obs, qs = [], [], []
+        with quiet(), torch.no_grad():
+            while True:
+                q = net(torch.FloatTensor(state).unsqueeze(0))
+                a = int(torch.max(q, 1)[1][0])                      # main.py:105
+                obs.append(_f(state)); qs.append(q[0].numpy().astype(np.float64)); acts.append(a)
+                state, r, done, info = env.step(a, None)
+                if done:
+                    break
+        out[f"{tag}/traj_obs"] = np.array(obs); out[f"{tag}/traj_q"] = np.array(qs)
+        out[f"{tag}/traj_actions"] = np.array(acts, np.uint8)
+        out[f"{tag}/result"] = np.array([len(acts), env.winner or 0, int(info["collision"]),
+                                         env.r1_accumulate, env.r2_accumulate])
+        print(tag, len(acts), env.winner, info, env.r1_accumulate, env.r2_accumulate)
+    np.savez_compressed(os.path.join(OUT, "dqn_policies.npz"), **out)
+
+
+if __name__ == "__main__" and "--policies" in sys.argv:
+    policy_fixtures()

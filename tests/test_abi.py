@@ -30,7 +30,7 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     assert declared_symbols() == sorted([
         "mg_version", "mg_last_error", "mg_get_constants", "mg_default_rewards", "mg_reset",
-        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host"])
+        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_mlp_act"])
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -99,6 +99,9 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mg_reset(C.byref(nat.MgState()), 0, None, None, None) == 0
     assert lib.mg_rollout(C.byref(nat.MgState()), 0, 1, 0, 0, 0, 4, None, C.byref(out), None, None, 1, None) == 0
     assert lib.mg_sample_actions(None, None, 0, 0, 0, 0, None) == 0
+    assert lib.mg_mlp_act(None, None, 0, 10, 5, None, None, None, None, None, None, None, None, None) == 0
+    assert lib.mg_mlp_act(None, None, 8, 9, 5, None, None, None, None, None, None, None, None, None) == -2
+    assert lib.mg_mlp_act(None, None, 8, 10, 5, None, None, None, None, None, None, None, None, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -1,0 +1,151 @@
+"""Policy-in-the-loop: the fused Q-network kernel `mg_mlp_act` against a plain
+PyTorch reference of the same op (fp32 on the GPU, fp64 on the CPU), and the reference's shipped
+DQN checkpoints played greedily in the env against the recorded reference-env episodes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import merging_gym_b200
+    return merging_gym_b200
+
+
+@pytest.fixture(scope="module")
+def ckpt():
+    z = np.load(os.path.join(GOLDEN, "dqn_policies.npz"))
+    def get(tag):
+        sd = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(tag + "/") and "traj" not in k and "result" not in k}
+        return sd, {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(tag + "/traj") or k.endswith("result") and k.startswith(tag)}
+    return get
+
+
+def mid_episode_obs(mg, n, steps=120, seed=3):
+    env = mg.MergeVecEnv(n, seed=seed)
+    env.rollout(steps)
+    a1, a2 = env.sample_actions()
+    return env.step(a1, a2)[0].clone()
+
+
+def q_fp64(policy, x):
+    sd = {k: v.double().cpu() for k, v in policy.state_dict().items()}
+    h = torch.relu(x @ sd["fc1.weight"].t() + sd["fc1.bias"])
+    h = torch.relu(h @ sd["fc2.weight"].t() + sd["fc2.bias"])
+    return h @ sd["out.weight"].t() + sd["out.bias"]
+
+
+@pytest.mark.parametrize("in_dim,out_dim,n", [(10, 5, 5000), (10, 3, 4099), (11, 5, 1031), (10, 5, 3), (11, 3, 256)])
+def test_fused_mlp_matches_torch_reference(mg, in_dim, out_dim, n):
+    obs = mid_episode_obs(mg, n)
+    goal = torch.randint(0, 3, (n,), dtype=torch.uint8, device="cuda") if in_dim == 11 else None
+    pol = mg.MLPPolicy(in_dim, out_dim, seed=in_dim * 10 + out_dim)
+    ref = mg.MLPPolicy(in_dim, out_dim, state_dict=pol.state_dict(), backend="torch")
+    q = torch.empty(n, out_dim, device="cuda")
+    a = pol.act(obs, goal=goal, q_out=q)
+    x = obs if goal is None else torch.cat([goal.float().unsqueeze(1), obs], 1)
+    q64 = q_fp64(pol, x.double().cpu())
+    q32 = ref.q_values_torch(obs, goal)
+    scale = q64.abs().max().item()
+    assert (q.double().cpu() - q64).abs().max().item() <= 2e-5 * scale      # fp32 accumulation noise
+    assert (q32.double().cpu() - q64).abs().max().item() <= 2e-5 * scale
+    # arg-max: identical wherever the top-2 margin is above the fp32 noise floor; first maximum on ties
+    top2 = q64.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4 * scale
+    assert clear.float().mean() > 0.9
+    assert torch.equal(a.cpu()[clear].long(), q64.argmax(1)[clear])
+    assert torch.equal(a.long(), q.argmax(1))                               # consistent with its own Q
+    assert torch.equal(ref.act(obs, goal=goal).cpu()[clear], a.cpu()[clear])
+
+
+@pytest.mark.parametrize("tag", ["L1_1445", "L0_2037"])
+def test_shipped_dqn_checkpoint_greedy_vs_L0(mg, ckpt, tag):
+    """Greedy DQN (test_params/dqn/*/eval.pth) vs the constant-speed opponent: 225 steps, P1 wins,
+    no collision, R1 = 0.589997, R2 = 1.0 — the episode recorded in the unmodified reference env."""
+    sd, traj = ckpt(tag)
+    pol = mg.MLPPolicy(10, 5, state_dict=sd)
+    env = mg.MergeVecEnv(64, mode="pve", auto_reset=False)
+    obs = env.reset()
+    q = torch.empty(64, 5, device="cuda")
+    T = len(traj["traj_actions"])
+    for t in range(T):
+        a = pol.act(obs, q_out=q)
+        assert a.cpu().tolist() == [int(traj["traj_actions"][t])] * 64, t
+        qr = traj["traj_q"][t]                                       # torch CPU fp32 forward in the reference loop
+        assert np.abs(q[0].cpu().numpy() - qr).max() <= 2e-5 * np.abs(qr).max(), t
+        assert rel_err(obs[0].cpu().numpy(), traj["traj_obs"][t]).max() <= 1e-5, t
+        obs, rew, done, info = env.step(a, None)
+    steps, winner, col, R1, R2 = traj["result"]
+    assert T == steps == 225 and bool(done.all()) and not bool(info["collision"].any())
+    assert env.winner.cpu().tolist() == [int(winner)] * 64 == [1] * 64
+    assert abs(float(env.ret1[0]) - R1) <= 1e-9 and abs(float(env.ret2[0]) - R2) <= 1e-9
+    assert abs(R1 - 0.5899968243808502) < 1e-12 and R2 == 1.0
+
+
+def test_policy_in_the_loop_cuda_graph(mg, ckpt):
+    """obs -> fused MLP -> uint8 actions -> mg_step, captured in one CUDA graph: no host sync, and
+    the replay equals the eager loop."""
+    sd, _ = ckpt("L1_1445")
+    n, K = 4096, 32
+    pol = mg.MLPPolicy(10, 5, state_dict=sd)
+    opp = mg.MLPPolicy(10, 5, state_dict=ckpt("L0_2037")[0])
+
+    def run(env, graph):
+        act1 = torch.empty(n, dtype=torch.uint8, device="cuda"); act2 = torch.empty_like(act1)
+        obs_box = [env.obs_buf[env._slot]]
+        def loop():
+            obs = obs_box[0]
+            for _ in range(K):
+                pol.act(obs, out=act1)
+                opp.act(mg.MergeVecEnv.opponent_view(obs).contiguous(), out=act2)   # main.py:199
+                obs = env.step(act1, act2)[0]
+            return obs
+        if not graph:
+            return loop().clone()
+        s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            pol.act(obs_box[0], out=act1)                           # warm-up (sets the smem attribute)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = loop()
+        g.replay()
+        torch.cuda.synchronize()
+        return out.clone()
+
+    a = mg.MergeVecEnv(n, seed=11); a.rollout(100)
+    b = mg.MergeVecEnv(n, seed=11); b.rollout(100)
+    a.step(*a.sample_actions()); b.step(*b.sample_actions())
+    oa, ob = run(a, False), run(b, True)
+    assert torch.equal(oa, ob) and torch.equal(a.pos1, b.pos1) and torch.equal(a.meta, b.meta)
+
+
+def test_explore_rule_and_goal_status(mg):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    greedy = torch.full((400000,), 3, dtype=torch.uint8, device="cuda")
+    a = mg.explore(greedy, 5, generator=g)
+    kept = (a == 3).float().mean().item()
+    # P(randn <= 0.7) = 0.758, plus 1/5 of the random draws land on 3 again
+    assert abs(kept - (0.7580 + 0.2420 / 5)) < 0.005
+    obs = torch.zeros(4, 10, device="cuda")
+    obs[:, 0] = torch.tensor([-20.0, -5.0, 5.0, 20.0]); obs[:, 9] = 20.0
+    assert mg.goal_status(obs).cpu().tolist() == [0, 1, 1, 2]          # hdqn.py:223-236
+
+
+def test_hdqn_policy_fused_equals_torch(mg):
+    n = 3000
+    obs = mid_episode_obs(mg, n, seed=9)
+    f = mg.HDQNPolicy(seed=5)
+    t = mg.HDQNPolicy(seed=5, backend="torch")
+    af, at = f.act(obs), t.act(obs)
+    assert (f.goal == t.goal).float().mean() > 0.98
+    same_goal = f.goal == t.goal
+    assert ((af == at) | ~same_goal).float().mean() > 0.98
+    env = mg.MergeVecEnv(n, mode="pve")
+    env.step(af, None)
