@@ -49,41 +49,80 @@ __device__ __forceinline__ double div_const(double x, double d, double y) {
 // ---- sin & cos on the lane-angle range ------------------------------------------------------
 // angle = atan2(H,R) - lon/R lies in [-0.64, 0.034] for any state reachable before the time
 // limit (lon <= 50 + 8*2501), so no range reduction is needed: fdlibm's k_sin/k_cos minimax
-// polynomials for |x| <= pi/4 (error < 2^-58) evaluated with FMAs.  Outside |x| <= 0.78 (only
-// reachable when a caller keeps stepping a finished env without auto-reset) fall back to the
-// CUDA library sincos.  Both stay within 1 ulp of glibc, which the reference's np.sin/np.cos use.
-__device__ __forceinline__ void sincos_lane(double x, double &s, double &c) {
-    if (fabs(x) > 0.78) {   // cold path, warp-uniformly false in normal operation
-        sincos(x, &s, &c);
-        return;
-    }
-    const double z = x * x;
-    const double w = z * z;
-    // sin
+// polynomials for |x| <= pi/4 (error < 2^-58) evaluated with FMAs, within 1 ulp of glibc (which
+// the reference's np.sin/np.cos call).  M angles are evaluated in lock-step, Horner stage by
+// Horner stage, so every 64-bit coefficient is materialised once per stage instead of once per
+// angle (the round-1 profile showed 12 % of all issued instructions were UMOV constant pairs).
+template <int M>
+__device__ __forceinline__ void sincos_poly(const double (&x)[M], double (&s)[M], double (&c)[M]) {
     const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
                  S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
                  S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-    const double rs = fma(z, fma(z, S4, S3), S2) + z * w * fma(z, S6, S5);
-    const double v = z * x;
-    s = fma(v, fma(z, rs, S1), x);
-    // cos
     const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
                  C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
                  C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
-    const double rc = z * fma(z, fma(z, C3, C2), C1) + (w * w) * fma(z, fma(z, C6, C5), C4);
-    const double hz = 0.5 * z;
-    const double ww = 1.0 - hz;
-    c = ww + (((1.0 - ww) - hz) + z * rc);
+    double z[M], w[M], p[M], q[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) { z[i] = x[i] * x[i]; w[i] = z[i] * z[i]; }
+    // sin(x) = x + x^3 (S1 + z (S2 + z S3 + z^2 S4 + z^3 (S5 + z S6)))
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fma(z[i], S4, S3);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fma(z[i], p[i], S2);
+#pragma unroll
+    for (int i = 0; i < M; ++i) q[i] = fma(z[i], S6, S5);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fma(z[i] * w[i], q[i], p[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fma(z[i], p[i], S1);
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = fma(z[i] * x[i], p[i], x[i]);
+    // cos(x) = t + (((1 - t) - z/2) + z r),  t = 1 - z/2   (FreeBSD k_cos: no cancellation near 1)
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fma(z[i], C3, C2);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fma(z[i], p[i], C1);
+#pragma unroll
+    for (int i = 0; i < M; ++i) q[i] = fma(z[i], C6, C5);
+#pragma unroll
+    for (int i = 0; i < M; ++i) q[i] = fma(z[i], q[i], C4);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fma(w[i] * w[i], q[i], z[i] * p[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const double hz = 0.5 * z[i];
+        const double t = 1.0 - hz;
+        c[i] = t + (((1.0 - t) - hz) + z[i] * p[i]);
+    }
 }
 
-// lon2coord (merging_env.py:48-58).  sign = +1 for "ego" (player 1), -1 for "opponent".
-__device__ __forceinline__ void lon2coord(double lon, double sign, double &x, double &y) {
-    const double angle = __dsub_rn(kAngle0, div_const(lon, kR, kInvR));
-    double s, c;
-    sincos_lane(angle, s, c);
-    x = __dmul_rn(kR, s);
-    const double d = __dsub_rn(kR, __dmul_rn(kR, c));
-    y = __fma_rn(sign, d, kHalfW);   // W/2 +/- d : sign*d is exact, one rounding like the reference
+// lon2coord (merging_env.py:48-58) for M cars at once.  sign[i] = +1 for "ego" (player 1), -1 for
+// "opponent".  Longitudes beyond kPolyMaxLon (only reachable when a caller keeps stepping a
+// finished env without auto-reset) leave the polynomial's range: one rarely-taken branch for the
+// whole batch then uses the CUDA library sincos.
+constexpr double kPolyMaxLon = 24000.0;   // |atan2(H,R) - lon/R| <= 0.767 < pi/4 for 0 <= lon <= 24000
+template <int M>
+__device__ __forceinline__ void lon2coord_batch(const double (&lon)[M], const double (&sign)[M],
+                                                double (&x)[M], double (&y)[M]) {
+    double ang[M], s[M], c[M];
+    bool wild = false;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        ang[i] = __dsub_rn(kAngle0, div_const(lon[i], kR, kInvR));
+        wild |= !(lon[i] >= 0.0 && lon[i] <= kPolyMaxLon);
+    }
+    if (wild) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) sincos(ang[i], &s[i], &c[i]);
+    } else {
+        sincos_poly<M>(ang, s, c);
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        x[i] = __dmul_rn(kR, s[i]);
+        const double d = __dsub_rn(kR, __dmul_rn(kR, c[i]));
+        y[i] = __fma_rn(sign[i], d, kHalfW);   // W/2 +/- d: sign*d is exact, one rounding like the reference
+    }
 }
 
 // ---- Philox4x32-10 (Salmon et al. SC'11) ----------------------------------------------------
@@ -130,10 +169,8 @@ __device__ __forceinline__ void reset_regs(EnvRegs &e) {   // merging_env.py:208
     e.R1 = 0.0; e.R2 = 0.0; e.meta = 0u;
 }
 
-__device__ __forceinline__ void observe(const EnvRegs &e, float *obs) {   // merging_env.py:118-132
-    double x1, y1, x2, y2;
-    lon2coord(e.p1, 1.0, x1, y1);
-    lon2coord(e.p2, -1.0, x2, y2);
+__device__ __forceinline__ void write_obs(double x1, double y1, double x2, double y2, const EnvRegs &e,
+                                          float *obs) {                    // merging_env.py:122-131
     const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1), dv = __dsub_rn(e.v2, e.v1);
     obs[0] = (float)dx;  obs[1] = (float)dy;  obs[2] = (float)dv;
     obs[3] = (float)__dsub_rn(kEnd, e.p1);  obs[4] = (float)e.v1;
@@ -141,89 +178,107 @@ __device__ __forceinline__ void observe(const EnvRegs &e, float *obs) {   // mer
     obs[8] = (float)__dsub_rn(kEnd, e.p2);  obs[9] = (float)e.v2;
 }
 
-// merging_env.py:138-195 for one env.  a1/a2 already validated into 0..4 (bad -> info bit).
-// PVP=false: `action2 is None` -> acc2 = 0 (merging_env.py:152).
-template <bool PVP>
-__device__ __forceinline__ void env_step(EnvRegs &e, int a1, int a2, bool bad_action,
-                                         const MgRewards &rw, StepResult &out) {
-    // :141-143  time_stamp += dT; > 500 first holds at step 2501 -> integer step counter
-    uint32_t steps = e.meta & MG_META_STEPS_MASK;
-    steps = min(steps + 1u, (uint32_t)MG_META_STEPS_MASK);
-    const bool was_done = (e.meta & MG_META_DONE) != 0u;
-    const bool timeout = steps >= (uint32_t)kMaxSteps;
-    bool done = was_done | timeout;
-    uint32_t winner = (e.meta >> MG_META_WINNER_SHIFT) & 3u;
+__device__ __forceinline__ void observe(const EnvRegs &e, float *obs) {   // merging_env.py:118-132
+    const double lon[2] = {e.p1, e.p2}, sign[2] = {1.0, -1.0};
+    double x[2], y[2];
+    lon2coord_batch<2>(lon, sign, x, y);
+    write_obs(x[0], y[0], x[1], y[1], e, obs);
+}
 
-    // :147-150  player 1: acc = mpc_1d(...) == (vt - v)/3 ; vel = max(0, vel + acc*dT) ; pos += vel*dT
-    {
-        const double vt = kActionDv * (double)a1;
-        const double acc = div_const(__dsub_rn(vt, e.v1), kPredT, kInvPredT);
-        const double v = __dadd_rn(e.v1, __dmul_rn(acc, kDT));
-        e.v1 = (v > 0.0) ? v : 0.0;
-        e.p1 = __dadd_rn(e.p1, __dmul_rn(e.v1, kDT));
+// merging_env.py:138-195 for E envs held by one thread, evaluated in lock-step (same operations
+// and roundings per env as the scalar reference; batching only lets the compiler share constants
+// and interleave independent float64 chains).  a1/a2 already validated into 0..4 (bad -> info
+// bit).  PVP=false: `action2 is None` -> acc2 = 0 (merging_env.py:152).
+template <bool PVP, int E>
+__device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1)[E], const int (&a2)[E],
+                                               const bool (&bad_action)[E], const MgRewards &rw,
+                                               StepResult (&out)[E]) {
+    uint32_t steps[E], winner[E];
+    bool was_done[E], timeout[E], done[E];
+    double lon[2 * E], sign[2 * E], x[2 * E], y[2 * E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        EnvRegs &e = env[i];
+        // :141-143  time_stamp += dT; > 500 first holds at step 2501 -> integer step counter
+        steps[i] = min((e.meta & MG_META_STEPS_MASK) + 1u, (uint32_t)MG_META_STEPS_MASK);
+        was_done[i] = (e.meta & MG_META_DONE) != 0u;
+        timeout[i] = steps[i] >= (uint32_t)kMaxSteps;
+        done[i] = was_done[i] | timeout[i];
+        winner[i] = (e.meta >> MG_META_WINNER_SHIFT) & 3u;
+        // :147-150  player 1: acc = mpc_1d(...) == (vt - v)/3; vel = max(0, vel + acc*dT); pos += vel*dT
+        {
+            const double vt = kActionDv * (double)a1[i];
+            const double acc = div_const(__dsub_rn(vt, e.v1), kPredT, kInvPredT);
+            const double v = __dadd_rn(e.v1, __dmul_rn(acc, kDT));
+            e.v1 = (v > 0.0) ? v : 0.0;
+            e.p1 = __dadd_rn(e.p1, __dmul_rn(e.v1, kDT));
+        }
+        // :152-154  player 2
+        if (PVP) {
+            const double vt = kActionDv * (double)a2[i];
+            const double acc = div_const(__dsub_rn(vt, e.v2), kPredT, kInvPredT);
+            const double v = __dadd_rn(e.v2, __dmul_rn(acc, kDT));
+            e.v2 = (v > 0.0) ? v : 0.0;
+        } else {
+            e.v2 = (e.v2 > 0.0) ? e.v2 : 0.0;          // max(0, vel + 0*dT)
+        }
+        e.p2 = __dadd_rn(e.p2, __dmul_rn(e.v2, kDT));
+        lon[2 * i] = e.p1; sign[2 * i] = 1.0;
+        lon[2 * i + 1] = e.p2; sign[2 * i + 1] = -1.0;
     }
-    // :152-154  player 2
-    if (PVP) {
-        const double vt = kActionDv * (double)a2;
-        const double acc = div_const(__dsub_rn(vt, e.v2), kPredT, kInvPredT);
-        const double v = __dadd_rn(e.v2, __dmul_rn(acc, kDT));
-        e.v2 = (v > 0.0) ? v : 0.0;
-    } else {
-        e.v2 = (e.v2 > 0.0) ? e.v2 : 0.0;          // max(0, vel + 0*dT)
-    }
-    e.p2 = __dadd_rn(e.p2, __dmul_rn(e.v2, kDT));
+    // :156, :118-132, :48-58  geometry once per car (the reference recomputes it in is_collided)
+    lon2coord_batch<2 * E>(lon, sign, x, y);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        EnvRegs &e = env[i];
+        const double x1 = x[2 * i], y1 = y[2 * i], x2 = x[2 * i + 1], y2 = y[2 * i + 1];
+        write_obs(x1, y1, x2, y2, e, out[i].obs);
 
-    // :156, :118-132, :48-58  geometry once (the reference recomputes it in is_collided)
-    double x1, y1, x2, y2;
-    lon2coord(e.p1, 1.0, x1, y1);
-    lon2coord(e.p2, -1.0, x2, y2);
-    {
-        const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1), dv = __dsub_rn(e.v2, e.v1);
-        out.obs[0] = (float)dx;  out.obs[1] = (float)dy;  out.obs[2] = (float)dv;
-        out.obs[3] = (float)__dsub_rn(kEnd, e.p1);  out.obs[4] = (float)e.v1;
-        out.obs[5] = (float)-dx; out.obs[6] = (float)-dy; out.obs[7] = (float)-dv;
-        out.obs[8] = (float)__dsub_rn(kEnd, e.p2);  out.obs[9] = (float)e.v2;
-    }
+        // :158-159  reward_i = -time_penalty - vel_penalty*|v_i - 20|
+        double r1 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v1, 20.0))));
+        double r2 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v2, 20.0))));
+        uint32_t w = winner[i];
+        bool dn = done[i];
+        // :163-171  player 1 crosses with strict '>' and is evaluated first (branch-free selects)
+        {
+            const bool f = e.p1 > kEnd;
+            const double bonus = (w == 0u) ? rw.r_first : rw.r_second;
+            const double r_cross = (w == 1u) ? 0.0 : __dadd_rn(r1, bonus);
+            r1 = f ? r_cross : r1;
+            dn |= f & (w == 2u);
+            w = (f & (w == 0u)) ? 1u : w;
+        }
+        // :173-181  player 2 crosses with '>='
+        {
+            const bool f = e.p2 >= kEnd;
+            const double bonus = (w == 0u) ? rw.r_first : rw.r_second;
+            const double r_cross = (w == 2u) ? 0.0 : __dadd_rn(r2, bonus);
+            r2 = f ? r_cross : r2;
+            dn |= f & (w == 1u);
+            w = (f & (w == 0u)) ? 2u : w;
+        }
+        // :183-187, :198-206, :232-239  integer pygame Rects (C truncation) 4 wide (lateral, y) x 8
+        // long (longitudinal, x); closed rectangles intersect iff both projections overlap.
+        const int ty1 = __double2int_rz(y1), ty2 = __double2int_rz(y2);
+        const int tx1 = __double2int_rz(x1), tx2 = __double2int_rz(x2);
+        const bool collided = (abs(ty1 - ty2) <= kVehicleW) & (abs(tx1 - tx2) <= kVehicleH);
+        dn |= collided;
+        r1 = collided ? __dadd_rn(r1, rw.r_collision) : r1;
+        r2 = collided ? __dadd_rn(r2, rw.r_collision) : r2;
+        // :191-192
+        e.R1 = __dadd_rn(e.R1, r1);
+        e.R2 = __dadd_rn(e.R2, r2);
+        e.meta = steps[i] | (w << MG_META_WINNER_SHIFT) | (dn ? MG_META_DONE : 0u);
 
-    // :158-159  reward_i = -time_penalty - vel_penalty*|v_i - 20|
-    double r1 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v1, 20.0))));
-    double r2 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v2, 20.0))));
-
-    // :163-171  player 1 crosses with strict '>' and is evaluated first
-    if (e.p1 > kEnd) {
-        if (winner == 0u)      { winner = 1u; r1 = __dadd_rn(r1, rw.r_first); }
-        else if (winner == 1u) { r1 = 0.0; }
-        else                   { r1 = __dadd_rn(r1, rw.r_second); done = true; }
+        out[i].r1 = (float)r1;
+        out[i].r2 = (float)r2;
+        out[i].steps = steps[i];
+        out[i].done = dn;
+        out[i].finished = dn & !was_done[i];
+        out[i].info = (collided ? MG_INFO_COLLISION : 0u) | (w << MG_INFO_WINNER_SHIFT) |
+                      (timeout[i] ? MG_INFO_TIMEOUT : 0u) | (dn ? MG_INFO_DONE : 0u) |
+                      (bad_action[i] ? MG_INFO_BAD_ACTION : 0u);
     }
-    // :173-181  player 2 crosses with '>='
-    if (e.p2 >= kEnd) {
-        if (winner == 0u)      { winner = 2u; r2 = __dadd_rn(r2, rw.r_first); }
-        else if (winner == 2u) { r2 = 0.0; }
-        else                   { r2 = __dadd_rn(r2, rw.r_second); done = true; }
-    }
-    // :183-187, :198-206, :232-239  integer pygame Rects (C truncation) 4 wide (lateral, y) x 8
-    // long (longitudinal, x); closed rectangles intersect iff both projections overlap.
-    const int ty1 = __double2int_rz(y1), ty2 = __double2int_rz(y2);
-    const int tx1 = __double2int_rz(x1), tx2 = __double2int_rz(x2);
-    const bool collided = (abs(ty1 - ty2) <= kVehicleW) & (abs(tx1 - tx2) <= kVehicleH);
-    if (collided) {
-        done = true;
-        r1 = __dadd_rn(r1, rw.r_collision);
-        r2 = __dadd_rn(r2, rw.r_collision);
-    }
-    // :191-192
-    e.R1 = __dadd_rn(e.R1, r1);
-    e.R2 = __dadd_rn(e.R2, r2);
-    e.meta = steps | (winner << MG_META_WINNER_SHIFT) | (done ? MG_META_DONE : 0u);
-
-    out.r1 = (float)r1;
-    out.r2 = (float)r2;
-    out.steps = steps;
-    out.done = done;
-    out.finished = done & !was_done;
-    out.info = (collided ? MG_INFO_COLLISION : 0u) | (winner << MG_INFO_WINNER_SHIFT) |
-               (timeout ? MG_INFO_TIMEOUT : 0u) | (done ? MG_INFO_DONE : 0u) |
-               (bad_action ? MG_INFO_BAD_ACTION : 0u);
 }
 
 // ---- per-thread episode statistics, packed so that one warp reduction covers several ---------

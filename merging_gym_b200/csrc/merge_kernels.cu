@@ -167,10 +167,11 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
     uint8_t done8[EPT], info8[EPT];
     float *my_stage = &stage[warp][lane * EPT * MG_OBS_DIM];
 
+    StepResult res[EPT];
+    env_step_batch<PVP, EPT>(env, act1, act2, bad, rw, res);
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-        StepResult r;
-        env_step<PVP>(env[j], act1[j], act2[j], bad[j], rw, r);
+        StepResult &r = res[j];
         rew[2 * j] = r.r1; rew[2 * j + 1] = r.r2;
         done8[j] = r.done ? 1 : 0;
         info8[j] = (uint8_t)r.info;
@@ -235,8 +236,11 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 // merge_rollout_kernel: k consecutive steps with in-kernel Philox actions; state stays in
 // registers, outputs are time-major.  One env per thread element, EPT=2 vector state I/O.
 // =================================================================================================
+#ifndef MG_ROLLOUT_MIN_BLOCKS
+#define MG_ROLLOUT_MIN_BLOCKS 1
+#endif
 template <bool PVP>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MG_ROLLOUT_MIN_BLOCKS)
 merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actions_out, const int64_t n,
                      const uint64_t seed, const uint64_t env_id_base, const uint64_t step0,
                      const int k_steps, const MgRewards rw, const uint32_t flags,
@@ -266,13 +270,18 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
     for (int t = 0; t < k_steps; ++t) {
         StatAcc st;
         const int64_t toff = (int64_t)t * n;
+        int act1[EPT], act2[EPT];
+        const bool nobad[EPT] = {};
+#pragma unroll
+        for (int j = 0; j < EPT; ++j)
+            philox_actions(seed, env_id_base + (uint64_t)(e0 + j), step0 + (uint64_t)t, act1[j], act2[j]);
+        StepResult res[EPT];
+        env_step_batch<PVP, EPT>(env, act1, act2, nobad, rw, res);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             const int64_t e = e0 + j;
-            int a1, a2;
-            philox_actions(seed, env_id_base + (uint64_t)e, step0 + (uint64_t)t, a1, a2);
-            StepResult r;
-            env_step<PVP>(env[j], a1, a2, false, rw, r);
+            const int a1 = act1[j], a2 = act2[j];
+            StepResult &r = res[j];
             if (valid[j]) {
                 if (stats) st.add(r, env[j].R1, env[j].R2);
                 if (r.finished) write_episode_outputs(o, e, r, env[j].R1, env[j].R2);
