@@ -178,6 +178,23 @@ MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, 
                       const float *b2, const float *w3, const float *b3, uint8_t *actions,
                       float *q_out_or_null, void *stream);
 
+/* ---- "next" rows: device-resident transition writer -----------------------
+ * Appends one row per selected env to a ring `ring[capacity][width]` (index = counter % capacity,
+ * exactly `DQN.store_transition`, scripts/main.py:115-119), envs in id order, deterministic.
+ *   mask_mode 0: every env;  1: `env.winner is not 1` after the step (main.py:209, human_player.py:180)
+ *   format 0 (width 22): [s(10), a_p, r_p, s'(10)] for player p (main.py:116);  s' is the stepped
+ *                        state's observation: term_obs where done (pass NULL without auto-reset)
+ *   format 1 (width 14): [s(10), a1, a2, r1, r2], the CSV row of scripts/human_player.py:111,180-181
+ * counter: device uint64, total rows ever appended (caller zero-initialises).
+ * scratch: device uint32[(n+31)/32 + 4].  env_ids_or_null: int32[capacity], env of each row. */
+MG_API int mg_record_transitions(const float *obs_prev, const float *obs_next,
+                                 const float *term_obs_or_null, const uint8_t *a1,
+                                 const uint8_t *a2_or_null, const float *rew, const uint8_t *done,
+                                 const uint8_t *info, int64_t n, int32_t mask_mode, int32_t format,
+                                 int32_t player, float *ring, int64_t capacity,
+                                 int32_t *env_ids_or_null, uint64_t *counter, uint32_t *scratch,
+                                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

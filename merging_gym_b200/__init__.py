@@ -7,10 +7,12 @@ The package holds only what the hot path needs:
   scalar_env.py `MergeEnv` / `make("merging_env-v0")`, the reference's scalar interface
   sharding.py  one-shard-per-rank helpers and the NCCL statistics all-reduce
   spaces.py    Discrete(5) / Box(10) stand-ins (gym is not a dependency)
+  replay.py    device-resident transition ring (replay rows) and per-episode CSV logs
   policy.py    policy-in-the-loop: the reference's Q-networks as one fused forward+argmax kernel
 """
 from ._native import NativeError  # noqa: F401
 from .policy import HDQNPolicy, MLPPolicy, explore, goal_status  # noqa: F401
+from .replay import CsvEpisodeLogger, TransitionRecorder  # noqa: F401
 from .scalar_env import ENV_ID, MergeEnv, make, make_vec  # noqa: F401
 from .sharding import all_reduce_stats, init_distributed, shard_range  # noqa: F401
 from .spaces import Box, Discrete, MultiDiscrete  # noqa: F401

@@ -1,0 +1,136 @@
+"""Transition recording for learners and logs.
+
+`TransitionRecorder` — device-resident ring of the reference's replay rows
+`[s(10), a, r, s'(10)]` (`DQN.store_transition`, scripts/main.py:115-119), appended for every env
+and step while `env.winner is not 1` (main.py:209-211) by the deterministic stream-compaction
+kernels behind `mg_record_transitions`; nothing leaves the GPU.
+
+`CsvEpisodeLogger` — host-side per-episode CSV files for a few selected envs in the column order
+of scripts/human_player.py:111 (`[obs(10), action1, action2, reward1, reward2]`, rows written
+while `env.winner is not 1`, :180-181), so the reference's analysis notebook can read GPU episodes.
+"""
+from __future__ import annotations
+
+import csv
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as nat
+
+REPLAY_WIDTH = 2 * nat.OBS_DIM + 2      # main.py:92  NUM_STATES * 2 + 2
+LOG_WIDTH = nat.OBS_DIM + 4
+
+# header of scripts/human_player.py:111, verbatim column names
+CSV_HEADER = ["x2 - x1", "y2 - y1", "self.state2['vel'] - self.state1['vel']", "END_POINT - self.state1['pos']",
+              "self.state1['vel']", "x1 - x2", "y1 - y2", "self.state1['vel'] - self.state2['vel']",
+              "END_POINT - self.state2['pos']", "self.state2['vel']", "action1", "action2", "reward1", "reward2"]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class TransitionRecorder:
+    """Ring buffer of transition rows on the device.
+
+    format "replay": rows `[s, a_p, r_p, s']` (22 floats) for `player` p in {1, 2}.
+    format "log":    rows `[s, a1, a2, r1, r2]` (14 floats).
+    mask "winner_not_1" is the reference's store condition; "all" stores every env every step.
+    """
+
+    def __init__(self, env, capacity: int, format: str = "replay", player: int = 1,
+                 mask: str = "winner_not_1", track_env_ids: bool = False):
+        if format not in ("replay", "log") or mask not in ("winner_not_1", "all") or player not in (1, 2):
+            raise ValueError("format in {'replay','log'}, mask in {'winner_not_1','all'}, player in {1,2}")
+        if format == "replay" and env.auto_reset and env.terminal_obs is None:
+            raise ValueError("replay rows need the terminal observation: create the env with episode_info=True")
+        self.env, self.capacity = env, int(capacity)
+        self.format, self.player, self.mask = format, player, mask
+        self.width = REPLAY_WIDTH if format == "replay" else LOG_WIDTH
+        dev = env.device
+        self.ring = torch.zeros(self.capacity, self.width, dtype=torch.float32, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)        # memory_counter, main.py:91
+        self.env_ids = torch.full((self.capacity,), -1, dtype=torch.int32, device=dev) if track_env_ids else None
+        self._scratch = torch.zeros((env.num_envs + 31) // 32 + 4, dtype=torch.int32, device=dev)
+        self._lib = nat.load()
+
+    def record(self, obs_prev: torch.Tensor, a1: torch.Tensor, a2: Optional[torch.Tensor], step_out) -> None:
+        """Append the transitions of one `env.step`: `obs_prev` is the observation the actions were
+        chosen from, `step_out` the tuple `env.step` returned.  uint8 actions; no host sync."""
+        obs, rew, done, info = step_out
+        env = self.env
+        term = env.terminal_obs if env.auto_reset else None
+        for t in (a1, a2):
+            if t is not None and t.dtype != torch.uint8:
+                raise TypeError("TransitionRecorder.record expects uint8 action tensors")
+        with torch.cuda.device(env.device):
+            nat.check(self._lib.mg_record_transitions(
+                _ptr(obs_prev), _ptr(obs), _ptr(term), _ptr(a1), _ptr(a2), _ptr(rew),
+                _ptr(done.view(torch.uint8)), _ptr(info["flags"]), env.num_envs,
+                1 if self.mask == "winner_not_1" else 0, 0 if self.format == "replay" else 1, self.player,
+                _ptr(self.ring), self.capacity, _ptr(self.env_ids), _ptr(self.counter), _ptr(self._scratch),
+                C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)), "mg_record_transitions")
+
+    def __len__(self) -> int:
+        """Rows currently valid (host sync)."""
+        return min(int(self.counter.item()), self.capacity)
+
+    def rows(self) -> torch.Tensor:
+        """Valid rows, oldest first (host sync)."""
+        c = int(self.counter.item())
+        if c <= self.capacity:
+            return self.ring[:c]
+        k = c % self.capacity
+        return torch.cat([self.ring[k:], self.ring[:k]], dim=0)
+
+    def sample(self, batch_size: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """`np.random.choice(MEMORY_CAPACITY, BATCH_SIZE)` (main.py:130) over a full ring, on device."""
+        idx = torch.randint(0, self.capacity, (batch_size,), device=self.ring.device, generator=generator)
+        return self.ring[idx]
+
+
+class CsvEpisodeLogger:
+    """Per-episode CSV logs of selected envs in the reference's `human_player.py` format."""
+
+    def __init__(self, env, env_ids: Sequence[int], directory: str, prefix: str = "episode"):
+        self.env = env
+        self.ids = torch.as_tensor(list(env_ids), dtype=torch.int64, device=env.device)
+        self.directory, self.prefix = directory, prefix
+        os.makedirs(directory, exist_ok=True)
+        self._rows = {int(i): [] for i in env_ids}
+        self._episode = {int(i): 0 for i in env_ids}
+        self.files = []
+
+    def log(self, obs_prev: torch.Tensor, a1, a2, step_out) -> None:
+        """Call once per `env.step` with the observation the actions were chosen from (host sync)."""
+        obs, rew, done, info = step_out
+        ids = self.ids
+        s = obs_prev.index_select(0, ids).cpu().tolist()
+        act1 = torch.as_tensor(a1, device=obs.device).index_select(0, ids).cpu().tolist()
+        act2 = [None] * len(s) if a2 is None else torch.as_tensor(a2, device=obs.device).index_select(0, ids).cpu().tolist()
+        r = rew.index_select(0, ids).cpu().tolist()
+        w = info["winner"].index_select(0, ids).cpu().tolist()
+        d = done.index_select(0, ids).cpu().tolist()
+        for k, e in enumerate(ids.cpu().tolist()):
+            if w[k] != 1:                                   # human_player.py:180 `if env.winner is not 1`
+                self._rows[e].append(s[k] + [act1[k], act2[k]] + r[k])
+            if d[k]:
+                self._flush(e)
+
+    def _flush(self, e: int) -> None:
+        path = os.path.join(self.directory, f"{self.prefix}{self._episode[e]} env{e}.csv")
+        with open(path, "w", newline="") as f:
+            wr = csv.writer(f)
+            wr.writerow(CSV_HEADER)
+            wr.writerows(self._rows[e])
+        self.files.append(path)
+        self._rows[e] = []
+        self._episode[e] += 1
+
+    def close(self) -> None:
+        for e, rows in self._rows.items():
+            if rows:
+                self._flush(e)

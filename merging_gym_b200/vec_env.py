@@ -340,12 +340,16 @@ class MergeVecEnv:
                                            self._flags(), self._stream()), "mg_rollout")
 
     # ------------------------------------------------------------------ host-buffer path
-    def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None):
+    def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, zero_copy: bool = False):
         """Drop-in for host-resident callers: uint8 NumPy actions in, NumPy outputs out.
 
-        One `mg_step_host` call = H2D of the actions, the fused step, D2H of obs/rew/done/info into
-        pinned host buffers, stream synchronise.  Returns (obs, rewards, done, info_flags) as NumPy
-        views of those pinned buffers (overwritten by the next call).
+        Default: one `mg_step_host` call = H2D of the actions, the fused step, D2H of
+        obs/rew/done/info into pinned host buffers, stream synchronise.
+        `zero_copy=True`: `mg_step` is handed the pinned host buffers themselves (pinned memory is
+        device-addressable under UVA), so the kernel reads the actions and streams its outputs
+        across PCIe while it computes — no staging copy in HBM, no separate memcpy.
+        Returns (obs, rewards, done, info_flags) as NumPy views of the pinned buffers (overwritten
+        by the next call).
         """
         n = self.num_envs
         if self._host is None:
@@ -362,14 +366,21 @@ class MergeVecEnv:
         h["a1"].numpy()[:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
         if a2 is not None:
             h["a2"].numpy()[:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
-        self._slot = (self._slot + 1) % self.out_slots
         with torch.cuda.device(self.device):
-            nat.check(self._lib.mg_step_host(C.byref(self._state), n, _ptr(h["a1"]),
-                                             _ptr(h["a2"]) if a2 is not None else None,
-                                             _ptr(self.act1), _ptr(self.act2), C.byref(self._rw),
-                                             C.byref(self._outs[self._slot]), C.byref(self._host_out),
-                                             _ptr(self.stats_buf), self._flags(), self._stream()),
-                      "mg_step_host")
+            if zero_copy:
+                nat.check(self._lib.mg_step(C.byref(self._state), n, _ptr(h["a1"]),
+                                            _ptr(h["a2"]) if a2 is not None else None, nat.ACT_U8,
+                                            C.byref(self._rw), C.byref(self._host_out), _ptr(self.stats_buf),
+                                            self._flags(), self._stream()), "mg_step (zero-copy)")
+                torch.cuda.current_stream(self.device).synchronize()
+            else:
+                self._slot = (self._slot + 1) % self.out_slots
+                nat.check(self._lib.mg_step_host(C.byref(self._state), n, _ptr(h["a1"]),
+                                                 _ptr(h["a2"]) if a2 is not None else None,
+                                                 _ptr(self.act1), _ptr(self.act2), C.byref(self._rw),
+                                                 C.byref(self._outs[self._slot]), C.byref(self._host_out),
+                                                 _ptr(self.stats_buf), self._flags(), self._stream()),
+                          "mg_step_host")
         return h["obs"].numpy(), h["rew"].numpy(), h["done"].numpy().view(np.bool_), h["info"].numpy()
 
     # ------------------------------------------------------------------ statistics

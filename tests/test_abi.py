@@ -30,7 +30,8 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     assert declared_symbols() == sorted([
         "mg_version", "mg_last_error", "mg_get_constants", "mg_default_rewards", "mg_reset",
-        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_mlp_act"])
+        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_mlp_act",
+        "mg_record_transitions"])
 
 
 def test_library_exports_every_declared_symbol(lib):

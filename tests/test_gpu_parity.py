@@ -328,6 +328,12 @@ def test_step_host_matches_device_path(mg):
         o, r, d, i = b.step(act[:, 0], act[:, 1])
         assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy())
         assert np.array_equal(hd, d.cpu().numpy()) and np.array_equal(hi, i["flags"].cpu().numpy())
+    for t in range(40):                                         # zero-copy variant: kernel writes pinned host memory
+        act = rng.integers(0, 5, (n, 2)).astype(np.uint8)
+        ho, hr, hd, hi = a.step_host(act[:, 0], act[:, 1], zero_copy=True)
+        o, r, d, i = b.step(act[:, 0], act[:, 1])
+        assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy())
+        assert np.array_equal(hd, d.cpu().numpy()) and np.array_equal(hi, i["flags"].cpu().numpy())
     ho, *_ = a.step_host(act[:, 0], None)                       # pve through the host path
     o, *_ = b.step(act[:, 0], None)
     assert np.array_equal(ho, o.cpu().numpy())

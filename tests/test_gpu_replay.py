@@ -1,0 +1,103 @@
+"""Device-resident transition ring and CSV episode logs against a
+sequential NumPy emulation of the reference's `store_transition` / CSV writer driven by the oracle."""
+import csv
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import merge_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import merging_gym_b200
+    return merging_gym_b200
+
+
+@pytest.mark.parametrize("n,cap,fmt,player", [(777, 5000, "replay", 1), (64, 100000, "replay", 2),
+                                               (1000, 300, "log", 1), (4096, 50000, "replay", 1)])
+def test_transition_ring_matches_sequential_store(mg, n, cap, fmt, player):
+    T = 260
+    env = mg.MergeVecEnv(n, out_slots=2, seed=21)
+    rec = mg.TransitionRecorder(env, cap, format=fmt, player=player, track_env_ids=True)
+    ref = mo.RefVecEnv(n)
+    width = 22 if fmt == "replay" else 14
+    mem = np.zeros((cap, width)); ids = np.full(cap, -1); counter = 0
+    obs_prev = env.reset(); robs_prev = ref.reset()
+    for t in range(T):
+        a1, a2 = env.sample_actions()
+        out = env.step(a1, a2)
+        rec.record(obs_prev, a1, a2, out)
+        h1, h2 = a1.cpu().numpy(), a2.cpu().numpy()
+        robs, rrew, rdone, rinfo = ref.step(h1, h2)
+        winner = (rinfo & mo.INFO_WINNER_MASK) >> 1
+        for e in np.nonzero(winner != 1)[0]:                    # main.py:209 `if env.winner is not 1`
+            if fmt == "replay":                                 # main.py:116 hstack((state, [action, reward], next_state))
+                nxt = ref.terminal_obs[e] if rdone[e] else robs[e]
+                row = np.hstack((robs_prev[e], [(h1, h2)[player - 1][e], rrew[e, player - 1]], nxt))
+            else:                                               # human_player.py:181 state + [a, a_op] + rewards
+                row = np.hstack((robs_prev[e], [h1[e], h2[e]], rrew[e]))
+            mem[counter % cap] = row; ids[counter % cap] = e; counter += 1
+        obs_prev, robs_prev = out[0], robs
+    assert int(rec.counter.item()) == counter and len(rec) == min(counter, cap)
+    assert np.array_equal(rec.env_ids.cpu().numpy(), ids)
+    assert rel_err(rec.ring.cpu().numpy(), mem).max() <= 1e-5
+    rows = rec.rows().cpu().numpy()
+    assert rows.shape == (min(counter, cap), width)
+    if counter > cap:
+        assert rel_err(rows[0], mem[counter % cap]).max() <= 1e-5      # oldest row first
+    assert rec.sample(128).shape == (128, width)
+
+
+def test_recorder_all_mask_and_sticky_done(mg):
+    n = 200
+    env = mg.MergeVecEnv(n, out_slots=2, auto_reset=False, episode_info=False)
+    rec = mg.TransitionRecorder(env, 100000, mask="all")
+    obs_prev = env.reset()
+    for t in range(50):
+        a1, a2 = env.sample_actions()
+        out = env.step(a1, a2)
+        rec.record(obs_prev, a1, a2, out)
+        obs_prev = out[0]
+    assert len(rec) == 50 * n
+    rows = rec.rows()
+    assert torch.equal(rows[-n:, 12:], out[0])          # s' of the last step is the returned obs (no auto-reset)
+    assert torch.equal(rows[-n:, 10], a1.float())
+
+
+def test_csv_episode_logger(mg, tmp_path):
+    n, ids = 32, [3, 17]
+    env = mg.MergeVecEnv(n, out_slots=2, seed=5)
+    log = mg.CsvEpisodeLogger(env, ids, str(tmp_path))
+    refs = {e: mo.RefEnv() for e in ids}
+    want = {e: [[]] for e in ids}
+    state = {e: refs[e].reset() for e in ids}
+    obs_prev = env.reset()
+    for t in range(450):
+        a1, a2 = env.sample_actions()
+        out = env.step(a1, a2)
+        log.log(obs_prev, a1, a2, out)
+        obs_prev = out[0]
+        for e in ids:
+            x1, x2 = int(a1[e]), int(a2[e])
+            nxt, rewards, done, info = refs[e].step(x1, x2)
+            if refs[e].winner != 1:                                # human_player.py:180
+                want[e][-1].append([float(v) for v in state[e]] + [x1, x2] + [float(v) for v in rewards])
+            state[e] = nxt
+            if done:
+                state[e] = refs[e].reset()
+                want[e].append([])
+    log.close()
+    for e in ids:
+        episodes = [w for w in want[e] if w]
+        files = sorted([f for f in log.files if f.endswith(f"env{e}.csv")], key=lambda p: int(p.split("episode")[-1].split(" ")[0]))
+        assert len(files) == len(episodes) >= 2
+        for path, rows in zip(files, episodes):
+            got = list(csv.reader(open(path)))
+            assert got[0] == mg.replay.CSV_HEADER and len(got) - 1 == len(rows)
+            g = np.array([[float(v) for v in r] for r in got[1:]])
+            assert rel_err(g, np.array(rows)).max() <= 1e-5
