@@ -35,7 +35,7 @@ extern "C" {
 #define MG_API __attribute__((visibility("default")))
 #endif
 
-#define MG_ABI_VERSION 1
+#define MG_ABI_VERSION 2
 #define MG_OBS_DIM 10      /* merging_env.py:75,118-132 */
 #define MG_NUM_ACTIONS 5   /* merging_env.py:101-102   */
 
@@ -68,6 +68,25 @@ typedef enum MgActionDtype { MG_ACT_U8 = 0, MG_ACT_I32 = 1, MG_ACT_I64 = 2 } MgA
 #define MG_META_STEPS_MASK 0x0FFFu /* steps since reset, saturating at 4095 (time limit = 2501) */
 #define MG_META_WINNER_SHIFT 12    /* bits 12-13 */
 #define MG_META_DONE 0x4000u       /* sticky done (only ever set when auto-reset is off)        */
+#define MG_META_RESETS_SHIFT 15    /* bits 15-31: number of resets this env has had (mod 2^17);
+                                      the Philox counter of the random-start draw               */
+
+/* How reset() initialises an env (explicit mg_reset and the auto-reset inside mg_step/mg_rollout).
+ *   MG_RESET_FIXED : pos = 50, vel = 20 for both cars            (merging_env.py:216-217, the live code)
+ *   MG_RESET_RANDOM: the reference's commented-out random start  (merging_env.py:219-221)
+ *       state1 = {pos: 50 + randn*5,        vel: 20 + randn*3}
+ *       state2 = {pos: 50 + uniform(-4, 4),  vel: 20 + uniform(-5, 10)}
+ *     drawn from Philox4x32-10 with key = seed ^ (0x52535445 << 32) and counter =
+ *     (global env id, reset count of that env), Box-Muller in float64 for the two normals: the
+ *     start of episode k of env e depends on (seed, e, k) only, never on sharding or launch order. */
+#define MG_RESET_FIXED 0u
+#define MG_RESET_RANDOM 1u
+typedef struct MgResetSpec {
+    uint32_t mode;
+    uint32_t reserved;
+    uint64_t seed;
+    uint64_t env_id_base; /* global id of env 0 of this shard */
+} MgResetSpec;
 
 /* Env state, structure-of-arrays, one element per env.  Replaces `self.state1/state2`
  * (pos, vel; merging_env.py:216-217), `self.r1_accumulate/r2_accumulate` (:191-192,223-224),
@@ -129,7 +148,7 @@ MG_API int mg_default_rewards(MgRewards *out); /* merging_env.py:28-32 / show_re
  * Writes the state and, if obs != NULL, obs[n,10] for ALL envs (masked-out rows get their
  * current observation, i.e. `observe()`, merging_env.py:118-132). */
 MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask_or_null, float *obs_or_null,
-                    void *stream);
+                    const MgResetSpec *reset_or_null /* NULL = MG_RESET_FIXED */, void *stream);
 
 /* MergeEnv.step(action1, action2)  (merging_env.py:138-195) for n envs in one fused launch:
  * kinematics of both cars incl. the mpc_1d controller (scripts/helper.py:152-191), lon2coord,
@@ -138,7 +157,7 @@ MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask_or_null
  * stats may be NULL. */
 MG_API int mg_step(const MgState *state, int64_t n, const void *a1, const void *a2_or_null,
                    int act_dtype, const MgRewards *rewards, const MgOut *out,
-                   int64_t *stats_or_null, uint32_t flags, void *stream);
+                   int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null, void *stream);
 
 /* Synthetic uniform-random discrete actions (the scripts' `env.action_space.sample()`,
  * scripts/main.py:26), counter-based: Philox4x32-10, key = seed, counter = (global env id, step).
@@ -154,7 +173,7 @@ MG_API int mg_sample_actions(uint8_t *a1, uint8_t *a2_or_null, int64_t n, uint64
 MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, uint64_t env_id_base,
                       uint64_t step0, int32_t k_steps, const MgRewards *rewards, const MgOut *out,
                       uint8_t *actions_out_or_null, int64_t *stats_or_null, uint32_t flags,
-                      void *stream);
+                      const MgResetSpec *reset_or_null, void *stream);
 
 /* Host-buffer convenience path (the drop-in for callers that keep Python/NumPy data on the
  * host, like the reference scripts): copies h_a1/h_a2 (uint8[n]) to the device scratch actions
@@ -163,7 +182,8 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
 MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
                         const uint8_t *h_a2_or_null, uint8_t *d_a1, uint8_t *d_a2,
                         const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out,
-                        int64_t *stats_or_null, uint32_t flags, void *stream);
+                        int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
+                        void *stream);
 
 /* ---- "next" row: policy in the loop -------------------------------------------
  * Fused forward + arg-max of the reference's Q-network `Net(in, out)`:

@@ -10,7 +10,7 @@ import os
 
 from ._paths import LIB_PATH
 
-MG_ABI_VERSION = 1
+MG_ABI_VERSION = 2
 OBS_DIM = 10
 NUM_ACTIONS = 5
 STATS_ROWS = 1024
@@ -29,6 +29,9 @@ INFO_BAD_ACTION = 0x80
 META_STEPS_MASK = 0x0FFF
 META_WINNER_SHIFT = 12
 META_DONE = 0x4000
+META_RESETS_SHIFT = 15
+
+RESET_FIXED, RESET_RANDOM = 0, 1
 
 STAT_NAMES = ["episodes", "collisions", "wins_p1", "wins_p2", "timeouts", "merges_ok",
               "sum_length", "bad_actions", "sum_return1_fx", "sum_return2_fx"]
@@ -44,6 +47,10 @@ class MgOut(C.Structure):
 
 class MgRewards(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("r_first", "r_second", "r_collision", "vel_penalty", "time_penalty")]
+
+
+class MgResetSpec(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("reserved", C.c_uint32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
 
 
 class MgConstants(C.Structure):
@@ -81,14 +88,15 @@ def load():
     lib.mg_last_error.restype = C.c_char_p
     lib.mg_get_constants.argtypes = [C.POINTER(MgConstants)]
     lib.mg_default_rewards.argtypes = [C.POINTER(MgRewards)]
-    lib.mg_reset.argtypes = [C.POINTER(MgState), i64, vp, vp, vp]
+    rsp = C.POINTER(MgResetSpec)
+    lib.mg_reset.argtypes = [C.POINTER(MgState), i64, vp, vp, rsp, vp]
     lib.mg_step.argtypes = [C.POINTER(MgState), i64, vp, vp, C.c_int, C.POINTER(MgRewards),
-                            C.POINTER(MgOut), vp, u32, vp]
+                            C.POINTER(MgOut), vp, u32, rsp, vp]
     lib.mg_sample_actions.argtypes = [vp, vp, i64, u64, u64, u64, vp]
     lib.mg_rollout.argtypes = [C.POINTER(MgState), i64, C.c_int, u64, u64, u64, i32,
-                               C.POINTER(MgRewards), C.POINTER(MgOut), vp, vp, u32, vp]
+                               C.POINTER(MgRewards), C.POINTER(MgOut), vp, vp, u32, rsp, vp]
     lib.mg_step_host.argtypes = [C.POINTER(MgState), i64, vp, vp, vp, vp, C.POINTER(MgRewards),
-                                 C.POINTER(MgOut), C.POINTER(MgOut), vp, u32, vp]
+                                 C.POINTER(MgOut), C.POINTER(MgOut), vp, u32, rsp, vp]
     lib.mg_mlp_act.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mg_mlp_act.restype = C.c_int
     lib.mg_record_transitions.argtypes = [vp] * 8 + [i64, i32, i32, i32, vp, i64, vp, vp, vp, vp]

@@ -164,7 +164,7 @@ struct StepResult {
     bool finished;           // done became true in this step (0 -> 1 transition)
 };
 
-__device__ __forceinline__ void reset_regs(EnvRegs &e) {   // merging_env.py:208-230
+__device__ __forceinline__ void reset_regs(EnvRegs &e) {   // merging_env.py:208-230, fixed start
     e.p1 = kStart; e.v1 = kInitVel; e.p2 = kStart; e.v2 = kInitVel;
     e.R1 = 0.0; e.R2 = 0.0; e.meta = 0u;
 }
@@ -183,6 +183,44 @@ __device__ __forceinline__ void observe(const EnvRegs &e, float *obs) {   // mer
     double x[2], y[2];
     lon2coord_batch<2>(lon, sign, x, y);
     write_obs(x[0], y[0], x[1], y[1], e, obs);
+}
+
+__device__ __forceinline__ void reset_obs_fixed(float *obs) {
+    obs[0] = 0.f; obs[1] = kResetDy; obs[2] = 0.f; obs[3] = kResetRemaining; obs[4] = (float)kInitVel;
+    obs[5] = 0.f; obs[6] = -kResetDy; obs[7] = 0.f; obs[8] = kResetRemaining; obs[9] = (float)kInitVel;
+}
+
+// MergeEnv.reset() for one env (merging_env.py:208-230): fixed start (:216-217) or the commented-out
+// random start (:219-221).  Keeps and advances the env's reset count (meta bits 15-31), which is the
+// Philox counter of the random draw.  Writes the reset observation.
+__device__ __noinline__ void random_start(EnvRegs &e, uint64_t seed, uint64_t env_id, uint32_t count) {
+    uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = count, c3 = 0u;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x52535445u);
+    const double k32 = 1.0 / 4294967296.0;
+    const double u1 = ((double)c0 + 1.0) * k32;             // (0, 1]
+    const double u2 = (double)c1 * k32;                     // [0, 1)
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    e.p1 = kStart + (r * cs) * 5.0;                         // START_POINT + np.random.randn() * 5
+    e.v1 = kInitVel + (r * sn) * 3.0;                       // 20.0 + np.random.randn() * 3
+    e.p2 = kStart + (-4.0 + 8.0 * (((double)c2 + 0.5) * k32));     // + uniform(-VEHICLE_H/2, VEHICLE_H/2)
+    e.v2 = kInitVel + (-5.0 + 15.0 * (((double)c3 + 0.5) * k32));  // 20.0 + uniform(-5, 10)
+}
+
+// RANDOM is a compile-time switch: the fixed-start kernels carry none of the random-start code.
+template <bool RANDOM>
+__device__ __forceinline__ void reset_env(EnvRegs &e, const MgResetSpec &rs, uint64_t local_id, float *obs) {
+    const uint32_t count = e.meta >> MG_META_RESETS_SHIFT;
+    if (RANDOM) {
+        random_start(e, rs.seed, rs.env_id_base + local_id, count);
+        observe(e, obs);
+    } else {
+        e.p1 = kStart; e.v1 = kInitVel; e.p2 = kStart; e.v2 = kInitVel;
+        reset_obs_fixed(obs);
+    }
+    e.R1 = 0.0; e.R2 = 0.0;
+    e.meta = (count + 1u) << MG_META_RESETS_SHIFT;
 }
 
 // merging_env.py:138-195 for E envs held by one thread, evaluated in lock-step (same operations
@@ -268,7 +306,8 @@ __device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1
         // :191-192
         e.R1 = __dadd_rn(e.R1, r1);
         e.R2 = __dadd_rn(e.R2, r2);
-        e.meta = steps[i] | (w << MG_META_WINNER_SHIFT) | (dn ? MG_META_DONE : 0u);
+        e.meta = (e.meta & ~((1u << MG_META_RESETS_SHIFT) - 1u)) | steps[i] | (w << MG_META_WINNER_SHIFT) |
+                 (dn ? MG_META_DONE : 0u);
 
         out[i].r1 = (float)r1;
         out[i].r2 = (float)r2;

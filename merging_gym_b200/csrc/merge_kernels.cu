@@ -99,21 +99,16 @@ __device__ __forceinline__ void write_episode_outputs(const MgOut &o, int64_t e,
     if (o.ep_len) o.ep_len[e] = (int32_t)r.steps;
 }
 
-__device__ __forceinline__ void reset_obs(float *obs) {
-    obs[0] = 0.f; obs[1] = kResetDy; obs[2] = 0.f; obs[3] = kResetRemaining; obs[4] = (float)kInitVel;
-    obs[5] = 0.f; obs[6] = -kResetDy; obs[7] = 0.f; obs[8] = kResetRemaining; obs[9] = (float)kInitVel;
-}
-
 // =================================================================================================
 // merge_step_kernel: one MergeEnv.step() for n envs.
 //   grid = ceil(n / (kBlock*EPT)), block = kBlock.  A warp owns 32*EPT consecutive envs.
 //   Full warps take the vector path; the (at most one) ragged warp takes the scalar path.
 // =================================================================================================
-template <int EPT, typename ActT, bool PVP>
+template <int EPT, typename ActT, bool PVP, bool RR>
 __global__ void __launch_bounds__(kBlock, MG_MIN_BLOCKS)
 merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
                   const ActT *__restrict__ a2g, const int64_t n, const MgRewards rw,
-                  const uint32_t flags, unsigned long long *__restrict__ stats) {
+                  const uint32_t flags, const MgResetSpec rs, unsigned long long *__restrict__ stats) {
     __shared__ __align__(16) float stage[kWarps][32 * EPT * MG_OBS_DIM];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -179,10 +174,8 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
             if (stats) st.add(r, env[j].R1, env[j].R2);
             if (r.finished) write_episode_outputs(o, e0 + j, r, env[j].R1, env[j].R2);
         }
-        if (r.done && auto_reset) {          // gym-0.20 vector convention: return the reset obs
-            reset_regs(env[j]);
-            reset_obs(r.obs);
-        }
+        if (r.done && auto_reset)            // gym-0.20 vector convention: return the reset obs
+            reset_env<RR>(env[j], rs, (uint64_t)(e0 + j), r.obs);
         if (full) {
 #pragma unroll
             for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = r.obs[k];
@@ -239,11 +232,11 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 #ifndef MG_ROLLOUT_MIN_BLOCKS
 #define MG_ROLLOUT_MIN_BLOCKS 1
 #endif
-template <bool PVP>
+template <bool PVP, bool RR>
 __global__ void __launch_bounds__(kBlock, MG_ROLLOUT_MIN_BLOCKS)
 merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actions_out, const int64_t n,
                      const uint64_t seed, const uint64_t env_id_base, const uint64_t step0,
-                     const int k_steps, const MgRewards rw, const uint32_t flags,
+                     const int k_steps, const MgRewards rw, const uint32_t flags, const MgResetSpec rs,
                      unsigned long long *__restrict__ stats) {
     constexpr int EPT = 2;
     __shared__ __align__(16) float stage[kWarps][32 * EPT * MG_OBS_DIM];
@@ -286,7 +279,7 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
                 if (stats) st.add(r, env[j].R1, env[j].R2);
                 if (r.finished) write_episode_outputs(o, e, r, env[j].R1, env[j].R2);
             }
-            if (r.done && auto_reset) { reset_regs(env[j]); reset_obs(r.obs); }
+            if (r.done && auto_reset) reset_env<RR>(env[j], rs, (uint64_t)e, r.obs);
             if (valid[j]) {
                 if (o.rew) __stcs(reinterpret_cast<float2 *>(o.rew + 2 * (toff + e)), make_float2(r.r1, r.r2));
                 if (o.done) __stcs(o.done + toff + e, (uint8_t)(r.done ? 1 : 0));
@@ -328,20 +321,21 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
 // merge_reset_kernel: MergeEnv.reset() (+ observe()) — one env per thread.
 // =================================================================================================
 __global__ void __launch_bounds__(kBlock)
-merge_reset_kernel(const MgState s, const int64_t n, const uint8_t *__restrict__ mask, float *__restrict__ obs) {
+merge_reset_kernel(const MgState s, const int64_t n, const uint8_t *__restrict__ mask, float *__restrict__ obs,
+                   const MgResetSpec rs) {
     const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (e >= n) return;
-    EnvRegs r;
+    EnvRegs r{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], 0.0, 0.0, s.meta[e]};
+    float ob[MG_OBS_DIM];
     if (!mask || mask[e]) {
-        reset_regs(r);
+        if (rs.mode == MG_RESET_RANDOM) reset_env<true>(r, rs, (uint64_t)e, ob);
+        else reset_env<false>(r, rs, (uint64_t)e, ob);
         s.pos1[e] = r.p1; s.vel1[e] = r.v1; s.pos2[e] = r.p2; s.vel2[e] = r.v2;
-        s.ret1[e] = 0.0; s.ret2[e] = 0.0; s.meta[e] = 0u;
+        s.ret1[e] = 0.0; s.ret2[e] = 0.0; s.meta[e] = r.meta;
     } else {
-        r = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], 0.0, 0.0, 0u};
+        observe(r, ob);
     }
     if (obs) {
-        float ob[MG_OBS_DIM];
-        observe(r, ob);
 #pragma unroll
         for (int k = 0; k < MG_OBS_DIM; ++k) obs[e * MG_OBS_DIM + k] = ob[k];
     }
@@ -387,20 +381,27 @@ int check_out(const MgOut *o, bool all_required) {
     return MG_OK;
 }
 const MgRewards kDefaultRewards = {2.0, 1.0, -10.0, 0.001, 0.0};
+const MgResetSpec kFixedReset = {MG_RESET_FIXED, 0u, 0ull, 0ull};
+
+int check_reset(const MgResetSpec *r) {
+    if (r && r->mode > MG_RESET_RANDOM) return fail(MG_ERR_BAD_FLAGS, "MgResetSpec.mode must be MG_RESET_FIXED or MG_RESET_RANDOM");
+    return MG_OK;
+}
 
 template <typename ActT>
 cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const void *a2, int64_t n,
-                        const MgRewards &rw, uint32_t flags, int64_t *stats, cudaStream_t st) {
+                        const MgRewards &rw, uint32_t flags, const MgResetSpec &rs, int64_t *stats, cudaStream_t st) {
     constexpr int EPT = MG_EPT;
     const int64_t per_block = (int64_t)mg::kBlock * EPT;
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
-    if (a2)
-        mg::merge_step_kernel<EPT, ActT, true><<<grid, mg::kBlock, 0, st>>>(
-            s, o, (const ActT *)a1, (const ActT *)a2, n, rw, flags, stp);
-    else
-        mg::merge_step_kernel<EPT, ActT, false><<<grid, mg::kBlock, 0, st>>>(
-            s, o, (const ActT *)a1, nullptr, n, rw, flags, stp);
+    const bool rr = rs.mode == MG_RESET_RANDOM;
+#define MG_LAUNCH(PVP, RR, A2)                                                              \
+    mg::merge_step_kernel<EPT, ActT, PVP, RR><<<grid, mg::kBlock, 0, st>>>(                 \
+        s, o, (const ActT *)a1, (const ActT *)(A2), n, rw, flags, rs, stp)
+    if (a2) { if (rr) MG_LAUNCH(true, true, a2); else MG_LAUNCH(true, false, a2); }
+    else    { if (rr) MG_LAUNCH(false, true, nullptr); else MG_LAUNCH(false, false, nullptr); }
+#undef MG_LAUNCH
     return cudaGetLastError();
 }
 }  // namespace
@@ -428,20 +429,23 @@ MG_API int mg_default_rewards(MgRewards *r) {
     return MG_OK;
 }
 
-MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask, float *obs, void *stream) {
+MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask, float *obs, const MgResetSpec *reset,
+                    void *stream) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (int rc = check_reset(reset)) return rc;
     if (n == 0) return MG_OK;
     if (int rc = check_state(state)) return rc;
     const unsigned grid = (unsigned)((n + mg::kBlock - 1) / mg::kBlock);
-    mg::merge_reset_kernel<<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(*state, n, mask, obs);
+    mg::merge_reset_kernel<<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(*state, n, mask, obs, reset ? *reset : kFixedReset);
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_reset launch");
     return MG_OK;
 }
 
 MG_API int mg_step(const MgState *state, int64_t n, const void *a1, const void *a2, int act_dtype,
                    const MgRewards *rewards, const MgOut *out, int64_t *stats, uint32_t flags,
-                   void *stream) {
+                   const MgResetSpec *reset, void *stream) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (int rc = check_reset(reset)) return rc;
     if (flags & ~MG_FLAG_AUTO_RESET) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
     if (act_dtype < MG_ACT_U8 || act_dtype > MG_ACT_I64)
         return fail(MG_ERR_BAD_DTYPE, "act_dtype must be MG_ACT_U8, MG_ACT_I32 or MG_ACT_I64");
@@ -450,11 +454,12 @@ MG_API int mg_step(const MgState *state, int64_t n, const void *a1, const void *
     if (int rc = check_out(out, true)) return rc;
     if (!a1) return fail(MG_ERR_NULL_POINTER, "a1 is NULL");
     const MgRewards rw = rewards ? *rewards : kDefaultRewards;
+    const MgResetSpec rs = reset ? *reset : kFixedReset;
     cudaError_t e;
     switch (act_dtype) {
-        case MG_ACT_U8:  e = launch_step<uint8_t>(*state, *out, a1, a2, n, rw, flags, stats, (cudaStream_t)stream); break;
-        case MG_ACT_I32: e = launch_step<int32_t>(*state, *out, a1, a2, n, rw, flags, stats, (cudaStream_t)stream); break;
-        case MG_ACT_I64: e = launch_step<int64_t>(*state, *out, a1, a2, n, rw, flags, stats, (cudaStream_t)stream); break;
+        case MG_ACT_U8:  e = launch_step<uint8_t>(*state, *out, a1, a2, n, rw, flags, rs, stats, (cudaStream_t)stream); break;
+        case MG_ACT_I32: e = launch_step<int32_t>(*state, *out, a1, a2, n, rw, flags, rs, stats, (cudaStream_t)stream); break;
+        case MG_ACT_I64: e = launch_step<int64_t>(*state, *out, a1, a2, n, rw, flags, rs, stats, (cudaStream_t)stream); break;
         default: return fail(MG_ERR_BAD_DTYPE, "act_dtype must be MG_ACT_U8, MG_ACT_I32 or MG_ACT_I64");
     }
     if (e) return cuda_fail(e, "mg_step launch");
@@ -474,7 +479,10 @@ MG_API int mg_sample_actions(uint8_t *a1, uint8_t *a2, int64_t n, uint64_t seed,
 
 MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, uint64_t env_id_base,
                       uint64_t step0, int32_t k_steps, const MgRewards *rewards, const MgOut *out,
-                      uint8_t *actions_out, int64_t *stats, uint32_t flags, void *stream) {
+                      uint8_t *actions_out, int64_t *stats, uint32_t flags, const MgResetSpec *reset,
+                      void *stream) {
+    if (int rc = check_reset(reset)) return rc;
+    const MgResetSpec rs = reset ? *reset : kFixedReset;
     if (n < 0 || k_steps < 0) return fail(MG_ERR_BAD_SIZE, "n < 0 or k_steps < 0");
     if (flags & ~MG_FLAG_AUTO_RESET) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
     if (n == 0 || k_steps == 0) return MG_OK;
@@ -484,19 +492,21 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
     const int64_t per_block = (int64_t)mg::kBlock * 2;
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
-    if (pvp)
-        mg::merge_rollout_kernel<true><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(
-            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, stp);
-    else
-        mg::merge_rollout_kernel<false><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(
-            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, stp);
+    const bool rr = rs.mode == MG_RESET_RANDOM;
+#define MG_LAUNCH(PVP, RR)                                                                       \
+    mg::merge_rollout_kernel<PVP, RR><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(            \
+        *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, rs, stp)
+    if (pvp) { if (rr) MG_LAUNCH(true, true); else MG_LAUNCH(true, false); }
+    else     { if (rr) MG_LAUNCH(false, true); else MG_LAUNCH(false, false); }
+#undef MG_LAUNCH
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_rollout launch");
     return MG_OK;
 }
 
 MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, const uint8_t *h_a2,
                         uint8_t *d_a1, uint8_t *d_a2, const MgRewards *rewards, const MgOut *d_out,
-                        const MgOut *h_out, int64_t *stats, uint32_t flags, void *stream) {
+                        const MgOut *h_out, int64_t *stats, uint32_t flags, const MgResetSpec *reset,
+                        void *stream) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     if (n == 0) return MG_OK;
     if (!h_a1 || !d_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "h_a1, d_a1, d_out or h_out is NULL");
@@ -507,7 +517,7 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
         if ((e = cudaMemcpyAsync(d_a1, h_a1, (size_t)n, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a1");
         if (h_a2 && (e = cudaMemcpyAsync(d_a2, h_a2, (size_t)n, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a2");
     }
-    if (int rc = mg_step(state, n, d_a1, h_a2 ? d_a2 : nullptr, MG_ACT_U8, rewards, d_out, stats, flags, stream)) return rc;
+    if (int rc = mg_step(state, n, d_a1, h_a2 ? d_a2 : nullptr, MG_ACT_U8, rewards, d_out, stats, flags, reset, stream)) return rc;
     if (n > 0) {
         const size_t N = (size_t)n;
         if (h_out->obs && (e = cudaMemcpyAsync(h_out->obs, d_out->obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H obs");

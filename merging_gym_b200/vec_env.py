@@ -91,16 +91,21 @@ class MergeVecEnv:
     episode_info  keep terminal_observation / episode_return / episode_length buffers.
     track_stats   accumulate episode statistics on the device (see `stats()`).
     rewards       dict overriding RFirst/RSecond/RCollision/vel_penalty/time_penalty (:28-32).
+    reset_mode    "fixed": pos=50, vel=20 (merging_env.py:216-217, the live code); "random": the
+                  reference's commented-out random start (:219-221) drawn per (reset_seed, global
+                  env id, reset count) with Philox + Box-Muller, for explicit and automatic resets.
     """
 
     def __init__(self, num_envs: int, mode: str = "pvp", device="cuda", auto_reset: bool = True,
                  seed: int = ACTION_SEED_DEFAULT, env_id_base: int = 0, out_slots: int = 1,
                  episode_info: bool = True, track_stats: bool = True, rewards: Optional[dict] = None,
-                 validate_actions: bool = False):
+                 validate_actions: bool = False, reset_mode: str = "fixed", reset_seed: Optional[int] = None):
         if mode not in ("pvp", "pve"):
             raise ValueError("mode must be 'pvp' or 'pve'")
         if num_envs < 0 or out_slots < 1:
             raise ValueError("num_envs must be >= 0 and out_slots >= 1")
+        if reset_mode not in ("fixed", "random"):
+            raise ValueError("reset_mode must be 'fixed' or 'random'")
         self._lib = nat.load()                       # raises if the CUDA library is not built
         if not torch.cuda.is_available():
             raise nat.NativeError("merging_gym_b200 needs a CUDA device (no CPU fallback exists)")
@@ -113,6 +118,9 @@ class MergeVecEnv:
         self.mode, self.auto_reset = mode, bool(auto_reset)
         self.philox_seed, self.env_id_base = int(seed), int(env_id_base)
         self.validate_actions = bool(validate_actions)
+        self.reset_mode = reset_mode
+        self._rs = nat.MgResetSpec(nat.RESET_RANDOM if reset_mode == "random" else nat.RESET_FIXED, 0,
+                                   int(seed if reset_seed is None else reset_seed), int(env_id_base))
         self.out_slots = int(out_slots)
         self._slot = 0
         self.step_count = 0                          # Philox step counter for sample_actions/rollout
@@ -213,7 +221,7 @@ class MergeVecEnv:
         obs = self.obs_buf[self._slot]
         with torch.cuda.device(self.device):
             nat.check(self._lib.mg_reset(C.byref(self._state), self.num_envs, _ptr(m), _ptr(obs),
-                                         self._stream()), "mg_reset")
+                                         C.byref(self._rs), self._stream()), "mg_reset")
         return obs
 
     def step_async(self, a1, a2=None) -> None:
@@ -228,7 +236,7 @@ class MergeVecEnv:
             nat.check(self._lib.mg_step(C.byref(self._state), self.num_envs, _ptr(a1), _ptr(a2),
                                         self._ACT_DTYPE[a1.dtype], C.byref(self._rw),
                                         C.byref(self._outs[k]), _ptr(self.stats_buf), self._flags(),
-                                        self._stream()), "mg_step")
+                                        C.byref(self._rs), self._stream()), "mg_step")
         self._pending = k
 
     def step_wait(self):
@@ -277,6 +285,11 @@ class MergeVecEnv:
     @property
     def done(self) -> torch.Tensor:
         return (self.meta & nat.META_DONE).bool()
+
+    @property
+    def resets(self) -> torch.Tensor:
+        """i32[N] number of resets each env has had, mod 2^17 (the random-start Philox counter)."""
+        return (self.meta >> nat.META_RESETS_SHIFT) & 0x1FFFF
 
     @property
     def r1_accumulate(self) -> torch.Tensor:
@@ -337,7 +350,7 @@ class MergeVecEnv:
             nat.check(self._lib.mg_rollout(C.byref(self._state), n, int(self.mode == "pvp"), self.philox_seed,
                                            self.env_id_base, int(step0), k, C.byref(self._rw),
                                            C.byref(out), _ptr(actions), _ptr(self.stats_buf),
-                                           self._flags(), self._stream()), "mg_rollout")
+                                           self._flags(), C.byref(self._rs), self._stream()), "mg_rollout")
 
     # ------------------------------------------------------------------ host-buffer path
     def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, zero_copy: bool = False):
@@ -371,7 +384,7 @@ class MergeVecEnv:
                 nat.check(self._lib.mg_step(C.byref(self._state), n, _ptr(h["a1"]),
                                             _ptr(h["a2"]) if a2 is not None else None, nat.ACT_U8,
                                             C.byref(self._rw), C.byref(self._host_out), _ptr(self.stats_buf),
-                                            self._flags(), self._stream()), "mg_step (zero-copy)")
+                                            self._flags(), C.byref(self._rs), self._stream()), "mg_step (zero-copy)")
                 torch.cuda.current_stream(self.device).synchronize()
             else:
                 self._slot = (self._slot + 1) % self.out_slots
@@ -379,7 +392,8 @@ class MergeVecEnv:
                                                  _ptr(h["a2"]) if a2 is not None else None,
                                                  _ptr(self.act1), _ptr(self.act2), C.byref(self._rw),
                                                  C.byref(self._outs[self._slot]), C.byref(self._host_out),
-                                                 _ptr(self.stats_buf), self._flags(), self._stream()),
+                                                 _ptr(self.stats_buf), self._flags(), C.byref(self._rs),
+                                                 self._stream()),
                           "mg_step_host")
         return h["obs"].numpy(), h["rew"].numpy(), h["done"].numpy().view(np.bool_), h["info"].numpy()
 

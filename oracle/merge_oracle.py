@@ -234,11 +234,14 @@ class RefVecEnv:
     assert that "time_stamp > 500" first holds at step 2501.
     """
 
-    def __init__(self, num_envs: int, pvp: bool = True, auto_reset: bool = True):
+    def __init__(self, num_envs: int, pvp: bool = True, auto_reset: bool = True,
+                 reset_mode: str = "fixed", reset_seed: int = 0x5EED, env_id_base: int = 0):
         self.n = int(num_envs)
         self.pvp = bool(pvp)
         self.auto_reset = bool(auto_reset)
+        self.reset_mode, self.reset_seed, self.env_id_base = reset_mode, int(reset_seed), int(env_id_base)
         n = self.n
+        self.resets = np.zeros(n, dtype=np.int64)     # resets each env has had: the random-start counter
         self.pos1 = np.empty(n); self.vel1 = np.empty(n)
         self.pos2 = np.empty(n); self.vel2 = np.empty(n)
         self.ret1 = np.zeros(n); self.ret2 = np.zeros(n)
@@ -256,8 +259,14 @@ class RefVecEnv:
 
     # -- helpers
     def _reset_rows(self, m):
-        self.pos1[m] = START_POINT; self.vel1[m] = 20.0
-        self.pos2[m] = START_POINT; self.vel2[m] = 20.0
+        if self.reset_mode == "random":
+            ids = np.nonzero(m)[0]
+            p1, v1, p2, v2 = random_start_draw(self.reset_seed, self.env_id_base + ids, self.resets[ids])
+            self.pos1[ids] = p1; self.vel1[ids] = v1; self.pos2[ids] = p2; self.vel2[ids] = v2
+        else:
+            self.pos1[m] = START_POINT; self.vel1[m] = 20.0
+            self.pos2[m] = START_POINT; self.vel2[m] = 20.0
+        self.resets[m] = (self.resets[m] + 1) & 0x1FFFF
         self.ret1[m] = 0.0; self.ret2[m] = 0.0
         self.time_stamp[m] = 0.0
         self.steps[m] = 0
@@ -417,3 +426,41 @@ def philox_actions(n, seed, env_id_base, step):
     a1 = ((out[:, 0] * np.uint64(5)) >> np.uint64(32)).astype(np.uint8)
     a2 = ((out[:, 1] * np.uint64(5)) >> np.uint64(32)).astype(np.uint8)
     return a1, a2
+
+
+RESET_KEY_XOR = 0x52535445      # "RSTE": separates the reset stream from the action stream
+
+
+def random_start_draw(seed, env_ids, counts):
+    """The reference's commented-out random start (merging_env.py:219-221)
+
+        state1 = {'pos': START_POINT + np.random.randn() * 5, 'vel': 20.0 + np.random.randn() * 3}
+        state2 = {'pos': START_POINT + np.random.uniform(-VEHICLE_H/2, VEHICLE_H/2),
+                  'vel': 20.0 + np.random.uniform(-5, 10)}
+
+    with counter-based draws: Philox4x32-10, key = (seed lo32, seed hi32 ^ RESET_KEY_XOR), counter =
+    (env id lo32, env id hi32, reset count, 0); outputs o0..o3:
+    Box-Muller in float64 on u1 = (o0+1)/2^32, u2 = o1/2^32 gives the two normals; o2, o3 the uniforms.
+    Same formulas as `merge_device.cuh::random_start` (transcendentals differ by an ulp or two).
+    """
+    env_ids = np.asarray(env_ids, dtype=np.uint64).reshape(-1)
+    counts = np.asarray(counts, dtype=np.uint64).reshape(-1)
+    n = env_ids.size
+    ctr = np.zeros((n, 4), dtype=np.uint32)
+    ctr[:, 0] = (env_ids & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[:, 1] = (env_ids >> np.uint64(32)).astype(np.uint32)
+    ctr[:, 2] = (counts & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    key = np.zeros((n, 2), dtype=np.uint32)
+    key[:, 0] = np.uint32(seed & 0xFFFFFFFF)
+    key[:, 1] = np.uint32(((seed >> 32) & 0xFFFFFFFF) ^ RESET_KEY_XOR)
+    o = philox4x32_10(ctr, key).astype(np.float64)
+    k32 = 1.0 / 4294967296.0
+    u1 = (o[:, 0] + 1.0) * k32
+    u2 = o[:, 1] * k32
+    r = np.sqrt(-2.0 * np.log(u1))
+    z1, z2 = r * np.cos(2.0 * np.pi * u2), r * np.sin(2.0 * np.pi * u2)
+    p1 = START_POINT + z1 * 5.0
+    v1 = 20.0 + z2 * 3.0
+    p2 = START_POINT + (-4.0 + 8.0 * ((o[:, 2] + 0.5) * k32))
+    v2 = 20.0 + (-5.0 + 15.0 * ((o[:, 3] + 0.5) * k32))
+    return p1, v1, p2, v2

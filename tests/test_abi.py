@@ -71,7 +71,8 @@ def test_header_macros_match_binding():
     for n, v in [("MG_INFO_COLLISION", nat.INFO_COLLISION), ("MG_INFO_TIMEOUT", nat.INFO_TIMEOUT),
                  ("MG_INFO_DONE", nat.INFO_DONE), ("MG_INFO_BAD_ACTION", nat.INFO_BAD_ACTION),
                  ("MG_INFO_WINNER_MASK", nat.INFO_WINNER_MASK), ("MG_META_DONE", nat.META_DONE),
-                 ("MG_META_STEPS_MASK", nat.META_STEPS_MASK), ("MG_FLAG_AUTO_RESET", nat.FLAG_AUTO_RESET)]:
+                 ("MG_META_STEPS_MASK", nat.META_STEPS_MASK), ("MG_FLAG_AUTO_RESET", nat.FLAG_AUTO_RESET),
+                 ("MG_META_RESETS_SHIFT", nat.META_RESETS_SHIFT)]:
         assert macro(n) == v, n
     # and with the oracle's copy of the info bits
     assert (nat.INFO_COLLISION, nat.INFO_TIMEOUT, nat.INFO_DONE, nat.INFO_BAD_ACTION) == \
@@ -80,25 +81,27 @@ def test_header_macros_match_binding():
 
 def test_struct_sizes():
     assert C.sizeof(nat.MgState) == 7 * 8 and C.sizeof(nat.MgOut) == 7 * 8
-    assert C.sizeof(nat.MgRewards) == 5 * 8
+    assert C.sizeof(nat.MgRewards) == 5 * 8 and C.sizeof(nat.MgResetSpec) == 24
     assert C.sizeof(nat.MgConstants) == 9 * 8 + 7 * 4 + 4 + 8      # 4 bytes padding before the double
 
 
 def test_argument_errors_without_gpu(lib):
     st, out, rw = nat.MgState(), nat.MgOut(), nat.default_rewards()
-    assert lib.mg_step(C.byref(st), -1, None, None, 0, C.byref(rw), C.byref(out), None, 0, None) == -2
-    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0x80, None) == -4
-    assert lib.mg_step(C.byref(st), 8, None, None, 7, C.byref(rw), C.byref(out), None, 0, None) == -5
-    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, None) == -1
+    assert lib.mg_step(C.byref(st), -1, None, None, 0, C.byref(rw), C.byref(out), None, 0, None, None) == -2
+    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0x80, None, None) == -4
+    assert lib.mg_step(C.byref(st), 8, None, None, 7, C.byref(rw), C.byref(out), None, 0, None, None) == -5
+    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, None, None) == -1
     assert b"NULL" in lib.mg_last_error()
+    bad_rs = nat.MgResetSpec(7, 0, 0, 0)
+    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, C.byref(bad_rs), None) == -4
     st = nat.MgState(*([0x1008] * 7))                                # not 16-byte aligned
-    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, None) == -3
-    assert lib.mg_reset(None, 8, None, None, None) == -1
+    assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, None, None) == -3
+    assert lib.mg_reset(None, 8, None, None, None, None) == -1
     assert lib.mg_get_constants(None) == -1
     # n == 0 is a no-op that needs no device
-    assert lib.mg_step(C.byref(nat.MgState()), 0, None, None, 0, None, C.byref(out), None, 1, None) == 0
-    assert lib.mg_reset(C.byref(nat.MgState()), 0, None, None, None) == 0
-    assert lib.mg_rollout(C.byref(nat.MgState()), 0, 1, 0, 0, 0, 4, None, C.byref(out), None, None, 1, None) == 0
+    assert lib.mg_step(C.byref(nat.MgState()), 0, None, None, 0, None, C.byref(out), None, 1, None, None) == 0
+    assert lib.mg_reset(C.byref(nat.MgState()), 0, None, None, None, None) == 0
+    assert lib.mg_rollout(C.byref(nat.MgState()), 0, 1, 0, 0, 0, 4, None, C.byref(out), None, None, 1, None, None) == 0
     assert lib.mg_sample_actions(None, None, 0, 0, 0, 0, None) == 0
     assert lib.mg_mlp_act(None, None, 0, 10, 5, None, None, None, None, None, None, None, None, None) == 0
     assert lib.mg_mlp_act(None, None, 8, 9, 5, None, None, None, None, None, None, None, None, None) == -2

@@ -370,3 +370,50 @@ def state_swap_ok(o):
     import merging_gym_b200 as m
     v = m.MergeVecEnv.opponent_view(torch.tensor([o]))[0].tolist()
     return v == o[5:] + o[:5]
+
+
+def test_random_start_reset(mg):
+    """reset_mode="random": the reference's commented-out random start (merging_env.py:219-221)."""
+    n, seed, base = 4096, 77, 1 << 33
+    env = mg.MergeVecEnv(n, reset_mode="random", reset_seed=seed, env_id_base=base)
+    ref = mo.RefVecEnv(n, reset_mode="random", reset_seed=seed, env_id_base=base)
+    obs = env.obs_buf[0].cpu().numpy()
+    for k in ("pos1", "vel1"):                                     # Box-Muller: log/sincospi differ by ulps
+        assert rel_err(getattr(env, k).cpu().numpy(), getattr(ref, k)).max() <= 1e-12, k
+    for k in ("pos2", "vel2"):                                     # uniforms use exact arithmetic only
+        assert np.array_equal(getattr(env, k).cpu().numpy(), getattr(ref, k)), k
+    assert rel_err(obs, ref.observe()).max() <= 1e-5
+    assert env.resets.cpu().tolist() == [1] * n
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n_resets = 0
+    for t in range(500):
+        # continue from the GPU's float64 start so the dynamics can be compared bit for bit
+        for k in ("pos1", "vel1"):
+            getattr(ref, k)[:] = getattr(env, k).cpu().numpy()
+        a = torch.randint(0, 5, (n, 2), dtype=torch.uint8, device="cuda", generator=g)
+        out = env.step(a[:, 0], a[:, 1])
+        r = ref.step(a[:, 0].cpu().numpy(), a[:, 1].cpu().numpy())
+        assert_step_equal(out, r, t)
+        n_resets += int(r[2].sum())
+    assert n_resets > n
+    assert np.array_equal(env.resets.cpu().numpy(), ref.resets)
+    assert np.array_equal(env.pos2.cpu().numpy(), ref.pos2) and np.array_equal(env.vel2.cpu().numpy(), ref.vel2)
+    p1 = env.pos1.cpu().numpy()
+    assert 30 < np.percentile(p1, 1)                               # sanity: every env keeps moving forward
+
+
+def test_random_start_is_shard_and_launch_invariant(mg):
+    n, K = 2048, 300
+    kw = dict(reset_mode="random", reset_seed=9, seed=3)
+    full = mg.MergeVecEnv(n, **kw); full.rollout(K)
+    halves = [mg.MergeVecEnv(n // 2, env_id_base=b, **kw) for b in (0, n // 2)]
+    for h in halves:
+        for t in range(K):
+            h.step(*h.sample_actions())
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "meta"):
+        assert torch.equal(torch.cat([getattr(h, k) for h in halves]), getattr(full, k)), k
+    assert int(full.resets.max()) >= 2
+    m = torch.zeros(n, dtype=torch.bool); m[:100] = True
+    before = full.resets.clone()
+    full.reset(m)
+    assert torch.equal(full.resets[:100], before[:100] + 1) and torch.equal(full.resets[100:], before[100:])

@@ -164,3 +164,18 @@ def test_sticky_done_without_auto_reset():
         assert np.all(done | ~seen)      # once done, always done
         seen |= done
     assert seen.all() and (env.steps == 200).all()
+
+
+def test_random_start_distribution():
+    """merging_env.py:219-221 (commented-out random start): N(50, 5), N(20, 3), U(46, 54), U(15, 30)."""
+    n = 200000
+    p1, v1, p2, v2 = mo.random_start_draw(123, np.arange(n), np.zeros(n))
+    assert abs(p1.mean() - 50) < 0.05 and abs(p1.std() - 5) < 0.05
+    assert abs(v1.mean() - 20) < 0.03 and abs(v1.std() - 3) < 0.03
+    assert 46 <= p2.min() < 46.01 and 53.99 < p2.max() <= 54 and abs(p2.mean() - 50) < 0.02
+    assert 15 <= v2.min() < 15.01 and 29.99 < v2.max() <= 30 and abs(v2.mean() - 22.5) < 0.04
+    assert abs(np.corrcoef(p1, v1)[0, 1]) < 0.01
+    q1, *_ = mo.random_start_draw(123, np.arange(n), np.ones(n))       # next episode: fresh draws
+    assert abs(np.corrcoef(p1, q1)[0, 1]) < 0.01
+    env = mo.RefVecEnv(64, reset_mode="random", reset_seed=123)
+    assert np.array_equal(env.pos1, p1[:64]) and env.resets.tolist() == [1] * 64
