@@ -199,7 +199,7 @@ def run_b200(args):
     # one distinct pre-generated action set per step of the captured graph
     unit = S * R // math.gcd(S, R)
     A = max(unit, (min(args.steps, args.graph_steps) // unit) * unit) if args.action_sets <= 0 else args.action_sets
-    # R independent 2^20-env shards stepped round-robin: 4 x 54.5 MB of float64 state cannot stay in
+    # R independent n-env shards (default 2^20) stepped round-robin: 4 x 54.5 MB of float64 state cannot stay in
     # the 126 MB L2 between two launches on the same shard, so every launch reads its inputs from HBM.
     envs = [mg.MergeVecEnv(n, mode="pvp", device=dev, auto_reset=True, seed=0x5EED,
                            env_id_base=(rank * R + r) * n, out_slots=S, episode_info=False, track_stats=True)
@@ -364,7 +364,7 @@ def run_b200(args):
                        "envs_per_launch": n, "shards_per_gpu": R,
                        "launch": (f"CUDA graph of {G} mg_step launches replayed {K // G}x + {eager} eager"
                                   if G else "eager ctypes launches"),
-                       "l2": f"inputs larger than L2, no flush: {R} independent 2^20-env shards per GPU stepped "
+                       "l2": f"inputs larger than L2, no flush: {R} independent {n}-env shards per GPU stepped "
                              f"round-robin ({R * n * 52 / 1e6:.0f} MB of float64 state + {A} action sets "
                              f"{A * n * 2 / 1e6:.0f} MB, outputs to {R}x{S} ring slots of {n * 50 / 1e6:.0f} MB); "
                              "each launch re-reads its shard's state from HBM",

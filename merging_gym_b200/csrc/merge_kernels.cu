@@ -25,6 +25,9 @@ namespace mg {
 #ifndef MG_EPT
 #define MG_EPT 2          // envs per thread in the step kernel: 2 -> 128-bit state accesses
 #endif
+#ifndef MG_PDL
+#define MG_PDL 1          // launch the step kernel with programmatic stream serialization (PDL): +2 % (profiles/)
+#endif
 #ifndef MG_MIN_BLOCKS
 #define MG_MIN_BLOCKS 8   // __launch_bounds__ min resident blocks per SM: caps the step kernel at 64 registers
 #endif
@@ -113,6 +116,13 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
+#if MG_PDL
+    // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the
+    // stream drains; nothing of global memory is touched before the previous grid has completed
+    // and flushed.  Triggering right away lets the NEXT launch pre-stage the same way.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+#endif
     if (warp_base >= n) return;
     const bool full = warp_base + 32 * EPT <= n;
     const int64_t e0 = warp_base + (int64_t)lane * EPT;
@@ -396,13 +406,20 @@ cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const 
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
     const bool rr = rs.mode == MG_RESET_RANDOM;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(mg::kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = MG_PDL ? 1 : 0;
+    cudaError_t le = cudaSuccess;
 #define MG_LAUNCH(PVP, RR, A2)                                                              \
-    mg::merge_step_kernel<EPT, ActT, PVP, RR><<<grid, mg::kBlock, 0, st>>>(                 \
-        s, o, (const ActT *)a1, (const ActT *)(A2), n, rw, flags, rs, stp)
+    le = cudaLaunchKernelEx(&cfg, mg::merge_step_kernel<EPT, ActT, PVP, RR>, s, o, (const ActT *)a1, \
+                            (const ActT *)(A2), n, rw, flags, rs, stp)
     if (a2) { if (rr) MG_LAUNCH(true, true, a2); else MG_LAUNCH(true, false, a2); }
     else    { if (rr) MG_LAUNCH(false, true, nullptr); else MG_LAUNCH(false, false, nullptr); }
 #undef MG_LAUNCH
-    return cudaGetLastError();
+    return le ? le : cudaGetLastError();
 }
 }  // namespace
 
