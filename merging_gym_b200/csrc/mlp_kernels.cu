@@ -11,8 +11,9 @@
 // Tiling (persistent CTAs, one per SM, 256 threads, tile = 256 envs):
 //   layer 1  thread t owns env t of the tile: h1[k][t] = relu(b1[k] + sum_i x[t][i] W1t[i][k]) for the
 //            50 k's of the current K-chunk, written K-major to shared memory;
-//   layer 2  thread t = (eg = t/4, ng = t%4) owns a 4-env x 25-neuron register tile (100 FFMA per k
-//            against 1 + 7 LDS.128): acc[e][j] += h1[k][4 eg + e] * W2t[k][25 ng + j];
+//   layer 2  thread t = (eg = t/4, ng = t%4) owns a 4-env x 25-neuron register tile held as float2
+//            pairs of adjacent neurons and updated with Blackwell's packed FFMA2 (fma.rn.f32x2;
+//            52 FFMA2 per k against 1 + 7 LDS.128): acc[e][j] += h1[k][4 eg + e] * W2t[k][25 ng + j];
 //   layer 3  each thread reduces its 25 neurons into 4 x OUT partial Q-values, the 4 ng-lanes of an
 //            env group are adjacent lanes -> two shuffle-xor steps; lane ng==0 adds b3, takes the
 //            first maximum and stores 4 actions with one 32-bit store.
@@ -28,8 +29,9 @@ constexpr int H1 = 200, H2 = 100;
 constexpr int TM = 256;            // envs per tile == threads per block
 constexpr int KC = 50;             // K-chunk of layer 2 (h1 rows resident in smem)
 constexpr int NG = 4, NJ = 25;     // neuron groups x neurons per group
-constexpr int NJP = 28;            // padded group width (16-byte aligned rows)
-constexpr int MAX_IN = 12, MAX_OUT = 8;
+constexpr int NJP = 28;            // padded group width (16-byte aligned rows, zero filled)
+constexpr int NP = (NJ + 1) / 2;   // float2 accumulator pairs per env (13: the 26th lane multiplies the zero pad)
+constexpr int MAX_OUT = 8;
 
 template <int IN, int OUT>
 struct Smem {
@@ -89,11 +91,13 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
 #pragma unroll
         for (int i = 0; i < IN; ++i) xr[i] = S.x[t][i];
 
-        float acc[4][NJ];
+        // accumulators as float2 pairs over adjacent neurons: Blackwell's packed FFMA2
+        // (fma.rn.f32x2) does two fp32 FMAs per issue slot with 64-bit register operands
+        float2 acc[4][NP];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) acc[e][j] = 0.f;
+            for (int j = 0; j < NP; ++j) acc[e][j] = make_float2(0.f, 0.f);
 
         for (int k0 = 0; k0 < H1; k0 += KC) {
             // ---- layer 1 for rows k0 .. k0+KC of h1 (thread = env) -------------------------------
@@ -116,18 +120,20 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
             for (int kk = 0; kk < KC; ++kk) {
                 const float4 a = *reinterpret_cast<const float4 *>(&S.h1[kk][4 * eg]);
                 const float4 *bp = reinterpret_cast<const float4 *>(&S.w2[k0 + kk][ng][0]);
-                float b[NJP];
+                float2 b[NJP / 2];
 #pragma unroll
                 for (int v = 0; v < NJP / 4; ++v) {
                     const float4 q = bp[v];
-                    b[4 * v] = q.x; b[4 * v + 1] = q.y; b[4 * v + 2] = q.z; b[4 * v + 3] = q.w;
+                    b[2 * v] = make_float2(q.x, q.y); b[2 * v + 1] = make_float2(q.z, q.w);
                 }
+                const float2 a0 = make_float2(a.x, a.x), a1 = make_float2(a.y, a.y),
+                             a2 = make_float2(a.z, a.z), a3 = make_float2(a.w, a.w);
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
-                    acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
-                    acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
-                    acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+                for (int j = 0; j < NP; ++j) {
+                    acc[0][j] = __ffma2_rn(a0, b[j], acc[0][j]);
+                    acc[1][j] = __ffma2_rn(a1, b[j], acc[1][j]);
+                    acc[2][j] = __ffma2_rn(a2, b[j], acc[2][j]);
+                    acc[3][j] = __ffma2_rn(a3, b[j], acc[3][j]);
                 }
             }
         }
@@ -145,7 +151,7 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
             for (int o = 0; o < OUT; ++o) w[o] = S.w3[o][ng * NJ + j];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float h = fmaxf(acc[e][j] + bias, 0.f);
+                const float h = fmaxf(((j & 1) ? acc[e][j >> 1].y : acc[e][j >> 1].x) + bias, 0.f);
 #pragma unroll
                 for (int o = 0; o < OUT; ++o) q[e][o] = fmaf(h, w[o], q[e][o]);
             }
