@@ -218,6 +218,8 @@ def run_b200(args):
 
     K, W = args.steps, args.warmup
 
+    reducer = mg.AsyncStatsReducer(env) if world > 1 else None
+
     def timed_region(shards, K, W, sample_clocks):
         """W warm-up + K timed mg_step launches round-robin over `shards`; returns (ms, G, eager, clocks)."""
         nsh = len(shards)
@@ -266,6 +268,8 @@ def run_b200(args):
             for _ in range(K // G):
                 graph.replay()
                 done_steps += G
+                if reducer is not None and sample_clocks:   # headline region only: async NCCL stats reduce
+                    reducer.submit()
         do_steps(K - done_steps)
         e1.record()
         torch.cuda.synchronize()
@@ -368,7 +372,9 @@ def run_b200(args):
                              f"round-robin ({R * n * 52 / 1e6:.0f} MB of float64 state + {A} action sets "
                              f"{A * n * 2 / 1e6:.0f} MB, outputs to {R}x{S} ring slots of {n * 50 / 1e6:.0f} MB); "
                              "each launch re-reads its shard's state from HBM",
-                       "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of 16 int64 stats"},
+                       "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of 16 int64 "
+                                      f"stats on a side stream every {G or K} steps inside the timed region "
+                                      f"({reducer.submissions if reducer else 0} reductions)"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
                          "frac": per_gpu_gbs / peak, "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
                          "kernel": "mg::merge_step_kernel<2, uint8_t, true>",

@@ -190,11 +190,13 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
  * Linear(in,200)-ReLU-Linear(200,100)-ReLU-Linear(100,out) in fp32 followed by
  * `torch.max(q, 1)[1]` (scripts/main.py:30-47,99-107; scripts/hdqn.py:38-55,82-95,165-177).
  * in = obs_dim (+1 if goal != NULL: the h-DQN controller's `[goal] + state`, hdqn.py:291) must be
- * 10 or 11, out_dim 5 or 3.  Weights are fp32 device arrays: w1t [in][200] and w2t [200][100] are
- * K-major (the transposes of fc1.weight / fc2.weight), w3 [out][100] is out.weight as stored.
+ * 10 or 11, out_dim 5 or 3.  Weights are fp32 device arrays, 16-byte aligned: w1t [in][200] is the
+ * transpose of fc1.weight; w2p [200][4][28] is the transpose of fc2.weight with its 100 columns
+ * split into 4 groups of 25 and each group zero-padded to 28 (w2p[k][g][j] = fc2.weight[25g+j][k]);
+ * w3 [out][100] is out.weight as stored.
  * actions: uint8[n] (first maximum wins); q_out: optional float[n][out]. */
 MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
-                      int32_t out_dim, const float *w1t, const float *b1, const float *w2t,
+                      int32_t out_dim, const float *w1t, const float *b1, const float *w2p,
                       const float *b2, const float *w3, const float *b3, uint8_t *actions,
                       float *q_out_or_null, void *stream);
 

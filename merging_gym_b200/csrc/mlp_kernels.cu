@@ -9,16 +9,18 @@
 // so no tf32/bf16 tensor-core path (45 kFLOP/env: ~250 us for 2^18 envs at FFMA rates).
 //
 // Tiling (persistent CTAs, one per SM, 256 threads, tile = 256 envs):
+//   input    thread t reads env t's row straight into registers; the next tile's row is requested
+//            before the epilogue of the current one so its latency is hidden;
 //   layer 1  thread t owns env t of the tile: h1[k][t] = relu(b1[k] + sum_i x[t][i] W1t[i][k]) for the
-//            50 k's of the current K-chunk, written K-major to shared memory;
+//            40 k's of the current K-chunk (four per 128-bit weight load), written K-major to smem;
 //   layer 2  thread t = (eg = t/4, ng = t%4) owns a 4-env x 25-neuron register tile held as float2
 //            pairs of adjacent neurons and updated with Blackwell's packed FFMA2 (fma.rn.f32x2;
 //            52 FFMA2 per k against 1 + 7 LDS.128): acc[e][j] += h1[k][4 eg + e] * W2t[k][25 ng + j];
 //   layer 3  each thread reduces its 25 neurons into 4 x OUT partial Q-values, the 4 ng-lanes of an
 //            env group are adjacent lanes -> two shuffle-xor steps; lane ng==0 adds b3, takes the
 //            first maximum and stores 4 actions with one 32-bit store.
-// Shared memory: W2t padded to [200][4][28] (89.6 KB), h1 chunk [50][256] (51.2 KB), W1t, W3, biases,
-// x tile [256][IN] -> ~158 KB, so one CTA per SM.
+// Shared memory: W2 pre-padded on the host to [200][4][28] (89.6 KB, copied with 128-bit loads),
+// h1 chunk [40][256] (41 KB), W1t, W3, biases -> ~143 KB, so one CTA per SM.
 #include <cstring>
 
 #include "abi_common.h"
@@ -27,7 +29,7 @@ namespace mgmlp {
 
 constexpr int H1 = 200, H2 = 100;
 constexpr int TM = 256;            // envs per tile == threads per block
-constexpr int KC = 50;             // K-chunk of layer 2 (h1 rows resident in smem)
+constexpr int KC = 40;             // K-chunk of layer 2 (h1 rows resident in smem), multiple of 4
 constexpr int NG = 4, NJ = 25;     // neuron groups x neurons per group
 constexpr int NJP = 28;            // padded group width (16-byte aligned rows, zero filled)
 constexpr int NP = (NJ + 1) / 2;   // float2 accumulator pairs per env (13: the 26th lane multiplies the zero pad)
@@ -35,62 +37,67 @@ constexpr int MAX_OUT = 8;
 
 template <int IN, int OUT>
 struct Smem {
-    float w2[H1][NG][NJP];         // 89 600 B
-    float h1[KC][TM];              // 51 200 B
+    float w2[H1][NG][NJP];         // 89 600 B, copied verbatim from the host-padded W2
+    float h1[KC][TM];              // 40 960 B
     float w1[IN][H1];
-    float x[TM][IN | 1];           // odd row stride keeps the per-thread row reads conflict-free
     float w3[OUT][H2];
     float b1[H1], b2[H2], b3[MAX_OUT];
 };
 
+// one env's input row [goal] + obs straight from global memory into registers (40-byte rows, 8-byte
+// aligned; a warp covers one contiguous 1280-byte span)
+template <int IN>
+__device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal,
+                                         int64_t e, int64_t n, int obs_dim, float (&x)[IN]) {
+    const int off = IN - obs_dim;      // 1 when a goal column is prepended (hdqn.py:291)
+    if (e < n) {
+        if (off) x[0] = (float)goal[e];
+        const float2 *src = reinterpret_cast<const float2 *>(obs + e * obs_dim);
+#pragma unroll
+        for (int i = 0; i < (IN - (IN & 1)) / 2; ++i) {     // obs_dim is 10: five float2
+            const float2 v = __ldg(src + i);
+            x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < IN; ++i) x[i] = 0.f;
+    }
+}
+
 template <int IN, int OUT>
 __global__ void __launch_bounds__(TM, 1)
 mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
-               const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2t,
+               const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2p,
                const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
                uint8_t *__restrict__ act, float *__restrict__ q_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<IN, OUT> &S = *reinterpret_cast<Smem<IN, OUT> *>(smem_raw);
     const int t = threadIdx.x;
-
-    // ---- weights -> shared memory, once per (persistent) CTA -----------------------------------
-    for (int i = t; i < H1 * H2; i += TM) {
-        const int k = i / H2, j = i - k * H2;
-        S.w2[k][j / NJ][j % NJ] = w2t[i];
-    }
-    for (int i = t; i < H1 * NG * (NJP - NJ); i += TM) {
-        const int k = i / (NG * (NJP - NJ)), r = i - k * (NG * (NJP - NJ));
-        S.w2[k][r / (NJP - NJ)][NJ + r % (NJP - NJ)] = 0.f;
-    }
-    for (int i = t; i < IN * H1; i += TM) (&S.w1[0][0])[i] = w1t[i];
-    for (int i = t; i < OUT * H2; i += TM) (&S.w3[0][0])[i] = w3[i];
-    for (int i = t; i < H1; i += TM) S.b1[i] = b1[i];
-    for (int i = t; i < H2; i += TM) S.b2[i] = b2[i];
-    if (t < OUT) S.b3[t] = b3[t];
-
     const int ng = t & 3, eg = t >> 2;
     const int64_t n_tiles = (n + TM - 1) / TM;
 
+    // first tile's input rows are requested before the weights so the two latencies overlap
+    float xr[IN];
+    load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + t, n, obs_dim, xr);
+
+    // ---- weights -> shared memory, once per (persistent) CTA: straight 128-bit copies -------------
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(w2p);
+        float4 *dst = reinterpret_cast<float4 *>(&S.w2[0][0][0]);
+#pragma unroll 11
+        for (int i = t; i < H1 * NG * NJP / 4; i += TM) dst[i] = __ldg(src + i);
+        const float4 *s1 = reinterpret_cast<const float4 *>(w1t);
+        float4 *d1 = reinterpret_cast<float4 *>(&S.w1[0][0]);
+        for (int i = t; i < IN * H1 / 4; i += TM) d1[i] = __ldg(s1 + i);
+        for (int i = t; i < OUT * H2; i += TM) (&S.w3[0][0])[i] = w3[i];
+        for (int i = t; i < H1; i += TM) S.b1[i] = b1[i];
+        for (int i = t; i < H2; i += TM) S.b2[i] = b2[i];
+        if (t < OUT) S.b3[t] = b3[t];
+    }
+    __syncthreads();
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * TM;
-        __syncthreads();                       // previous tile done with S.x / S.h1; weights visible
-        // ---- x tile: [goal] + obs rows, coalesced ------------------------------------------------
-        {
-            const int64_t rows = min((int64_t)TM, n - base);
-            const int64_t total = rows * obs_dim;
-            const float *src = obs + base * obs_dim;
-            const int off = IN - obs_dim;      // 1 when a goal column is prepended (hdqn.py:291)
-            for (int64_t i = t; i < (int64_t)TM * obs_dim; i += TM) {
-                const int r = (int)(i / obs_dim), c = (int)(i - (int64_t)r * obs_dim);
-                S.x[r][off + c] = i < total ? __ldg(src + i) : 0.f;
-            }
-            if (off) S.x[t][0] = (base + t < n) ? (float)goal[base + t] : 0.f;
-        }
-        __syncthreads();
-        float xr[IN];
-#pragma unroll
-        for (int i = 0; i < IN; ++i) xr[i] = S.x[t][i];
-
         // accumulators as float2 pairs over adjacent neurons: Blackwell's packed FFMA2
         // (fma.rn.f32x2) does two fp32 FMAs per issue slot with 64-bit register operands
         float2 acc[4][NP];
@@ -100,31 +107,43 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
             for (int j = 0; j < NP; ++j) acc[e][j] = make_float2(0.f, 0.f);
 
         for (int k0 = 0; k0 < H1; k0 += KC) {
-            // ---- layer 1 for rows k0 .. k0+KC of h1 (thread = env) -------------------------------
-            if (k0) __syncthreads();           // everyone finished reading the previous chunk
+            // ---- layer 1 for rows k0 .. k0+KC of h1 (thread = env), 4 rows per 128-bit weight load ----
+            __syncthreads();                   // everyone finished reading the previous chunk of h1
 #pragma unroll 2
-            for (int kk = 0; kk < KC; kk += 2) {
-                float h0 = S.b1[k0 + kk], h1v = S.b1[k0 + kk + 1];
+            for (int kk = 0; kk < KC; kk += 4) {
+                float4 h = *reinterpret_cast<const float4 *>(&S.b1[k0 + kk]);
 #pragma unroll
                 for (int i = 0; i < IN; ++i) {
-                    const float2 w = *reinterpret_cast<const float2 *>(&S.w1[i][k0 + kk]);
-                    h0 = fmaf(xr[i], w.x, h0);
-                    h1v = fmaf(xr[i], w.y, h1v);
+                    const float4 w = *reinterpret_cast<const float4 *>(&S.w1[i][k0 + kk]);
+                    h.x = fmaf(xr[i], w.x, h.x); h.y = fmaf(xr[i], w.y, h.y);
+                    h.z = fmaf(xr[i], w.z, h.z); h.w = fmaf(xr[i], w.w, h.w);
                 }
-                S.h1[kk][t] = fmaxf(h0, 0.f);
-                S.h1[kk + 1][t] = fmaxf(h1v, 0.f);
+                S.h1[kk][t] = fmaxf(h.x, 0.f); S.h1[kk + 1][t] = fmaxf(h.y, 0.f);
+                S.h1[kk + 2][t] = fmaxf(h.z, 0.f); S.h1[kk + 3][t] = fmaxf(h.w, 0.f);
             }
             __syncthreads();
-            // ---- layer 2 partial sums over this chunk (4 envs x 25 neurons per thread) ------------
+            // ---- layer 2 partial sums over this chunk (4 envs x 25 neurons per thread), operands of
+            //      step kk+1 are fetched from shared memory while step kk multiplies ------------------
+            float4 a_n = *reinterpret_cast<const float4 *>(&S.h1[0][4 * eg]);
+            float4 b_n[NJP / 4];
+            {
+                const float4 *bp = reinterpret_cast<const float4 *>(&S.w2[k0][ng][0]);
+#pragma unroll
+                for (int v = 0; v < NJP / 4; ++v) b_n[v] = bp[v];
+            }
 #pragma unroll 2
             for (int kk = 0; kk < KC; ++kk) {
-                const float4 a = *reinterpret_cast<const float4 *>(&S.h1[kk][4 * eg]);
-                const float4 *bp = reinterpret_cast<const float4 *>(&S.w2[k0 + kk][ng][0]);
+                const float4 a = a_n;
                 float2 b[NJP / 2];
 #pragma unroll
                 for (int v = 0; v < NJP / 4; ++v) {
-                    const float4 q = bp[v];
-                    b[2 * v] = make_float2(q.x, q.y); b[2 * v + 1] = make_float2(q.z, q.w);
+                    b[2 * v] = make_float2(b_n[v].x, b_n[v].y); b[2 * v + 1] = make_float2(b_n[v].z, b_n[v].w);
+                }
+                if (kk + 1 < KC) {
+                    a_n = *reinterpret_cast<const float4 *>(&S.h1[kk + 1][4 * eg]);
+                    const float4 *bp = reinterpret_cast<const float4 *>(&S.w2[k0 + kk + 1][ng][0]);
+#pragma unroll
+                    for (int v = 0; v < NJP / 4; ++v) b_n[v] = bp[v];
                 }
                 const float2 a0 = make_float2(a.x, a.x), a1 = make_float2(a.y, a.y),
                              a2 = make_float2(a.z, a.z), a3 = make_float2(a.w, a.w);
@@ -137,6 +156,9 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
                 }
             }
         }
+        // next tile's input rows: issued now, consumed after the epilogue
+        load_row<IN>(obs, goal, (tile + gridDim.x) * TM + t, n, obs_dim, xr);
+
         // ---- layer 3 + arg-max ---------------------------------------------------------------------
         float q[4][OUT];
 #pragma unroll
@@ -215,22 +237,24 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
 }  // namespace mgmlp
 
 extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
-                                 int32_t out_dim, const float *w1t, const float *b1, const float *w2t,
+                                 int32_t out_dim, const float *w1t, const float *b1, const float *w2p,
                                  const float *b2, const float *w3, const float *b3, uint8_t *actions,
                                  float *q_out_or_null, void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
-    if (!((in_dim == 10 || in_dim == 11) && (out_dim == 5 || out_dim == 3)))
-        return fail(MG_ERR_BAD_SIZE, "mg_mlp_act supports Net(10|11, 5|3) (main.py:30-47, hdqn.py:38-55)");
+    if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
+        return fail(MG_ERR_BAD_SIZE, "mg_mlp_act supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs "
+                                     "(Net(10|11, 5|3): main.py:30-47, hdqn.py:38-55)");
     if (n == 0) return MG_OK;
-    if (!obs || !w1t || !b1 || !w2t || !b2 || !w3 || !b3 || !actions)
+    if (!obs || !w1t || !b1 || !w2p || !b2 || !w3 || !b3 || !actions)
         return fail(MG_ERR_NULL_POINTER, "mg_mlp_act: NULL pointer");
-    if (!aligned16(actions)) return fail(MG_ERR_ALIGNMENT, "actions must be 16-byte aligned");
+    if (!aligned16(actions) || !aligned16(obs) || !aligned16(w1t) || !aligned16(w2p) || !aligned16(b1))
+        return fail(MG_ERR_ALIGNMENT, "obs, actions and weight arrays must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #define MG_MLP_CASE(I, O) \
-    if (in_dim == I && out_dim == O) e = mgmlp::launch<I, O>(obs, goal_or_null, n, obs_dim, w1t, b1, w2t, b2, w3, b3, actions, q_out_or_null, st); else
+    if (in_dim == I && out_dim == O) e = mgmlp::launch<I, O>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st); else
     MG_MLP_CASE(10, 5) MG_MLP_CASE(10, 3) MG_MLP_CASE(11, 5) MG_MLP_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_MLP_CASE
     if (e) return cuda_fail(e, "mg_mlp_act launch");

@@ -63,8 +63,12 @@ class MLPPolicy:
         if tuple(self.w1.shape) != (HIDDEN1, self.in_dim) or tuple(self.w2.shape) != (HIDDEN2, HIDDEN1) \
                 or tuple(self.w3.shape) != (self.out_dim, HIDDEN2):
             raise ValueError("state_dict does not match Net(%d, %d)" % (self.in_dim, self.out_dim))
-        # K-major copies for the fused kernel (built once)
-        self.w1_t = self.w1.t().contiguous(); self.w2_t = self.w2.t().contiguous()
+        # layouts of the fused kernel, built once: W1 K-major; W2 K-major with its 100 output columns split
+        # into 4 groups of 25, each zero-padded to 28 floats (16-byte aligned rows in shared memory)
+        self.w1_t = self.w1.t().contiguous()
+        w2p = torch.zeros(HIDDEN1, 4, 28, dtype=torch.float32, device=self.device)
+        w2p[:, :, :25] = self.w2.t().reshape(HIDDEN1, 4, 25)
+        self.w2_p = w2p.contiguous()
 
     def state_dict(self) -> dict:
         return {"fc1.weight": self.w1, "fc1.bias": self.b1, "fc2.weight": self.w2, "fc2.bias": self.b2,
@@ -113,7 +117,7 @@ class MLPPolicy:
             raise ValueError("goal must be a contiguous uint8 tensor")
         with torch.cuda.device(self.device):
             nat.check(lib.mg_mlp_act(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
-                                     _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_t), _ptr(self.b2),
+                                     _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_p), _ptr(self.b2),
                                      _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out),
                                      C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
                       "mg_mlp_act")

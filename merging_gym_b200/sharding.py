@@ -63,6 +63,43 @@ def all_reduce_stats(stats: torch.Tensor, async_op: bool = False):
     return (stats, work) if async_op else stats
 
 
+class AsyncStatsReducer:
+    """Periodic, off-critical-path reduction of the episode statistics over all ranks.
+
+    `submit()` snapshots this rank's int64[16] totals on the current stream and all-reduces them
+    on a side stream (NCCL on GPUs); the env's launches are never blocked.  `latest()` waits for the
+    most recent submission and returns the reduced totals.  This is the path's only collective.
+    """
+
+    def __init__(self, env):
+        self.env = env
+        self.side = torch.cuda.Stream(device=env.device)
+        self._work = None
+        self._buf = None
+        self.submissions = 0
+
+    def submit(self) -> None:
+        import torch.distributed as dist
+        snap = self.env.stats_tensor()                      # tiny sum kernel on the current stream
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            snap.record_stream(self.side)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self._work = dist.all_reduce(snap, op=dist.ReduceOp.SUM, async_op=True)
+            self._buf = snap
+        self.submissions += 1
+
+    def latest(self) -> torch.Tensor:
+        if self._buf is None:
+            raise RuntimeError("AsyncStatsReducer.latest() before submit()")
+        if self._work is not None:
+            self._work.wait()
+        torch.cuda.current_stream(self.env.device).wait_stream(self.side)
+        return self._buf
+
+
 def stats_to_dict(totals: np.ndarray, ret_scale: float) -> dict:
     """int64 totals -> named dict with derived rates (what scripts/main.py:203-227 tracks by hand)."""
     t = [int(v) for v in np.asarray(totals).reshape(-1)[:len(STAT_NAMES)]]

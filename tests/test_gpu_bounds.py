@@ -52,7 +52,7 @@ def test_no_kernel_writes_out_of_bounds(n, random_reset):
     ring = ar.take(4 * 22 * 50, 0); counter = ar.take(8, 0); ids = ar.take(4 * 50, 0)
     scratch = ar.take(4 * ((n + 31) // 32 + 4), 0)
     act_out = ar.take(n); q_out = ar.take(4 * 5 * n)
-    w1t = ar.take(4 * 10 * 200, 0); b1 = ar.take(4 * 200, 0); w2t = ar.take(4 * 200 * 100, 0)
+    w1t = ar.take(4 * 10 * 200, 0); b1 = ar.take(4 * 200, 0); w2t = ar.take(4 * 200 * 4 * 28, 0)
     b2 = ar.take(4 * 100, 0); w3 = ar.take(4 * 5 * 100, 0); b3 = ar.take(4 * 5, 0)
     p = lambda t: C.c_void_p(t.data_ptr())
     st = nat.MgState(*[t.data_ptr() for t in f64], meta.data_ptr())
