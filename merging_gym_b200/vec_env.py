@@ -135,10 +135,13 @@ class MergeVecEnv:
 
         dev = self.device
         f64 = dict(dtype=torch.float64, device=dev)
-        self.pos1 = torch.empty(n, **f64); self.vel1 = torch.empty(n, **f64)
-        self.pos2 = torch.empty(n, **f64); self.vel2 = torch.empty(n, **f64)
-        self.ret1 = torch.zeros(n, **f64); self.ret2 = torch.zeros(n, **f64)
-        self.meta = torch.zeros(n, dtype=torch.int32, device=dev)
+        # one contiguous state allocation: 6 float64 arrays + the uint32 meta array, each padded to a
+        # multiple of 32 envs (keeps every array 256-byte aligned)
+        n32 = (n + 31) // 32 * 32
+        self._state_block = torch.zeros(n32 * 52, dtype=torch.uint8, device=dev)
+        f = self._state_block[:n32 * 48].view(torch.float64).view(6, n32)
+        self.pos1, self.vel1, self.pos2, self.vel2, self.ret1, self.ret2 = (f[i, :n] for i in range(6))
+        self.meta = self._state_block[n32 * 48:].view(torch.int32)[:n]
         self._state = nat.MgState(*[t.data_ptr() for t in
                                     (self.pos1, self.vel1, self.pos2, self.vel2, self.ret1, self.ret2, self.meta)])
         K = self.out_slots
