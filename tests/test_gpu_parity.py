@@ -417,3 +417,20 @@ def test_random_start_is_shard_and_launch_invariant(mg):
     before = full.resets.clone()
     full.reset(m)
     assert torch.equal(full.resets[:100], before[:100] + 1) and torch.equal(full.resets[100:], before[100:])
+
+
+def test_far_beyond_the_merge_zone(mg):
+    """Sticky-done envs that keep being stepped: longitudes past 24 000 leave the polynomial's range
+    (library sincos fallback) and the step counter saturates at 4095 instead of wrapping."""
+    n, T = 6, 4300
+    env = mg.MergeVecEnv(n, auto_reset=False)
+    ref = mo.RefVecEnv(n, auto_reset=False)
+    a1 = np.array([4, 4, 3, 0, 2, 4], np.uint8); a2 = np.array([4, 0, 4, 4, 2, 1], np.uint8)
+    for t in range(T):
+        out = env.step(a1, a2)
+        r = ref.step(a1, a2)
+        if t % 50 == 0 or t > T - 20:
+            assert_step_equal(out, r, t)
+    assert float(env.pos1.max()) > 24000.0 and int(ref.steps.max()) == T
+    assert_state_bit_exact(env, ref)                    # pos/vel stay bit-identical; steps compare saturated
+    assert env.steps.cpu().tolist() == [4095] * n

@@ -81,3 +81,33 @@ def test_subsample_matches_oracle(mg):
         assert np.array_equal(done.cpu().numpy(), rdone) and np.array_equal(info["flags"].cpu().numpy(), rinfo)
         assert rel_err(obs.cpu().numpy(), robs).max() <= 1e-5 and rel_err(rew.cpu().numpy(), rrew).max() <= 1e-5
     assert np.array_equal(env.pos1.cpu().numpy(), ref.pos1)
+
+
+def test_player_mirror_symmetry(mg):
+    """Swapping the two players' action streams mirrors the float64 state bit for bit (the two
+    lanes are mirror images, merging_env.py:48-58) and leaves `done` / collisions unchanged.  Rewards
+    mirror too, except on steps where both cars cross END_POINT together: player 1 is evaluated
+    first and takes RFirst in both runs (merging_env.py:163-181)."""
+    n, K = N, 230
+    a = mg.MergeVecEnv(n, seed=42, episode_info=False)
+    b = mg.MergeVecEnv(n, seed=42, episode_info=False)
+    mismatch = torch.zeros((), dtype=torch.int64, device="cuda")
+    bad = torch.zeros((), dtype=torch.int64, device="cuda")
+    for t in range(K):
+        a1, a2 = a.sample_actions(t)
+        oa, ra, da, ia = a.step(a1, a2)
+        ob, rb, db, ib = b.step(a2, a1)
+        assert torch.equal(da, db)
+        assert torch.equal(ia["collision"], ib["collision"])
+        diff = (ra[:, 0] != rb[:, 1]) | (ra[:, 1] != rb[:, 0])
+        mismatch += diff.sum()
+        # every asymmetric step is a simultaneous crossing: the bonuses 2 and 1 are exchanged
+        tie = ((ra[:, 0] - rb[:, 1]).abs() - 1.0).abs() < 1e-6
+        bad += (diff & ~tie).sum()
+    torch.cuda.synchronize()
+    assert torch.equal(a.pos1, b.pos2) and torch.equal(a.vel1, b.vel2)
+    assert torch.equal(a.pos2, b.pos1) and torch.equal(a.vel2, b.vel1)
+    assert int(bad) == 0
+    assert int(mismatch) < 0.01 * n * K
+    sa, sb = a.stats(), b.stats()
+    assert sa["episodes"] == sb["episodes"] and sa["collisions"] == sb["collisions"]
