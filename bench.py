@@ -81,7 +81,8 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # noqa
             self.err = repr(e)
 
-    def run(self):
+    def sample_now(self):
+        """One sample from the calling thread (used while the GPU is still busy with the timed work)."""
         if not self.ok:
             return
         nv = self.nv
@@ -90,15 +91,18 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
                  nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            self.sample_now()
             time.sleep(self.period)
 
     def stop(self):
@@ -272,6 +276,8 @@ def run_b200(args):
                     reducer.submit()
         do_steps(K - done_steps)
         e1.record()
+        if sampler:
+            sampler.sample_now()                          # the queue is still draining: a sample under load
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -28,6 +28,9 @@ namespace mg {
 #ifndef MG_PDL
 #define MG_PDL 1          // launch the step kernel with programmatic stream serialization (PDL): +2 % (profiles/)
 #endif
+#ifndef MG_TMA_OBS
+#define MG_TMA_OBS 0      // 1: write each warp's observation tile with one TMA bulk copy (experiment)
+#endif
 #ifndef MG_MIN_BLOCKS
 #define MG_MIN_BLOCKS 8   // __launch_bounds__ min resident blocks per SM: caps the step kernel at 64 registers
 #endif
@@ -213,6 +216,18 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
         st_pack_stream<uint8_t, EPT>(o.done + e0, done8);
         st_pack_stream<uint8_t, EPT>(o.info + e0, info8);
         // obs rows of this warp are one contiguous, 16-byte aligned span of 32*EPT*40 bytes
+#if MG_TMA_OBS
+        // One TMA bulk copy (shared -> global, 2560 B) per warp instead of 5 LDS.128 + 5 STG.128 per lane.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy STS -> async proxy
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(&stage[warp][0]);
+            float *gdst = o.obs + warp_base * MG_OBS_DIM;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(gdst), "r"(saddr), "n"(32 * EPT * MG_OBS_DIM * 4) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#else
         __syncwarp();
         const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
         float4 *dst = reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM);
@@ -220,6 +235,7 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 #pragma unroll
         for (int k = 0; k < (kVec + 31) / 32; ++k)
             if (kVec % 32 == 0 || lane + 32 * k < kVec) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+#endif
     } else {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
@@ -233,6 +249,10 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
     }
 
     if (stats) flush_stats(st, stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS, 0xFFFFFFFFu, lane);
+#if MG_TMA_OBS
+    // the staging tile must stay intact until the bulk copy has read it
+    if (full && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
 }
 
 // =================================================================================================
