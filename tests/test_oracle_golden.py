@@ -179,3 +179,30 @@ def test_random_start_distribution():
     assert abs(np.corrcoef(p1, q1)[0, 1]) < 0.01
     env = mo.RefVecEnv(64, reset_mode="random", reset_seed=123)
     assert np.array_equal(env.pos1, p1[:64]) and env.resets.tolist() == [1] * 64
+
+
+def test_collision_rule_equals_reference_polygons():
+    """`is_collided_xy` against the reference's own `corners()` + Polygon.intersects code path
+    (merging_env.py:198-206, 232-239) driven with random float centres, through the stand-in
+    pygame Rect / shapely Polygon (needs /root/reference, i.e. the build container)."""
+    from oracle.ref_loader import load_reference_env, quiet, reference_available
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    import sys
+    env = load_reference_env()
+    from shapely.geometry import Polygon          # the shim put on sys.path by the loader
+    rng = np.random.default_rng(0)
+    n = 4000
+    x1 = rng.uniform(-30, 1000, n); y1 = rng.uniform(120, 180, n)
+    # second car close to the first so that both outcomes are frequent, incl. touching cases
+    x2 = x1 + rng.choice([-9.5, -8.6, -8.0, -7.4, 0.0, 3.3, 7.9, 8.0, 8.2, 9.9], n) + rng.uniform(-0.6, 0.6, n)
+    y2 = y1 + rng.choice([-5.5, -4.4, -4.0, -3.6, 0.0, 2.2, 3.9, 4.0, 4.1, 5.2], n) + rng.uniform(-0.6, 0.6, n)
+    want = mo.is_collided_xy(x1, y1, x2, y2)
+    got = np.zeros(n, bool)
+    with quiet():
+        for i in range(n):
+            p1 = Polygon([(p.x, p.y) for p in env.corners(env.ego, x1[i], y1[i], 0)])
+            p2 = Polygon([(p.x, p.y) for p in env.corners(env.opponent, x2[i], y2[i], 0)])
+            got[i] = p1.intersects(p2)
+    assert np.array_equal(got, want)
+    assert 0.2 < want.mean() < 0.8
