@@ -101,5 +101,22 @@ def make(env_id: str = ENV_ID, **kwargs):
     return MergeEnv(**kwargs)
 
 
+def register_gym(env_id: str = ENV_ID) -> str:
+    """Register this env under the reference's id in gym's registry, exactly as
+    merging_gym/__init__.py:3-6 does for the Python env, so that the reference scripts'
+    `gym.make("merging_env-v0")` (scripts/main.py:20, hdqn.py:26, human_player.py:27,
+    ranbowdqn.py:628) returns the GPU-backed env.  Needs gym (or gymnasium) to be importable; it is
+    not a dependency of this package."""
+    try:
+        from gym.envs.registration import register
+    except ImportError:
+        try:
+            from gymnasium.envs.registration import register
+        except ImportError as e:
+            raise ImportError("register_gym() needs gym or gymnasium") from e
+    register(id=env_id, entry_point="merging_gym_b200.scalar_env:MergeEnv")
+    return env_id
+
+
 def make_vec(num_envs: int, **kwargs) -> MergeVecEnv:
     return MergeVecEnv(num_envs, **kwargs)

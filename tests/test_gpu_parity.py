@@ -434,3 +434,27 @@ def test_far_beyond_the_merge_zone(mg):
     assert float(env.pos1.max()) > 24000.0 and int(ref.steps.max()) == T
     assert_state_bit_exact(env, ref)                    # pos/vel stay bit-identical; steps compare saturated
     assert env.steps.cpu().tolist() == [4095] * n
+
+
+def test_gym_registration_drop_in(mg, monkeypatch):
+    """The reference's plugin boundary is gym's registry (merging_gym/__init__.py:3-6): after
+    `register_gym()`, `gym.make("merging_env-v0")` hands the scripts the GPU-backed env.  gym itself
+    is absent from the image, so the registry used here is the stand-in from oracle/ref_shims."""
+    import sys
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "ref_shims")
+    monkeypatch.syspath_prepend(shims)
+    for m in [k for k in sys.modules if k == "gym" or k.startswith("gym.")]:
+        monkeypatch.delitem(sys.modules, m)
+    import gym
+    assert mg.register_gym() == "merging_env-v0"
+    env = gym.make("merging_env-v0")
+    env = env.unwrapped                                           # scripts/main.py:20-23
+    assert isinstance(env, mg.MergeEnv)
+    assert env.action_space.n == 5 and env.observation_space.shape[0] == 10      # main.py:24-25
+    state = env.reset()
+    for t in range(151):                                          # main.py:192-218 loop body
+        action_op = None
+        next_state, rewards, done, info = env.step(2, action_op)
+        reward, reward_op = rewards
+        state = next_state
+    assert done and info["collision"] and env.winner is None and t == 150
