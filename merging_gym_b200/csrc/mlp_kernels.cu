@@ -12,7 +12,8 @@
 //   input    thread t reads env t's row straight into registers; the next tile's row is requested
 //            before the epilogue of the current one so its latency is hidden;
 //   layer 1  thread t owns env t of the tile: h1[k][t] = relu(b1[k] + sum_i x[t][i] W1t[i][k]) for the
-//            40 k's of the current K-chunk (four per 128-bit weight load), written K-major to smem;
+//            100 k's of the current K-chunk (four per 128-bit weight load, packed FFMA2), written
+//            K-major to shared memory;
 //   layer 2  thread t = (eg = t/4, ng = t%4) owns a 4-env x 25-neuron register tile held as float2
 //            pairs of adjacent neurons and updated with Blackwell's packed FFMA2 (fma.rn.f32x2;
 //            52 FFMA2 per k against 1 + 7 LDS.128): acc[e][j] += h1[k][4 eg + e] * W2t[k][25 ng + j];
@@ -20,7 +21,7 @@
 //            env group are adjacent lanes -> two shuffle-xor steps; lane ng==0 adds b3, takes the
 //            first maximum and stores 4 actions with one 32-bit store.
 // Shared memory: W2 pre-padded on the host to [200][4][28] (89.6 KB, copied with 128-bit loads),
-// h1 chunk [40][256] (41 KB), W1t, W3, biases -> ~143 KB, so one CTA per SM.
+// h1 chunk [100][256] (102 KB), W1t, W3, biases -> ~204 KB, so one CTA per SM.
 #include <cstring>
 
 #include "abi_common.h"
@@ -29,7 +30,7 @@ namespace mgmlp {
 
 constexpr int H1 = 200, H2 = 100;
 constexpr int TM = 256;            // envs per tile == threads per block
-constexpr int KC = 40;             // K-chunk of layer 2 (h1 rows resident in smem), multiple of 4
+constexpr int KC = 100;            // K-chunk of layer 2 (h1 rows resident in smem), multiple of 4
 constexpr int NG = 4, NJ = 25;     // neuron groups x neurons per group
 constexpr int NJP = 28;            // padded group width (16-byte aligned rows, zero filled)
 constexpr int NP = (NJ + 1) / 2;   // float2 accumulator pairs per env (13: the 26th lane multiplies the zero pad)
@@ -38,7 +39,7 @@ constexpr int MAX_OUT = 8;
 template <int IN, int OUT>
 struct Smem {
     float w2[H1][NG][NJP];         // 89 600 B, copied verbatim from the host-padded W2
-    float h1[KC][TM];              // 40 960 B
+    float h1[KC][TM];              // 102 400 B
     float w1[IN][H1];
     float w3[OUT][H2];
     float b1[H1], b2[H2], b3[MAX_OUT];
@@ -111,15 +112,17 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
             __syncthreads();                   // everyone finished reading the previous chunk of h1
 #pragma unroll 2
             for (int kk = 0; kk < KC; kk += 4) {
-                float4 h = *reinterpret_cast<const float4 *>(&S.b1[k0 + kk]);
+                const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k0 + kk]);
+                float2 h01 = make_float2(bb.x, bb.y), h23 = make_float2(bb.z, bb.w);
 #pragma unroll
                 for (int i = 0; i < IN; ++i) {
                     const float4 w = *reinterpret_cast<const float4 *>(&S.w1[i][k0 + kk]);
-                    h.x = fmaf(xr[i], w.x, h.x); h.y = fmaf(xr[i], w.y, h.y);
-                    h.z = fmaf(xr[i], w.z, h.z); h.w = fmaf(xr[i], w.w, h.w);
+                    const float2 xx = make_float2(xr[i], xr[i]);
+                    h01 = __ffma2_rn(xx, make_float2(w.x, w.y), h01);
+                    h23 = __ffma2_rn(xx, make_float2(w.z, w.w), h23);
                 }
-                S.h1[kk][t] = fmaxf(h.x, 0.f); S.h1[kk + 1][t] = fmaxf(h.y, 0.f);
-                S.h1[kk + 2][t] = fmaxf(h.z, 0.f); S.h1[kk + 3][t] = fmaxf(h.w, 0.f);
+                S.h1[kk][t] = fmaxf(h01.x, 0.f); S.h1[kk + 1][t] = fmaxf(h01.y, 0.f);
+                S.h1[kk + 2][t] = fmaxf(h23.x, 0.f); S.h1[kk + 3][t] = fmaxf(h23.y, 0.f);
             }
             __syncthreads();
             // ---- layer 2 partial sums over this chunk (4 envs x 25 neurons per thread), operands of
