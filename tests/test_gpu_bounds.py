@@ -3,7 +3,6 @@ is carved out of one guarded allocation with 0xAB-filled gaps before and after i
 every kernel on ragged sizes the gaps must be untouched."""
 import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 

@@ -188,7 +188,6 @@ def test_collision_rule_equals_reference_polygons():
     from oracle.ref_loader import load_reference_env, quiet, reference_available
     if not reference_available():
         pytest.skip("reference tree not present")
-    import sys
     env = load_reference_env()
     from shapely.geometry import Polygon          # the shim put on sys.path by the loader
     rng = np.random.default_rng(0)
