@@ -223,6 +223,11 @@ def run_b200(args):
     K, W = args.steps, args.warmup
 
     reducer = mg.AsyncStatsReducer(env) if world > 1 else None
+    if reducer is not None:                               # NCCL communicator set-up happens here, untimed
+        reducer.submit()
+        reducer.latest()
+        torch.cuda.synchronize()
+        reducer.submissions = 0
 
     def timed_region(shards, K, W, sample_clocks):
         """W warm-up + K timed mg_step launches round-robin over `shards`; returns (ms, G, eager, clocks)."""
