@@ -134,7 +134,6 @@ class MergeVecEnv:
         self.constants = nat.constants()
 
         dev = self.device
-        f64 = dict(dtype=torch.float64, device=dev)
         # one contiguous state allocation: 6 float64 arrays + the uint32 meta array, each padded to a
         # multiple of 32 envs (keeps every array 256-byte aligned)
         n32 = (n + 31) // 32 * 32
@@ -214,7 +213,8 @@ class MergeVecEnv:
     def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """`MergeEnv.reset()` (merging_env.py:208-230) for all envs, or where `mask` is set.
 
-        Returns obs f32[N,10] (current slot).  Deterministic start: pos=50, vel=20 for both cars.
+        Returns obs f32[N,10] (current slot).  Start state per `reset_mode`: fixed pos=50, vel=20 for
+        both cars (the reference's live code), or the random start of its commented-out lines.
         """
         m = None
         if mask is not None:
