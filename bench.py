@@ -299,6 +299,32 @@ def run_b200(args):
     # same kernel, ONE shard stepped in place: its 54.5 MB state is partly L2-resident between steps
     ms_warm, _, _, _ = timed_region(envs[:1], K, W, False)
 
+    # ---- cross-check of the L2 methodology: ONE shard stepped in place with L2 flushed (a 512 MB
+    #      buffer overwritten) before every timed launch, each launch bracketed by its own events ------
+    flushed = None
+    if args.flush_steps > 0:
+        fl = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        fr = torch.zeros(64 << 20, dtype=torch.int64, device=dev)          # 512 MB, only ever read
+        sink = torch.zeros((), dtype=torch.int64, device=dev)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.flush_steps)]
+        for i, (a, b) in enumerate(evs):
+            fl.fill_(i & 0xFF)                            # evicts the shard's state and outputs from L2 ...
+            sink += fr.sum()                              # ... and a read pass leaves L2 full of CLEAN lines, so
+            a.record()                                    # the timed launch does not pay for the flush's write-back
+            env.step_async(acts1[i % A], acts2[i % A])
+            b.record()
+        torch.cuda.synchronize()
+        fms = sorted(a.elapsed_time(b) for a, b in evs)
+        fmed = fms[len(fms) // 2]
+        flushed = {"ms_per_step_median": fmed, "ms_per_step_min": fms[0], "steps": len(fms),
+                   "value": n / (fmed * 1e-3), "unit": UNIT + " per GPU",
+                   "frac_of_peak": n * BYTES_PER_ENV_STEP / (fmed * 1e-3) / 1e9 / peak,
+                   "note": "single shard in place; before every launch 512 MB are written and then 512 MB read to "
+                           "flush the 126 MB L2 (leaving clean lines); one event pair per eager launch, so the "
+                           "figure includes launch/event overhead and has no PDL or graph overlap"}
+        del fl, fr
+
     # ---- extra: K fused steps per launch with in-kernel Philox actions (mg_rollout), all outputs on ----
     RK = args.rollout_k
     rollout = None
@@ -395,6 +421,7 @@ def run_b200(args):
                         "note": "one 2^20-env shard stepped in place (the literal 1M-envs/GPU deployment): its "
                                 "54.5 MB state is partly L2-resident between steps, so it runs faster than the "
                                 "HBM roofline allows; not used for value/roofline"},
+            "l2_flushed": flushed,
             "rollout_fused": rollout,
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "collision_rate", "merge_success_rate",
@@ -421,6 +448,7 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=200)
     ap.add_argument("--mix-steps", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--flush-steps", type=int, default=100, help="launches of the L2-flushed cross-check (0 = skip)")
     ap.add_argument("--rollout-k", type=int, default=32, help="steps per mg_rollout launch for the extra rollout_fused figure (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-graph", action="store_true")
