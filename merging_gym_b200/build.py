@@ -14,7 +14,7 @@ import sys
 
 from ._paths import CSRC, INCLUDE_DIR, LIB_DIR, LIB_PATH
 
-SOURCES = [os.path.join(CSRC, "merge_kernels.cu"), os.path.join(CSRC, "mlp_kernels.cu"),
+SOURCES = [os.path.join(CSRC, "merge_kernels.cu"), os.path.join(CSRC, "mlp_kernels.cu"), os.path.join(CSRC, "mlp_tc_kernels.cu"),
            os.path.join(CSRC, "record_kernels.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "merge_device.cuh"), os.path.join(CSRC, "abi_common.h"),
                   os.path.join(INCLUDE_DIR, "merging_b200.h")]

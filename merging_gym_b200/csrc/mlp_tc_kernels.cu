@@ -1,0 +1,319 @@
+// mlp_tc_kernels.cu — tensor-core version of the Q-network forward + arg-max (sm_100a: tcgen05 + TMEM).
+//
+// Same operator as mlp_kernels.cu (`Net(in, out)`: Linear(in,200)-ReLU-Linear(200,100)-ReLU-
+// Linear(100,out) + arg-max; scripts/main.py:30-47, hdqn.py:38-55), but the 200x100 layer — 89 % of the
+// FLOPs — runs on the 5th-generation tensor cores as a "3xTF32" product that keeps fp32-level
+// accuracy:   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,   a_hi = tf32(a) (top 19 bits), a_lo = a - a_hi
+// (the tensor core reads the top 19 bits of an fp32 operand, so a_lo loses only bits below 2^-22 |a|).
+// Opt-in (`MLPPolicy(backend="tf32x3")`); the FFMA kernel stays the default because it evaluates
+// exactly the reference's fp32 arithmetic.
+//
+// One persistent CTA per SM, tile = 128 envs (UMMA M = 128, N = 112 = 100 neurons + zero pad, K = 8):
+//   warps 0-3  producers : thread = env; layer 1 for one K-step (8 hidden units) at a time on the CUDA
+//                          cores, split into hi/lo and written straight into the canonical K-major
+//                          core-matrix layout of a 4-stage shared-memory ring  -> mbarrier full[s]
+//   warp  8    MMA issue : one thread; per K-step three tcgen05.mma.kind::tf32 (hi*hi, lo*hi, hi*lo)
+//                          accumulating in TMEM; tcgen05.commit -> empty[s] / tmem_full[b]
+//   warps 4-7  epilogue  : tcgen05.ld of the 128x112 fp32 accumulator (row = env), bias + ReLU, the
+//                          100x{5,3} layer and the arg-max in registers, one action byte per thread
+// TMEM: 2 accumulator buffers x 128 columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Shared memory: W2 hi + lo in canonical layout 2 x 89.6 KB (prepared on the host), A ring 32 KB,
+// W1 / W3 / biases 11 KB.  Every mbarrier wait is bounded and traps instead of hanging.
+#include "abi_common.h"
+
+namespace mgtc {
+
+constexpr int H1 = 200, H2 = 100;
+constexpr int TM = 128;                       // envs per tile = UMMA M
+constexpr int UN = 112;                       // UMMA N (multiple of 16 for M = 128)
+constexpr int KSTEPS = H1 / 8;                // 25 K-steps of 8 (tf32: 32 bytes of K per MMA)
+constexpr int STAGES = 4;
+constexpr int A_STEP = (TM / 8) * 256;        // 4096 B : 16 row groups x 2 core matrices x 128 B
+constexpr int B_STEP = (UN / 8) * 256;        // 3584 B
+constexpr int B_BYTES = KSTEPS * B_STEP;      // 89 600 B per hi / lo copy
+constexpr int TMEM_COLS = 256;                // 2 accumulator buffers x 128 columns
+constexpr int NUM_THREADS = 288;              // 4 producer warps + 4 epilogue warps + 1 MMA warp
+constexpr int MAX_OUT = 8;
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+template <int IN, int OUT>
+struct Smem {
+    unsigned char b_hi[B_BYTES];              // canonical K-major core-matrix layout, see make_desc
+    unsigned char b_lo[B_BYTES];
+    unsigned char a_hi[STAGES][A_STEP];
+    unsigned char a_lo[STAGES][A_STEP];
+    float w1[IN][H1];
+    float w3[OUT][H2];
+    float b1[H1], b2[H2 + 12], b3[MAX_OUT];
+    unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// tcgen05 shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes stored as
+// 128 contiguous bytes; LBO = byte distance between the two core matrices of a K-step (128), SBO = byte
+// distance between 8-row groups (256).  Verified numerically in profiles/exp_tcgen05.cu.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void mbar_init(unsigned long long *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < kSpinLimit && !done; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(b)), "r"(parity)
+            : "memory");
+    }
+    if (!done) __trap();                      // never hang the GPU on a protocol bug
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long *b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+
+template <int IN>
+__device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal, int64_t e,
+                                         int64_t n, int obs_dim, float (&x)[IN]) {
+    const int off = IN - obs_dim;
+    if (e < n) {
+        if (off) x[0] = (float)goal[e];
+        const float2 *src = reinterpret_cast<const float2 *>(obs + e * obs_dim);
+#pragma unroll
+        for (int i = 0; i < (IN - (IN & 1)) / 2; ++i) {
+            const float2 v = __ldg(src + i);
+            x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < IN; ++i) x[i] = 0.f;
+    }
+}
+
+template <int IN, int OUT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
+                  const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2_tc,
+                  const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
+                  uint8_t *__restrict__ act, float *__restrict__ q_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem<IN, OUT> &S = *reinterpret_cast<Smem<IN, OUT> *>(smem_raw);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int64_t n_tiles = (n + TM - 1) / TM;
+
+    // ---- one-time setup: weights -> smem, barriers, TMEM -------------------------------------------
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(w2_tc);          // [hi | lo], already canonical
+        float4 *dst = reinterpret_cast<float4 *>(S.b_hi);
+        for (int i = t; i < 2 * B_BYTES / 16; i += NUM_THREADS) dst[i] = __ldg(src + i);
+        const float4 *s1 = reinterpret_cast<const float4 *>(w1t);
+        float4 *d1 = reinterpret_cast<float4 *>(&S.w1[0][0]);
+        for (int i = t; i < IN * H1 / 4; i += NUM_THREADS) d1[i] = __ldg(s1 + i);
+        for (int i = t; i < OUT * H2; i += NUM_THREADS) (&S.w3[0][0])[i] = w3[i];
+        for (int i = t; i < H1; i += NUM_THREADS) S.b1[i] = b1[i];
+        for (int i = t; i < H2 + 12; i += NUM_THREADS) S.b2[i] = i < H2 ? b2[i] : 0.f;
+        if (t < OUT) S.b3[t] = b3[t];
+    }
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], TM); mbar_init(&S.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], TM); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W2 hi/lo written by the generic proxy
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                     "r"((uint32_t)TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = S.tmem_base;
+
+    if (warp < 4) {
+        // =================================== PRODUCERS: layer 1 ===================================
+        const int m = t;                                        // env row of the tile
+        const uint32_t row_off = (uint32_t)((m >> 3) * 256 + (m & 7) * 16);
+        uint32_t it = 0;                                        // global K-step counter -> stage / phase
+        float xr[IN];
+        load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m, n, obs_dim, xr);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            float xn[IN];
+            load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m, n, obs_dim, xn);    // next tile's row, in flight
+            for (int ks = 0; ks < KSTEPS; ++ks, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                // 8 hidden units of this K-step: h = relu(b1 + sum_i x_i W1[i][k])
+                const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[8 * ks]);
+                const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[8 * ks + 4]);
+                float2 h01 = make_float2(ba.x, ba.y), h23 = make_float2(ba.z, ba.w);
+                float2 h45 = make_float2(bb.x, bb.y), h67 = make_float2(bb.z, bb.w);
+#pragma unroll
+                for (int i = 0; i < IN; ++i) {
+                    const float4 wa = *reinterpret_cast<const float4 *>(&S.w1[i][8 * ks]);
+                    const float4 wb = *reinterpret_cast<const float4 *>(&S.w1[i][8 * ks + 4]);
+                    const float2 xx = make_float2(xr[i], xr[i]);
+                    h01 = __ffma2_rn(xx, make_float2(wa.x, wa.y), h01);
+                    h23 = __ffma2_rn(xx, make_float2(wa.z, wa.w), h23);
+                    h45 = __ffma2_rn(xx, make_float2(wb.x, wb.y), h45);
+                    h67 = __ffma2_rn(xx, make_float2(wb.z, wb.w), h67);
+                }
+                float h[8] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y, h67.x, h67.y};
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = fmaxf(h[j], 0.f);
+                    hi[j] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // what kind::tf32 reads
+                    lo[j] = v - hi[j];                                           // exact
+                }
+                mbar_wait(&S.empty[s], ph ^ 1u);                // MMAs that read this stage have completed
+                unsigned char *ah = S.a_hi[s] + row_off, *al = S.a_lo[s] + row_off;
+                *reinterpret_cast<float4 *>(ah) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(ah + 128) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<float4 *>(al) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4 *>(al + 128) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core
+                mbar_arrive(&S.full[s]);
+            }
+#pragma unroll
+            for (int i = 0; i < IN; ++i) xr[i] = xn[i];
+        }
+    } else if (warp == 8) {
+        // =================================== MMA ISSUER ==========================================
+        if (lane == 0) {
+            uint32_t it = 0, tl = 0;
+            const uint32_t b_hi = smem_u32(S.b_hi), b_lo = smem_u32(S.b_lo);
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+                const uint32_t buf = tl & 1u;
+                mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);            // epilogue drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + buf * 128u;
+                for (int ks = 0; ks < KSTEPS; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&S.full[s], (it / STAGES) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t ahi = make_desc(smem_u32(S.a_hi[s])), alo = make_desc(smem_u32(S.a_lo[s]));
+                    const uint64_t bhi = make_desc(b_hi + ks * B_STEP), blo = make_desc(b_lo + ks * B_STEP);
+                    umma_tf32(d, ahi, bhi, ks > 0 ? 1u : 0u);
+                    umma_tf32(d, alo, bhi, 1u);
+                    umma_tf32(d, ahi, blo, 1u);
+                    umma_commit(&S.empty[s]);                   // stage reusable once these MMAs are done
+                }
+                umma_commit(&S.tmem_full[buf]);                 // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // =================================== EPILOGUE: layer 3 + arg-max ===========================
+        const int q4 = warp - 4;                                // TMEM lane quarter of this warp (warp % 4)
+        const int m = q4 * 32 + lane;
+        uint32_t tl = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            const uint32_t buf = tl & 1u;
+            mbar_wait(&S.tmem_full[buf], (tl >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + buf * 128u + ((uint32_t)(q4 * 32) << 16);
+            float q[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) q[o] = S.b3[o];
+#pragma unroll
+            for (int c0 = 0; c0 < UN; c0 += 16) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (c0 + j < H2) {
+                        const float h = fmaxf(__uint_as_float(v[j]) + S.b2[c0 + j], 0.f);
+#pragma unroll
+                        for (int o = 0; o < OUT; ++o) q[o] = fmaf(h, S.w3[o][c0 + j], q[o]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&S.tmem_empty[buf]);                    // this thread is done reading the buffer
+            const int64_t e = tile * TM + m;
+            if (e < n) {
+                int best = 0;
+                float bv = q[0];
+#pragma unroll
+                for (int o = 1; o < OUT; ++o)
+                    if (q[o] > bv) { bv = q[o]; best = o; }     // first maximum, like torch.max
+                act[e] = (uint8_t)best;
+                if (q_out) {
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) q_out[e * OUT + o] = q[o];
+                }
+            }
+        }
+    }
+    // ---- teardown -------------------------------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+}
+
+template <int IN, int OUT>
+cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t, const float *b1,
+                   const float *w2_tc, const float *b2, const float *w3, const float *b3, uint8_t *act, float *q_out,
+                   cudaStream_t st) {
+    auto kern = mlp_act_tc_kernel<IN, OUT>;
+    const size_t smem = sizeof(Smem<IN, OUT>) + 1024;           // slack for the 1024-byte alignment of the base
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (n + TM - 1) / TM;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    kern<<<grid, NUM_THREADS, smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, act, q_out);
+    return cudaGetLastError();
+}
+
+}  // namespace mgtc
+
+extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
+                                    int32_t out_dim, const float *w1t, const float *b1, const float *w2_tc,
+                                    const float *b2, const float *w3, const float *b3, uint8_t *actions,
+                                    float *q_out_or_null, void *stream) {
+    using namespace mg_abi;
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
+    if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
+        return fail(MG_ERR_BAD_SIZE, "mg_mlp_act_tc supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs");
+    if (n == 0) return MG_OK;
+    if (!obs || !w1t || !b1 || !w2_tc || !b2 || !w3 || !b3 || !actions)
+        return fail(MG_ERR_NULL_POINTER, "mg_mlp_act_tc: NULL pointer");
+    if (!aligned16(obs) || !aligned16(w1t) || !aligned16(w2_tc))
+        return fail(MG_ERR_ALIGNMENT, "obs and weight arrays must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+#define MG_TC_CASE(I, O) \
+    if (in_dim == I && out_dim == O) e = mgtc::launch<I, O>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st); else
+    MG_TC_CASE(10, 5) MG_TC_CASE(10, 3) MG_TC_CASE(11, 5) MG_TC_CASE(11, 3) e = cudaErrorInvalidValue;
+#undef MG_TC_CASE
+    if (e) return cuda_fail(e, "mg_mlp_act_tc launch");
+    return MG_OK;
+}

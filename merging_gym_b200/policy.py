@@ -9,9 +9,11 @@ Reference pieces mirrored here
     with probability Phi(0.7) ~ 0.758 (main.py:103, hdqn.py:84, 168) — note it is NOT epsilon-greedy.
   * `goal_status` (hdqn.py:223-236) and the opponent view `state[5:] + state[:5]` (main.py:199).
 
-`backend="fused"` runs the hand-written CUDA kernel `mg_mlp_act` (one launch: three layers,
-bias, ReLU, arg-max, fp32 FFMA); `backend="torch"` is the plain PyTorch fp32 reference of the same
-op (cuBLAS), kept for the numerics tests.
+`backend="fused"` (default) runs the hand-written CUDA kernel `mg_mlp_act` (one launch: three layers,
+bias, ReLU, arg-max, exactly the reference's fp32 arithmetic on FFMA2); `backend="tf32x3"` runs
+`mg_mlp_act_tc`, the same operator with the 200x100 layer on the tcgen05 tensor cores as an
+error-compensated 3xTF32 product (fp32-level accuracy, not bit-identical); `backend="torch"` is the
+plain PyTorch fp32 reference of the same op (cuBLAS), kept for the numerics tests.
 """
 from __future__ import annotations
 
@@ -36,8 +38,8 @@ class MLPPolicy:
 
     def __init__(self, in_dim: int = 10, out_dim: int = 5, device="cuda", state_dict: Optional[dict] = None,
                  seed: Optional[int] = None, backend: str = "fused"):
-        if backend not in ("fused", "torch"):
-            raise ValueError("backend must be 'fused' or 'torch'")
+        if backend not in ("fused", "tf32x3", "torch"):
+            raise ValueError("backend must be 'fused', 'tf32x3' or 'torch'")
         self.in_dim, self.out_dim, self.backend = int(in_dim), int(out_dim), backend
         self.device = torch.device(device)
         if state_dict is None:
@@ -69,6 +71,17 @@ class MLPPolicy:
         w2p = torch.zeros(HIDDEN1, 4, 28, dtype=torch.float32, device=self.device)
         w2p[:, :, :25] = self.w2.t().reshape(HIDDEN1, 4, 25)
         self.w2_p = w2p.contiguous()
+        # tensor-core backend: W2 as the UMMA B operand (N = 112 rows = 100 neurons + zero pad, K-major),
+        # split into tf32 hi (top 19 bits) and lo = w - hi, each in the canonical core-matrix layout
+        # [K-step 25][row group 14][k half 2][row 8][k 4]
+        bp = torch.zeros(112, HIDDEN1, dtype=torch.float32, device=self.device)
+        bp[:HIDDEN2] = self.w2
+        hi = (bp.view(torch.int32) & -8192).view(torch.float32)
+        lo = bp - hi
+
+        def canon(x):
+            return x.view(14, 8, 25, 2, 4).permute(2, 0, 3, 1, 4).contiguous().view(-1)
+        self.w2_tc = torch.cat([canon(hi), canon(lo)]).contiguous()
 
     def state_dict(self) -> dict:
         return {"fc1.weight": self.w1, "fc1.bias": self.b1, "fc2.weight": self.w2, "fc2.bias": self.b2,
@@ -115,12 +128,18 @@ class MLPPolicy:
             raise ValueError("obs/goal widths do not match the network input")
         if goal is not None and not (goal.dtype == torch.uint8 and goal.is_contiguous()):
             raise ValueError("goal must be a contiguous uint8 tensor")
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
-            nat.check(lib.mg_mlp_act(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
-                                     _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_p), _ptr(self.b2),
-                                     _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out),
-                                     C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
-                      "mg_mlp_act")
+            if self.backend == "tf32x3":
+                nat.check(lib.mg_mlp_act_tc(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
+                                            _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_tc), _ptr(self.b2),
+                                            _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), stream),
+                          "mg_mlp_act_tc")
+            else:
+                nat.check(lib.mg_mlp_act(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
+                                         _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_p), _ptr(self.b2),
+                                         _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), stream),
+                          "mg_mlp_act")
         return out
 
     __call__ = act

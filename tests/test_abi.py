@@ -30,7 +30,7 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     assert declared_symbols() == sorted([
         "mg_version", "mg_last_error", "mg_get_constants", "mg_default_rewards", "mg_reset",
-        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_mlp_act",
+        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_mlp_act", "mg_mlp_act_tc",
         "mg_record_transitions"])
 
 
