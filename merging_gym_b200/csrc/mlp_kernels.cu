@@ -50,10 +50,11 @@ struct Smem {
 template <int IN>
 __device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal,
                                          int64_t e, int64_t n, int obs_dim, float (&x)[IN]) {
-    const int off = IN - obs_dim;      // 1 when a goal column is prepended (hdqn.py:291)
+    constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
+    (void)obs_dim;
     if (e < n) {
         if (off) x[0] = (float)goal[e];
-        const float2 *src = reinterpret_cast<const float2 *>(obs + e * obs_dim);
+        const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
         for (int i = 0; i < (IN - (IN & 1)) / 2; ++i) {     // obs_dim is 10: five float2
             const float2 v = __ldg(src + i);

@@ -9,12 +9,12 @@
 // exactly the reference's fp32 arithmetic.
 //
 // One persistent CTA per SM, tile = 128 envs (UMMA M = 128, N = 112 = 100 neurons + zero pad, K = 8):
-//   warps 0-3  producers : thread = env; layer 1 for one K-step (8 hidden units) at a time on the CUDA
-//                          cores, split into hi/lo and written straight into the canonical K-major
-//                          core-matrix layout of a 4-stage shared-memory ring  -> mbarrier full[s]
-//   warp  8    MMA issue : one thread; per K-step three tcgen05.mma.kind::tf32 (hi*hi, lo*hi, hi*lo)
+//   warps 0-7  producers : thread = (env pair, 4 hidden units of the stage); layer 1 on the CUDA cores
+//                          (FFMA2), split into hi/lo and written straight into the canonical K-major
+//                          core-matrix layout of a 2-stage ring (stage = 2 K-steps) -> full[s]
+//   warp  12   MMA issue : one thread; per K-step three tcgen05.mma.kind::tf32 (hi*hi, lo*hi, hi*lo)
 //                          accumulating in TMEM; tcgen05.commit -> empty[s] / tmem_full[b]
-//   warps 4-7  epilogue  : tcgen05.ld of the 128x112 fp32 accumulator (row = env), bias + ReLU, the
+//   warps 8-11 epilogue  : tcgen05.ld of the 128x112 fp32 accumulator (row = env), bias + ReLU, the
 //                          100x{5,3} layer and the arg-max in registers, one action byte per thread
 // TMEM: 2 accumulator buffers x 128 columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Shared memory: W2 hi + lo in canonical layout 2 x 89.6 KB (prepared on the host), A ring 32 KB,
@@ -27,12 +27,14 @@ constexpr int H1 = 200, H2 = 100;
 constexpr int TM = 128;                       // envs per tile = UMMA M
 constexpr int UN = 112;                       // UMMA N (multiple of 16 for M = 128)
 constexpr int KSTEPS = H1 / 8;                // 25 K-steps of 8 (tf32: 32 bytes of K per MMA)
-constexpr int STAGES = 4;
+constexpr int STAGES = 2;                     // ring stages; one stage = 2 K-steps (16 hidden units)
+constexpr int NSTAGE_TILE = (KSTEPS + 1) / 2; // 13 stage fills per tile (the last holds one K-step)
 constexpr int A_STEP = (TM / 8) * 256;        // 4096 B : 16 row groups x 2 core matrices x 128 B
 constexpr int B_STEP = (UN / 8) * 256;        // 3584 B
 constexpr int B_BYTES = KSTEPS * B_STEP;      // 89 600 B per hi / lo copy
 constexpr int TMEM_COLS = 256;                // 2 accumulator buffers x 128 columns
-constexpr int NUM_THREADS = 288;              // 4 producer warps + 4 epilogue warps + 1 MMA warp
+constexpr int NUM_PRODUCERS = 256;            // 8 producer warps: thread = (env, which K-step of the stage)
+constexpr int NUM_THREADS = 416;              // 8 producer warps + 4 epilogue warps + 1 MMA warp
 constexpr int MAX_OUT = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -40,8 +42,8 @@ template <int IN, int OUT>
 struct Smem {
     unsigned char b_hi[B_BYTES];              // canonical K-major core-matrix layout, see make_desc
     unsigned char b_lo[B_BYTES];
-    unsigned char a_hi[STAGES][A_STEP];
-    unsigned char a_lo[STAGES][A_STEP];
+    unsigned char a_hi[STAGES][2][A_STEP];
+    unsigned char a_lo[STAGES][2][A_STEP];
     float w1[IN][H1];
     float w3[OUT][H2];
     float b1[H1], b2[H2 + 12], b3[MAX_OUT];
@@ -92,10 +94,11 @@ __device__ __forceinline__ void umma_commit(unsigned long long *b) {
 template <int IN>
 __device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal, int64_t e,
                                          int64_t n, int obs_dim, float (&x)[IN]) {
-    const int off = IN - obs_dim;
+    constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
+    (void)obs_dim;
     if (e < n) {
         if (off) x[0] = (float)goal[e];
-        const float2 *src = reinterpret_cast<const float2 *>(obs + e * obs_dim);
+        const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
         for (int i = 0; i < (IN - (IN & 1)) / 2; ++i) {
             const float2 v = __ldg(src + i);
@@ -132,12 +135,12 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         if (t < OUT) S.b3[t] = b3[t];
     }
     if (t == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], TM); mbar_init(&S.empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], NUM_PRODUCERS); mbar_init(&S.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], TM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W2 hi/lo written by the generic proxy
-    if (warp == 8) {
+    if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
                      "r"((uint32_t)TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -147,55 +150,64 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = S.tmem_base;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =================================== PRODUCERS: layer 1 ===================================
-        const int m = t;                                        // env row of the tile
-        const uint32_t row_off = (uint32_t)((m >> 3) * 256 + (m & 7) * 16);
-        uint32_t it = 0;                                        // global K-step counter -> stage / phase
-        float xr[IN];
-        load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m, n, obs_dim, xr);
+        // thread = (env pair {ep, ep+64}, quarter kq of the stage's 16 hidden units): a broadcast
+        // 128-bit load of W1 is shared by both envs (shared-memory bandwidth bounds this kernel)
+        const int ep = t & 63, kq = t >> 6;                     // kq: K-step half = kq >> 1, core matrix = kq & 1
+        const int half = kq >> 1, kg = kq & 1;
+        const int m0 = ep, m1 = ep + 64;
+        const uint32_t off0 = (uint32_t)((m0 >> 3) * 256 + kg * 128 + (m0 & 7) * 16);
+        const uint32_t off1 = (uint32_t)((m1 >> 3) * 256 + kg * 128 + (m1 & 7) * 16);
+        uint32_t it = 0;                                        // global stage-fill counter -> stage / phase
+        float x0[IN], x1[IN];
+        load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m0, n, obs_dim, x0);
+        load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m1, n, obs_dim, x1);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            float xn[IN];
-            load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m, n, obs_dim, xn);    // next tile's row, in flight
-            for (int ks = 0; ks < KSTEPS; ++ks, ++it) {
+            float n0[IN], n1[IN];                               // next tile's rows, in flight during this tile
+            load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m0, n, obs_dim, n0);
+            load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m1, n, obs_dim, n1);
+            for (int st = 0; st < NSTAGE_TILE; ++st, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
-                // 8 hidden units of this K-step: h = relu(b1 + sum_i x_i W1[i][k])
-                const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[8 * ks]);
-                const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[8 * ks + 4]);
-                float2 h01 = make_float2(ba.x, ba.y), h23 = make_float2(ba.z, ba.w);
-                float2 h45 = make_float2(bb.x, bb.y), h67 = make_float2(bb.z, bb.w);
+                const int ks = 2 * st + half;
+                const int k = 8 * ks + 4 * kg;                  // first of this thread's 4 hidden units
+                float4 h0, h1v;
+                if (ks < KSTEPS) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k]);
+                    float2 a01 = make_float2(bb.x, bb.y), a23 = make_float2(bb.z, bb.w), c01 = a01, c23 = a23;
 #pragma unroll
-                for (int i = 0; i < IN; ++i) {
-                    const float4 wa = *reinterpret_cast<const float4 *>(&S.w1[i][8 * ks]);
-                    const float4 wb = *reinterpret_cast<const float4 *>(&S.w1[i][8 * ks + 4]);
-                    const float2 xx = make_float2(xr[i], xr[i]);
-                    h01 = __ffma2_rn(xx, make_float2(wa.x, wa.y), h01);
-                    h23 = __ffma2_rn(xx, make_float2(wa.z, wa.w), h23);
-                    h45 = __ffma2_rn(xx, make_float2(wb.x, wb.y), h45);
-                    h67 = __ffma2_rn(xx, make_float2(wb.z, wb.w), h67);
-                }
-                float h[8] = {h01.x, h01.y, h23.x, h23.y, h45.x, h45.y, h67.x, h67.y};
-                float hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float v = fmaxf(h[j], 0.f);
-                    hi[j] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);   // what kind::tf32 reads
-                    lo[j] = v - hi[j];                                           // exact
+                    for (int i = 0; i < IN; ++i) {
+                        const float4 w = *reinterpret_cast<const float4 *>(&S.w1[i][k]);
+                        const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+                        const float2 xa = make_float2(x0[i], x0[i]), xb = make_float2(x1[i], x1[i]);
+                        a01 = __ffma2_rn(xa, w01, a01); a23 = __ffma2_rn(xa, w23, a23);
+                        c01 = __ffma2_rn(xb, w01, c01); c23 = __ffma2_rn(xb, w23, c23);
+                    }
+                    h0 = make_float4(fmaxf(a01.x, 0.f), fmaxf(a01.y, 0.f), fmaxf(a23.x, 0.f), fmaxf(a23.y, 0.f));
+                    h1v = make_float4(fmaxf(c01.x, 0.f), fmaxf(c01.y, 0.f), fmaxf(c23.x, 0.f), fmaxf(c23.y, 0.f));
                 }
                 mbar_wait(&S.empty[s], ph ^ 1u);                // MMAs that read this stage have completed
-                unsigned char *ah = S.a_hi[s] + row_off, *al = S.a_lo[s] + row_off;
-                *reinterpret_cast<float4 *>(ah) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4 *>(ah + 128) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<float4 *>(al) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<float4 *>(al + 128) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core
-                mbar_arrive(&S.full[s]);
+                if (ks < KSTEPS) {
+                    auto split_store = [&](const float4 &h, uint32_t off) {
+                        float4 hi, lo;                          // hi = what kind::tf32 reads (top 19 bits), lo exact
+                        hi.x = __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u); lo.x = h.x - hi.x;
+                        hi.y = __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u); lo.y = h.y - hi.y;
+                        hi.z = __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u); lo.z = h.z - hi.z;
+                        hi.w = __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u); lo.w = h.w - hi.w;
+                        *reinterpret_cast<float4 *>(S.a_hi[s][half] + off) = hi;
+                        *reinterpret_cast<float4 *>(S.a_lo[s][half] + off) = lo;
+                    };
+                    split_store(h0, off0);
+                    split_store(h1v, off1);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core
+                }
+                mbar_arrive(&S.full[s]);                        // (a per-warp elected arrive measured slower)
             }
 #pragma unroll
-            for (int i = 0; i < IN; ++i) xr[i] = xn[i];
+            for (int i = 0; i < IN; ++i) { x0[i] = n0[i]; x1[i] = n1[i]; }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // =================================== MMA ISSUER ==========================================
         if (lane == 0) {
             uint32_t it = 0, tl = 0;
@@ -205,15 +217,21 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                 mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);            // epilogue drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem_base + buf * 128u;
-                for (int ks = 0; ks < KSTEPS; ++ks, ++it) {
+                for (int st = 0; st < NSTAGE_TILE; ++st, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&S.full[s], (it / STAGES) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t ahi = make_desc(smem_u32(S.a_hi[s])), alo = make_desc(smem_u32(S.a_lo[s]));
-                    const uint64_t bhi = make_desc(b_hi + ks * B_STEP), blo = make_desc(b_lo + ks * B_STEP);
-                    umma_tf32(d, ahi, bhi, ks > 0 ? 1u : 0u);
-                    umma_tf32(d, alo, bhi, 1u);
-                    umma_tf32(d, ahi, blo, 1u);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int ks = 2 * st + half;
+                        if (ks < KSTEPS) {
+                            const uint64_t ahi = make_desc(smem_u32(S.a_hi[s][half])), alo = make_desc(smem_u32(S.a_lo[s][half]));
+                            const uint64_t bhi = make_desc(b_hi + ks * B_STEP), blo = make_desc(b_lo + ks * B_STEP);
+                            umma_tf32(d, ahi, bhi, ks > 0 ? 1u : 0u);
+                            umma_tf32(d, alo, bhi, 1u);
+                            umma_tf32(d, ahi, blo, 1u);
+                        }
+                    }
                     umma_commit(&S.empty[s]);                   // stage reusable once these MMAs are done
                 }
                 umma_commit(&S.tmem_full[buf]);                 // accumulator complete
@@ -222,7 +240,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         __syncwarp();
     } else {
         // =================================== EPILOGUE: layer 3 + arg-max ===========================
-        const int q4 = warp - 4;                                // TMEM lane quarter of this warp (warp % 4)
+        const int q4 = warp - 8;                                // TMEM lane quarter of this warp (warp % 4)
         const int m = q4 * 32 + lane;
         uint32_t tl = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
@@ -243,11 +261,19 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                     : "r"(taddr + (uint32_t)c0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (c0 + j < H2) {
-                        const float h = fmaxf(__uint_as_float(v[j]) + S.b2[c0 + j], 0.f);
+                for (int j4 = 0; j4 < 16; j4 += 4) {
+                    if (c0 + j4 < H2) {                         // 100 = 25 groups of 4: no partial group
+                        const float4 bias = *reinterpret_cast<const float4 *>(&S.b2[c0 + j4]);
+                        const float h0 = fmaxf(__uint_as_float(v[j4]) + bias.x, 0.f);
+                        const float h1 = fmaxf(__uint_as_float(v[j4 + 1]) + bias.y, 0.f);
+                        const float h2 = fmaxf(__uint_as_float(v[j4 + 2]) + bias.z, 0.f);
+                        const float h3 = fmaxf(__uint_as_float(v[j4 + 3]) + bias.w, 0.f);
 #pragma unroll
-                        for (int o = 0; o < OUT; ++o) q[o] = fmaf(h, S.w3[o][c0 + j], q[o]);
+                        for (int o = 0; o < OUT; ++o) {
+                            const float4 w = *reinterpret_cast<const float4 *>(&S.w3[o][c0 + j4]);
+                            q[o] = fmaf(h0, w.x, q[o]); q[o] = fmaf(h1, w.y, q[o]);
+                            q[o] = fmaf(h2, w.z, q[o]); q[o] = fmaf(h3, w.w, q[o]);
+                        }
                     }
                 }
             }
@@ -271,7 +297,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
     // ---- teardown -------------------------------------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8)
+    if (warp == 12)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
 }
 
