@@ -2,7 +2,7 @@
 """bench_policy.py — BASELINE.json configs[4]: pve rollout with the DQN policy forward in the loop,
 2^18 envs per GPU, observations and actions handed over on the device (no host round-trip).
 
-    python bench_policy.py [--envs 262144] [--steps 400] [--policy dqn|hdqn] [--backend fused|torch]
+    python bench_policy.py [--envs 262144] [--steps 400] [--policy dqn|hdqn] [--backend fused|tf32x3|torch]
 
 One step = fused Q-network forward + arg-max (`mg_mlp_act`) -> `mg_step` (pve, auto-reset), captured
 in a CUDA graph.  Prints one JSON line with env-steps/s and the share of the step spent in the env
@@ -41,7 +41,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 18)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--policy", default="dqn", choices=["dqn", "hdqn"])
-    ap.add_argument("--backend", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--backend", default="fused", choices=["fused", "tf32x3", "torch"])
     args = ap.parse_args()
     n = args.envs
     env = mg.MergeVecEnv(n, mode="pve", auto_reset=True, episode_info=False)

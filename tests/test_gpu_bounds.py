@@ -79,6 +79,9 @@ def test_no_kernel_writes_out_of_bounds(n, random_reset):
                                         p(ring), 50, None, p(counter), p(scratch), s), "record log")
     nat.check(lib.mg_mlp_act(p(obs), None, n, 10, 5, p(w1t), p(b1), p(w2t), p(b2), p(w3), p(b3), p(act_out),
                              p(q_out), s), "mlp")
+    w2tc = ar.take(4 * 2 * 25 * 14 * 2 * 8 * 4, 0)
+    nat.check(lib.mg_mlp_act_tc(p(obs), None, n, 10, 5, p(w1t), p(b1), p(w2tc), p(b2), p(w3), p(b3), p(act_out),
+                                p(q_out), s), "mlp tc")
     torch.cuda.synchronize()
     ar.check()
     assert int(counter.view(torch.int64)[0]) > 0
