@@ -9,9 +9,9 @@
 // exactly the reference's fp32 arithmetic.
 //
 // One persistent CTA per SM, tile = 128 envs (UMMA M = 128, N = 112 = 100 neurons + zero pad, K = 8):
-//   warps 0-7  producers : thread = (env pair, 4 hidden units of the stage); layer 1 on the CUDA cores
-//                          (FFMA2), split into hi/lo and written straight into the canonical K-major
-//                          core-matrix layout of a 2-stage ring (stage = 2 K-steps) -> full[s]
+//   warps 0-7  producers : two groups of 4 warps, each owning one slot of a 2-slot ring (slot = 2
+//                          K-steps); thread = (env pair, K-step): layer 1 on the CUDA cores (FFMA2), split
+//                          into hi/lo, written straight into the canonical K-major core-matrix layout -> full[s]
 //   warp  12   MMA issue : one thread; per K-step three tcgen05.mma.kind::tf32 (hi*hi, lo*hi, hi*lo)
 //                          accumulating in TMEM; tcgen05.commit -> empty[s] / tmem_full[b]
 //   warps 8-11 epilogue  : tcgen05.ld of the 128x112 fp32 accumulator (row = env), bias + ReLU, the
@@ -135,7 +135,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         if (t < OUT) S.b3[t] = b3[t];
     }
     if (t == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], NUM_PRODUCERS); mbar_init(&S.empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], NUM_PRODUCERS / 2); mbar_init(&S.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], TM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -152,42 +152,53 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
 
     if (warp < 8) {
         // =================================== PRODUCERS: layer 1 ===================================
-        // thread = (env pair {ep, ep+64}, quarter kq of the stage's 16 hidden units): a broadcast
-        // 128-bit load of W1 is shared by both envs (shared-memory bandwidth bounds this kernel)
-        const int ep = t & 63, kq = t >> 6;                     // kq: K-step half = kq >> 1, core matrix = kq & 1
-        const int half = kq >> 1, kg = kq & 1;
+        // Two independent groups of 4 warps; group g owns ring slot g and fills every second stage, so the
+        // write chain of one slot (wait empty -> STS -> proxy fence -> arrive) overlaps the MMAs of the other.
+        // thread = (env pair {ep, ep+64}, K-step kh of the stage): 8 hidden units for 2 envs.
+        const int grp = warp >> 2, tg = t & 127;
+        const int ep = tg & 63, kh = tg >> 6;
         const int m0 = ep, m1 = ep + 64;
-        const uint32_t off0 = (uint32_t)((m0 >> 3) * 256 + kg * 128 + (m0 & 7) * 16);
-        const uint32_t off1 = (uint32_t)((m1 >> 3) * 256 + kg * 128 + (m1 & 7) * 16);
-        uint32_t it = 0;                                        // global stage-fill counter -> stage / phase
+        const uint32_t off0 = (uint32_t)((m0 >> 3) * 256 + (m0 & 7) * 16);
+        const uint32_t off1 = (uint32_t)((m1 >> 3) * 256 + (m1 & 7) * 16);
         float x0[IN], x1[IN];
         load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m0, n, obs_dim, x0);
         load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m1, n, obs_dim, x1);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t tl = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             float n0[IN], n1[IN];                               // next tile's rows, in flight during this tile
             load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m0, n, obs_dim, n0);
             load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m1, n, obs_dim, n1);
-            for (int st = 0; st < NSTAGE_TILE; ++st, ++it) {
-                const int s = it % STAGES;
+            const uint32_t it0 = tl * NSTAGE_TILE;              // global stage-fill counter of this tile's stage 0
+            for (int st = (int)((grp + it0) & 1u); st < NSTAGE_TILE; st += 2) {     // stages with (it0 + st) % 2 == grp
+                const uint32_t it = it0 + (uint32_t)st;
+                const int s = it % STAGES;                      // == grp
                 const uint32_t ph = (it / STAGES) & 1u;
-                const int ks = 2 * st + half;
-                const int k = 8 * ks + 4 * kg;                  // first of this thread's 4 hidden units
-                float4 h0, h1v;
+                const int ks = 2 * st + kh;
+                float4 ha0, ha1, hb0, hb1;                      // env m0: units 0-3, 4-7; env m1: units 0-3, 4-7
                 if (ks < KSTEPS) {
-                    const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k]);
-                    float2 a01 = make_float2(bb.x, bb.y), a23 = make_float2(bb.z, bb.w), c01 = a01, c23 = a23;
+                    const int k = 8 * ks;
+                    const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[k]);
+                    const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k + 4]);
+                    float2 a01 = make_float2(ba.x, ba.y), a23 = make_float2(ba.z, ba.w), a45 = make_float2(bb.x, bb.y), a67 = make_float2(bb.z, bb.w);
+                    float2 c01 = a01, c23 = a23, c45 = a45, c67 = a67;
 #pragma unroll
                     for (int i = 0; i < IN; ++i) {
-                        const float4 w = *reinterpret_cast<const float4 *>(&S.w1[i][k]);
-                        const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+                        const float4 wa = *reinterpret_cast<const float4 *>(&S.w1[i][k]);
+                        const float4 wb = *reinterpret_cast<const float4 *>(&S.w1[i][k + 4]);
+                        const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+                        const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
                         const float2 xa = make_float2(x0[i], x0[i]), xb = make_float2(x1[i], x1[i]);
                         a01 = __ffma2_rn(xa, w01, a01); a23 = __ffma2_rn(xa, w23, a23);
+                        a45 = __ffma2_rn(xa, w45, a45); a67 = __ffma2_rn(xa, w67, a67);
                         c01 = __ffma2_rn(xb, w01, c01); c23 = __ffma2_rn(xb, w23, c23);
+                        c45 = __ffma2_rn(xb, w45, c45); c67 = __ffma2_rn(xb, w67, c67);
                     }
-                    h0 = make_float4(fmaxf(a01.x, 0.f), fmaxf(a01.y, 0.f), fmaxf(a23.x, 0.f), fmaxf(a23.y, 0.f));
-                    h1v = make_float4(fmaxf(c01.x, 0.f), fmaxf(c01.y, 0.f), fmaxf(c23.x, 0.f), fmaxf(c23.y, 0.f));
+                    ha0 = make_float4(fmaxf(a01.x, 0.f), fmaxf(a01.y, 0.f), fmaxf(a23.x, 0.f), fmaxf(a23.y, 0.f));
+                    ha1 = make_float4(fmaxf(a45.x, 0.f), fmaxf(a45.y, 0.f), fmaxf(a67.x, 0.f), fmaxf(a67.y, 0.f));
+                    hb0 = make_float4(fmaxf(c01.x, 0.f), fmaxf(c01.y, 0.f), fmaxf(c23.x, 0.f), fmaxf(c23.y, 0.f));
+                    hb1 = make_float4(fmaxf(c45.x, 0.f), fmaxf(c45.y, 0.f), fmaxf(c67.x, 0.f), fmaxf(c67.y, 0.f));
                 }
-                mbar_wait(&S.empty[s], ph ^ 1u);                // MMAs that read this stage have completed
+                mbar_wait(&S.empty[s], ph ^ 1u);                // MMAs that read this slot have completed
                 if (ks < KSTEPS) {
                     auto split_store = [&](const float4 &h, uint32_t off) {
                         float4 hi, lo;                          // hi = what kind::tf32 reads (top 19 bits), lo exact
@@ -195,11 +206,11 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                         hi.y = __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u); lo.y = h.y - hi.y;
                         hi.z = __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u); lo.z = h.z - hi.z;
                         hi.w = __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u); lo.w = h.w - hi.w;
-                        *reinterpret_cast<float4 *>(S.a_hi[s][half] + off) = hi;
-                        *reinterpret_cast<float4 *>(S.a_lo[s][half] + off) = lo;
+                        *reinterpret_cast<float4 *>(S.a_hi[s][kh] + off) = hi;
+                        *reinterpret_cast<float4 *>(S.a_lo[s][kh] + off) = lo;
                     };
-                    split_store(h0, off0);
-                    split_store(h1v, off1);
+                    split_store(ha0, off0); split_store(ha1, off0 + 128);
+                    split_store(hb0, off1); split_store(hb1, off1 + 128);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core
                 }
                 mbar_arrive(&S.full[s]);                        // (a per-warp elected arrive measured slower)

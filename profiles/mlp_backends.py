@@ -7,7 +7,7 @@ for n in (128, 1000, 5000, 1<<18):
     env = mg.MergeVecEnv(n, seed=3); env.rollout(120); obs = env.step(*env.sample_actions())[0].clone()
     for name, sdict in (("ckpt", sd), ("rand", None)):
         f = mg.MLPPolicy(10, 5, state_dict=sdict, seed=7)
-        tc = mg.MLPPolicy(10, 5, state_dict=f.state_dict(), backend="tf32x3")
+        tc = mg.MLPPolicy(10, 5, state_dict=f.state_dict(), backend=os.environ.get("TC", "tf32x3"))
         qf = torch.empty(n, 5, device='cuda'); qt = torch.empty(n, 5, device='cuda')
         af = f.act(obs, q_out=qf); at = tc.act(obs, q_out=qt)
         torch.cuda.synchronize()
