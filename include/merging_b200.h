@@ -203,9 +203,9 @@ MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, 
 /* Tensor-core variant of mg_mlp_act (tcgen05 + TMEM): the 200x100 layer as an error-compensated 3xTF32
  * product (a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) — fp32-level accuracy but not bit-identical to the
  * fp32 FFMA evaluation, hence a separate, opt-in entry point.  Same arguments except w2_tc: float
- * [2][25][14][2][8][4] = the tf32 hi part (top 19 bits) and the remainder lo = w - hi of fc2.weight
- * (zero-padded to 112 rows), each in the canonical UMMA K-major core-matrix layout
- * [K-step][8-row group][K half][row][4 k]. */
+ * [25][28][2][8][4] = fc2.weight (zero-padded to 112 rows) split into its tf32 hi part (top 19 bits; row
+ * groups 0-13) and the remainder lo = w - hi (row groups 14-27), stacked as one 224-row UMMA B operand in
+ * the canonical K-major core-matrix layout [K-step][8-row group][K half][row][4 k]. */
 MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                          int32_t out_dim, const float *w1t, const float *b1, const float *w2_tc,
                          const float *b2, const float *w3, const float *b3, uint8_t *actions,

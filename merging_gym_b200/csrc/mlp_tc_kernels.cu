@@ -12,12 +12,13 @@
 //   warps 0-7  producers : two groups of 4 warps, each owning one slot of a 2-slot ring (slot = 2
 //                          K-steps); thread = (env pair, K-step): layer 1 on the CUDA cores (FFMA2), split
 //                          into hi/lo, written straight into the canonical K-major core-matrix layout -> full[s]
-//   warp  12   MMA issue : one thread; per K-step three tcgen05.mma.kind::tf32 (hi*hi, lo*hi, hi*lo)
-//                          accumulating in TMEM; tcgen05.commit -> empty[s] / tmem_full[b]
+//   warp  12   MMA issue : one thread; per K-step two tcgen05.mma.kind::tf32: a_hi x [W2_hi ; W2_lo] (N = 224)
+//                          and a_lo x W2_hi (N = 112), accumulating in TMEM; tcgen05.commit -> empty[s] / tmem_full[b]
 //   warps 8-11 epilogue  : tcgen05.ld of the 128x112 fp32 accumulator (row = env), bias + ReLU, the
 //                          100x{5,3} layer and the arg-max in registers, one action byte per thread
-// TMEM: 2 accumulator buffers x 128 columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Shared memory: W2 hi + lo in canonical layout 2 x 89.6 KB (prepared on the host), A ring 32 KB,
+// TMEM: 2 accumulator buffers x 256 columns ([0,112): hi.hi + lo.hi, [112,224): hi.lo, summed in the epilogue),
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Shared memory: W2 as one stacked B operand [hi ; lo] of 224 rows, 179.2 KB (prepared on the host), A ring 32 KB,
 // W1 / W3 / biases 11 KB.  Every mbarrier wait is bounded and traps instead of hanging.
 #include "abi_common.h"
 
@@ -30,9 +31,9 @@ constexpr int KSTEPS = H1 / 8;                // 25 K-steps of 8 (tf32: 32 bytes
 constexpr int STAGES = 2;                     // ring stages; one stage = 2 K-steps (16 hidden units)
 constexpr int NSTAGE_TILE = (KSTEPS + 1) / 2; // 13 stage fills per tile (the last holds one K-step)
 constexpr int A_STEP = (TM / 8) * 256;        // 4096 B : 16 row groups x 2 core matrices x 128 B
-constexpr int B_STEP = (UN / 8) * 256;        // 3584 B
-constexpr int B_BYTES = KSTEPS * B_STEP;      // 89 600 B per hi / lo copy
-constexpr int TMEM_COLS = 256;                // 2 accumulator buffers x 128 columns
+constexpr int B_STEP = (2 * UN / 8) * 256;    // 7168 B: one K-step of the stacked B operand [W2_hi ; W2_lo] (224 rows)
+constexpr int B_BYTES = KSTEPS * B_STEP;      // 179 200 B
+constexpr int TMEM_COLS = 512;                // 2 accumulator buffers x 256 columns (224 used)
 constexpr int NUM_PRODUCERS = 256;            // 8 producer warps: thread = (env, which K-step of the stage)
 constexpr int NUM_THREADS = 416;              // 8 producer warps + 4 epilogue warps + 1 MMA warp
 constexpr int MAX_OUT = 8;
@@ -40,8 +41,7 @@ constexpr uint32_t kSpinLimit = 1u << 26;
 
 template <int IN, int OUT>
 struct Smem {
-    unsigned char b_hi[B_BYTES];              // canonical K-major core-matrix layout, see make_desc
-    unsigned char b_lo[B_BYTES];
+    unsigned char b_cat[B_BYTES];             // [K-step][28 row groups: W2_hi rows 0-111, W2_lo rows 112-223], canonical layout
     unsigned char a_hi[STAGES][2][A_STEP];
     unsigned char a_lo[STAGES][2][A_STEP];
     float w1[IN][H1];
@@ -61,7 +61,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
            ((uint64_t)1 << 46);
 }
 // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24); }
+constexpr uint32_t kIdesc112 = idesc_n(UN), kIdesc224 = idesc_n(2 * UN);
 
 __device__ __forceinline__ void mbar_init(unsigned long long *b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
@@ -80,11 +81,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity
     }
     if (!done) __trap();                      // never hang the GPU on a protocol bug
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned long long *b) {
@@ -123,9 +124,9 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
 
     // ---- one-time setup: weights -> smem, barriers, TMEM -------------------------------------------
     {
-        const float4 *src = reinterpret_cast<const float4 *>(w2_tc);          // [hi | lo], already canonical
-        float4 *dst = reinterpret_cast<float4 *>(S.b_hi);
-        for (int i = t; i < 2 * B_BYTES / 16; i += NUM_THREADS) dst[i] = __ldg(src + i);
+        const float4 *src = reinterpret_cast<const float4 *>(w2_tc);          // already in the canonical layout
+        float4 *dst = reinterpret_cast<float4 *>(S.b_cat);
+        for (int i = t; i < B_BYTES / 16; i += NUM_THREADS) dst[i] = __ldg(src + i);
         const float4 *s1 = reinterpret_cast<const float4 *>(w1t);
         float4 *d1 = reinterpret_cast<float4 *>(&S.w1[0][0]);
         for (int i = t; i < IN * H1 / 4; i += NUM_THREADS) d1[i] = __ldg(s1 + i);
@@ -222,12 +223,12 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         // =================================== MMA ISSUER ==========================================
         if (lane == 0) {
             uint32_t it = 0, tl = 0;
-            const uint32_t b_hi = smem_u32(S.b_hi), b_lo = smem_u32(S.b_lo);
+            const uint32_t b_cat = smem_u32(S.b_cat);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t buf = tl & 1u;
                 mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);            // epilogue drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d = tmem_base + buf * 128u;
+                const uint32_t d = tmem_base + buf * 256u;
                 for (int st = 0; st < NSTAGE_TILE; ++st, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&S.full[s], (it / STAGES) & 1u);
@@ -237,10 +238,11 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                         const int ks = 2 * st + half;
                         if (ks < KSTEPS) {
                             const uint64_t ahi = make_desc(smem_u32(S.a_hi[s][half])), alo = make_desc(smem_u32(S.a_lo[s][half]));
-                            const uint64_t bhi = make_desc(b_hi + ks * B_STEP), blo = make_desc(b_lo + ks * B_STEP);
-                            umma_tf32(d, ahi, bhi, ks > 0 ? 1u : 0u);
-                            umma_tf32(d, alo, bhi, 1u);
-                            umma_tf32(d, ahi, blo, 1u);
+                            const uint64_t bcat = make_desc(b_cat + ks * B_STEP);
+                            // columns [0,112) += a_hi.W2_hi, columns [112,224) += a_hi.W2_lo  (one N = 224 MMA: 123 cycles
+                            // instead of two N = 112 MMAs at 76 each, and A_hi is read once)
+                            umma_tf32(d, ahi, bcat, kIdesc224, ks > 0 ? 1u : 0u);
+                            umma_tf32(d, alo, bcat, kIdesc112, 1u);           // columns [0,112) += a_lo.W2_hi
                         }
                     }
                     umma_commit(&S.empty[s]);                   // stage reusable once these MMAs are done
@@ -258,19 +260,26 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
             const uint32_t buf = tl & 1u;
             mbar_wait(&S.tmem_full[buf], (tl >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + buf * 128u + ((uint32_t)(q4 * 32) << 16);
+            const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q4 * 32) << 16);
             float q[OUT];
 #pragma unroll
             for (int o = 0; o < OUT; ++o) q[o] = S.b3[o];
 #pragma unroll
             for (int c0 = 0; c0 < UN; c0 += 16) {
-                uint32_t v[16];
+                uint32_t v[16], u[16];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                     : "r"(taddr + (uint32_t)c0));
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                    : "r"(taddr + (uint32_t)(UN + c0)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
 #pragma unroll
                 for (int j4 = 0; j4 < 16; j4 += 4) {
                     if (c0 + j4 < H2) {                         // 100 = 25 groups of 4: no partial group

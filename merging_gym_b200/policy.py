@@ -73,15 +73,14 @@ class MLPPolicy:
         self.w2_p = w2p.contiguous()
         # tensor-core backend: W2 as the UMMA B operand (N = 112 rows = 100 neurons + zero pad, K-major),
         # split into tf32 hi (top 19 bits) and lo = w - hi, each in the canonical core-matrix layout
-        # [K-step 25][row group 14][k half 2][row 8][k 4]
+        # [K-step 25][row group 28 = 14 hi + 14 lo][k half 2][row 8][k 4]
         bp = torch.zeros(112, HIDDEN1, dtype=torch.float32, device=self.device)
         bp[:HIDDEN2] = self.w2
         hi = (bp.view(torch.int32) & -8192).view(torch.float32)
         lo = bp - hi
 
-        def canon(x):
-            return x.view(14, 8, 25, 2, 4).permute(2, 0, 3, 1, 4).contiguous().view(-1)
-        self.w2_tc = torch.cat([canon(hi), canon(lo)]).contiguous()
+        cat = torch.cat([hi, lo], dim=0)                      # 224 rows: hi 0-111, lo 112-223 (one stacked B operand)
+        self.w2_tc = cat.view(28, 8, 25, 2, 4).permute(2, 0, 3, 1, 4).contiguous().view(-1)
 
     def state_dict(self) -> dict:
         return {"fc1.weight": self.w1, "fc1.bias": self.b1, "fc2.weight": self.w2, "fc2.bias": self.b2,
