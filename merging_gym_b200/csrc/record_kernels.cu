@@ -78,41 +78,87 @@ scan_kernel(uint32_t *__restrict__ warp_counts, int64_t m, unsigned long long *_
 
 // format 0 (replay, main.py:115-119): [s(10), a_p, r_p, s'(10)]              22 floats, player p
 // format 1 (log, human_player.py:111) : [s(10), a1, a2, r1, r2]               14 floats
+// One warp handles 32 consecutive envs: their observation rows are one contiguous 1280-byte span, loaded
+// with coalesced 128-bit loads into shared memory; the selected lanes assemble their rows in shared memory
+// at consecutive ranks; the warp then writes that contiguous piece of the ring with coalesced stores.
+template <int FORMAT>
 __global__ void __launch_bounds__(kBlock)
 write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_next,
              const float *__restrict__ term_obs, const uint8_t *__restrict__ a1, const uint8_t *__restrict__ a2,
              const float *__restrict__ rew, const uint8_t *__restrict__ done, const uint8_t *__restrict__ info,
-             int64_t n, int mask_mode, int format, int player, const uint32_t *__restrict__ warp_offsets,
+             int64_t n, int mask_mode, int player, const uint32_t *__restrict__ warp_offsets,
              const unsigned long long *__restrict__ base, const unsigned long long *__restrict__ counter,
              float *__restrict__ ring, int64_t capacity, int32_t *__restrict__ env_ids) {
-    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    constexpr int WIDTH = FORMAT == 0 ? 2 * kObs + 2 : kObs + 4;
+    constexpr int kWarps = kBlock / 32;
+    __shared__ __align__(16) float s_prev[kWarps][32 * kObs];
+    __shared__ __align__(16) float s_next[kWarps][FORMAT == 0 ? 32 * kObs : 4];
+    __shared__ __align__(16) float s_out[kWarps][32 * WIDTH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w0 = ((int64_t)blockIdx.x * kBlock + warp * 32);          // first env of this warp
+    if (w0 >= n) return;
+    const int64_t e = w0 + lane;
+    const int rows = (int)min((int64_t)32, n - w0);
+    // ---- coalesced loads of the warp's observation rows (w0 * 40 bytes is 16-byte aligned: w0 % 32 == 0) ----
+    {
+        const float4 *gp = reinterpret_cast<const float4 *>(obs_prev + w0 * kObs);
+        float4 *sp = reinterpret_cast<float4 *>(s_prev[warp]);
+        for (int i = lane; i < rows * kObs / 4; i += 32) sp[i] = __ldg(gp + i);
+        for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) s_prev[warp][i] = obs_prev[w0 * kObs + i];
+        if (FORMAT == 0) {
+            const float4 *gn = reinterpret_cast<const float4 *>(obs_next + w0 * kObs);
+            float4 *sn = reinterpret_cast<float4 *>(s_next[warp]);
+            for (int i = lane; i < rows * kObs / 4; i += 32) sn[i] = __ldg(gn + i);
+            for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) s_next[warp][i] = obs_next[w0 * kObs + i];
+        }
+    }
+    __syncwarp();
     const bool sel = e < n && selected(info, e, mask_mode);
     const unsigned b = __ballot_sync(0xFFFFFFFFu, sel);
-    if (!sel) return;
-    const int lane = threadIdx.x & 31;
-    const uint64_t rank = warp_offsets[e >> 5] + __popc(b & ((1u << lane) - 1u));
-    // more selected rows than the ring holds: rows a sequential writer would overwrite are skipped
-    if (rank + (uint64_t)capacity < *counter - *base) return;
-    const int64_t slot = (int64_t)((*base + rank) % (unsigned long long)capacity);
-    const int width = format == 0 ? 2 * kObs + 2 : kObs + 4;
-    float *row = ring + slot * width;
-    const float *s = obs_prev + e * kObs;
+    const int cnt = __popc(b);
+    const uint64_t rank0 = warp_offsets[w0 >> 5];
+    const uint64_t total = *counter - *base;
+    if (sel) {
+        const int r = __popc(b & ((1u << lane) - 1u));
+        float *row = s_out[warp] + r * WIDTH;
+        const float *sp = s_prev[warp] + lane * kObs;
 #pragma unroll
-    for (int k = 0; k < kObs; ++k) row[k] = s[k];
-    const float act1 = (float)a1[e], act2 = a2 ? (float)a2[e] : 0.f;
-    if (format == 0) {
-        row[kObs] = player == 2 ? act2 : act1;
-        row[kObs + 1] = rew[2 * e + (player == 2 ? 1 : 0)];
-        // s' is the observation of the stepped state: under auto-reset obs_next holds the RESET
-        // observation for finished envs, the terminal one is in term_obs
-        const float *sn = (term_obs && done[e]) ? term_obs + e * kObs : obs_next + e * kObs;
+        for (int k = 0; k < kObs; ++k) row[k] = sp[k];
+        const float act1 = (float)a1[e], act2 = a2 ? (float)a2[e] : 0.f;
+        if (FORMAT == 0) {
+            row[kObs] = player == 2 ? act2 : act1;
+            row[kObs + 1] = rew[2 * e + (player == 2 ? 1 : 0)];
+            // s' is the observation of the stepped state: under auto-reset obs_next holds the RESET
+            // observation for finished envs, the terminal one is in term_obs
+            const bool use_term = term_obs && done[e];
+            const float *sn = use_term ? term_obs + e * kObs : s_next[warp] + lane * kObs;
 #pragma unroll
-        for (int k = 0; k < kObs; ++k) row[kObs + 2 + k] = sn[k];
-    } else {
-        row[kObs] = act1; row[kObs + 1] = act2;
-        row[kObs + 2] = rew[2 * e]; row[kObs + 3] = rew[2 * e + 1];
+            for (int k = 0; k < kObs; ++k) row[kObs + 2 + k] = sn[k];
+        } else {
+            row[kObs] = act1; row[kObs + 1] = act2;
+            row[kObs + 2] = rew[2 * e]; row[kObs + 3] = rew[2 * e + 1];
+        }
+        // rows a sequential writer would overwrite later in this same call are skipped below via `skip`
+        if (env_ids && !(rank0 + r + (uint64_t)capacity < total))
+            env_ids[(int64_t)((*base + rank0 + r) % (unsigned long long)capacity)] = (int32_t)e;
     }
-    if (env_ids) env_ids[slot] = (int32_t)e;
+    __syncwarp();
+    // ---- coalesced write of the warp's cnt rows: ring positions (base + rank0 + r) % capacity ----------
+    const unsigned long long cap = (unsigned long long)capacity;
+    const unsigned long long slot0 = (*base + rank0) % cap;
+    if (total <= cap && slot0 + (unsigned long long)cnt <= cap) {
+        // common case: one contiguous span, 8-byte aligned (row width 88 or 56 bytes) -> 64-bit stores
+        const float2 *src = reinterpret_cast<const float2 *>(s_out[warp]);
+        float2 *dst = reinterpret_cast<float2 *>(ring + slot0 * WIDTH);
+        for (int i = lane; i < cnt * WIDTH / 2; i += 32) dst[i] = src[i];
+    } else {
+        for (int i = lane; i < cnt * WIDTH; i += 32) {
+            const int r = i / WIDTH, c = i - r * WIDTH;
+            if (rank0 + r + (uint64_t)capacity < total) continue;          // overwritten later in this call
+            const unsigned long long slot = (slot0 + (unsigned long long)r) % cap;
+            ring[slot * WIDTH + c] = s_out[warp][i];
+        }
+    }
 }
 
 }  // namespace mgrec
@@ -131,6 +177,8 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     if (n == 0) return MG_OK;
     if (!obs_prev || !obs_next || !a1 || !rew || !done || !info || !ring || !counter || !scratch)
         return fail(MG_ERR_NULL_POINTER, "mg_record_transitions: NULL pointer");
+    if (!aligned16(obs_prev) || !aligned16(obs_next))
+        return fail(MG_ERR_ALIGNMENT, "obs_prev and obs_next must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((n + mgrec::kBlock - 1) / mgrec::kBlock);
     const int64_t m = (n + 31) / 32;
@@ -139,10 +187,16 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     auto *base = reinterpret_cast<unsigned long long *>(scratch + ((m + 1) & ~(int64_t)1));
     mgrec::count_kernel<<<grid, mgrec::kBlock, 0, st>>>(info, n, mask_mode, warp_counts);
     mgrec::scan_kernel<<<1, 1024, 0, st>>>(warp_counts, m, reinterpret_cast<unsigned long long *>(counter), base);
-    mgrec::write_kernel<<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew,
-                                                         done, info, n, mask_mode, format, player, warp_counts, base,
-                                                         reinterpret_cast<unsigned long long *>(counter), ring,
-                                                         capacity, env_ids_or_null);
+    if (format == 0)
+        mgrec::write_kernel<0><<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew,
+                                                                done, info, n, mask_mode, player, warp_counts, base,
+                                                                reinterpret_cast<unsigned long long *>(counter), ring,
+                                                                capacity, env_ids_or_null);
+    else
+        mgrec::write_kernel<1><<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew,
+                                                                done, info, n, mask_mode, player, warp_counts, base,
+                                                                reinterpret_cast<unsigned long long *>(counter), ring,
+                                                                capacity, env_ids_or_null);
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_record_transitions launch");
     return MG_OK;
 }
