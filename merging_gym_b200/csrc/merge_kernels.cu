@@ -353,19 +353,40 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
 __global__ void __launch_bounds__(kBlock)
 merge_reset_kernel(const MgState s, const int64_t n, const uint8_t *__restrict__ mask, float *__restrict__ obs,
                    const MgResetSpec rs) {
-    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (e >= n) return;
-    EnvRegs r{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], 0.0, 0.0, s.meta[e]};
+    __shared__ __align__(16) float stage[kWarps][32 * MG_OBS_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * 32;
+    const int64_t e = warp_base + lane;
+    const bool valid = e < n;
+    const bool hit = valid && (!mask || mask[e]);
+    EnvRegs r;
+    reset_regs(r);
+    if (valid) r.meta = s.meta[e];                      // the reset count in it survives a reset
     float ob[MG_OBS_DIM];
-    if (!mask || mask[e]) {
+    if (hit) {
         if (rs.mode == MG_RESET_RANDOM) reset_env<true>(r, rs, (uint64_t)e, ob);
         else reset_env<false>(r, rs, (uint64_t)e, ob);
         s.pos1[e] = r.p1; s.vel1[e] = r.v1; s.pos2[e] = r.p2; s.vel2[e] = r.v2;
         s.ret1[e] = 0.0; s.ret2[e] = 0.0; s.meta[e] = r.meta;
     } else {
+        if (valid) { r.p1 = s.pos1[e]; r.v1 = s.vel1[e]; r.p2 = s.pos2[e]; r.v2 = s.vel2[e]; }
         observe(r, ob);
     }
-    if (obs) {
+    if (!obs) return;
+    if (warp_base + 32 <= n) {
+        // the warp's 32 rows are one contiguous 1280-byte span: stage, then linear 128-bit stores
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM; ++k) stage[warp][lane * MG_OBS_DIM + k] = ob[k];
+        __syncwarp();
+        const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
+        float4 *dst = reinterpret_cast<float4 *>(obs + warp_base * MG_OBS_DIM);
+        constexpr int kVec = 32 * MG_OBS_DIM / 4;
+#pragma unroll
+        for (int k = 0; k < (kVec + 31) / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i < kVec) dst[i] = src[i];
+        }
+    } else if (valid) {
 #pragma unroll
         for (int k = 0; k < MG_OBS_DIM; ++k) obs[e * MG_OBS_DIM + k] = ob[k];
     }
