@@ -9,45 +9,71 @@
 // exactly the reference's fp32 arithmetic.
 //
 // One persistent CTA per SM, tile = 128 envs (UMMA M = 128, N = 112 = 100 neurons + zero pad, K = 8):
-//   warps 0-7  producers : two groups of 4 warps, each owning one slot of a 2-slot ring (slot = 2
-//                          K-steps); thread = (env pair, K-step): layer 1 on the CUDA cores (FFMA2), split
-//                          into hi/lo, written straight into the canonical K-major core-matrix layout -> full[s]
-//   warp  12   MMA issue : one thread; per K-step two tcgen05.mma.kind::tf32: a_hi x [W2_hi ; W2_lo] (N = 224)
-//                          and a_lo x W2_hi (N = 112), accumulating in TMEM; tcgen05.commit -> empty[s] / tmem_full[b]
-//   warps 8-11 epilogue  : tcgen05.ld of the 128x112 fp32 accumulator (row = env), bias + ReLU, the
-//                          100x{5,3} layer and the arg-max in registers, one action byte per thread
+//   warps 0-7  producers : warp w owns every 8th K-step of the CTA's K-step sequence (25 per tile); a thread
+//                          computes 8 hidden units of layer 1 for 4 envs on the CUDA cores (FFMA2, each weight
+//                          read from shared memory feeds 4 envs), splits them into hi/lo and writes them straight
+//                          into the canonical K-major core-matrix layout of ring slot (K-step % 4) -> full[slot]
+//   warps 12-13 MMA issue: K-steps interleaved between the two warps (one issuing warp needs ~370 cycles per K-step,
+//                          the tensor pipe ~180); per K-step two tcgen05.mma.kind::tf32 — a_hi x [W2_hi ; W2_lo]
+//                          (N = 224) and a_lo x W2_hi (N = 112) — issued by predication from one elected lane,
+//                          accumulating in TMEM; tcgen05.commit -> empty[next producer] / first_done[b] / tmem_full[b]
+//   warps 8-11 epilogue  : tcgen05.ld.16x256b fragments of the 128x112 fp32 accumulator — a thread holds 4 envs x
+//                          2 adjacent neurons per 8-column block, so one read of the layer-3 weights feeds 4 envs —
+//                          bias + ReLU, the 100x{5,3} layer, a 4-lane shuffle reduction and the arg-max
 // TMEM: 2 accumulator buffers x 256 columns ([0,112): hi.hi + lo.hi, [112,224): hi.lo, summed in the epilogue),
 // so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Shared memory: W2 as one stacked B operand [hi ; lo] of 224 rows, 179.2 KB (prepared on the host), A ring 32 KB,
-// W1 / W3 / biases 11 KB.  Every mbarrier wait is bounded and traps instead of hanging.
+// Shared memory: W2 as one stacked B operand [hi ; lo] of 224 rows, 179.2 KB (prepared on the host), A ring 32 KB
+// (4 slots of one K-step), W1 / W3 / biases 11 KB.  The kernel is bound by shared-memory bandwidth: ~320 wavefronts per
+// K-step (tensor-core operand reads 148, producer stores 70, weight broadcasts 100) against a K-step period of ~336
+// cycles — which is what the two 4-envs-per-thread mappings cut (the first version moved 470).  The hand-over
+// timeline is measured by profiles/exp_tc_trace.cu (-DMG_TC_TRACE=1).
+// Every mbarrier wait is bounded and traps instead of hanging.
 #include "abi_common.h"
 
+#ifndef MG_TC_MMA_WARPS
+#define MG_TC_MMA_WARPS 2
+#endif
+#ifndef MG_TC_TRACE
+#define MG_TC_TRACE 0            // 1: CTA 0 records clock64() at the hand-over points (profiles/exp_tc_trace.cu)
+#endif
+
 namespace mgtc {
+
+#if MG_TC_TRACE
+constexpr int TRACE_G = 25 * 10;                // K-steps traced (10 tiles of CTA 0)
+__device__ long long g_trace_prod[TRACE_G][5];  // compute start, wait start, wait end, fence done, arrive done
+__device__ long long g_trace_mma[TRACE_G][8];   // wait start, wait end, issued
+__device__ long long g_trace_epi[16][3];        // wait start, wait end, done (warp 8)
+#define MG_TRACE(arr, idx, k) do { if (blockIdx.x == 0 && lane == 0 && (idx) < (uint32_t)(sizeof(arr) / sizeof(arr[0]))) arr[idx][k] = clock64(); } while (0)
+#else
+#define MG_TRACE(arr, idx, k) do { } while (0)
+#endif
 
 constexpr int H1 = 200, H2 = 100;
 constexpr int TM = 128;                       // envs per tile = UMMA M
 constexpr int UN = 112;                       // UMMA N (multiple of 16 for M = 128)
 constexpr int KSTEPS = H1 / 8;                // 25 K-steps of 8 (tf32: 32 bytes of K per MMA)
-constexpr int STAGES = 2;                     // ring stages; one stage = 2 K-steps (16 hidden units)
-constexpr int NSTAGE_TILE = (KSTEPS + 1) / 2; // 13 stage fills per tile (the last holds one K-step)
+constexpr int STAGES = 4;                     // ring slots; one slot = one K-step (8 hidden units) of all 128 envs
+constexpr int H2P = 104;                      // layer-3 weights padded to whole 8-column blocks
 constexpr int A_STEP = (TM / 8) * 256;        // 4096 B : 16 row groups x 2 core matrices x 128 B
 constexpr int B_STEP = (2 * UN / 8) * 256;    // 7168 B: one K-step of the stacked B operand [W2_hi ; W2_lo] (224 rows)
 constexpr int B_BYTES = KSTEPS * B_STEP;      // 179 200 B
 constexpr int TMEM_COLS = 512;                // 2 accumulator buffers x 256 columns (224 used)
-constexpr int NUM_PRODUCERS = 256;            // 8 producer warps: thread = (env, which K-step of the stage)
-constexpr int NUM_THREADS = 416;              // 8 producer warps + 4 epilogue warps + 1 MMA warp
+constexpr int PRODUCER_WARPS = 8;             // thread = 4 envs x one K-step
+constexpr int MMA_WARPS = MG_TC_MMA_WARPS;     // warps 12.. issue the MMAs, K-steps interleaved
+constexpr int NUM_THREADS = 384 + 32 * MMA_WARPS;   // 8 producer warps + 4 epilogue warps + the MMA warps
 constexpr int MAX_OUT = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 template <int IN, int OUT>
 struct Smem {
     unsigned char b_cat[B_BYTES];             // [K-step][28 row groups: W2_hi rows 0-111, W2_lo rows 112-223], canonical layout
-    unsigned char a_hi[STAGES][2][A_STEP];
-    unsigned char a_lo[STAGES][2][A_STEP];
+    unsigned char a_hi[STAGES][A_STEP];
+    unsigned char a_lo[STAGES][A_STEP];
     float w1[IN][H1];
-    float w3[OUT][H2];
+    float w3[OUT][H2P];
     float b1[H1], b2[H2 + 12], b3[MAX_OUT];
-    unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    unsigned long long full[PRODUCER_WARPS], empty[PRODUCER_WARPS], tmem_full[2], tmem_empty[2], first_done[2];
     uint32_t tmem_base;
 };
 
@@ -60,6 +86,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
+constexpr uint64_t kDescHi = ((uint64_t)(256u >> 4) << 32) | ((uint64_t)1 << 46);   // SBO and version: the constant high word
 // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24); }
 constexpr uint32_t kIdesc112 = idesc_n(UN), kIdesc224 = idesc_n(2 * UN);
@@ -81,15 +108,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity
     }
     if (!done) __trap();                      // never hang the GPU on a protocol bug
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ uint32_t mbar_test(unsigned long long *b, uint32_t parity) {   // one non-blocking poll
+    uint32_t done;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(b)), "r"(parity)
         : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned long long *b) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+    return done;
 }
 
 template <int IN>
@@ -130,14 +156,17 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         const float4 *s1 = reinterpret_cast<const float4 *>(w1t);
         float4 *d1 = reinterpret_cast<float4 *>(&S.w1[0][0]);
         for (int i = t; i < IN * H1 / 4; i += NUM_THREADS) d1[i] = __ldg(s1 + i);
-        for (int i = t; i < OUT * H2; i += NUM_THREADS) (&S.w3[0][0])[i] = w3[i];
+        for (int i = t; i < OUT * H2P; i += NUM_THREADS) {
+            const int o = i / H2P, c = i - o * H2P;
+            S.w3[o][c] = c < H2 ? w3[o * H2 + c] : 0.f;
+        }
         for (int i = t; i < H1; i += NUM_THREADS) S.b1[i] = b1[i];
         for (int i = t; i < H2 + 12; i += NUM_THREADS) S.b2[i] = i < H2 ? b2[i] : 0.f;
         if (t < OUT) S.b3[t] = b3[t];
     }
     if (t == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], NUM_PRODUCERS / 2); mbar_init(&S.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], TM); }
+        for (int s = 0; s < PRODUCER_WARPS; ++s) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], MMA_WARPS); mbar_init(&S.tmem_empty[b], TM); mbar_init(&S.first_done[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W2 hi/lo written by the generic proxy
@@ -151,165 +180,228 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = S.tmem_base;
 
-    if (warp < 8) {
+    if (warp < PRODUCER_WARPS) {
         // =================================== PRODUCERS: layer 1 ===================================
-        // Two independent groups of 4 warps; group g owns ring slot g and fills every second stage, so the
-        // write chain of one slot (wait empty -> STS -> proxy fence -> arrive) overlaps the MMAs of the other.
-        // thread = (env pair {ep, ep+64}, K-step kh of the stage): 8 hidden units for 2 envs.
-        const int grp = warp >> 2, tg = t & 127;
-        const int ep = tg & 63, kh = tg >> 6;
-        const int m0 = ep, m1 = ep + 64;
-        const uint32_t off0 = (uint32_t)((m0 >> 3) * 256 + (m0 & 7) * 16);
-        const uint32_t off1 = (uint32_t)((m1 >> 3) * 256 + (m1 & 7) * 16);
-        float x0[IN], x1[IN];
-        load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m0, n, obs_dim, x0);
-        load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + m1, n, obs_dim, x1);
+        // The CTA's K-steps are numbered g = 25 * (local tile) + ks; warp w produces g = w, w + 8, ... into ring
+        // slot g % 4.  Its layer-1 arithmetic for K-step g runs while the MMAs of g-8 .. g-1 are in flight; only the
+        // stores wait for the slot.  lane = envs {lane, lane+32, lane+64, lane+96} of the tile.
+        const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint32_t total = (uint32_t)my_tiles * KSTEPS;
+        uint32_t off[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = lane + 32 * j;
+            off[j] = (uint32_t)((m >> 3) * 256 + (m & 7) * 16);
+        }
+        float x[4][IN];
+        uint32_t cur = 0xFFFFFFFFu;
+        for (uint32_t g = (uint32_t)warp; g < total; g += PRODUCER_WARPS) {
+            const uint32_t tl = g / KSTEPS, ks = g - tl * KSTEPS;
+            MG_TRACE(g_trace_prod, g, 0);
+            if (tl != cur) {                                    // first K-step of this warp in a new tile
+                cur = tl;
+                const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TM + lane;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load_row<IN>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+            }
+            const int k = 8 * (int)ks;
+            const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[k]);
+            const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k + 4]);
+            float2 acc[4][4];                                   // [env][unit pair]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[j][0] = make_float2(ba.x, ba.y); acc[j][1] = make_float2(ba.z, ba.w);
+                acc[j][2] = make_float2(bb.x, bb.y); acc[j][3] = make_float2(bb.z, bb.w);
+            }
+#pragma unroll
+            for (int i = 0; i < IN; ++i) {
+                const float4 wa = *reinterpret_cast<const float4 *>(&S.w1[i][k]);
+                const float4 wb = *reinterpret_cast<const float4 *>(&S.w1[i][k + 4]);
+                const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+                const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 xx = make_float2(x[j][i], x[j][i]);
+                    acc[j][0] = __ffma2_rn(xx, w01, acc[j][0]); acc[j][1] = __ffma2_rn(xx, w23, acc[j][1]);
+                    acc[j][2] = __ffma2_rn(xx, w45, acc[j][2]); acc[j][3] = __ffma2_rn(xx, w67, acc[j][3]);
+                }
+            }
+            // Ring slot s = g % 4 is filled alternately by warps s and s + 4.  A parity wait is only meaningful when
+            // the waiter is at most one phase behind the barrier, so every producer warp has its OWN pair of
+            // barriers: the MMA thread commits K-step k to empty[(k + 4) % 8] — the warp that reuses the slot next.
+            const int s = (int)(g % STAGES);
+            const uint32_t v = g / PRODUCER_WARPS;              // this warp's visit number
+            MG_TRACE(g_trace_prod, g, 1);
+            mbar_wait(&S.empty[warp], warp < STAGES ? (v & 1u) ^ 1u : (v & 1u));
+            MG_TRACE(g_trace_prod, g, 2);
+            auto split_store = [&](const float2 &p, const float2 &q, uint32_t o) {
+                const float4 h = make_float4(fmaxf(p.x, 0.f), fmaxf(p.y, 0.f), fmaxf(q.x, 0.f), fmaxf(q.y, 0.f));
+                float4 hi, lo;                                  // hi = what kind::tf32 reads (top 19 bits), lo exact
+                hi.x = __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u); lo.x = h.x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u); lo.y = h.y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u); lo.z = h.z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u); lo.w = h.w - hi.w;
+                *reinterpret_cast<float4 *>(S.a_hi[s] + o) = hi;
+                *reinterpret_cast<float4 *>(S.a_lo[s] + o) = lo;
+            };
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                split_store(acc[j][0], acc[j][1], off[j]);      // units 0-3: first core matrix of the K-step
+                split_store(acc[j][2], acc[j][3], off[j] + 128);// units 4-7: second core matrix
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core
+            MG_TRACE(g_trace_prod, g, 3);
+            mbar_arrive(&S.full[warp]);
+            MG_TRACE(g_trace_prod, g, 4);
+        }
+    } else if (warp >= 12) {
+        // =================================== MMA ISSUERS =========================================
+        // One issuing warp needs ~370 cycles per K-step (wait, index arithmetic, two tcgen05.mma, commit: a serial
+        // instruction stream), the tensor pipe ~180 — so MMA_WARPS warps share the K-steps of every tile: warp j
+        // issues ks = j, j + MMA_WARPS, ...  Each runs the loop whole-warp and issues by PREDICATION from one elected
+        // lane (inside an `if (lane == 0)` region the compiler rebuilt every descriptor through R2UR and wrapped each
+        // tcgen05 instruction in a per-lane retry loop — ~55 dependent instructions per K-step).
+        // Ordering between the two issuers: accumulation commutes, but the overwriting MMA (ks = 0, accumulate off)
+        // must come first.  K-steps >= 4 reuse a ring slot that the completion of ks - 4 >= 0 freed, so they are
+        // ordered after it by data flow; warp 1 waits for first_done[buf] (committed right after ks = 0) before its
+        // first K-step of a tile.  tmem_full[buf] expects one commit per issuing warp.
+        const int j = warp - 12;
         uint32_t tl = 0;
+        // low descriptor words: (address >> 4) | (LBO >> 4) << 16; stepping an operand = adding (bytes >> 4)
+        const uint32_t b_cat = (uint32_t)make_desc(smem_u32(S.b_cat)), a_hi0 = (uint32_t)make_desc(smem_u32(S.a_hi[0])),
+                       a_lo0 = (uint32_t)make_desc(smem_u32(S.a_lo[0]));
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-            float n0[IN], n1[IN];                               // next tile's rows, in flight during this tile
-            load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m0, n, obs_dim, n0);
-            load_row<IN>(obs, goal, (tile + gridDim.x) * TM + m1, n, obs_dim, n1);
-            const uint32_t it0 = tl * NSTAGE_TILE;              // global stage-fill counter of this tile's stage 0
-            for (int st = (int)((grp + it0) & 1u); st < NSTAGE_TILE; st += 2) {     // stages with (it0 + st) % 2 == grp
-                const uint32_t it = it0 + (uint32_t)st;
-                const int s = it % STAGES;                      // == grp
-                const uint32_t ph = (it / STAGES) & 1u;
-                const int ks = 2 * st + kh;
-                float4 ha0, ha1, hb0, hb1;                      // env m0: units 0-3, 4-7; env m1: units 0-3, 4-7
-                if (ks < KSTEPS) {
-                    const int k = 8 * ks;
-                    const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[k]);
-                    const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k + 4]);
-                    float2 a01 = make_float2(ba.x, ba.y), a23 = make_float2(ba.z, ba.w), a45 = make_float2(bb.x, bb.y), a67 = make_float2(bb.z, bb.w);
-                    float2 c01 = a01, c23 = a23, c45 = a45, c67 = a67;
-#pragma unroll
-                    for (int i = 0; i < IN; ++i) {
-                        const float4 wa = *reinterpret_cast<const float4 *>(&S.w1[i][k]);
-                        const float4 wb = *reinterpret_cast<const float4 *>(&S.w1[i][k + 4]);
-                        const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
-                        const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
-                        const float2 xa = make_float2(x0[i], x0[i]), xb = make_float2(x1[i], x1[i]);
-                        a01 = __ffma2_rn(xa, w01, a01); a23 = __ffma2_rn(xa, w23, a23);
-                        a45 = __ffma2_rn(xa, w45, a45); a67 = __ffma2_rn(xa, w67, a67);
-                        c01 = __ffma2_rn(xb, w01, c01); c23 = __ffma2_rn(xb, w23, c23);
-                        c45 = __ffma2_rn(xb, w45, c45); c67 = __ffma2_rn(xb, w67, c67);
-                    }
-                    ha0 = make_float4(fmaxf(a01.x, 0.f), fmaxf(a01.y, 0.f), fmaxf(a23.x, 0.f), fmaxf(a23.y, 0.f));
-                    ha1 = make_float4(fmaxf(a45.x, 0.f), fmaxf(a45.y, 0.f), fmaxf(a67.x, 0.f), fmaxf(a67.y, 0.f));
-                    hb0 = make_float4(fmaxf(c01.x, 0.f), fmaxf(c01.y, 0.f), fmaxf(c23.x, 0.f), fmaxf(c23.y, 0.f));
-                    hb1 = make_float4(fmaxf(c45.x, 0.f), fmaxf(c45.y, 0.f), fmaxf(c67.x, 0.f), fmaxf(c67.y, 0.f));
-                }
-                mbar_wait(&S.empty[s], ph ^ 1u);                // MMAs that read this slot have completed
-                if (ks < KSTEPS) {
-                    auto split_store = [&](const float4 &h, uint32_t off) {
-                        float4 hi, lo;                          // hi = what kind::tf32 reads (top 19 bits), lo exact
-                        hi.x = __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u); lo.x = h.x - hi.x;
-                        hi.y = __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u); lo.y = h.y - hi.y;
-                        hi.z = __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u); lo.z = h.z - hi.z;
-                        hi.w = __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u); lo.w = h.w - hi.w;
-                        *reinterpret_cast<float4 *>(S.a_hi[s][kh] + off) = hi;
-                        *reinterpret_cast<float4 *>(S.a_lo[s][kh] + off) = lo;
-                    };
-                    split_store(ha0, off0); split_store(ha1, off0 + 128);
-                    split_store(hb0, off1); split_store(hb1, off1 + 128);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core
-                }
-                mbar_arrive(&S.full[s]);                        // (a per-warp elected arrive measured slower)
-            }
-#pragma unroll
-            for (int i = 0; i < IN; ++i) { x0[i] = n0[i]; x1[i] = n1[i]; }
-        }
-    } else if (warp == 12) {
-        // =================================== MMA ISSUER ==========================================
-        if (lane == 0) {
-            uint32_t it = 0, tl = 0;
-            const uint32_t b_cat = smem_u32(S.b_cat);
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-                const uint32_t buf = tl & 1u;
-                mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);            // epilogue drained this buffer
+            const uint32_t buf = tl & 1u;
+            if (j == 0) mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);    // epilogue drained this buffer
+            else        mbar_wait(&S.first_done[buf], (tl >> 1) & 1u);           // ... and ks = 0 has overwritten it
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d = tmem_base + buf * 256u;
+            const uint32_t tm_full = smem_u32(&S.tmem_full[buf]), first = smem_u32(&S.first_done[buf]);
+            uint32_t have = 0;                              // the barrier about to be waited for was already seen complete
+#pragma unroll 1
+            for (int ks = j; ks < KSTEPS; ks += MMA_WARPS) {
+                const uint32_t it = tl * KSTEPS + (uint32_t)ks;
+                const uint32_t s = it % STAGES, pw = it % PRODUCER_WARPS;
+                // everything the elected lane needs is computed BEFORE the wait, in ordinary registers
+                uint32_t lo_a = a_hi0 + s * (A_STEP >> 4), lo_l = a_lo0 + s * (A_STEP >> 4);
+                uint32_t lo_b = b_cat + (uint32_t)ks * (B_STEP >> 4);
+                uint32_t done_bar = smem_u32(&S.empty[(it + STAGES) % PRODUCER_WARPS]);
+                asm volatile("" : "+r"(lo_a), "+r"(lo_l), "+r"(lo_b), "+r"(done_bar));   // pin the values here (no sinking below the wait)
+                const uint32_t acc = ks > 0 ? 1u : 0u;
+                const uint32_t last = ks + MMA_WARPS >= KSTEPS ? 1u : 0u;            // this warp's last K-step of the tile
+                const uint32_t sig_first = (MMA_WARPS > 1 && ks == 0) ? 1u : 0u;
+                MG_TRACE(g_trace_mma, it, 0);
+                if (!have) mbar_wait(&S.full[pw], (it / PRODUCER_WARPS) & 1u);
+                // poll this warp's NEXT K-step now: the answer arrives while the MMAs below are being issued
+                have = last ? 0u : mbar_test(&S.full[(it + MMA_WARPS) % PRODUCER_WARPS], ((it + MMA_WARPS) / PRODUCER_WARPS) & 1u);
+                MG_TRACE(g_trace_mma, it, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d = tmem_base + buf * 256u;
-                for (int st = 0; st < NSTAGE_TILE; ++st, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&S.full[s], (it / STAGES) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int ks = 2 * st + half;
-                        if (ks < KSTEPS) {
-                            const uint64_t ahi = make_desc(smem_u32(S.a_hi[s][half])), alo = make_desc(smem_u32(S.a_lo[s][half]));
-                            const uint64_t bcat = make_desc(b_cat + ks * B_STEP);
-                            // columns [0,112) += a_hi.W2_hi, columns [112,224) += a_hi.W2_lo  (one N = 224 MMA: 123 cycles
-                            // instead of two N = 112 MMAs at 76 each, and A_hi is read once)
-                            umma_tf32(d, ahi, bcat, kIdesc224, ks > 0 ? 1u : 0u);
-                            umma_tf32(d, alo, bcat, kIdesc112, 1u);           // columns [0,112) += a_lo.W2_hi
-                        }
-                    }
-                    umma_commit(&S.empty[s]);                   // stage reusable once these MMAs are done
-                }
-                umma_commit(&S.tmem_full[buf]);                 // accumulator complete
+                // columns [0,112) += a_hi.W2_hi and [112,224) += a_hi.W2_lo in one N = 224 MMA (123 cycles instead of two
+                // N = 112 MMAs at 76 each, A_hi read once); then columns [0,112) += a_lo.W2_hi.  Commits: the warp that fills
+                // this slot next; after ks = 0 the other issuer; after this warp's last K-step the epilogue.
+                asm volatile(
+                    "{\n\t.reg .pred E, A, L, F;\n\t.reg .b64 da, dl, db;\n\t"
+                    "elect.sync _|E, 0xffffffff;\n\t"
+                    "setp.ne.b32 A, %5, 0;\n\t"
+                    "setp.ne.and.b32 L, %8, 0, E;\n\t"
+                    "setp.ne.and.b32 F, %11, 0, E;\n\t"
+                    "mov.b64 da, {%1, %4};\n\tmov.b64 dl, {%2, %4};\n\tmov.b64 db, {%3, %4};\n\t"
+                    "@E tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %6, A;\n\t"
+                    "@F tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+                    "@E tcgen05.mma.cta_group::1.kind::tf32 [%0], dl, db, %7, 1;\n\t"
+                    "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+                    "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t}\n"
+                    :: "r"(d), "r"(lo_a), "r"(lo_l), "r"(lo_b), "r"((uint32_t)(kDescHi >> 32)), "r"(acc), "r"(kIdesc224), "r"(kIdesc112),
+                       "r"(last), "r"(done_bar), "r"(tm_full), "r"(sig_first), "r"(first)
+                    : "memory");
+                MG_TRACE(g_trace_mma, it, 2);
             }
         }
-        __syncwarp();
     } else {
         // =================================== EPILOGUE: layer 3 + arg-max ===========================
+        // tcgen05.ld.16x256b.x2: lanes 16h .. 16h+15 of this warp's TMEM quarter, 16 columns; thread (t1 = lane / 4,
+        // t0 = lane % 4) receives rows t1 and t1 + 8 at columns 8b + 2 t0 + {0, 1} of both 8-column blocks b:
+        //   r[0..1] = (row t1, block 0)  r[2..3] = (row t1+8, block 0)  r[4..5] = (row t1, block 1)  r[6..7] = (row t1+8, block 1)
         const int q4 = warp - 8;                                // TMEM lane quarter of this warp (warp % 4)
-        const int m = q4 * 32 + lane;
+        const int t0 = lane & 3, t1 = lane >> 2;
         uint32_t tl = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             const uint32_t buf = tl & 1u;
+            if (q4 == 0) MG_TRACE(g_trace_epi, tl, 0);
             mbar_wait(&S.tmem_full[buf], (tl >> 1) & 1u);
+            if (q4 == 0) MG_TRACE(g_trace_epi, tl, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q4 * 32) << 16);
-            float q[OUT];
+            float q[4][OUT];                                    // rows t1 + 8 * {0, 1, 2, 3}: partial sums over this thread's neurons
 #pragma unroll
-            for (int o = 0; o < OUT; ++o) q[o] = S.b3[o];
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c0 = 0; c0 < UN; c0 += 16) {
-                uint32_t v[16], u[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr + (uint32_t)c0));
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-                    : "r"(taddr + (uint32_t)(UN + c0)));
+                for (int o = 0; o < OUT; ++o) q[r][o] = 0.f;
+#pragma unroll
+            for (int cb = 0; cb < UN / 16; ++cb) {
+                uint32_t a[2][8], l[2][8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ad = taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(16 * cb);
+                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(a[h][0]), "=r"(a[h][1]), "=r"(a[h][2]), "=r"(a[h][3]), "=r"(a[h][4]), "=r"(a[h][5]),
+                                   "=r"(a[h][6]), "=r"(a[h][7])
+                                 : "r"(ad));
+                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(l[h][0]), "=r"(l[h][1]), "=r"(l[h][2]), "=r"(l[h][3]), "=r"(l[h][4]), "=r"(l[h][5]),
+                                   "=r"(l[h][6]), "=r"(l[h][7])
+                                 : "r"(ad + (uint32_t)UN));
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                for (int blk = 0; blk < 2; ++blk) {
+                    if (16 * cb + 8 * blk < H2P) {              // blocks 0..12 hold the 100 neurons (+4 zero-weight pads)
+                        const int c = 16 * cb + 8 * blk + 2 * t0;
+                        const float2 bias = *reinterpret_cast<const float2 *>(&S.b2[c]);
+                        float2 w[OUT];
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4 += 4) {
-                    if (c0 + j4 < H2) {                         // 100 = 25 groups of 4: no partial group
-                        const float4 bias = *reinterpret_cast<const float4 *>(&S.b2[c0 + j4]);
-                        const float h0 = fmaxf(__uint_as_float(v[j4]) + bias.x, 0.f);
-                        const float h1 = fmaxf(__uint_as_float(v[j4 + 1]) + bias.y, 0.f);
-                        const float h2 = fmaxf(__uint_as_float(v[j4 + 2]) + bias.z, 0.f);
-                        const float h3 = fmaxf(__uint_as_float(v[j4 + 3]) + bias.w, 0.f);
+                        for (int o = 0; o < OUT; ++o) w[o] = *reinterpret_cast<const float2 *>(&S.w3[o][c]);
 #pragma unroll
-                        for (int o = 0; o < OUT; ++o) {
-                            const float4 w = *reinterpret_cast<const float4 *>(&S.w3[o][c0 + j4]);
-                            q[o] = fmaf(h0, w.x, q[o]); q[o] = fmaf(h1, w.y, q[o]);
-                            q[o] = fmaf(h2, w.z, q[o]); q[o] = fmaf(h3, w.w, q[o]);
-                        }
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int rr = 0; rr < 2; ++rr) {
+                                const int i0 = 4 * blk + 2 * rr;
+                                const float h0 = fmaxf(__uint_as_float(a[h][i0]) + __uint_as_float(l[h][i0]) + bias.x, 0.f);
+                                const float h1 = fmaxf(__uint_as_float(a[h][i0 + 1]) + __uint_as_float(l[h][i0 + 1]) + bias.y, 0.f);
+#pragma unroll
+                                for (int o = 0; o < OUT; ++o) {
+                                    q[2 * h + rr][o] = fmaf(h0, w[o].x, q[2 * h + rr][o]);
+                                    q[2 * h + rr][o] = fmaf(h1, w[o].y, q[2 * h + rr][o]);
+                                }
+                            }
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&S.tmem_empty[buf]);                    // this thread is done reading the buffer
-            const int64_t e = tile * TM + m;
+            if (q4 == 0) MG_TRACE(g_trace_epi, tl, 2);
+            // sum the 4 lanes that share a row group, then lane t0 finishes row t1 + 8 * t0
+            float mine[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    q[r][o] += __shfl_xor_sync(0xffffffffu, q[r][o], 1);
+                    q[r][o] += __shfl_xor_sync(0xffffffffu, q[r][o], 2);
+                }
+                mine[o] = (t0 == 0 ? q[0][o] : t0 == 1 ? q[1][o] : t0 == 2 ? q[2][o] : q[3][o]) + S.b3[o];
+            }
+            const int64_t e = tile * TM + q4 * 32 + t1 + 8 * t0;
             if (e < n) {
                 int best = 0;
-                float bv = q[0];
+                float bv = mine[0];
 #pragma unroll
                 for (int o = 1; o < OUT; ++o)
-                    if (q[o] > bv) { bv = q[o]; best = o; }     // first maximum, like torch.max
+                    if (mine[o] > bv) { bv = mine[o]; best = o; }   // first maximum, like torch.max
                 act[e] = (uint8_t)best;
                 if (q_out) {
 #pragma unroll
-                    for (int o = 0; o < OUT; ++o) q_out[e * OUT + o] = q[o];
+                    for (int o = 0; o < OUT; ++o) q_out[e * OUT + o] = mine[o];
                 }
             }
         }
