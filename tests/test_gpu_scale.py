@@ -68,6 +68,30 @@ def test_shard_invariance(mg, full_run):
     assert torch.equal(tot, env.stats_tensor())
 
 
+def test_shards_on_separate_streams_match_the_single_stream_run(mg, full_run):
+    """bench.py's `overlapped_streams` set-up: independent shards stepped concurrently, each on its own
+    CUDA stream (every entry point launches on the caller's current stream; the library keeps no global
+    state), must reproduce the single-stream run bit for bit — state, statistics and outputs."""
+    env, _ = full_run
+    R = 4
+    lanes = [torch.cuda.Stream() for _ in range(2)]
+    shards = [mg.MergeVecEnv(N // R, seed=0x5EED, env_id_base=r * (N // R)) for r in range(R)]
+    for ln in lanes:
+        ln.wait_stream(torch.cuda.current_stream())
+    last = [None] * R
+    for t in range(K):
+        for r, sh in enumerate(shards):
+            with torch.cuda.stream(lanes[r % 2]):
+                last[r] = sh.step(*sh.sample_actions())
+    for ln in lanes:
+        torch.cuda.current_stream().wait_stream(ln)
+    torch.cuda.synchronize()
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta"):
+        assert torch.equal(torch.cat([getattr(sh, k) for sh in shards]), getattr(env, k)), k
+    assert torch.equal(sum(sh.stats_tensor() for sh in shards), env.stats_tensor())
+    assert torch.equal(torch.cat([o[0] for o in last]), env.obs_buf[env._slot])
+
+
 def test_subsample_matches_oracle(mg):
     """Envs [base, base+512) of the 1M-env Philox stream against the oracle, every step."""
     base, n = 777_216, 512
