@@ -162,3 +162,28 @@ def test_soak_parity_8e8_env_steps(mg):
     for k in ("episodes", "collisions", "wins_p1", "wins_p2", "timeouts", "merges_ok", "sum_length"):
         assert s[k] == rs[k], k
     assert s["episodes"] > 3000000
+
+
+def test_quarter_billion_envs_index_arithmetic(mg):
+    """Largest size tested: 2^28 + 37 envs (27 GB of state + outputs; obs element offsets pass 2^31, a
+    ragged last warp at the far end).  All envs get the same actions, so every env must equal env 0,
+    which must equal a 64-env run — any 32-bit overflow in the index arithmetic would break that."""
+    n = (1 << 28) + 37
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 << 30:
+        pytest.skip("needs ~35 GB of free device memory")
+    env = mg.MergeVecEnv(n, episode_info=False)
+    small = mg.MergeVecEnv(64, episode_info=False)
+    a1 = torch.full((n,), 4, dtype=torch.uint8, device="cuda"); a2 = torch.full((n,), 1, dtype=torch.uint8, device="cuda")
+    for _ in range(5):
+        obs, rew, done, info = env.step(a1, a2)
+        so, sr, sd, si = small.step(a1[:64], a2[:64])
+    torch.cuda.synchronize()
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta"):
+        v = getattr(env, k)
+        assert bool((v == getattr(small, k)[0]).all()), k
+    assert bool((obs == so[0]).all()) and bool((rew == sr[0]).all())
+    assert not bool(done.any()) and not bool(info["flags"].any())
+    assert int(env.steps.min()) == int(env.steps.max()) == 5 and env.stats()["episodes"] == 0
+    del env, obs, rew, done, info, a1, a2
+    torch.cuda.empty_cache()
