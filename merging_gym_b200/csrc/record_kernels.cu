@@ -8,9 +8,10 @@
 //
 // Deterministic three-pass compaction (no atomics, so the ring content is reproducible and equals a
 // sequential loop over env ids):
-//   count  : one warp ballot + popc per 32 envs  -> warp_counts
-//   scan   : one CTA, exclusive scan of warp_counts (<= 2^20 entries), advances the ring counter
-//   write  : every selected env writes its row at (counter + offset) % capacity
+//   count  : ballot + popc per warp, summed per 256-env block          -> block_counts
+//   scan   : one CTA, exclusive scan of block_counts (n / 256 entries), advances the ring counter
+//   write  : a block re-derives its warps' ranks from the ballots; every selected env writes its row at
+//            (counter + offset) % capacity
 #include "abi_common.h"
 
 namespace mgrec {
@@ -25,14 +26,22 @@ __device__ __forceinline__ bool selected(const uint8_t *info, int64_t e, int mas
 }
 
 __global__ void __launch_bounds__(kBlock)
-count_kernel(const uint8_t *__restrict__ info, int64_t n, int mask_mode, uint32_t *__restrict__ warp_counts) {
+count_kernel(const uint8_t *__restrict__ info, int64_t n, int mask_mode, uint32_t *__restrict__ block_counts) {
+    __shared__ uint32_t s_cnt[kBlock / 32];
     const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool sel = e < n && selected(info, e, mask_mode);
     const unsigned b = __ballot_sync(0xFFFFFFFFu, sel);
-    if ((threadIdx.x & 31) == 0 && e < n) warp_counts[e >> 5] = __popc(b);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) tot += s_cnt[w];
+        block_counts[blockIdx.x] = tot;
+    }
 }
 
-// Single CTA: in-place exclusive scan of warp_counts[0..m), total added to *counter (int64 rows
+// Single CTA: in-place exclusive scan of block_counts[0..m), total added to *counter (int64 rows
 // written so far); the pre-increment value is left in *base for the write pass.
 __global__ void __launch_bounds__(1024)
 scan_kernel(uint32_t *__restrict__ warp_counts, int64_t m, unsigned long long *__restrict__ counter,
@@ -42,10 +51,13 @@ scan_kernel(uint32_t *__restrict__ warp_counts, int64_t m, unsigned long long *_
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) carry_s = 0;
     __syncthreads();
-    for (int64_t i0 = 0; i0 < m; i0 += 1024) {
-        const int64_t i = i0 + t;
-        const uint32_t v = i < m ? warp_counts[i] : 0u;
-        uint32_t x = v;
+    for (int64_t i0 = 0; i0 < m; i0 += 4096) {             // 4 entries per thread and pass
+        const int64_t i = i0 + 4 * t;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = i + k < m ? warp_counts[i + k] : 0u;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t x = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
@@ -64,8 +76,12 @@ scan_kernel(uint32_t *__restrict__ warp_counts, int64_t m, unsigned long long *_
         }
         __syncthreads();
         const uint32_t carry = carry_s;
-        const uint32_t before = carry + (w ? warp_tot[w - 1] : 0u) + (x - v);
-        if (i < m) warp_counts[i] = before;
+        uint32_t before = carry + (w ? warp_tot[w - 1] : 0u) + (x - mine);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < m) warp_counts[i + k] = before;
+            before += v[k];
+        }
         __syncthreads();
         if (t == 1023) carry_s = carry + warp_tot[31];
         __syncthreads();
@@ -86,7 +102,7 @@ __global__ void __launch_bounds__(kBlock)
 write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_next,
              const float *__restrict__ term_obs, const uint8_t *__restrict__ a1, const uint8_t *__restrict__ a2,
              const float *__restrict__ rew, const uint8_t *__restrict__ done, const uint8_t *__restrict__ info,
-             int64_t n, int mask_mode, int player, const uint32_t *__restrict__ warp_offsets,
+             int64_t n, int mask_mode, int player, const uint32_t *__restrict__ block_offsets,
              const unsigned long long *__restrict__ base, const unsigned long long *__restrict__ counter,
              float *__restrict__ ring, int64_t capacity, int32_t *__restrict__ env_ids) {
     constexpr int WIDTH = FORMAT == 0 ? 2 * kObs + 2 : kObs + 4;
@@ -94,10 +110,19 @@ write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_n
     __shared__ __align__(16) float s_prev[kWarps][32 * kObs];
     __shared__ __align__(16) float s_next[kWarps][FORMAT == 0 ? 32 * kObs : 4];
     __shared__ __align__(16) float s_out[kWarps][32 * WIDTH];
+    __shared__ uint32_t s_cnt[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t w0 = ((int64_t)blockIdx.x * kBlock + warp * 32);          // first env of this warp
-    if (w0 >= n) return;
     const int64_t e = w0 + lane;
+    const bool sel = e < n && selected(info, e, mask_mode);
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, sel);
+    const int cnt = __popc(b);
+    if (lane == 0) s_cnt[warp] = (uint32_t)cnt;
+    __syncthreads();                                                         // the only block-wide step
+    if (w0 >= n) return;
+    uint32_t before = 0;                                                     // selected envs of the lower warps of this block
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) before += w < warp ? s_cnt[w] : 0u;
     const int rows = (int)min((int64_t)32, n - w0);
     // ---- coalesced loads of the warp's observation rows (w0 * 40 bytes is 16-byte aligned: w0 % 32 == 0) ----
     {
@@ -113,10 +138,7 @@ write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_n
         }
     }
     __syncwarp();
-    const bool sel = e < n && selected(info, e, mask_mode);
-    const unsigned b = __ballot_sync(0xFFFFFFFFu, sel);
-    const int cnt = __popc(b);
-    const uint64_t rank0 = warp_offsets[w0 >> 5];
+    const uint64_t rank0 = (uint64_t)block_offsets[blockIdx.x] + before;
     const uint64_t total = *counter - *base;
     if (sel) {
         const int r = __popc(b & ((1u << lane) - 1u));
@@ -182,11 +204,12 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((n + mgrec::kBlock - 1) / mgrec::kBlock);
     const int64_t m = (n + 31) / 32;
-    // scratch: uint32[m + 2] — warp counts/offsets followed by the 64-bit pre-increment counter (8-byte aligned)
+    // scratch: uint32[m + 2] (the documented size) — the first `grid` entries hold the block counts / offsets, the
+    // 64-bit pre-increment counter sits behind entry m (8-byte aligned)
     uint32_t *warp_counts = scratch;
     auto *base = reinterpret_cast<unsigned long long *>(scratch + ((m + 1) & ~(int64_t)1));
     mgrec::count_kernel<<<grid, mgrec::kBlock, 0, st>>>(info, n, mask_mode, warp_counts);
-    mgrec::scan_kernel<<<1, 1024, 0, st>>>(warp_counts, m, reinterpret_cast<unsigned long long *>(counter), base);
+    mgrec::scan_kernel<<<1, 1024, 0, st>>>(warp_counts, (int64_t)grid, reinterpret_cast<unsigned long long *>(counter), base);
     if (format == 0)
         mgrec::write_kernel<0><<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew,
                                                                 done, info, n, mask_mode, player, warp_counts, base,

@@ -53,6 +53,32 @@ def test_transition_ring_matches_sequential_store(mg, n, cap, fmt, player):
     assert rec.sample(128).shape == (128, width)
 
 
+def test_transition_ring_large_n_multi_pass_scan(mg):
+    """n = 5 * 2^20 + 300 envs: 20 482 blocks, so the single-CTA scan of the block counts takes several passes and
+    carries between them.  Checked on the device: the ring must hold the selected envs' rows in env-id order
+    (the order `torch.nonzero` gives), appended call after call."""
+    n = 5 * (1 << 20) + 300
+    env = mg.MergeVecEnv(n, out_slots=2, seed=5, episode_info=True)
+    env.rollout(215)                                           # mid-run: many envs finish every step
+    rec = mg.TransitionRecorder(env, 3 * n, track_env_ids=True)
+    obs_prev = env.obs_buf[env._slot].clone()
+    expect_ids, expect_rows = [], []
+    for t in range(2):
+        a1, a2 = env.sample_actions()
+        out = env.step(a1, a2)
+        rec.record(obs_prev, a1, a2, out)
+        obs, rew, done, info = out
+        keep = torch.nonzero(info["winner"] != 1).squeeze(1)
+        nxt = torch.where(done.bool().unsqueeze(1), info["terminal_observation"], obs)
+        expect_ids.append(keep)
+        expect_rows.append(torch.cat([obs_prev[keep], a1[keep].float().unsqueeze(1), rew[keep, 0:1], nxt[keep]], 1))
+        obs_prev = obs.clone()
+    ids, rows = torch.cat(expect_ids), torch.cat(expect_rows)
+    assert int(rec.counter.item()) == ids.numel() and 0 < ids.numel() < 2 * n
+    assert torch.equal(rec.env_ids[:ids.numel()].long(), ids)
+    assert torch.equal(rec.ring[:ids.numel()], rows)
+
+
 def test_recorder_all_mask_and_sticky_done(mg):
     n = 200
     env = mg.MergeVecEnv(n, out_slots=2, auto_reset=False, episode_info=False)
