@@ -1,0 +1,41 @@
+"""bench.py's output contract, checked on CPU through the arm that needs no GPU (`--impl reference` =
+the plain-C oracle port on the host cores): one JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_bench(*args, env=None):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    return lines
+
+
+def test_reference_arm_prints_one_contract_line():
+    lines = run_bench("--impl", "reference", "--gpus", "1", "--steps", "3", "--warmup", "3")
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"]
+    assert d["value"] > 0 and abs(d["value"] - d["config"]["envs"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["unit"] == d["unit"]
+    assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_under_torchrun_env_only_rank0_prints():
+    """N > 1: rank 0 alone runs and prints; the other ranks exit 0 without work (no rendezvous needed)."""
+    base = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r1 = run_bench("--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3", env=dict(base, RANK="1", LOCAL_RANK="1"))
+    assert r1 == []
+    r0 = run_bench("--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3", env=dict(base, RANK="0", LOCAL_RANK="0"))
+    assert len(r0) == 1 and json.loads(r0[0])["n_gpus"] == 2
