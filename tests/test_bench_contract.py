@@ -39,3 +39,32 @@ def test_reference_arm_under_torchrun_env_only_rank0_prints():
     assert r1 == []
     r0 = run_bench("--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3", env=dict(base, RANK="0", LOCAL_RANK="0"))
     assert len(r0) == 1 and json.loads(r0[0])["n_gpus"] == 2
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_contract_line():
+    """The product arm on one GPU, short run: every key of the contract, roofline consistent with the timing,
+    e2e bytes counted from the copied tensors, launches counted."""
+    lines = run_bench("--gpus", "1", "--steps", "48", "--warmup", "3", "--cpu-seconds", "1", "--flush-steps", "4",
+                      "--rollout-k", "4", "--e2e-steps", "3")
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    n = d["config"]["envs_per_gpu"]
+    assert "impl" not in d and d["metric"] == "env_steps_per_sec" and d["n_gpus"] == 1 and d["steps"] == 48
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert abs(d["value"] - n / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - 156 * n / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert 0.3 < r["frac"] < 1.05
+    assert d["gpu_launches"] == 48
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 2 * n and e["d2h_bytes_per_step"] == 50 * n and 0 < e["value"] < d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert "l2" in d["config"] and "workload" in d["config"]
+    assert d["overlapped_streams"]["value"] > 0 and d["l2_warm"]["value"] > 0
