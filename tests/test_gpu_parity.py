@@ -458,3 +458,35 @@ def test_gym_registration_drop_in(mg, monkeypatch):
         reward, reward_op = rewards
         state = next_state
     assert done and info["collision"] and env.winner is None and t == 150
+
+
+@pytest.mark.parametrize("pvp", [True, False])
+def test_injected_states_parity(mg, pvp):
+    """States no trajectory from the fixed start reaches: both cars anywhere on [0, 1100) with any speed in
+    [0, 45), many of them inside the 8 x 4 collision box around the merge point, on either side of END_POINT,
+    or crossing it together.  The float64 state is written into both implementations, then 12 steps with
+    random actions: flags bit-exact, float64 state bit-identical, obs / rewards within 1e-5."""
+    n, T = 1 << 15, 12
+    rng = np.random.default_rng(77 + pvp)
+    p1 = rng.uniform(0.0, 1100.0, n); p2 = rng.uniform(0.0, 1100.0, n)
+    k = n // 2                                                   # half of them: close pairs near the merge zone
+    p1[:k] = rng.uniform(900.0, 1010.0, k); p2[:k] = p1[:k] + rng.normal(0.0, 6.0, k)
+    p1[k:k + 4096] = 950.0 - rng.uniform(0.0, 9.0, 4096); p2[k:k + 4096] = 950.0 - rng.uniform(0.0, 9.0, 4096)   # photo finishes
+    v1 = rng.uniform(0.0, 45.0, n); v2 = rng.uniform(0.0, 45.0, n)
+    v1[::7] = 0.0
+    env = mg.MergeVecEnv(n, mode="pvp" if pvp else "pve", auto_reset=True)
+    ref = mo.RefVecEnv(n, pvp=pvp, auto_reset=True)
+    for name, val in (("pos1", p1), ("vel1", v1), ("pos2", p2), ("vel2", v2)):
+        getattr(env, name).copy_(torch.from_numpy(val))
+        getattr(ref, name)[:] = val
+    acts = rng.integers(0, 5, (T, 2, n)).astype(np.uint8)
+    seen_collision = seen_w1 = seen_w2 = 0
+    for t in range(T):
+        a1, a2 = acts[t]
+        out = env.step(torch.from_numpy(a1).cuda(), torch.from_numpy(a2).cuda() if pvp else None)
+        r = ref.step(a1, a2 if pvp else None)
+        assert_step_equal(out, r, t)
+        seen_collision += int((r[3] & 1).sum()); w = (r[3] & mo.INFO_WINNER_MASK) >> 1
+        seen_w1 += int((w == 1).sum()); seen_w2 += int((w == 2).sum())
+    assert_state_bit_exact(env, ref)
+    assert seen_collision > 1000 and seen_w1 > 1000 and seen_w2 > 1000     # the interesting branches were all taken
