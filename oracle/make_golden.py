@@ -18,6 +18,10 @@ stores what `reset()` / `step()` return:
   the fixture the CUDA kernel is compared with directly.
 * `kat.json`               known-answer episodes for scripted action pairs
   (SURVEY.md §8c): steps, winner, collision, returns, final positions, last obs.
+* `injected_states.npz`    (`--injected`) 6 000 single steps from states written into the reference env
+  (`state1/state2['pos'|'vel']`) — close pairs around the merge point, photo finishes at END_POINT, stopped
+  cars, far-apart cars — with the winner the reference would hold there; pins the closed-form collision /
+  winner / reward logic of the oracle away from the trajectories the fixed start can reach.
 * `dqn_policies.npz`       (`--policies`) weights of two shipped DQN checkpoints and their greedy
   episodes against the L0 opponent in the reference env (policy-in-the-loop).
 """
@@ -126,7 +130,42 @@ def main():
         print(k["a1"], k["a2"], k["steps"], k["winner"], k["collision"], k["R1"], k["R2"], k["pos1"], k["pos2"])
 
 
-if __name__ == "__main__" and "--policies" not in sys.argv:
+def injected(env, m, seed):
+    """One reference step from each of m injected states.  `winner` before the step is what the reference's
+    own logic implies for the injected positions: a car already past END_POINT can only be there as the winner
+    (both past it would have ended the episode), so states with both cars past END_POINT are not generated."""
+    rng = np.random.default_rng(seed)
+    p1 = rng.uniform(0.0, 1100.0, m); p2 = rng.uniform(0.0, 1100.0, m)
+    k = m // 2
+    p1[:k] = rng.uniform(900.0, 1010.0, k); p2[:k] = p1[:k] + rng.normal(0.0, 6.0, k)
+    q = m // 8
+    p1[k:k + q] = 950.0 - rng.uniform(0.0, 9.0, q); p2[k:k + q] = 950.0 - rng.uniform(0.0, 9.0, q)
+    v1 = rng.uniform(0.0, 45.0, m); v2 = rng.uniform(0.0, 45.0, m)
+    v1[::7] = 0.0; v2[3::11] = 0.0
+    both = (p1 > 950.0) & (p2 >= 950.0)
+    p2[both] = rng.uniform(800.0, 949.0, int(both.sum()))
+    pvp = rng.random(m) < 0.75
+    acts = rng.integers(0, 5, (m, 2)).astype(np.uint8)
+    win0 = np.where(p1 > 950.0, 1, np.where(p2 >= 950.0, 2, 0)).astype(np.uint8)
+    out = dict(pos=np.stack([p1, v1, p2, v2], 1), pvp=pvp, actions=acts, winner_before=win0,
+               obs=np.zeros((m, 10)), rewards=np.zeros((m, 2)), done=np.zeros(m, bool), collision=np.zeros(m, bool),
+               winner=np.zeros(m, np.uint8), state_after=np.zeros((m, 4)))
+    with quiet():
+        for i in range(m):
+            env.reset()
+            env.state1['pos'], env.state1['vel'] = float(p1[i]), float(v1[i])
+            env.state2['pos'], env.state2['vel'] = float(p2[i]), float(v2[i])
+            env.winner = int(win0[i]) or None
+            o, r, d, info = env.step(int(acts[i, 0]), int(acts[i, 1]) if pvp[i] else None)
+            out["obs"][i], out["rewards"][i], out["done"][i], out["collision"][i] = _f(o), _f(r), d, info["collision"]
+            out["winner"][i] = env.winner or 0
+            out["state_after"][i] = (env.state1['pos'], env.state1['vel'], env.state2['pos'], env.state2['vel'])
+    return out
+
+
+if __name__ == "__main__" and "--injected" in sys.argv:
+    np.savez_compressed(os.path.join(OUT, "injected_states.npz"), **injected(load_reference_env(), 6000, 11))
+elif __name__ == "__main__" and "--policies" not in sys.argv:
     main()
 
 

@@ -490,3 +490,27 @@ def test_injected_states_parity(mg, pvp):
         seen_w1 += int((w == 1).sum()); seen_w2 += int((w == 2).sum())
     assert_state_bit_exact(env, ref)
     assert seen_collision > 1000 and seen_w1 > 1000 and seen_w2 > 1000     # the interesting branches were all taken
+
+
+def test_injected_states_against_the_reference_fixture(mg, golden):
+    """tests/golden/injected_states.npz: one step of the UNMODIFIED reference env from 6 000 injected states
+    (oracle/make_golden.py --injected).  The CUDA kernel, fed the same float64 state and winner through the
+    state arrays, must return the reference's collision / done / winner bit for bit, its float64 state after
+    the step, and its observations and rewards within 1e-5."""
+    tr = golden("injected_states.npz")
+    for pvp in (True, False):
+        idx = np.nonzero(tr["pvp"] == pvp)[0]
+        n = len(idx)
+        env = mg.MergeVecEnv(n, mode="pvp" if pvp else "pve", auto_reset=False)
+        for j, k in enumerate(("pos1", "vel1", "pos2", "vel2")):
+            getattr(env, k).copy_(torch.from_numpy(tr["pos"][idx, j]))
+        env.meta.copy_(torch.from_numpy(tr["winner_before"][idx].astype(np.int32) << 12).to(env.meta.dtype))
+        a1 = torch.from_numpy(tr["actions"][idx, 0]).cuda(); a2 = torch.from_numpy(tr["actions"][idx, 1]).cuda()
+        obs, rew, done, info = env.step(a1, a2 if pvp else None)
+        assert np.array_equal(done.cpu().numpy().astype(bool), tr["done"][idx])
+        assert np.array_equal(info["collision"].cpu().numpy(), tr["collision"][idx])
+        assert np.array_equal(env.winner.cpu().numpy(), tr["winner"][idx])
+        after = torch.stack([env.pos1, env.vel1, env.pos2, env.vel2], 1).cpu().numpy()
+        assert rel_err(after, tr["state_after"][idx]).max() < 1e-12
+        assert rel_err(obs.cpu().numpy(), tr["obs"][idx]).max() <= TOL
+        assert rel_err(rew.cpu().numpy(), tr["rewards"][idx]).max() <= TOL

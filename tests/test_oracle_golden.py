@@ -205,3 +205,36 @@ def test_collision_rule_equals_reference_polygons():
             got[i] = p1.intersects(p2)
     assert np.array_equal(got, want)
     assert 0.2 < want.mean() < 0.8
+
+
+def _injected_batches(tr):
+    for pvp in (True, False):
+        idx = np.nonzero(tr["pvp"] == pvp)[0]
+        yield pvp, idx
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_injected_states(golden, impl):
+    """One step of the unmodified reference from 6 000 injected states (close pairs around the merge point,
+    photo finishes, stopped cars, a winner already past END_POINT): collision / done / winner bit-exact, the
+    float64 state after the step bit-identical, observations and rewards to 1e-9."""
+    tr = golden("injected_states.npz")
+    assert tr["collision"].sum() > 1000 and (tr["winner"] == 2).sum() > 300
+    for pvp, idx in _injected_batches(tr):
+        n = len(idx)
+        if impl == "numpy":
+            env = mo.RefVecEnv(n, pvp=pvp, auto_reset=False)
+        else:
+            from oracle import c_oracle
+            env = c_oracle.CVecEnv(n, pvp=pvp, auto_reset=False)
+        for j, k in enumerate(("pos1", "vel1", "pos2", "vel2")):
+            getattr(env, k)[:] = tr["pos"][idx, j]
+        env.winner[:] = tr["winner_before"][idx]
+        obs, rew, done, info = env.step(tr["actions"][idx, 0], tr["actions"][idx, 1])
+        assert np.array_equal(done, tr["done"][idx])
+        assert np.array_equal((info & 1).astype(bool), tr["collision"][idx])
+        assert np.array_equal(np.asarray(env.winner), tr["winner"][idx])
+        after = np.stack([env.pos1, env.vel1, env.pos2, env.vel2], 1)
+        assert rel_err(after, tr["state_after"][idx]).max() < CONT_TOL
+        assert rel_err(obs, tr["obs"][idx]).max() < CONT_TOL
+        assert rel_err(rew, tr["rewards"][idx]).max() < CONT_TOL
