@@ -211,6 +211,32 @@ def policy_fixtures():
         out[f"{tag}/result"] = np.array([len(acts), env.winner or 0, int(info["collision"]),
                                          env.r1_accumulate, env.r2_accumulate])
         print(tag, len(acts), env.winner, info, env.r1_accumulate, env.r2_accumulate)
+    # pvp: the "OP:L2" agent (21:33:10) against the second "OP:L1" net (21:36:59) as opponent, which sees the
+    # mirrored observation `state[NUM_STATES//2:] + state[:NUM_STATES//2]` (main.py:196-199); both greedy.
+    # 432 steps: the agent holds action 4 and wins, the opponent switches between actions 0, 1 and 2.
+    nets = {}
+    for tag, prefix in (("L2_2133", "2022--03--31 21:33:10"), ("L1_2136", "2022--03--31 21:36:59")):
+        d = [p for p in sorted(glob.glob(os.path.join(root, "*"))) if os.path.basename(p).startswith(prefix)][0]
+        sd = torch.load(os.path.join(d, "eval.pth"), map_location="cpu", weights_only=True)
+        net = Net(); net.load_state_dict(sd); nets[tag] = net.eval()
+        for k, v in sd.items():
+            out[f"{tag}/{k}"] = v.numpy().astype(np.float32)
+    state = env.reset()
+    acts, obs = [], []
+    with quiet(), torch.no_grad():
+        while True:
+            a = int(torch.max(nets["L2_2133"](torch.FloatTensor(state).unsqueeze(0)), 1)[1][0])
+            mirrored = state[5:] + state[:5]
+            b = int(torch.max(nets["L1_2136"](torch.FloatTensor(mirrored).unsqueeze(0)), 1)[1][0])
+            obs.append(_f(state)); acts.append((a, b))
+            state, r, done, info = env.step(a, b)
+            if done:
+                break
+    out["pvp_L2_vs_L1/traj_obs"] = np.array(obs)
+    out["pvp_L2_vs_L1/traj_actions"] = np.array(acts, np.uint8)
+    out["pvp_L2_vs_L1/result"] = np.array([len(acts), env.winner or 0, int(info["collision"]),
+                                           env.r1_accumulate, env.r2_accumulate])
+    print("pvp_L2_vs_L1", len(acts), env.winner, info, env.r1_accumulate, env.r2_accumulate)
     np.savez_compressed(os.path.join(OUT, "dqn_policies.npz"), **out)
 
 

@@ -131,6 +131,31 @@ def test_shipped_dqn_checkpoint_greedy_vs_L0(mg, ckpt, tag, backend):
     assert abs(R1 - 0.5899968243808502) < 1e-12 and R2 == 1.0
 
 
+@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+def test_two_shipped_checkpoints_play_each_other(mg, ckpt, backend):
+    """pvp with a policy on both sides, the opponent acting on the mirrored observation
+    `state[5:] + state[:5]` (main.py:196-199 = `env.opponent_view`): the "OP:L2" checkpoint against the
+    second "OP:L1" checkpoint, both greedy, in the unmodified reference env — 432 steps, the agent
+    holds action 4 and wins, the opponent switches between actions 0, 1 and 2."""
+    sd1, _ = ckpt("L2_2133"); sd2, _ = ckpt("L1_2136"); _, traj = ckpt("pvp_L2_vs_L1")
+    p1 = mg.MLPPolicy(10, 5, state_dict=sd1, backend=backend)
+    p2 = mg.MLPPolicy(10, 5, state_dict=sd2, backend=backend)
+    env = mg.MergeVecEnv(64, mode="pvp", auto_reset=False)
+    obs = env.reset()
+    T = len(traj["traj_actions"])
+    assert len(set(traj["traj_actions"][:, 1].tolist())) == 3
+    for t in range(T):
+        a1, a2 = p1.act(obs), p2.act(env.opponent_view(obs))
+        assert a1.cpu().tolist() == [int(traj["traj_actions"][t, 0])] * 64, t
+        assert a2.cpu().tolist() == [int(traj["traj_actions"][t, 1])] * 64, t
+        assert rel_err(obs[0].cpu().numpy(), traj["traj_obs"][t]).max() <= 1e-5, t
+        obs, rew, done, info = env.step(a1, a2)
+    steps, winner, col, R1, R2 = traj["result"]
+    assert T == steps == 432 and bool(done.all()) and not bool(info["collision"].any()) and not col
+    assert env.winner.cpu().tolist() == [int(winner)] * 64 == [1] * 64
+    assert abs(float(env.ret1[0]) - R1) <= 1e-9 and abs(float(env.ret2[0]) - R2) <= 1e-9
+
+
 def test_policy_in_the_loop_cuda_graph(mg, ckpt):
     """obs -> fused MLP -> uint8 actions -> mg_step, captured in one CUDA graph: no host sync, and
     the replay equals the eager loop."""
