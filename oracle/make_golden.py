@@ -22,6 +22,8 @@ stores what `reset()` / `step()` return:
   (`state1/state2['pos'|'vel']`) — close pairs around the merge point, photo finishes at END_POINT, stopped
   cars, far-apart cars — with the winner the reference would hold there; pins the closed-form collision /
   winner / reward logic of the oracle away from the trajectories the fixed start can reach.
+* `hdqn_policies.npz`      (`--hdqn`) the reference's own h-DQN classes (scripts/hdqn.py) under fixed torch seeds,
+  greedy, against the constant-speed opponent and in self-play: weights, goals and actions per step.
 * `dqn_policies.npz`       (`--policies`) weights of two shipped DQN checkpoints and their greedy
   episodes against the L0 opponent in the reference env (policy-in-the-loop).
 """
@@ -165,7 +167,7 @@ def injected(env, m, seed):
 
 if __name__ == "__main__" and "--injected" in sys.argv:
     np.savez_compressed(os.path.join(OUT, "injected_states.npz"), **injected(load_reference_env(), 6000, 11))
-elif __name__ == "__main__" and "--policies" not in sys.argv:
+elif __name__ == "__main__" and "--policies" not in sys.argv and "--hdqn" not in sys.argv:
     main()
 
 
@@ -240,5 +242,56 @@ def policy_fixtures():
     np.savez_compressed(os.path.join(OUT, "dqn_policies.npz"), **out)
 
 
+# h-DQN fixtures: the reference's OWN classes (scripts/hdqn.py: Net, Goal_DQN.choose_goal, HDQN.choose_action)
+# with their own initialisation under a fixed torch seed, made greedy by pinning the `np.random.randn() <= EPISILO`
+# draw, driven by the episode loop of hdqn.py:276-312 (goal from the state, action from [goal] + state, goal
+# re-chosen from next_state after every step; the opponent on the mirrored observation in self-play).
+def hdqn_fixtures():
+    import torch
+    env = load_reference_env()                      # also puts the shims and scripts/ on sys.path
+    import warnings
+    with warnings.catch_warnings(), quiet():
+        warnings.simplefilter("ignore")
+        import hdqn as ref                          # the unmodified scripts/hdqn.py (creates its own env at import)
+    ref.USE_CUDA = False
+    ref.np.random.randn = lambda *a: -1e9           # `np.random.randn() <= EPISILO` is always true: greedy
+    out = {}
+    for seed in (7, 36):       # 7: the controller switches action mid-episode; 36: the meta-controller switches goal
+        torch.manual_seed(seed)
+        upper, lower = ref.Goal_DQN(None), ref.HDQN(None)
+        tag = f"seed{seed}"
+        for name, net in (("meta", upper.meta_eval_net), ("ctrl", lower.eval_net)):
+            for k, v in net.state_dict().items():
+                out[f"{tag}/{name}/{k}"] = v.numpy().astype(np.float32)
+        for mode in ("L0", "selfplay"):
+            state = env.reset()
+            rows, obs = [], []
+            done = False
+            with quiet(), torch.no_grad():
+                goal = upper.choose_goal(state)
+                goal_op = upper.choose_goal(state[5:] + state[:5]) if mode == "selfplay" else 0
+                while not done:
+                    gs = torch.unsqueeze(torch.FloatTensor([goal] + state), dim=0)
+                    action = int(lower.choose_action(gs))
+                    action_op = None
+                    if mode == "selfplay":
+                        gso = torch.unsqueeze(torch.FloatTensor([goal_op] + state[5:] + state[:5]), dim=0)
+                        action_op = int(lower.choose_action(gso))
+                    obs.append(_f(state)); rows.append((goal, action, goal_op, action_op or 0))
+                    state, rewards, done, info = env.step(action, action_op)
+                    goal = upper.choose_goal(state)
+                    if mode == "selfplay":
+                        goal_op = upper.choose_goal(state[5:] + state[:5])
+            out[f"{tag}/{mode}/traj_obs"] = np.array(obs)
+            out[f"{tag}/{mode}/traj"] = np.array(rows, np.uint8)          # goal, action, goal_op, action_op
+            out[f"{tag}/{mode}/result"] = np.array([len(rows), env.winner or 0, int(info["collision"]),
+                                                    env.r1_accumulate, env.r2_accumulate])
+            r = np.array(rows)
+            print(tag, mode, len(rows), env.winner, info, [np.bincount(r[:, c], minlength=5).tolist() for c in range(4)])
+    np.savez_compressed(os.path.join(OUT, "hdqn_policies.npz"), **out)
+
+
+if __name__ == "__main__" and "--hdqn" in sys.argv:
+    hdqn_fixtures()
 if __name__ == "__main__" and "--policies" in sys.argv:
     policy_fixtures()

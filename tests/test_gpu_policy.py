@@ -206,6 +206,38 @@ def test_explore_rule_and_goal_status(mg):
     assert mg.goal_status(obs).cpu().tolist() == [0, 1, 1, 2]          # hdqn.py:223-236
 
 
+@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("seed,mode", [(7, "L0"), (7, "selfplay"), (36, "L0"), (36, "selfplay")])
+def test_hdqn_against_the_reference_classes(mg, seed, mode, backend):
+    """tests/golden/hdqn_policies.npz: episodes played by the reference's OWN h-DQN classes (scripts/hdqn.py
+    `Goal_DQN.choose_goal`, `HDQN.choose_action`, their initialisation under a fixed torch seed, greedy) in
+    the unmodified env — against the constant-speed opponent and in self-play on the mirrored observation.
+    `HDQNPolicy` must pick the same goal and the same action at every step (seed 7: the controller switches
+    action mid-episode; seed 36: the meta-controller switches goal)."""
+    z = np.load(os.path.join(GOLDEN, "hdqn_policies.npz"))
+    tag = f"seed{seed}"
+    sd = lambda name: {k.split("/")[-1]: z[k] for k in z.files if k.startswith(f"{tag}/{name}/")}
+    traj, tobs, result = z[f"{tag}/{mode}/traj"], z[f"{tag}/{mode}/traj_obs"], z[f"{tag}/{mode}/result"]
+    pol = mg.HDQNPolicy(meta_state=sd("meta"), ctrl_state=sd("ctrl"), backend=backend)
+    pvp = mode == "selfplay"
+    env = mg.MergeVecEnv(32, mode="pvp" if pvp else "pve", auto_reset=False)
+    obs = env.reset()
+    for t in range(len(traj)):
+        g, a, g_op, a_op = (int(v) for v in traj[t])
+        a1 = pol.act(obs).clone(); g1 = pol.goal.clone()
+        assert g1.cpu().tolist() == [g] * 32 and a1.cpu().tolist() == [a] * 32, t
+        a2 = None
+        if pvp:
+            a2 = pol.act(env.opponent_view(obs)).clone()
+            assert pol.goal.cpu().tolist() == [g_op] * 32 and a2.cpu().tolist() == [a_op] * 32, t
+        assert rel_err(obs[0].cpu().numpy(), tobs[t]).max() <= 1e-5, t
+        obs, rew, done, info = env.step(a1, a2)
+    steps, winner, col, R1, R2 = result
+    assert len(traj) == steps and bool(done.all()) and bool(info["collision"].all()) == bool(col)
+    assert env.winner.cpu().tolist() == [int(winner)] * 32
+    assert abs(float(env.ret1[0]) - R1) <= 1e-9 * max(1.0, abs(R1)) and abs(float(env.ret2[0]) - R2) <= 1e-9 * max(1.0, abs(R2))
+
+
 def test_hdqn_policy_fused_equals_torch(mg):
     n = 3000
     obs = mid_episode_obs(mg, n, seed=9)
