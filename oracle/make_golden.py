@@ -22,6 +22,8 @@ stores what `reset()` / `step()` return:
   (`state1/state2['pos'|'vel']`) — close pairs around the merge point, photo finishes at END_POINT, stopped
   cars, far-apart cars — with the winner the reference would hold there; pins the closed-form collision /
   winner / reward logic of the oracle away from the trajectories the fixed start can reach.
+* `replay_memory.npz`      (`--replay`) three episodes driven by the reference's own `DQN` learner class
+  (scripts/main.py: epsilon rule under a fixed NumPy seed, `store_transition`): actions and the memory rows.
 * `hdqn_policies.npz`      (`--hdqn`) the reference's own h-DQN classes (scripts/hdqn.py) under fixed torch seeds,
   greedy, against the constant-speed opponent and in self-play: weights, goals and actions per step.
 * `dqn_policies.npz`       (`--policies`) weights of two shipped DQN checkpoints and their greedy
@@ -167,7 +169,7 @@ def injected(env, m, seed):
 
 if __name__ == "__main__" and "--injected" in sys.argv:
     np.savez_compressed(os.path.join(OUT, "injected_states.npz"), **injected(load_reference_env(), 6000, 11))
-elif __name__ == "__main__" and "--policies" not in sys.argv and "--hdqn" not in sys.argv:
+elif __name__ == "__main__" and not {"--policies", "--hdqn", "--replay"} & set(sys.argv):
     main()
 
 
@@ -291,6 +293,52 @@ def hdqn_fixtures():
     np.savez_compressed(os.path.join(OUT, "hdqn_policies.npz"), **out)
 
 
+# Replay-memory fixture: the reference's OWN learner class (scripts/main.py `DQN`: choose_action with its
+# epsilon rule under a fixed NumPy seed, store_transition) in the episode loop of main.py:190-221 — the agent
+# loaded from the "OP:L1" checkpoint, the opponent from the "OP:L0" one acting on the mirrored observation —
+# for three episodes (no learn(): the memory stays below MEMORY_CAPACITY).  Records both players' actions per
+# step and the resulting `dqn.memory` rows.
+def replay_fixture():
+    import glob
+    import torch
+    env = load_reference_env()
+    import warnings
+    with warnings.catch_warnings(), quiet():
+        warnings.simplefilter("ignore")
+        import main as ref                          # the unmodified scripts/main.py
+    ref.USE_CUDA = False
+    root = os.path.join(os.environ.get("MERGING_GYM_REFERENCE", "/root/reference"), "test_params", "dqn")
+    find = lambda prefix: [p for p in sorted(glob.glob(os.path.join(root, "*"))) if os.path.basename(p).startswith(prefix)][0]
+    _load = torch.load
+    torch.load = lambda f, *a, **k: _load(f, map_location="cpu", weights_only=True)     # checkpoints were saved from CUDA
+    dqn, opponent = ref.DQN(find("2022--03--31 14:45:59")), ref.DQN(find("2022--03--31 03:37:35"))
+    torch.load = _load
+    np.random.seed(3)
+    acts, dones = [], []
+    with quiet(), torch.no_grad():
+        for ep in range(3):
+            state = env.reset()
+            while True:
+                action = int(dqn.choose_action(state))
+                action_op = int(opponent.choose_action(state[5:] + state[:5]))
+                next_state, rewards, done, info = env.step(action, action_op)
+                if env.winner is not 1:
+                    dqn.store_transition(state, action, rewards[0], next_state)
+                acts.append((action, action_op)); dones.append(done)
+                if done:
+                    break
+                state = next_state
+    c = dqn.memory_counter
+    assert c < ref.MEMORY_CAPACITY
+    a = np.array(acts, np.uint8)
+    print("replay fixture:", len(acts), "steps,", c, "rows stored, action histograms",
+          np.bincount(a[:, 0], minlength=5).tolist(), np.bincount(a[:, 1], minlength=5).tolist())
+    np.savez_compressed(os.path.join(OUT, "replay_memory.npz"), actions=a, done=np.array(dones),
+                        memory=dqn.memory[:c].copy(), counter=np.array(c))
+
+
+if __name__ == "__main__" and "--replay" in sys.argv:
+    replay_fixture()
 if __name__ == "__main__" and "--hdqn" in sys.argv:
     hdqn_fixtures()
 if __name__ == "__main__" and "--policies" in sys.argv:

@@ -127,3 +127,28 @@ def test_csv_episode_logger(mg, tmp_path):
             assert got[0] == mg.replay.CSV_HEADER and len(got) - 1 == len(rows)
             g = np.array([[float(v) for v in r] for r in got[1:]])
             assert rel_err(g, np.array(rows)).max() <= 1e-5
+
+
+def test_replay_rows_against_the_reference_learner(mg):
+    """tests/golden/replay_memory.npz: three episodes driven by the reference's OWN `DQN` class (scripts/main.py:
+    `choose_action` with its epsilon rule under a fixed NumPy seed, `store_transition`, the `env.winner is not 1`
+    guard of the episode loop) in the unmodified env.  Replaying the recorded actions through MergeVecEnv +
+    TransitionRecorder must leave the same rows in the ring: 517 of 680 steps stored."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "replay_memory.npz"))
+    acts, dones, mem, counter = z["actions"], z["done"], z["memory"], int(z["counter"])
+    env = mg.MergeVecEnv(1, mode="pvp", auto_reset=False, out_slots=2)
+    rec = mg.TransitionRecorder(env, 2000)                      # MEMORY_CAPACITY, main.py:16
+    obs = env.reset().clone()
+    for t in range(len(acts)):
+        a1 = torch.tensor([acts[t, 0]], dtype=torch.uint8, device="cuda")
+        a2 = torch.tensor([acts[t, 1]], dtype=torch.uint8, device="cuda")
+        out = env.step(a1, a2)
+        rec.record(obs, a1, a2, out)
+        assert bool(out[2][0]) == bool(dones[t]), t
+        obs = (env.reset() if dones[t] else out[0]).clone()
+    assert int(rec.counter.item()) == counter == 517 and mem.shape == (517, 22)
+    ring = rec.ring[:counter].cpu().numpy()
+    assert np.array_equal(ring[:, 10], mem[:, 10])                               # the action column, exactly
+    assert rel_err(ring, mem).max() <= 1e-5
