@@ -168,7 +168,13 @@ def injected(env, m, seed):
 
 
 if __name__ == "__main__" and "--injected" in sys.argv:
-    np.savez_compressed(os.path.join(OUT, "injected_states.npz"), **injected(load_reference_env(), 6000, 11))
+    _inj = injected(load_reference_env(), 6000, 11)
+    import warnings
+    with warnings.catch_warnings(), quiet():
+        warnings.simplefilter("ignore")
+        import hdqn as _ref_hdqn                    # the reference's goal_status (scripts/hdqn.py:223-236) on those observations
+    _inj["goal_status"] = np.array([_ref_hdqn.goal_status(list(o)) for o in _inj["obs"]], np.uint8)
+    np.savez_compressed(os.path.join(OUT, "injected_states.npz"), **_inj)
 elif __name__ == "__main__" and not {"--policies", "--hdqn", "--replay"} & set(sys.argv):
     main()
 

@@ -204,6 +204,12 @@ def test_explore_rule_and_goal_status(mg):
     obs = torch.zeros(4, 10, device="cuda")
     obs[:, 0] = torch.tensor([-20.0, -5.0, 5.0, 20.0]); obs[:, 9] = 20.0
     assert mg.goal_status(obs).cpu().tolist() == [0, 1, 1, 2]          # hdqn.py:223-236
+    # ... and on the 6 000 observations of the injected-state fixture, labelled by the reference's own function
+    z = np.load(os.path.join(GOLDEN, "injected_states.npz"))
+    got = mg.goal_status(torch.from_numpy(z["obs"]).float().cuda()).cpu().numpy()
+    exact = z["goal_status"]
+    knife = np.abs(np.abs(z["obs"][:, 0]) - 0.5 * z["obs"][:, 9]) < 1e-4 * np.maximum(1.0, np.abs(z["obs"][:, 0]))   # fp32 vs fp64 at the threshold
+    assert np.array_equal(got[~knife], exact[~knife]) and knife.mean() < 0.01 and len(set(exact.tolist())) == 3
 
 
 @pytest.mark.parametrize("backend", ["fused", "tf32x3"])
