@@ -383,7 +383,8 @@ def run_b200(args):
     # ---- end-to-end through the host-buffer C-ABI entry (mg_step_host) -------------------------
     import numpy as np
     E = max(3, min(K, args.e2e_steps))
-    h1 = acts1[0].cpu().numpy().copy(); h2 = acts2[0].cpu().numpy().copy()
+    h1, h2 = env.host_action_buffers()                    # pinned host memory: this step's inputs live here
+    h1[:] = acts1[0].cpu().numpy(); h2[:] = acts2[0].cpu().numpy()
     for _ in range(2):
         env.step_host(h1, h2)
     if world > 1:
@@ -399,9 +400,11 @@ def run_b200(args):
     e2e_s = float(t.item())
     e2e = {"value": total_envs * E / e2e_s, "unit": UNIT, "steps": E,
            "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": n * (40 + 8 + 1 + 1),
-           "api": "MergeVecEnv.step_host -> mg_step_host (pinned host buffers, stream sync per step)",
-           "bound": "PCIe: 52 B/env-step cross the bus; this box sustains ~46 GB/s device->host whether the "
-                    "copy engine or the kernel's own stores move the data (profiles/README.md)"}
+           "api": "MergeVecEnv.step_host -> mg_step_host (actions in pinned host memory, outputs into pinned host "
+                  "memory, stream synchronised every step)",
+           "pcie_gbs": total_envs / world * 52 * E / e2e_s / 1e9,
+           "bound": "PCIe: 52 B/env-step cross the bus (2 up, 50 down); a plain 52 MB device->host copy reaches "
+                    "~56 GB/s on this pool (profiles/README.md)"}
 
     # ---- episode statistics: the one collective on this path (tiny int64 all-reduce over NCCL) --
     stats = env.stats(reduce=world > 1)

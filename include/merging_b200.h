@@ -35,7 +35,7 @@ extern "C" {
 #define MG_API __attribute__((visibility("default")))
 #endif
 
-#define MG_ABI_VERSION 2
+#define MG_ABI_VERSION 3
 #define MG_OBS_DIM 10      /* merging_env.py:75,118-132 */
 #define MG_NUM_ACTIONS 5   /* merging_env.py:101-102   */
 
@@ -178,12 +178,16 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
 /* Host-buffer convenience path (the drop-in for callers that keep Python/NumPy data on the
  * host, like the reference scripts): copies h_a1/h_a2 (uint8[n]) to the device scratch actions
  * d_a1/d_a2, runs mg_step, copies obs/rew/done/info back into the h_out arrays and SYNCHRONISES
- * the stream.  Optional members of h_out may be NULL.  Pinned host memory is recommended. */
+ * the stream(s).  Optional members of h_out may be NULL.  Pinned host memory is recommended.
+ * copy_stream_or_null + chunks > 1: the envs are stepped in `chunks` (<= 16) pieces of whole 256-env
+ * blocks and the device-to-host copies of a piece run on copy_stream while the next piece is uploaded
+ * and stepped on `stream` (the bus is the bottleneck of this path: 52 bytes per env-step).  Results are
+ * identical to the single-piece call.  Both streams must belong to the current device. */
 MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
                         const uint8_t *h_a2_or_null, uint8_t *d_a1, uint8_t *d_a2,
                         const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out,
                         int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
-                        void *stream);
+                        void *stream, void *copy_stream_or_null, int32_t chunks);
 
 /* ---- "next" row: policy in the loop -------------------------------------------
  * Fused forward + arg-max of the reference's Q-network `Net(in, out)`:

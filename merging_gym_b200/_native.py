@@ -10,7 +10,7 @@ import os
 
 from ._paths import LIB_PATH
 
-MG_ABI_VERSION = 2
+MG_ABI_VERSION = 3
 OBS_DIM = 10
 NUM_ACTIONS = 5
 STATS_ROWS = 1024
@@ -96,7 +96,7 @@ def load():
     lib.mg_rollout.argtypes = [C.POINTER(MgState), i64, C.c_int, u64, u64, u64, i32,
                                C.POINTER(MgRewards), C.POINTER(MgOut), vp, vp, u32, rsp, vp]
     lib.mg_step_host.argtypes = [C.POINTER(MgState), i64, vp, vp, vp, vp, C.POINTER(MgRewards),
-                                 C.POINTER(MgOut), C.POINTER(MgOut), vp, u32, rsp, vp]
+                                 C.POINTER(MgOut), C.POINTER(MgOut), vp, u32, rsp, vp, vp, i32]
     lib.mg_mlp_act.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mg_mlp_act.restype = C.c_int
     lib.mg_mlp_act_tc.argtypes = lib.mg_mlp_act.argtypes

@@ -432,6 +432,23 @@ int check_out(const MgOut *o, bool all_required) {
     return MG_OK;
 }
 const MgRewards kDefaultRewards = {2.0, 1.0, -10.0, 0.001, 0.0};
+constexpr int kMaxHostChunks = 16;
+// Events that order mg_step_host's copy stream behind its kernels: created on first use, one set per host thread
+// and device, never destroyed (the only objects the library ever creates; no device memory).
+cudaEvent_t *host_chunk_events() {
+    constexpr int kMaxDev = 32;
+    thread_local cudaEvent_t ev[kMaxDev][kMaxHostChunks];
+    thread_local bool ready[kMaxDev] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    if (!ready[dev]) {
+        for (int i = 0; i < kMaxHostChunks; ++i)
+            if (cudaEventCreateWithFlags(&ev[dev][i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ready[dev] = true;
+    }
+    return ev[dev];
+}
+
 const MgResetSpec kFixedReset = {MG_RESET_FIXED, 0u, 0ull, 0ull};
 
 int check_reset(const MgResetSpec *r) {
@@ -564,28 +581,55 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
 MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, const uint8_t *h_a2,
                         uint8_t *d_a1, uint8_t *d_a2, const MgRewards *rewards, const MgOut *d_out,
                         const MgOut *h_out, int64_t *stats, uint32_t flags, const MgResetSpec *reset,
-                        void *stream) {
+                        void *stream, void *copy_stream, int32_t chunks) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     if (n == 0) return MG_OK;
-    if (!h_a1 || !d_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "h_a1, d_a1, d_out or h_out is NULL");
+    if (!state || !h_a1 || !d_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "state, h_a1, d_a1, d_out or h_out is NULL");
     if (h_a2 && !d_a2) return fail(MG_ERR_NULL_POINTER, "h_a2 given without d_a2 scratch");
-    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_reset(reset)) return rc;
+    cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+    // Chunked pipeline: with a second stream the envs are stepped in `chunks` pieces; the D2H of piece c (copy
+    // stream) overlaps the H2D + kernel of piece c+1 (main stream), so the bus idles only while the first
+    // piece is uploaded and stepped.  Pieces are multiples of 256 envs (whole blocks, every array 16-byte aligned).
+    int nch = (copy_stream && copy_stream != stream && chunks > 1) ? (chunks > kMaxHostChunks ? kMaxHostChunks : chunks) : 1;
+    int64_t piece = ((n + nch - 1) / nch + 255) / 256 * 256;
+    cudaEvent_t *ev = nullptr;
+    if (nch > 1) {
+        ev = host_chunk_events();
+        if (!ev) return cuda_fail(cudaGetLastError(), "mg_step_host event");
+    }
+    const MgResetSpec rs0 = reset ? *reset : kFixedReset;
     cudaError_t e;
-    if (n > 0) {
-        if ((e = cudaMemcpyAsync(d_a1, h_a1, (size_t)n, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a1");
-        if (h_a2 && (e = cudaMemcpyAsync(d_a2, h_a2, (size_t)n, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a2");
+    int c = 0;
+    for (int64_t off = 0; off < n; off += piece, ++c) {
+        const int64_t m = n - off < piece ? n - off : piece;
+        const size_t M = (size_t)m;
+        if ((e = cudaMemcpyAsync(d_a1 + off, h_a1 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a1");
+        if (h_a2 && (e = cudaMemcpyAsync(d_a2 + off, h_a2 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a2");
+        const MgState sub = {state->pos1 + off, state->vel1 + off, state->pos2 + off, state->vel2 + off,
+                             state->ret1 + off, state->ret2 + off, state->meta + off};
+        const MgOut d = {d_out->obs ? d_out->obs + off * MG_OBS_DIM : nullptr, d_out->rew ? d_out->rew + off * 2 : nullptr,
+                         d_out->done ? d_out->done + off : nullptr, d_out->info ? d_out->info + off : nullptr,
+                         d_out->term_obs ? d_out->term_obs + off * MG_OBS_DIM : nullptr,
+                         d_out->ep_ret ? d_out->ep_ret + off * 2 : nullptr, d_out->ep_len ? d_out->ep_len + off : nullptr};
+        MgResetSpec rs = rs0;
+        rs.env_id_base += (uint64_t)off;
+        if (int rc = mg_step(&sub, m, d_a1 + off, h_a2 ? d_a2 + off : nullptr, MG_ACT_U8, rewards, &d, stats, flags, &rs, stream)) return rc;
+        cudaStream_t out_st = st;
+        if (nch > 1) {
+            if ((e = cudaEventRecord(ev[c], st))) return cuda_fail(e, "mg_step_host event record");
+            if ((e = cudaStreamWaitEvent(cs, ev[c], 0))) return cuda_fail(e, "mg_step_host event wait");
+            out_st = cs;
+        }
+#define MG_D2H(field, count, type)                                                                                    \
+        if (h_out->field && d.field &&                                                                                \
+            (e = cudaMemcpyAsync(h_out->field + off * (count), d.field, M * (count) * sizeof(type), cudaMemcpyDeviceToHost, out_st))) \
+            return cuda_fail(e, "D2H " #field);
+        MG_D2H(obs, MG_OBS_DIM, float) MG_D2H(rew, 2, float) MG_D2H(done, 1, uint8_t) MG_D2H(info, 1, uint8_t)
+        MG_D2H(term_obs, MG_OBS_DIM, float) MG_D2H(ep_ret, 2, float) MG_D2H(ep_len, 1, int32_t)
+#undef MG_D2H
     }
-    if (int rc = mg_step(state, n, d_a1, h_a2 ? d_a2 : nullptr, MG_ACT_U8, rewards, d_out, stats, flags, reset, stream)) return rc;
-    if (n > 0) {
-        const size_t N = (size_t)n;
-        if (h_out->obs && (e = cudaMemcpyAsync(h_out->obs, d_out->obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H obs");
-        if (h_out->rew && (e = cudaMemcpyAsync(h_out->rew, d_out->rew, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H rew");
-        if (h_out->done && (e = cudaMemcpyAsync(h_out->done, d_out->done, N, cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H done");
-        if (h_out->info && (e = cudaMemcpyAsync(h_out->info, d_out->info, N, cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H info");
-        if (h_out->term_obs && d_out->term_obs && (e = cudaMemcpyAsync(h_out->term_obs, d_out->term_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H term_obs");
-        if (h_out->ep_ret && d_out->ep_ret && (e = cudaMemcpyAsync(h_out->ep_ret, d_out->ep_ret, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H ep_ret");
-        if (h_out->ep_len && d_out->ep_len && (e = cudaMemcpyAsync(h_out->ep_len, d_out->ep_len, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H ep_len");
-    }
+    if (nch > 1 && (e = cudaStreamSynchronize(cs))) return cuda_fail(e, "mg_step_host copy-stream sync");
     if ((e = cudaStreamSynchronize(st))) return cuda_fail(e, "mg_step_host sync");
     return MG_OK;
 }

@@ -169,6 +169,7 @@ class MergeVecEnv:
         self.act1 = torch.zeros(n, dtype=torch.uint8, device=dev)     # sample_actions / step_host scratch
         self.act2 = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._host = None
+        self._copy_stream = None
         self._pending = None
 
         self.single_observation_space: Box = merge_observation_space()
@@ -356,11 +357,43 @@ class MergeVecEnv:
                                            self._flags(), C.byref(self._rs), self._stream()), "mg_rollout")
 
     # ------------------------------------------------------------------ host-buffer path
-    def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, zero_copy: bool = False):
+    def _host_buffers(self) -> dict:
+        if self._host is None:
+            n, pin = self.num_envs, dict(pin_memory=True)
+            self._host = dict(a1=torch.zeros(n, dtype=torch.uint8, **pin), a2=torch.zeros(n, dtype=torch.uint8, **pin),
+                              obs=torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, **pin),
+                              rew=torch.zeros(n, 2, dtype=torch.float32, **pin),
+                              done=torch.zeros(n, dtype=torch.uint8, **pin),
+                              info=torch.zeros(n, dtype=torch.uint8, **pin))
+            h = self._host
+            self._host_np = (h["a1"].numpy(), h["a2"].numpy())
+            self._host_out = nat.MgOut(h["obs"].data_ptr(), h["rew"].data_ptr(), h["done"].data_ptr(),
+                                       h["info"].data_ptr(), None, None, None)
+        return self._host
+
+    def _copy_stream_ptr(self, chunks: int):
+        if chunks <= 1:
+            return None
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return C.c_void_p(self._copy_stream.cuda_stream)
+
+    def host_action_buffers(self):
+        """(a1, a2): uint8[N] NumPy views of the PINNED staging buffers `step_host` uploads from.  A caller that
+        writes its actions into them and passes them back to `step_host` saves the extra host-side copy."""
+        self._host_buffers()
+        return self._host_np
+
+    def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, zero_copy: bool = False,
+                  chunks: int = 1):
         """Drop-in for host-resident callers: uint8 NumPy actions in, NumPy outputs out.
 
         Default: one `mg_step_host` call = H2D of the actions, the fused step, D2H of
-        obs/rew/done/info into pinned host buffers, stream synchronise.
+        obs/rew/done/info into pinned host buffers, stream synchronise.  `chunks > 1` steps the envs in
+        that many pieces so that the device-to-host copy of one piece (on a private copy stream)
+        overlaps the upload and the kernel of the next; on a PCIe 5 x16 B200 this does not pay (the
+        upload + kernel it can hide are 0.07 ms of 1.04 ms, the extra small copies cost more:
+        `profiles/e2e_paths.py`), so the default is one piece.
         `zero_copy=True`: `mg_step` is handed the pinned host buffers themselves (pinned memory is
         device-addressable under UVA), so the kernel reads the actions and streams its outputs
         across PCIe while it computes — no staging copy in HBM, no separate memcpy.
@@ -368,20 +401,13 @@ class MergeVecEnv:
         by the next call).
         """
         n = self.num_envs
-        if self._host is None:
-            pin = dict(pin_memory=True)
-            self._host = dict(a1=torch.zeros(n, dtype=torch.uint8, **pin), a2=torch.zeros(n, dtype=torch.uint8, **pin),
-                              obs=torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, **pin),
-                              rew=torch.zeros(n, 2, dtype=torch.float32, **pin),
-                              done=torch.zeros(n, dtype=torch.uint8, **pin),
-                              info=torch.zeros(n, dtype=torch.uint8, **pin))
-            h = self._host
-            self._host_out = nat.MgOut(h["obs"].data_ptr(), h["rew"].data_ptr(), h["done"].data_ptr(),
-                                       h["info"].data_ptr(), None, None, None)
-        h = self._host
-        h["a1"].numpy()[:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
-        if a2 is not None:
-            h["a2"].numpy()[:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
+        h = self._host_buffers()
+        # actions written in place into `host_action_buffers()` are used as they are; anything else is
+        # staged into those pinned buffers first (an extra host copy of n bytes per player)
+        if a1 is not self._host_np[0]:
+            self._host_np[0][:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
+        if a2 is not None and a2 is not self._host_np[1]:
+            self._host_np[1][:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
         with torch.cuda.device(self.device):
             if zero_copy:
                 nat.check(self._lib.mg_step(C.byref(self._state), n, _ptr(h["a1"]),
@@ -396,7 +422,7 @@ class MergeVecEnv:
                                                  _ptr(self.act1), _ptr(self.act2), C.byref(self._rw),
                                                  C.byref(self._outs[self._slot]), C.byref(self._host_out),
                                                  _ptr(self.stats_buf), self._flags(), C.byref(self._rs),
-                                                 self._stream()),
+                                                 self._stream(), self._copy_stream_ptr(chunks), int(chunks)),
                           "mg_step_host")
         return h["obs"].numpy(), h["rew"].numpy(), h["done"].numpy().view(np.bool_), h["info"].numpy()
 

@@ -339,6 +339,29 @@ def test_step_host_matches_device_path(mg):
     assert np.array_equal(ho, o.cpu().numpy())
 
 
+@pytest.mark.parametrize("chunks", [1, 3, 16])
+def test_step_host_pipeline_pieces(mg, chunks):
+    """`mg_step_host` stepping the envs in pieces on two streams (D2H of one piece under the upload + kernel of the
+    next) gives exactly the single-launch result — ragged last piece, random-start resets (their Philox counter
+    is the GLOBAL env id, so each piece must carry its offset), statistics, actions passed in the pinned buffers."""
+    n = 100_037
+    kw = dict(reset_mode="random", reset_seed=5, env_id_base=1 << 33)
+    a = mg.MergeVecEnv(n, **kw); b = mg.MergeVecEnv(n, **kw)
+    p1, p2 = a.host_action_buffers()
+    rng = np.random.default_rng(chunks)
+    for t in range(260):
+        p1[:] = rng.integers(0, 5, n); p2[:] = rng.integers(0, 5, n)
+        ho, hr, hd, hi = a.step_host(p1, p2, chunks=chunks)
+        o, r, d, i = b.step(p1.copy(), p2.copy())
+        if t % 20 == 0 or t > 250:
+            assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy())
+            assert np.array_equal(hd, d.cpu().numpy()) and np.array_equal(hi, i["flags"].cpu().numpy())
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert a.stats() == b.stats() and a.stats()["episodes"] > n // 2
+    assert torch.equal(a.terminal_obs, b.terminal_obs)
+
+
 def test_scalar_reference_interface(mg):
     """`gym.make("merging_env-v0")`-style use, as scripts/main.py:190-218 drives it."""
     env = mg.make("merging_env-v0")
