@@ -432,6 +432,18 @@ int check_out(const MgOut *o, bool all_required) {
     return MG_OK;
 }
 const MgRewards kDefaultRewards = {2.0, 1.0, -10.0, 0.001, 0.0};
+// true when obs < rew < done < info follow each other (gaps < 4 KB in total) with the same byte offsets in the
+// device and the host set, and no optional per-episode array is requested on the host side
+bool outputs_joined(const MgOut &d, const MgOut &h, size_t m) {
+    if (!h.obs || !h.rew || !h.done || !h.info || h.term_obs || h.ep_ret || h.ep_len) return false;
+    const char *d0 = (const char *)d.obs, *h0 = (const char *)h.obs;
+    const ptrdiff_t o1 = (const char *)d.rew - d0, o2 = (const char *)d.done - d0, o3 = (const char *)d.info - d0;
+    if (o1 != (const char *)h.rew - h0 || o2 != (const char *)h.done - h0 || o3 != (const char *)h.info - h0) return false;
+    if (!(0 < o1 && o1 < o2 && o2 < o3)) return false;
+    const size_t need = m * (MG_OBS_DIM * sizeof(float) + 2 * sizeof(float) + 1 + 1);
+    return (size_t)o1 >= m * MG_OBS_DIM * sizeof(float) && (size_t)(o2 - o1) >= m * 2 * sizeof(float) && (size_t)(o3 - o2) >= m &&
+           (size_t)o3 + m <= need + 4096;
+}
 constexpr int kMaxHostChunks = 16;
 // Events that order mg_step_host's copy stream behind its kernels: created on first use, one set per host thread
 // and device, never destroyed (the only objects the library ever creates; no device memory).
@@ -604,8 +616,14 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
     for (int64_t off = 0; off < n; off += piece, ++c) {
         const int64_t m = n - off < piece ? n - off : piece;
         const size_t M = (size_t)m;
-        if ((e = cudaMemcpyAsync(d_a1 + off, h_a1 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a1");
-        if (h_a2 && (e = cudaMemcpyAsync(d_a2 + off, h_a2 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a2");
+        // one upload when the two action vectors sit at the same distance on both sides (single piece only)
+        const bool acts_joined = nch == 1 && h_a2 && d_a2 > d_a1 && (d_a2 - d_a1) == (h_a2 - h_a1) && (size_t)(d_a2 - d_a1) < M + 4096;
+        if (acts_joined) {
+            if ((e = cudaMemcpyAsync(d_a1, h_a1, (size_t)(d_a2 - d_a1) + M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D actions");
+        } else {
+            if ((e = cudaMemcpyAsync(d_a1 + off, h_a1 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a1");
+            if (h_a2 && (e = cudaMemcpyAsync(d_a2 + off, h_a2 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a2");
+        }
         const MgState sub = {state->pos1 + off, state->vel1 + off, state->pos2 + off, state->vel2 + off,
                              state->ret1 + off, state->ret2 + off, state->meta + off};
         const MgOut d = {d_out->obs ? d_out->obs + off * MG_OBS_DIM : nullptr, d_out->rew ? d_out->rew + off * 2 : nullptr,
@@ -620,6 +638,12 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
             if ((e = cudaEventRecord(ev[c], st))) return cuda_fail(e, "mg_step_host event record");
             if ((e = cudaStreamWaitEvent(cs, ev[c], 0))) return cuda_fail(e, "mg_step_host event wait");
             out_st = cs;
+        }
+        // one download when [obs | rew | done | info] are laid out back to back identically on both sides
+        if (nch == 1 && outputs_joined(d, *h_out, M)) {
+            const size_t span = (size_t)((const char *)d.info - (const char *)d.obs) + M;
+            if ((e = cudaMemcpyAsync(h_out->obs, d.obs, span, cudaMemcpyDeviceToHost, out_st))) return cuda_fail(e, "D2H outputs");
+            continue;
         }
 #define MG_D2H(field, count, type)                                                                                    \
         if (h_out->field && d.field &&                                                                                \

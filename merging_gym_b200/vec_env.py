@@ -36,6 +36,18 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _slot_views(block: torch.Tensor, K: int, n: int, n_pad: int):
+    """obs f32[K,n,10], rew f32[K,n,2], done u8[K,n], info u8[K,n] views of a uint8 block of K slots of
+    n_pad * 50 bytes laid out [obs | rew | done | info] (n_pad a multiple of 16: every piece 16-byte aligned)."""
+    f = block.view(torch.float32)
+    sf = n_pad * 50 // 4                                   # slot stride in floats
+    obs = torch.as_strided(f, (K, n, 10), (sf, 10, 1), 0)
+    rew = torch.as_strided(f, (K, n, 2), (sf, 2, 1), n_pad * 10)
+    done = torch.as_strided(block, (K, n), (n_pad * 50, 1), n_pad * 48)
+    info = torch.as_strided(block, (K, n), (n_pad * 50, 1), n_pad * 49)
+    return obs, rew, done, info
+
+
 class StepInfo(Mapping):
     """Lazy `info` of one vector step: device tensors decoded from the info byte on access.
 
@@ -145,10 +157,10 @@ class MergeVecEnv:
                                     (self.pos1, self.vel1, self.pos2, self.vel2, self.ret1, self.ret2, self.meta)])
         K = self.out_slots
         n_pad = (n + 15) // 16 * 16                  # keeps every slot's base pointer 16-byte aligned
-        self.obs_buf = torch.zeros(K, n_pad, nat.OBS_DIM, dtype=torch.float32, device=dev)[:, :n]
-        self.rew_buf = torch.zeros(K, n_pad, 2, dtype=torch.float32, device=dev)[:, :n]
-        self.done_buf = torch.zeros(K, n_pad, dtype=torch.uint8, device=dev)[:, :n]
-        self.info_buf = torch.zeros(K, n_pad, dtype=torch.uint8, device=dev)[:, :n]
+        # one allocation, slot-major: [obs | rew | done | info] of a slot are back to back (50 bytes per env), so the
+        # host-buffer path can fetch a whole slot with ONE device-to-host copy
+        self._out_block = torch.zeros(K * n_pad * 50, dtype=torch.uint8, device=dev)
+        self.obs_buf, self.rew_buf, self.done_buf, self.info_buf = _slot_views(self._out_block, K, n, n_pad)
         self._extras = {}
         if episode_info:
             self.terminal_obs = torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, device=dev)
@@ -166,8 +178,8 @@ class MergeVecEnv:
                       for k in range(K)]
         self.stats_buf = (torch.zeros(nat.STATS_ROWS, nat.STATS_COLS, dtype=torch.int64, device=dev)
                           if track_stats else None)
-        self.act1 = torch.zeros(n, dtype=torch.uint8, device=dev)     # sample_actions / step_host scratch
-        self.act2 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._act_block = torch.zeros(2 * n_pad, dtype=torch.uint8, device=dev)   # sample_actions / step_host scratch
+        self.act1, self.act2 = self._act_block[:n], self._act_block[n_pad:n_pad + n]
         self._host = None
         self._copy_stream = None
         self._pending = None
@@ -359,12 +371,15 @@ class MergeVecEnv:
     # ------------------------------------------------------------------ host-buffer path
     def _host_buffers(self) -> dict:
         if self._host is None:
-            n, pin = self.num_envs, dict(pin_memory=True)
-            self._host = dict(a1=torch.zeros(n, dtype=torch.uint8, **pin), a2=torch.zeros(n, dtype=torch.uint8, **pin),
-                              obs=torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, **pin),
-                              rew=torch.zeros(n, 2, dtype=torch.float32, **pin),
-                              done=torch.zeros(n, dtype=torch.uint8, **pin),
-                              info=torch.zeros(n, dtype=torch.uint8, **pin))
+            # pinned mirrors with the device layout (actions: [a1 | a2]; outputs: [obs | rew | done | info]), so that
+            # mg_step_host needs one copy per direction
+            n = self.num_envs
+            n_pad = (n + 15) // 16 * 16
+            acts = torch.zeros(2 * n_pad, dtype=torch.uint8, pin_memory=True)
+            outs = torch.zeros(n_pad * 50, dtype=torch.uint8, pin_memory=True)
+            obs, rew, done, info = _slot_views(outs, 1, n, n_pad)
+            self._host = dict(a1=acts[:n], a2=acts[n_pad:n_pad + n], obs=obs[0], rew=rew[0], done=done[0], info=info[0],
+                              _blocks=(acts, outs))
             h = self._host
             self._host_np = (h["a1"].numpy(), h["a2"].numpy())
             self._host_out = nat.MgOut(h["obs"].data_ptr(), h["rew"].data_ptr(), h["done"].data_ptr(),
