@@ -142,7 +142,7 @@ def test_soak_parity_8e8_env_steps(mg):
     step: done / info flags bit-exact, rewards and observations within 1e-5, and at the end the float64
     state bit-identical.  A knife-edge trunc()/threshold disagreement anywhere would show up here."""
     from oracle import c_oracle
-    n, T = 1 << 18, 3000
+    n, T = int(__import__("os").environ.get("MG_SOAK_ENVS", 1 << 18)), 3000   # MG_SOAK_ENVS=4194304: the 1.3e10-step run in profiles/README.md
     env = mg.MergeVecEnv(n, seed=2024, episode_info=False)
     ref = c_oracle.CVecEnv(n, nthreads=min(16, max(1, __import__("os").cpu_count() or 1)))
     worst_obs = worst_rew = 0.0
