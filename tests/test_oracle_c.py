@@ -78,3 +78,31 @@ def test_division_by_constant_identity():
 
 def test_angle_constant():
     assert co.lib().mgo_atan2_h_r() == float(np.arctan2(1000, 30000)) == float.fromhex("0x1.10f7317226afdp-5")
+
+
+@pytest.mark.parametrize("pvp", [True, False])
+def test_c_equals_numpy_from_injected_states(pvp):
+    """Same comparison from states no trajectory reaches (anywhere on [-50, 1300), speeds in [0, 60), close pairs,
+    photo finishes, a winner already past the line), 25 steps with auto-reset: bit for bit."""
+    n = 20000
+    rng = np.random.default_rng(123 + pvp)
+    p1 = rng.uniform(-50.0, 1300.0, n); p2 = rng.uniform(-50.0, 1300.0, n)
+    k = n // 2
+    p1[:k] = rng.uniform(900.0, 1010.0, k); p2[:k] = p1[:k] + rng.normal(0.0, 6.0, k)
+    p1[k:k + 2000] = 950.0 - rng.uniform(0.0, 9.0, 2000); p2[k:k + 2000] = 950.0 - rng.uniform(0.0, 9.0, 2000)
+    v1 = rng.uniform(0.0, 60.0, n); v2 = rng.uniform(0.0, 60.0, n)
+    both = (p1 > 950.0) & (p2 >= 950.0)
+    p2[both] = 900.0
+    w0 = np.where(p1 > 950.0, 1, np.where(p2 >= 950.0, 2, 0)).astype(np.uint8)
+    v = mo.RefVecEnv(n, pvp=pvp, auto_reset=True); c = co.CVecEnv(n, pvp=pvp, auto_reset=True, nthreads=4)
+    for env in (v, c):
+        env.pos1[:] = p1; env.vel1[:] = v1; env.pos2[:] = p2; env.vel2[:] = v2; env.winner[:] = w0
+    for t in range(25):
+        a = rng.integers(0, 5, (n, 2)).astype(np.uint8)
+        o, r, d, i = v.step(a[:, 0], a[:, 1] if pvp else None)
+        o2, r2, d2, i2 = c.step(a[:, 0], a[:, 1])
+        assert np.array_equal(d, d2) and np.array_equal(i, i2), t
+        assert np.array_equal(r, r2) and np.array_equal(o, o2), t
+    for k_ in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "steps", "winner"):
+        assert np.array_equal(getattr(v, k_), getattr(c, k_)), k_
+    assert v.stats["collisions"] > 1000 and v.stats["episodes"] > 5000
