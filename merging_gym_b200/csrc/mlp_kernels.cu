@@ -9,11 +9,12 @@
 // so no tf32/bf16 tensor-core path (45 kFLOP/env: ~250 us for 2^18 envs at FFMA rates).
 //
 // Tiling (persistent CTAs, one per SM, 256 threads, tile = 256 envs):
-//   input    thread t reads env t's row straight into registers; the next tile's row is requested
-//            before the epilogue of the current one so its latency is hidden;
-//   layer 1  thread t owns env t of the tile: h1[k][t] = relu(b1[k] + sum_i x[t][i] W1t[i][k]) for the
-//            100 k's of the current K-chunk (four per 128-bit weight load, packed FFMA2), written
-//            K-major to shared memory;
+//   input    thread t reads the rows of envs {t % 64 + 64 r, r = 0..3} straight into registers; the next tile's
+//            rows are requested before the epilogue of the current one so their latency is hidden;
+//   layer 1  thread t owns those 4 envs and one quarter (t / 64) of the current K-chunk's 100 units:
+//            h1[k][e] = relu(b1[k] + sum_i x[e][i] W1t[i][k]), four k's per warp-uniform 128-bit weight load
+//            feeding all 4 envs (packed FFMA2), written K-major to shared memory (thread = 1 env made layer 1
+//            shared-memory bound: 500 weight loads x 2.4 wavefronts per warp and tile);
 //   layer 2  thread t = (eg = t/4, ng = t%4) owns a 4-env x 25-neuron register tile held as float2
 //            pairs of adjacent neurons and updated with Blackwell's packed FFMA2 (fma.rn.f32x2;
 //            52 FFMA2 per k against 1 + 7 LDS.128): acc[e][j] += h1[k][4 eg + e] * W2t[k][25 ng + j];
@@ -35,6 +36,10 @@ constexpr int NG = 4, NJ = 25;     // neuron groups x neurons per group
 constexpr int NJP = 28;            // padded group width (16-byte aligned rows, zero filled)
 constexpr int NP = (NJ + 1) / 2;   // float2 accumulator pairs per env (13: the 26th lane multiplies the zero pad)
 constexpr int MAX_OUT = 8;
+#ifndef MG_MLP_LR
+#define MG_MLP_LR 4
+#endif
+constexpr int LR = MG_MLP_LR;       // layer 1: envs per thread (each weight load feeds LR envs); the units are split LR ways
 
 template <int IN, int OUT>
 struct Smem {
@@ -78,9 +83,13 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
     const int ng = t & 3, eg = t >> 2;
     const int64_t n_tiles = (n + TM - 1) / TM;
 
+    // layer-1 mapping: thread = env pair {e0, e0 + 128} x one half of the K-chunk's units, so that every weight
+    // read from shared memory (a warp-uniform LDS.128, 2.4 wavefronts) feeds two envs instead of one
+    const int e0 = t & (TM / LR - 1), uh = t / (TM / LR);
     // first tile's input rows are requested before the weights so the two latencies overlap
-    float xr[IN];
-    load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + t, n, obs_dim, xr);
+    float xr[LR][IN];
+#pragma unroll
+    for (int r = 0; r < LR; ++r) load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
 
     // ---- weights -> shared memory, once per (persistent) CTA: straight 128-bit copies -------------
     {
@@ -111,19 +120,32 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
         for (int k0 = 0; k0 < H1; k0 += KC) {
             // ---- layer 1 for rows k0 .. k0+KC of h1 (thread = env), 4 rows per 128-bit weight load ----
             __syncthreads();                   // everyone finished reading the previous chunk of h1
+            constexpr int kGroups = KC / 4;                                   // 25 groups of 4 units, split LR ways
+            const int g_begin = kGroups * uh / LR, g_end = kGroups * (uh + 1) / LR;
 #pragma unroll 2
-            for (int kk = 0; kk < KC; kk += 4) {
+            for (int g = g_begin; g < g_end; ++g) {
+                const int kk = 4 * g;
                 const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k0 + kk]);
-                float2 h01 = make_float2(bb.x, bb.y), h23 = make_float2(bb.z, bb.w);
+                float2 h01[LR], h23[LR];
+#pragma unroll
+                for (int r = 0; r < LR; ++r) { h01[r] = make_float2(bb.x, bb.y); h23[r] = make_float2(bb.z, bb.w); }
 #pragma unroll
                 for (int i = 0; i < IN; ++i) {
                     const float4 w = *reinterpret_cast<const float4 *>(&S.w1[i][k0 + kk]);
-                    const float2 xx = make_float2(xr[i], xr[i]);
-                    h01 = __ffma2_rn(xx, make_float2(w.x, w.y), h01);
-                    h23 = __ffma2_rn(xx, make_float2(w.z, w.w), h23);
+                    const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+#pragma unroll
+                    for (int r = 0; r < LR; ++r) {
+                        const float2 xx = make_float2(xr[r][i], xr[r][i]);
+                        h01[r] = __ffma2_rn(xx, w01, h01[r]);
+                        h23[r] = __ffma2_rn(xx, w23, h23[r]);
+                    }
                 }
-                S.h1[kk][t] = fmaxf(h01.x, 0.f); S.h1[kk + 1][t] = fmaxf(h01.y, 0.f);
-                S.h1[kk + 2][t] = fmaxf(h23.x, 0.f); S.h1[kk + 3][t] = fmaxf(h23.y, 0.f);
+#pragma unroll
+                for (int r = 0; r < LR; ++r) {
+                    const int e = e0 + r * (TM / LR);
+                    S.h1[kk][e] = fmaxf(h01[r].x, 0.f); S.h1[kk + 1][e] = fmaxf(h01[r].y, 0.f);
+                    S.h1[kk + 2][e] = fmaxf(h23[r].x, 0.f); S.h1[kk + 3][e] = fmaxf(h23[r].y, 0.f);
+                }
             }
             __syncthreads();
             // ---- layer 2 partial sums over this chunk (4 envs x 25 neurons per thread), operands of
@@ -161,7 +183,8 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
             }
         }
         // next tile's input rows: issued now, consumed after the epilogue
-        load_row<IN>(obs, goal, (tile + gridDim.x) * TM + t, n, obs_dim, xr);
+#pragma unroll
+        for (int r = 0; r < LR; ++r) load_row<IN>(obs, goal, (tile + gridDim.x) * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
 
         // ---- layer 3 + arg-max ---------------------------------------------------------------------
         float q[4][OUT];
