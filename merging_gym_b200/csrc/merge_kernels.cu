@@ -259,8 +259,10 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 // merge_rollout_kernel: k consecutive steps with in-kernel Philox actions; state stays in
 // registers, outputs are time-major.  One env per thread element, EPT=2 vector state I/O.
 // =================================================================================================
+// 4 resident blocks per SM (120 registers, no spills): the rollout is latency-bound (FP64 chains), so 16 warps per SM
+// beat 12 at 158 registers (15.5 vs 16.1 us per 2^20-env step with all outputs); 5 and 6 blocks spill and tie, 8 loses.
 #ifndef MG_ROLLOUT_MIN_BLOCKS
-#define MG_ROLLOUT_MIN_BLOCKS 1
+#define MG_ROLLOUT_MIN_BLOCKS 4
 #endif
 template <bool PVP, bool RR>
 __global__ void __launch_bounds__(kBlock, MG_ROLLOUT_MIN_BLOCKS)
