@@ -1,7 +1,8 @@
 import sys, os, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import merging_gym_b200 as mg
-z = np.load('/root/repo/tests/golden/dqn_policies.npz')
+z = np.load(os.path.join(ROOT, 'tests', 'golden', 'dqn_policies.npz'))
 sd = {k.split('/',1)[1]: z[k] for k in z.files if k.startswith('L1_1445/') and 'traj' not in k and 'result' not in k}
 for n in (128, 1000, 5000, 1<<18):
     env = mg.MergeVecEnv(n, seed=3); env.rollout(120); obs = env.step(*env.sample_actions())[0].clone()
