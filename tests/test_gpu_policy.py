@@ -255,3 +255,13 @@ def test_hdqn_policy_fused_equals_torch(mg):
     assert ((af == at) | ~same_goal).float().mean() > 0.98
     env = mg.MergeVecEnv(n, mode="pve")
     env.step(af, None)
+
+
+@pytest.mark.parametrize("script,args", [("random_rollout.py", ["--envs", "65536", "--steps", "300"]),
+                                         ("dqn_vs_dqn.py", ["--steps", "400"]), ("dqn_vs_dqn.py", ["--steps", "400", "--backend", "tf32x3"])])
+def test_examples_run(script, args):
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", script), *args], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "episodes" in out.stdout
