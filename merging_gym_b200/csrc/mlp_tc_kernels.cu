@@ -16,7 +16,7 @@
 //   warps 12-13 MMA issue: K-steps interleaved between the two warps (one issuing warp needs ~370 cycles per K-step,
 //                          the tensor pipe ~180); per K-step two tcgen05.mma.kind::tf32 — a_hi x [W2_hi ; W2_lo]
 //                          (N = 224) and a_lo x W2_hi (N = 112) — issued by predication from one elected lane,
-//                          accumulating in TMEM; tcgen05.commit -> empty[next producer] / first_done[b] / tmem_full[b]
+//                          accumulating in TMEM (always accumulate: buffers are handed back zeroed); tcgen05.commit -> empty[next producer] / tmem_full[b]
 //   warps 8-11 epilogue  : tcgen05.ld.16x256b fragments of the 128x112 fp32 accumulator — a thread holds 4 envs x
 //                          2 adjacent neurons per 8-column block, so one read of the layer-3 weights feeds 4 envs —
 //                          bias + ReLU, the 100x{5,3} layer, a 4-lane shuffle reduction and the arg-max
@@ -73,7 +73,7 @@ struct Smem {
     float w1[IN][H1];
     float w3[OUT][H2P];
     float b1[H1], b2[H2 + 12], b3[MAX_OUT];
-    unsigned long long full[PRODUCER_WARPS], empty[PRODUCER_WARPS], tmem_full[2], tmem_empty[2], first_done[2];
+    unsigned long long full[PRODUCER_WARPS], empty[PRODUCER_WARPS], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
@@ -107,6 +107,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity
             : "memory");
     }
     if (!done) __trap();                      // never hang the GPU on a protocol bug
+}
+// zero 16 columns of the calling warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_test(unsigned long long *b, uint32_t parity) {   // one non-blocking poll
     uint32_t done;
@@ -166,7 +171,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
     }
     if (t == 0) {
         for (int s = 0; s < PRODUCER_WARPS; ++s) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], MMA_WARPS); mbar_init(&S.tmem_empty[b], TM); mbar_init(&S.first_done[b], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], MMA_WARPS); mbar_init(&S.tmem_empty[b], TM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W2 hi/lo written by the generic proxy
@@ -179,6 +184,16 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = S.tmem_base;
+    // Every MMA accumulates (no overwriting first K-step: two warps issue, and only accumulation commutes), so the
+    // accumulators start at zero and each epilogue zeroes what it has read.
+    if (warp >= 8 && warp < 12) {
+        const uint32_t lanes = (uint32_t)((warp - 8) * 32) << 16;
+        for (uint32_t c = 0; c < (uint32_t)TMEM_COLS; c += 16) tmem_zero16(tmem_base + lanes + c);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp < PRODUCER_WARPS) {
         // =================================== PRODUCERS: layer 1 ===================================
@@ -261,10 +276,8 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         // issues ks = j, j + MMA_WARPS, ...  Each runs the loop whole-warp and issues by PREDICATION from one elected
         // lane (inside an `if (lane == 0)` region the compiler rebuilt every descriptor through R2UR and wrapped each
         // tcgen05 instruction in a per-lane retry loop — ~55 dependent instructions per K-step).
-        // Ordering between the two issuers: accumulation commutes, but the overwriting MMA (ks = 0, accumulate off)
-        // must come first.  K-steps >= 4 reuse a ring slot that the completion of ks - 4 >= 0 freed, so they are
-        // ordered after it by data flow; warp 1 waits for first_done[buf] (committed right after ks = 0) before its
-        // first K-step of a tile.  tmem_full[buf] expects one commit per issuing warp.
+        // Both issuers always accumulate (the epilogue hands every buffer back zeroed), so the order in which their
+        // MMAs reach the tensor pipe does not matter.  tmem_full[buf] expects one commit per issuing warp.
         const int j = warp - 12;
         uint32_t tl = 0;
         // low descriptor words: (address >> 4) | (LBO >> 4) << 16; stepping an operand = adding (bytes >> 4)
@@ -272,11 +285,10 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                        a_lo0 = (uint32_t)make_desc(smem_u32(S.a_lo[0]));
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             const uint32_t buf = tl & 1u;
-            if (j == 0) mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);    // epilogue drained this buffer
-            else        mbar_wait(&S.first_done[buf], (tl >> 1) & 1u);           // ... and ks = 0 has overwritten it
+            mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);                // epilogue drained (and zeroed) this buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + buf * 256u;
-            const uint32_t tm_full = smem_u32(&S.tmem_full[buf]), first = smem_u32(&S.first_done[buf]);
+            const uint32_t tm_full = smem_u32(&S.tmem_full[buf]);
             uint32_t have = 0;                              // the barrier about to be waited for was already seen complete
 #pragma unroll 1
             for (int ks = j; ks < KSTEPS; ks += MMA_WARPS) {
@@ -287,9 +299,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                 uint32_t lo_b = b_cat + (uint32_t)ks * (B_STEP >> 4);
                 uint32_t done_bar = smem_u32(&S.empty[(it + STAGES) % PRODUCER_WARPS]);
                 asm volatile("" : "+r"(lo_a), "+r"(lo_l), "+r"(lo_b), "+r"(done_bar));   // pin the values here (no sinking below the wait)
-                const uint32_t acc = ks > 0 ? 1u : 0u;
                 const uint32_t last = ks + MMA_WARPS >= KSTEPS ? 1u : 0u;            // this warp's last K-step of the tile
-                const uint32_t sig_first = (MMA_WARPS > 1 && ks == 0) ? 1u : 0u;
                 MG_TRACE(g_trace_mma, it, 0);
                 if (!have) mbar_wait(&S.full[pw], (it / PRODUCER_WARPS) & 1u);
                 // poll this warp's NEXT K-step now: the answer arrives while the MMAs below are being issued
@@ -298,21 +308,18 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // columns [0,112) += a_hi.W2_hi and [112,224) += a_hi.W2_lo in one N = 224 MMA (123 cycles instead of two
                 // N = 112 MMAs at 76 each, A_hi read once); then columns [0,112) += a_lo.W2_hi.  Commits: the warp that fills
-                // this slot next; after ks = 0 the other issuer; after this warp's last K-step the epilogue.
+                // this slot next; after this warp's last K-step of the tile the epilogue.
                 asm volatile(
-                    "{\n\t.reg .pred E, A, L, F;\n\t.reg .b64 da, dl, db;\n\t"
+                    "{\n\t.reg .pred E, L;\n\t.reg .b64 da, dl, db;\n\t"
                     "elect.sync _|E, 0xffffffff;\n\t"
-                    "setp.ne.b32 A, %5, 0;\n\t"
-                    "setp.ne.and.b32 L, %8, 0, E;\n\t"
-                    "setp.ne.and.b32 F, %11, 0, E;\n\t"
+                    "setp.ne.and.b32 L, %7, 0, E;\n\t"
                     "mov.b64 da, {%1, %4};\n\tmov.b64 dl, {%2, %4};\n\tmov.b64 db, {%3, %4};\n\t"
-                    "@E tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %6, A;\n\t"
-                    "@F tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
-                    "@E tcgen05.mma.cta_group::1.kind::tf32 [%0], dl, db, %7, 1;\n\t"
-                    "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-                    "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t}\n"
-                    :: "r"(d), "r"(lo_a), "r"(lo_l), "r"(lo_b), "r"((uint32_t)(kDescHi >> 32)), "r"(acc), "r"(kIdesc224), "r"(kIdesc112),
-                       "r"(last), "r"(done_bar), "r"(tm_full), "r"(sig_first), "r"(first)
+                    "@E tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t"
+                    "@E tcgen05.mma.cta_group::1.kind::tf32 [%0], dl, db, %6, 1;\n\t"
+                    "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+                    "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t}\n"
+                    :: "r"(d), "r"(lo_a), "r"(lo_l), "r"(lo_b), "r"((uint32_t)(kDescHi >> 32)), "r"(kIdesc224), "r"(kIdesc112),
+                       "r"(last), "r"(done_bar), "r"(tm_full)
                     : "memory");
                 MG_TRACE(g_trace_mma, it, 2);
             }
@@ -353,6 +360,8 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                                  : "r"(ad + (uint32_t)UN));
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_zero16(taddr + (uint32_t)(16 * cb));       // read done: give the 16 + 16 columns back zeroed
+                tmem_zero16(taddr + (uint32_t)(UN + 16 * cb));
 #pragma unroll
                 for (int blk = 0; blk < 2; ++blk) {
                     if (16 * cb + 8 * blk < H2P) {              // blocks 0..12 hold the 100 neurons (+4 zero-weight pads)
@@ -377,8 +386,9 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                     }
                 }
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&S.tmem_empty[buf]);                    // this thread is done reading the buffer
+            mbar_arrive(&S.tmem_empty[buf]);                    // this thread has read and zeroed its part of the buffer
             if (q4 == 0) MG_TRACE(g_trace_epi, tl, 2);
             // sum the 4 lanes that share a row group, then lane t0 finishes row t1 + 8 * t0
             float mine[OUT];
