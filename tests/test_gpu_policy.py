@@ -87,7 +87,7 @@ def test_tensor_core_backend_matches_fp32(mg, in_dim, out_dim, n):
 
 def test_tensor_core_backend_is_stable_under_repetition(mg):
     """The tensor-core kernel is a multi-role pipeline (8 producer warps, two MMA-issuing warps that
-    accumulate into the same TMEM columns, 4 epilogue warps, 18 mbarriers).  A protocol race would
+    accumulate into the same TMEM columns, 4 epilogue warps that hand the buffers back zeroed, 20 mbarriers).  A protocol race would
     show up as an occasional lost update or a stale tile: 150 launches over many tiles per SM
     (2^17 envs = 1024 tiles on 148 SMs) on changing inputs must all agree with the fp32 kernel."""
     n = 1 << 17
