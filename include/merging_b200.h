@@ -11,7 +11,9 @@
  *  - Plain C types only.  All array pointers are CUDA device pointers unless the parameter
  *    name starts with `h_` (host memory).  Array pointers must be 16-byte aligned.
  *  - The library never allocates or frees memory and keeps no global state except the
- *    per-thread last-error string.  The caller (PyTorch on the Python side) owns every buffer.
+ *    per-thread last-error string (and, only if mg_step_host is used with a copy stream, a
+ *    per-thread, per-device set of CUDA events).  The caller (PyTorch on the Python side) owns
+ *    every buffer.
  *  - Launches are asynchronous on the caller's stream (`stream` is a cudaStream_t passed as
  *    void*; NULL = legacy default stream).  No entry point synchronises unless documented.
  *    All device entry points are CUDA-graph capturable.
