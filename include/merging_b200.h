@@ -224,13 +224,18 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
  *   format 0 (width 22): [s(10), a_p, r_p, s'(10)] for player p (main.py:116);  s' is the stepped
  *                        state's observation: term_obs where done (pass NULL without auto-reset)
  *   format 1 (width 14): [s(10), a1, a2, r1, r2], the CSV row of scripts/human_player.py:111,180-181
+ *   format 2 (width 24): [g, s(10), a_p, r_int, g', s'(10)], the h-DQN controller's row (scripts/hdqn.py:180-184,
+ *                        291-316): g / g' = goal_prev / goal_next (uint8[n], the goals chosen from s and from s'),
+ *                        r_int = 1 if g' == goal_status(s) else 0 (hdqn.py:223-236,314); the reference stores it
+ *                        every step (mask_mode 0)
  * counter: device uint64, total rows ever appended (caller zero-initialises).
  * scratch: device uint32[(n+31)/32 + 4].  env_ids_or_null: int32[capacity], env of each row. */
 MG_API int mg_record_transitions(const float *obs_prev, const float *obs_next,
                                  const float *term_obs_or_null, const uint8_t *a1,
                                  const uint8_t *a2_or_null, const float *rew, const uint8_t *done,
-                                 const uint8_t *info, int64_t n, int32_t mask_mode, int32_t format,
-                                 int32_t player, float *ring, int64_t capacity,
+                                 const uint8_t *info, const uint8_t *goal_prev_or_null,
+                                 const uint8_t *goal_next_or_null, int64_t n, int32_t mask_mode,
+                                 int32_t format, int32_t player, float *ring, int64_t capacity,
                                  int32_t *env_ids_or_null, uint64_t *counter, uint32_t *scratch,
                                  void *stream);
 

@@ -101,7 +101,7 @@ def load():
     lib.mg_mlp_act.restype = C.c_int
     lib.mg_mlp_act_tc.argtypes = lib.mg_mlp_act.argtypes
     lib.mg_mlp_act_tc.restype = C.c_int
-    lib.mg_record_transitions.argtypes = [vp] * 8 + [i64, i32, i32, i32, vp, i64, vp, vp, vp, vp]
+    lib.mg_record_transitions.argtypes = [vp] * 10 + [i64, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.mg_record_transitions.restype = C.c_int
     for f in (lib.mg_get_constants, lib.mg_default_rewards, lib.mg_reset, lib.mg_step,
               lib.mg_sample_actions, lib.mg_rollout, lib.mg_step_host):

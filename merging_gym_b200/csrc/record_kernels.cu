@@ -94,6 +94,9 @@ scan_kernel(uint32_t *__restrict__ warp_counts, int64_t m, unsigned long long *_
 
 // format 0 (replay, main.py:115-119): [s(10), a_p, r_p, s'(10)]              22 floats, player p
 // format 1 (log, human_player.py:111) : [s(10), a1, a2, r1, r2]               14 floats
+// format 2 (h-DQN controller, hdqn.py:180-184,291-316): [g, s(10), a, r_int, g', s'(10)]   24 floats, with
+//          r_int = 1 if g' == goal_status(s) else 0 (hdqn.py:314; goal_status :223-236 on the state the action was
+//          chosen from, g' the goal re-chosen from the next state)
 // One warp handles 32 consecutive envs: their observation rows are one contiguous 1280-byte span, loaded
 // with coalesced 128-bit loads into shared memory; the selected lanes assemble their rows in shared memory
 // at consecutive ranks; the warp then writes that contiguous piece of the ring with coalesced stores.
@@ -102,13 +105,14 @@ __global__ void __launch_bounds__(kBlock)
 write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_next,
              const float *__restrict__ term_obs, const uint8_t *__restrict__ a1, const uint8_t *__restrict__ a2,
              const float *__restrict__ rew, const uint8_t *__restrict__ done, const uint8_t *__restrict__ info,
+             const uint8_t *__restrict__ goal_prev, const uint8_t *__restrict__ goal_next,
              int64_t n, int mask_mode, int player, const uint32_t *__restrict__ block_offsets,
              const unsigned long long *__restrict__ base, const unsigned long long *__restrict__ counter,
              float *__restrict__ ring, int64_t capacity, int32_t *__restrict__ env_ids) {
-    constexpr int WIDTH = FORMAT == 0 ? 2 * kObs + 2 : kObs + 4;
+    constexpr int WIDTH = FORMAT == 0 ? 2 * kObs + 2 : FORMAT == 1 ? kObs + 4 : 2 * kObs + 4;
     constexpr int kWarps = kBlock / 32;
     __shared__ __align__(16) float s_prev[kWarps][32 * kObs];
-    __shared__ __align__(16) float s_next[kWarps][FORMAT == 0 ? 32 * kObs : 4];
+    __shared__ __align__(16) float s_next[kWarps][FORMAT != 1 ? 32 * kObs : 4];
     __shared__ __align__(16) float s_out[kWarps][32 * WIDTH];
     __shared__ uint32_t s_cnt[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -130,7 +134,7 @@ write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_n
         float4 *sp = reinterpret_cast<float4 *>(s_prev[warp]);
         for (int i = lane; i < rows * kObs / 4; i += 32) sp[i] = __ldg(gp + i);
         for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) s_prev[warp][i] = obs_prev[w0 * kObs + i];
-        if (FORMAT == 0) {
+        if (FORMAT != 1) {
             const float4 *gn = reinterpret_cast<const float4 *>(obs_next + w0 * kObs);
             float4 *sn = reinterpret_cast<float4 *>(s_next[warp]);
             for (int i = lane; i < rows * kObs / 4; i += 32) sn[i] = __ldg(gn + i);
@@ -144,21 +148,35 @@ write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_n
         const int r = __popc(b & ((1u << lane) - 1u));
         float *row = s_out[warp] + r * WIDTH;
         const float *sp = s_prev[warp] + lane * kObs;
-#pragma unroll
-        for (int k = 0; k < kObs; ++k) row[k] = sp[k];
         const float act1 = (float)a1[e], act2 = a2 ? (float)a2[e] : 0.f;
-        if (FORMAT == 0) {
-            row[kObs] = player == 2 ? act2 : act1;
-            row[kObs + 1] = rew[2 * e + (player == 2 ? 1 : 0)];
-            // s' is the observation of the stepped state: under auto-reset obs_next holds the RESET
-            // observation for finished envs, the terminal one is in term_obs
-            const bool use_term = term_obs && done[e];
-            const float *sn = use_term ? term_obs + e * kObs : s_next[warp] + lane * kObs;
+        // s' is the observation of the stepped state: under auto-reset obs_next holds the RESET
+        // observation for finished envs, the terminal one is in term_obs
+        const bool use_term = FORMAT != 1 && term_obs && done[e];
+        const float *sn = use_term ? term_obs + e * kObs : s_next[warp] + lane * kObs;
+        if (FORMAT == 2) {
+            const float g = (float)goal_prev[e], gn = (float)goal_next[e];
+            const float dx1 = sp[0], v2 = sp[9];                                  // goal_status, hdqn.py:223-236
+            const float status = dx1 < -0.5f * v2 ? 0.f : dx1 < 0.5f * v2 ? 1.f : 2.f;
+            row[0] = g;
 #pragma unroll
-            for (int k = 0; k < kObs; ++k) row[kObs + 2 + k] = sn[k];
+            for (int k = 0; k < kObs; ++k) row[1 + k] = sp[k];
+            row[kObs + 1] = player == 2 ? act2 : act1;
+            row[kObs + 2] = gn == status ? 1.f : 0.f;
+            row[kObs + 3] = gn;
+#pragma unroll
+            for (int k = 0; k < kObs; ++k) row[kObs + 4 + k] = sn[k];
         } else {
-            row[kObs] = act1; row[kObs + 1] = act2;
-            row[kObs + 2] = rew[2 * e]; row[kObs + 3] = rew[2 * e + 1];
+#pragma unroll
+            for (int k = 0; k < kObs; ++k) row[k] = sp[k];
+            if (FORMAT == 0) {
+                row[kObs] = player == 2 ? act2 : act1;
+                row[kObs + 1] = rew[2 * e + (player == 2 ? 1 : 0)];
+#pragma unroll
+                for (int k = 0; k < kObs; ++k) row[kObs + 2 + k] = sn[k];
+            } else {
+                row[kObs] = act1; row[kObs + 1] = act2;
+                row[kObs + 2] = rew[2 * e]; row[kObs + 3] = rew[2 * e + 1];
+            }
         }
         // rows a sequential writer would overwrite later in this same call are skipped below via `skip`
         if (env_ids && !(rank0 + r + (uint64_t)capacity < total))
@@ -188,17 +206,20 @@ write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_n
 extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *obs_next,
                                             const float *term_obs_or_null, const uint8_t *a1,
                                             const uint8_t *a2_or_null, const float *rew, const uint8_t *done,
-                                            const uint8_t *info, int64_t n, int32_t mask_mode, int32_t format,
+                                            const uint8_t *info, const uint8_t *goal_prev_or_null,
+                                            const uint8_t *goal_next_or_null, int64_t n, int32_t mask_mode, int32_t format,
                                             int32_t player, float *ring, int64_t capacity,
                                             int32_t *env_ids_or_null, uint64_t *counter, uint32_t *scratch,
                                             void *stream) {
     using namespace mg_abi;
     if (n < 0 || capacity <= 0) return fail(MG_ERR_BAD_SIZE, "n < 0 or capacity <= 0");
-    if (mask_mode < 0 || mask_mode > 1 || format < 0 || format > 1 || player < 1 || player > 2)
-        return fail(MG_ERR_BAD_FLAGS, "mask_mode in {0,1}, format in {0,1}, player in {1,2}");
+    if (mask_mode < 0 || mask_mode > 1 || format < 0 || format > 2 || player < 1 || player > 2)
+        return fail(MG_ERR_BAD_FLAGS, "mask_mode in {0,1}, format in {0,1,2}, player in {1,2}");
     if (n == 0) return MG_OK;
     if (!obs_prev || !obs_next || !a1 || !rew || !done || !info || !ring || !counter || !scratch)
         return fail(MG_ERR_NULL_POINTER, "mg_record_transitions: NULL pointer");
+    if (format == 2 && (!goal_prev_or_null || !goal_next_or_null))
+        return fail(MG_ERR_NULL_POINTER, "format 2 (h-DQN rows) needs goal_prev and goal_next");
     if (!aligned16(obs_prev) || !aligned16(obs_next))
         return fail(MG_ERR_ALIGNMENT, "obs_prev and obs_next must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -210,16 +231,15 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     auto *base = reinterpret_cast<unsigned long long *>(scratch + ((m + 1) & ~(int64_t)1));
     mgrec::count_kernel<<<grid, mgrec::kBlock, 0, st>>>(info, n, mask_mode, warp_counts);
     mgrec::scan_kernel<<<1, 1024, 0, st>>>(warp_counts, (int64_t)grid, reinterpret_cast<unsigned long long *>(counter), base);
-    if (format == 0)
-        mgrec::write_kernel<0><<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew,
-                                                                done, info, n, mask_mode, player, warp_counts, base,
-                                                                reinterpret_cast<unsigned long long *>(counter), ring,
-                                                                capacity, env_ids_or_null);
-    else
-        mgrec::write_kernel<1><<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew,
-                                                                done, info, n, mask_mode, player, warp_counts, base,
-                                                                reinterpret_cast<unsigned long long *>(counter), ring,
-                                                                capacity, env_ids_or_null);
+#define MG_REC_LAUNCH(F)                                                                                            \
+    mgrec::write_kernel<F><<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew, done, \
+                                                           info, goal_prev_or_null, goal_next_or_null, n, mask_mode, player, \
+                                                           warp_counts, base, reinterpret_cast<unsigned long long *>(counter), \
+                                                           ring, capacity, env_ids_or_null)
+    if (format == 0) MG_REC_LAUNCH(0);
+    else if (format == 1) MG_REC_LAUNCH(1);
+    else MG_REC_LAUNCH(2);
+#undef MG_REC_LAUNCH
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_record_transitions launch");
     return MG_OK;
 }

@@ -22,6 +22,8 @@ from . import _native as nat
 
 REPLAY_WIDTH = 2 * nat.OBS_DIM + 2      # main.py:92  NUM_STATES * 2 + 2
 LOG_WIDTH = nat.OBS_DIM + 4
+HDQN_WIDTH = 2 * (nat.OBS_DIM + 1) + 2   # hdqn.py:158  (NUM_STATES + 1) * 2 + 2
+_FORMATS = {"replay": (0, REPLAY_WIDTH), "log": (1, LOG_WIDTH), "hdqn": (2, HDQN_WIDTH)}
 
 # header of scripts/human_player.py:111, verbatim column names
 CSV_HEADER = ["x2 - x1", "y2 - y1", "self.state2['vel'] - self.state1['vel']", "END_POINT - self.state1['pos']",
@@ -38,18 +40,22 @@ class TransitionRecorder:
 
     format "replay": rows `[s, a_p, r_p, s']` (22 floats) for `player` p in {1, 2}.
     format "log":    rows `[s, a1, a2, r1, r2]` (14 floats).
+    format "hdqn":   rows `[g, s, a_p, r_int, g', s']` (24 floats), the h-DQN controller's transitions
+                     (hdqn.py:180-184,291-316): pass the goals chosen from s and from s' to `record`; the
+                     intrinsic reward `1 if g' == goal_status(s) else 0` (hdqn.py:314) is computed on the device.
+                     The reference stores these every step: use mask="all".
     mask "winner_not_1" is the reference's store condition; "all" stores every env every step.
     """
 
     def __init__(self, env, capacity: int, format: str = "replay", player: int = 1,
                  mask: str = "winner_not_1", track_env_ids: bool = False):
-        if format not in ("replay", "log") or mask not in ("winner_not_1", "all") or player not in (1, 2):
-            raise ValueError("format in {'replay','log'}, mask in {'winner_not_1','all'}, player in {1,2}")
-        if format == "replay" and env.auto_reset and env.terminal_obs is None:
+        if format not in _FORMATS or mask not in ("winner_not_1", "all") or player not in (1, 2):
+            raise ValueError("format in {'replay','log','hdqn'}, mask in {'winner_not_1','all'}, player in {1,2}")
+        if format != "log" and env.auto_reset and env.terminal_obs is None:
             raise ValueError("replay rows need the terminal observation: create the env with episode_info=True")
         self.env, self.capacity = env, int(capacity)
         self.format, self.player, self.mask = format, player, mask
-        self.width = REPLAY_WIDTH if format == "replay" else LOG_WIDTH
+        self.width = _FORMATS[format][1]
         dev = env.device
         self.ring = torch.zeros(self.capacity, self.width, dtype=torch.float32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)        # memory_counter, main.py:91
@@ -57,20 +63,24 @@ class TransitionRecorder:
         self._scratch = torch.zeros((env.num_envs + 31) // 32 + 4, dtype=torch.int32, device=dev)
         self._lib = nat.load()
 
-    def record(self, obs_prev: torch.Tensor, a1: torch.Tensor, a2: Optional[torch.Tensor], step_out) -> None:
+    def record(self, obs_prev: torch.Tensor, a1: torch.Tensor, a2: Optional[torch.Tensor], step_out,
+               goal_prev: Optional[torch.Tensor] = None, goal_next: Optional[torch.Tensor] = None) -> None:
         """Append the transitions of one `env.step`: `obs_prev` is the observation the actions were
-        chosen from, `step_out` the tuple `env.step` returned.  uint8 actions; no host sync."""
+        chosen from, `step_out` the tuple `env.step` returned.  uint8 actions (and, for format "hdqn",
+        uint8 goals chosen from `obs_prev` and from the new observation); no host sync."""
         obs, rew, done, info = step_out
         env = self.env
         term = env.terminal_obs if env.auto_reset else None
-        for t in (a1, a2):
+        for t in (a1, a2, goal_prev, goal_next):
             if t is not None and t.dtype != torch.uint8:
-                raise TypeError("TransitionRecorder.record expects uint8 action tensors")
+                raise TypeError("TransitionRecorder.record expects uint8 action / goal tensors")
+        if (self.format == "hdqn") != (goal_prev is not None and goal_next is not None):
+            raise ValueError("goal_prev and goal_next are required for, and only for, format 'hdqn'")
         with torch.cuda.device(env.device):
             nat.check(self._lib.mg_record_transitions(
                 _ptr(obs_prev), _ptr(obs), _ptr(term), _ptr(a1), _ptr(a2), _ptr(rew),
-                _ptr(done.view(torch.uint8)), _ptr(info["flags"]), env.num_envs,
-                1 if self.mask == "winner_not_1" else 0, 0 if self.format == "replay" else 1, self.player,
+                _ptr(done.view(torch.uint8)), _ptr(info["flags"]), _ptr(goal_prev), _ptr(goal_next), env.num_envs,
+                1 if self.mask == "winner_not_1" else 0, _FORMATS[self.format][0], self.player,
                 _ptr(self.ring), self.capacity, _ptr(self.env_ids), _ptr(self.counter), _ptr(self._scratch),
                 C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)), "mg_record_transitions")
 

@@ -152,3 +152,34 @@ def test_replay_rows_against_the_reference_learner(mg):
     ring = rec.ring[:counter].cpu().numpy()
     assert np.array_equal(ring[:, 10], mem[:, 10])                               # the action column, exactly
     assert rel_err(ring, mem).max() <= 1e-5
+
+
+@pytest.mark.parametrize("seed", [7, 36])
+def test_hdqn_controller_rows_against_the_reference(mg, seed):
+    """tests/golden/hdqn_policies.npz `controller_memory`: the rows the reference's OWN `HDQN.store_transition`
+    (scripts/hdqn.py:180-184) left in `lower.memory` over one greedy episode driven by its nested option loop
+    (:276-324) — `[g, s, a, r_int, g', s']`, r_int = 1 where the re-chosen goal equals goal_status(s).
+    HDQNPolicy + TransitionRecorder(format="hdqn") must leave the same rows in the ring."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "hdqn_policies.npz"))
+    tag = f"seed{seed}"
+    sd = lambda name: {k.split("/")[-1]: z[k] for k in z.files if k.startswith(f"{tag}/{name}/")}
+    mem = z[f"{tag}/L0/controller_memory"]
+    pol = mg.HDQNPolicy(meta_state=sd("meta"), ctrl_state=sd("ctrl"))
+    env = mg.MergeVecEnv(1, mode="pve", auto_reset=False, out_slots=2)
+    rec = mg.TransitionRecorder(env, 2000, format="hdqn", mask="all")         # MEMORY_CAPACITY, hdqn.py:21
+    obs = env.reset().clone()
+    done = torch.zeros(1, dtype=torch.bool)
+    for t in range(len(mem)):
+        a = pol.act(obs).clone(); g = pol.goal.clone()
+        out = env.step(a, None)
+        g_next = pol.meta.act(out[0]).clone()                                   # hdqn.py:303
+        rec.record(obs, a, None, out, goal_prev=g, goal_next=g_next)
+        obs = out[0].clone()
+    assert bool(out[2][0]) and int(rec.counter.item()) == len(mem)
+    ring = rec.ring[:len(mem)].cpu().numpy()
+    for col in (0, 11, 12, 13):                                                 # g, a, r_int, g': exact
+        assert np.array_equal(ring[:, col], mem[:, col]), col
+    assert rel_err(ring, mem).max() <= 1e-5
+    assert mem[:, 12].sum() == (71 if seed == 36 else 0)
