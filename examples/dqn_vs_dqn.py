@@ -32,7 +32,7 @@ gen = torch.Generator(device="cuda").manual_seed(0)
 obs = env.reset()
 for _ in range(args.steps):
     a1 = mg.explore(agent.act(obs), 5, generator=gen)
-    a2 = mg.explore(opponent.act(env.opponent_view(obs)), 5, generator=gen)
+    a2 = mg.explore(opponent.act(obs, mirror=True), 5, generator=gen)      # = opponent.act(env.opponent_view(obs)), fused
     obs, rew, done, info = env.step(a1, a2)
 s = env.stats()
 print(f"{s['episodes']} episodes: agent wins {s['win_rate_p1']:.3f}, opponent wins {s['win_rate_p2']:.3f}, "

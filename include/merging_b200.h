@@ -191,6 +191,10 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
                         int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
                         void *stream, void *copy_stream_or_null, int32_t chunks);
 
+#define MG_MLP_FLAG_MIRROR 0x1u /* evaluate the network on the OPPONENT's view of each observation row,
+                                   `state[5:] + state[:5]` (scripts/main.py:199, hdqn.py:285,299): the half-swap
+                                   is done while the row is read, no mirrored copy is materialised */
+
 /* ---- "next" row: policy in the loop -------------------------------------------
  * Fused forward + arg-max of the reference's Q-network `Net(in, out)`:
  * Linear(in,200)-ReLU-Linear(200,100)-ReLU-Linear(100,out) in fp32 followed by
@@ -204,7 +208,7 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
 MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                       int32_t out_dim, const float *w1t, const float *b1, const float *w2p,
                       const float *b2, const float *w3, const float *b3, uint8_t *actions,
-                      float *q_out_or_null, void *stream);
+                      float *q_out_or_null, uint32_t flags, void *stream);
 
 /* Tensor-core variant of mg_mlp_act (tcgen05 + TMEM): the 200x100 layer as an error-compensated 3xTF32
  * product (a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) — fp32-level accuracy but not bit-identical to the
@@ -215,7 +219,7 @@ MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, 
 MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                          int32_t out_dim, const float *w1t, const float *b1, const float *w2_tc,
                          const float *b2, const float *w3, const float *b3, uint8_t *actions,
-                         float *q_out_or_null, void *stream);
+                         float *q_out_or_null, uint32_t flags, void *stream);
 
 /* ---- "next" rows: device-resident transition writer -----------------------
  * Appends one row per selected env to a ring `ring[capacity][width]` (index = counter % capacity,

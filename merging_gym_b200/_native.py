@@ -97,7 +97,7 @@ def load():
                                C.POINTER(MgRewards), C.POINTER(MgOut), vp, vp, u32, rsp, vp]
     lib.mg_step_host.argtypes = [C.POINTER(MgState), i64, vp, vp, vp, vp, C.POINTER(MgRewards),
                                  C.POINTER(MgOut), C.POINTER(MgOut), vp, u32, rsp, vp, vp, i32]
-    lib.mg_mlp_act.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.mg_mlp_act.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]
     lib.mg_mlp_act.restype = C.c_int
     lib.mg_mlp_act_tc.argtypes = lib.mg_mlp_act.argtypes
     lib.mg_mlp_act_tc.restype = C.c_int

@@ -52,18 +52,23 @@ struct Smem {
 
 // one env's input row [goal] + obs straight from global memory into registers (40-byte rows, 8-byte
 // aligned; a warp covers one contiguous 1280-byte span)
-template <int IN>
+template <int IN, bool MIRROR>
 __device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal,
                                          int64_t e, int64_t n, int obs_dim, float (&x)[IN]) {
     constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
     (void)obs_dim;
     if (e < n) {
         if (off) x[0] = (float)goal[e];
-        const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
+        if (!MIRROR) {
+            const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
-        for (int i = 0; i < (IN - (IN & 1)) / 2; ++i) {     // obs_dim is 10: five float2
-            const float2 v = __ldg(src + i);
-            x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+            for (int i = 0; i < MG_OBS_DIM / 2; ++i) {          // obs_dim is 10: five float2
+                const float2 v = __ldg(src + i);
+                x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+            }
+        } else {                                                // the opponent's view: state[5:] + state[:5] (main.py:199)
+#pragma unroll
+            for (int i = 0; i < MG_OBS_DIM; ++i) x[off + i] = __ldg(obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM);
         }
     } else {
 #pragma unroll
@@ -71,7 +76,7 @@ __device__ __forceinline__ void load_row(const float *__restrict__ obs, const ui
     }
 }
 
-template <int IN, int OUT>
+template <int IN, int OUT, bool MIRROR>
 __global__ void __launch_bounds__(TM, 1)
 mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
                const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2p,
@@ -89,7 +94,7 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
     // first tile's input rows are requested before the weights so the two latencies overlap
     float xr[LR][IN];
 #pragma unroll
-    for (int r = 0; r < LR; ++r) load_row<IN>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
+    for (int r = 0; r < LR; ++r) load_row<IN, MIRROR>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
 
     // ---- weights -> shared memory, once per (persistent) CTA: straight 128-bit copies -------------
     {
@@ -184,7 +189,7 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
         }
         // next tile's input rows: issued now, consumed after the epilogue
 #pragma unroll
-        for (int r = 0; r < LR; ++r) load_row<IN>(obs, goal, (tile + gridDim.x) * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
+        for (int r = 0; r < LR; ++r) load_row<IN, MIRROR>(obs, goal, (tile + gridDim.x) * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
 
         // ---- layer 3 + arg-max ---------------------------------------------------------------------
         float q[4][OUT];
@@ -244,11 +249,11 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
     }
 }
 
-template <int IN, int OUT>
+template <int IN, int OUT, bool MIRROR>
 cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t,
                    const float *b1, const float *w2t, const float *b2, const float *w3, const float *b3,
                    uint8_t *act, float *q_out, cudaStream_t st) {
-    auto kern = mlp_act_kernel<IN, OUT>;
+    auto kern = mlp_act_kernel<IN, OUT, MIRROR>;
     const size_t smem = sizeof(Smem<IN, OUT>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
@@ -266,9 +271,11 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
 extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                                  int32_t out_dim, const float *w1t, const float *b1, const float *w2p,
                                  const float *b2, const float *w3, const float *b3, uint8_t *actions,
-                                 float *q_out_or_null, void *stream) {
+                                 float *q_out_or_null, uint32_t flags, void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (flags & ~MG_MLP_FLAG_MIRROR) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u;
     const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
     if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
         return fail(MG_ERR_BAD_SIZE, "mg_mlp_act supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs "
@@ -281,7 +288,7 @@ extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #define MG_MLP_CASE(I, O) \
-    if (in_dim == I && out_dim == O) e = mgmlp::launch<I, O>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st); else
+    if (in_dim == I && out_dim == O) e = mirror ? mgmlp::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st) : mgmlp::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st); else
     MG_MLP_CASE(10, 5) MG_MLP_CASE(10, 3) MG_MLP_CASE(11, 5) MG_MLP_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_MLP_CASE
     if (e) return cuda_fail(e, "mg_mlp_act launch");

@@ -13,9 +13,8 @@
 //                          computes 8 hidden units of layer 1 for 4 envs on the CUDA cores (FFMA2, each weight
 //                          read from shared memory feeds 4 envs), splits them into hi/lo and writes them straight
 //                          into the canonical K-major core-matrix layout of ring slot (K-step % 4) -> full[slot]
-//   warps 12-13 MMA issue: K-steps interleaved between the two warps (one issuing warp needs ~370 cycles per K-step,
-//                          the tensor pipe ~180); per K-step two tcgen05.mma.kind::tf32 — a_hi x [W2_hi ; W2_lo]
-//                          (N = 224) and a_lo x W2_hi (N = 112) — issued by predication from one elected lane,
+//   warp  12   MMA issue : per K-step two tcgen05.mma.kind::tf32 — a_hi x [W2_hi ; W2_lo] (N = 224) and
+//                          a_lo x W2_hi (N = 112) — issued by predication from one elected lane, K loop unrolled,
 //                          accumulating in TMEM (always accumulate: buffers are handed back zeroed); tcgen05.commit -> empty[next producer] / tmem_full[b]
 //   warps 8-11 epilogue  : tcgen05.ld.16x256b fragments of the 128x112 fp32 accumulator — a thread holds 4 envs x
 //                          2 adjacent neurons per 8-column block, so one read of the layer-3 weights feeds 4 envs —
@@ -30,8 +29,12 @@
 // Every mbarrier wait is bounded and traps instead of hanging.
 #include "abi_common.h"
 
+// 1 = a single MMA-issuing warp with its K loop fully unrolled: accumulation order in TMEM is the K-step order, the
+//     kernel is bitwise reproducible (69.6 us per 2^18 envs);
+// 2 = two issuing warps with interleaved K-steps (68.6 us): fp32 accumulation order follows the run-to-run
+//     interleaving of the two instruction streams, so 57 % of the Q rows differ in their last bits between launches.
 #ifndef MG_TC_MMA_WARPS
-#define MG_TC_MMA_WARPS 2
+#define MG_TC_MMA_WARPS 1
 #endif
 #ifndef MG_TC_TRACE
 #define MG_TC_TRACE 0            // 1: CTA 0 records clock64() at the hand-over points (profiles/exp_tc_trace.cu)
@@ -123,18 +126,23 @@ __device__ __forceinline__ uint32_t mbar_test(unsigned long long *b, uint32_t pa
     return done;
 }
 
-template <int IN>
+template <int IN, bool MIRROR>
 __device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal, int64_t e,
                                          int64_t n, int obs_dim, float (&x)[IN]) {
     constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
     (void)obs_dim;
     if (e < n) {
         if (off) x[0] = (float)goal[e];
-        const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
+        if (!MIRROR) {
+            const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
-        for (int i = 0; i < (IN - (IN & 1)) / 2; ++i) {
-            const float2 v = __ldg(src + i);
-            x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+            for (int i = 0; i < MG_OBS_DIM / 2; ++i) {          // obs_dim is 10: five float2
+                const float2 v = __ldg(src + i);
+                x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+            }
+        } else {                                                // the opponent's view: state[5:] + state[:5] (main.py:199)
+#pragma unroll
+            for (int i = 0; i < MG_OBS_DIM; ++i) x[off + i] = __ldg(obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM);
         }
     } else {
 #pragma unroll
@@ -142,7 +150,7 @@ __device__ __forceinline__ void load_row(const float *__restrict__ obs, const ui
     }
 }
 
-template <int IN, int OUT>
+template <int IN, int OUT, bool MIRROR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
                   const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2_tc,
@@ -217,7 +225,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                 cur = tl;
                 const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TM + lane;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) load_row<IN>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
             }
             const int k = 8 * (int)ks;
             const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[k]);
@@ -271,13 +279,13 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         }
     } else if (warp >= 12) {
         // =================================== MMA ISSUERS =========================================
-        // One issuing warp needs ~370 cycles per K-step (wait, index arithmetic, two tcgen05.mma, commit: a serial
-        // instruction stream), the tensor pipe ~180 — so MMA_WARPS warps share the K-steps of every tile: warp j
-        // issues ks = j, j + MMA_WARPS, ...  Each runs the loop whole-warp and issues by PREDICATION from one elected
-        // lane (inside an `if (lane == 0)` region the compiler rebuilt every descriptor through R2UR and wrapped each
-        // tcgen05 instruction in a per-lane retry loop — ~55 dependent instructions per K-step).
-        // Both issuers always accumulate (the epilogue hands every buffer back zeroed), so the order in which their
-        // MMAs reach the tensor pipe does not matter.  tmem_full[buf] expects one commit per issuing warp.
+        // The issuing warp runs its loop whole-warp and issues by PREDICATION from one elected lane (inside an
+        // `if (lane == 0)` region the compiler rebuilt every descriptor through R2UR and wrapped each tcgen05
+        // instruction in a per-lane retry loop — ~55 dependent instructions and ~470 cycles per K-step against ~180
+        // cycles of tensor work); with the K loop fully unrolled one warp keeps up with the shared-memory-bound
+        // K-step period.  Every MMA accumulates (the epilogue hands each buffer back zeroed); MMA_WARPS = 2 interleaves
+        // the K-steps over two warps, which is 1.5 % faster but makes the fp32 accumulation order — and so the last
+        // bits of the Q-values — vary from launch to launch.  tmem_full[buf] expects one commit per issuing warp.
         const int j = warp - 12;
         uint32_t tl = 0;
         // low descriptor words: (address >> 4) | (LBO >> 4) << 16; stepping an operand = adding (bytes >> 4)
@@ -290,7 +298,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
             const uint32_t d = tmem_base + buf * 256u;
             const uint32_t tm_full = smem_u32(&S.tmem_full[buf]);
             uint32_t have = 0;                              // the barrier about to be waited for was already seen complete
-#pragma unroll 1
+#pragma unroll                                      // fully unrolled: 74.7 -> 69.6 us with one issuing warp
             for (int ks = j; ks < KSTEPS; ks += MMA_WARPS) {
                 const uint32_t it = tl * KSTEPS + (uint32_t)ks;
                 const uint32_t s = it % STAGES, pw = it % PRODUCER_WARPS;
@@ -423,11 +431,11 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
 }
 
-template <int IN, int OUT>
+template <int IN, int OUT, bool MIRROR>
 cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t, const float *b1,
                    const float *w2_tc, const float *b2, const float *w3, const float *b3, uint8_t *act, float *q_out,
                    cudaStream_t st) {
-    auto kern = mlp_act_tc_kernel<IN, OUT>;
+    auto kern = mlp_act_tc_kernel<IN, OUT, MIRROR>;
     const size_t smem = sizeof(Smem<IN, OUT>) + 1024;           // slack for the 1024-byte alignment of the base
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
@@ -445,9 +453,11 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
 extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                                     int32_t out_dim, const float *w1t, const float *b1, const float *w2_tc,
                                     const float *b2, const float *w3, const float *b3, uint8_t *actions,
-                                    float *q_out_or_null, void *stream) {
+                                    float *q_out_or_null, uint32_t flags, void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (flags & ~MG_MLP_FLAG_MIRROR) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u;
     const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
     if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
         return fail(MG_ERR_BAD_SIZE, "mg_mlp_act_tc supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs");
@@ -459,7 +469,7 @@ extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_nul
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #define MG_TC_CASE(I, O) \
-    if (in_dim == I && out_dim == O) e = mgtc::launch<I, O>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st); else
+    if (in_dim == I && out_dim == O) e = mirror ? mgtc::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st) : mgtc::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st); else
     MG_TC_CASE(10, 5) MG_TC_CASE(10, 3) MG_TC_CASE(11, 5) MG_TC_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_TC_CASE
     if (e) return cuda_fail(e, "mg_mlp_act_tc launch");

@@ -108,9 +108,13 @@ class MLPPolicy:
         return torch.addmm(self.b3, h, self.w3.t())
 
     def act(self, obs: torch.Tensor, goal: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-            q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Greedy actions uint8[N] = argmax_a Q(obs)[a] (first maximum wins, as torch.max does)."""
+            q_out: Optional[torch.Tensor] = None, mirror: bool = False) -> torch.Tensor:
+        """Greedy actions uint8[N] = argmax_a Q(obs)[a] (first maximum wins, as torch.max does).
+        `mirror=True` evaluates the network on the opponent's view `state[5:] + state[:5]` (main.py:199) of every
+        row; the fused kernels swap the halves while they read the row."""
         n = obs.shape[0]
+        if mirror and self.backend == "torch":
+            obs = torch.cat([obs[:, 5:], obs[:, :5]], dim=1)
         if out is None:
             out = torch.empty(n, dtype=torch.uint8, device=self.device)
         if self.backend == "torch":
@@ -132,12 +136,12 @@ class MLPPolicy:
             if self.backend == "tf32x3":
                 nat.check(lib.mg_mlp_act_tc(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
                                             _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_tc), _ptr(self.b2),
-                                            _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), stream),
+                                            _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), 1 if mirror else 0, stream),
                           "mg_mlp_act_tc")
             else:
                 nat.check(lib.mg_mlp_act(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
                                          _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_p), _ptr(self.b2),
-                                         _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), stream),
+                                         _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), 1 if mirror else 0, stream),
                           "mg_mlp_act")
         return out
 

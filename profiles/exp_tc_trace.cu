@@ -19,9 +19,9 @@ int main() {
     cudaMalloc(&act, n);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) mg_mlp_act_tc(obs, nullptr, n, 10, 5, w1t, b1, w2, b2, w3, b3, act, nullptr, 0);
+    for (int i = 0; i < 3; ++i) mg_mlp_act_tc(obs, nullptr, n, 10, 5, w1t, b1, w2, b2, w3, b3, act, nullptr, 0u, 0);
     cudaEventRecord(e0);
-    for (int i = 0; i < 20; ++i) mg_mlp_act_tc(obs, nullptr, n, 10, 5, w1t, b1, w2, b2, w3, b3, act, nullptr, 0);
+    for (int i = 0; i < 20; ++i) mg_mlp_act_tc(obs, nullptr, n, 10, 5, w1t, b1, w2, b2, w3, b3, act, nullptr, 0u, 0);
     cudaEventRecord(e1);
     if (cudaError_t e = cudaDeviceSynchronize()) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
     float ms; cudaEventElapsedTime(&ms, e0, e1);

@@ -103,9 +103,13 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mg_reset(C.byref(nat.MgState()), 0, None, None, None, None) == 0
     assert lib.mg_rollout(C.byref(nat.MgState()), 0, 1, 0, 0, 0, 4, None, C.byref(out), None, None, 1, None, None) == 0
     assert lib.mg_sample_actions(None, None, 0, 0, 0, 0, None) == 0
-    assert lib.mg_mlp_act(None, None, 0, 10, 5, None, None, None, None, None, None, None, None, None) == 0
-    assert lib.mg_mlp_act(None, None, 8, 9, 5, None, None, None, None, None, None, None, None, None) == -2
-    assert lib.mg_mlp_act(None, None, 8, 10, 5, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.mg_mlp_act(None, None, 0, 10, 5, None, None, None, None, None, None, None, None, 0, None) == 0
+    assert lib.mg_mlp_act(None, None, 8, 9, 5, None, None, None, None, None, None, None, None, 0, None) == -2
+    assert lib.mg_mlp_act(None, None, 8, 10, 5, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.mg_mlp_act(None, None, 8, 10, 5, None, None, None, None, None, None, None, None, 0x10, None) == -4
+    assert lib.mg_mlp_act_tc(None, None, 8, 10, 5, None, None, None, None, None, None, None, None, 0x10, None) == -4
+    assert lib.mg_record_transitions(*([None] * 10), 8, 0, 3, 1, None, 16, None, None, None, None) == -4
+    assert lib.mg_step_host(None, 8, *([None] * 8), 0, None, None, None, 1) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

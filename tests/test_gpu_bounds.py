@@ -73,15 +73,19 @@ def test_no_kernel_writes_out_of_bounds(n, random_reset):
         nat.check(lib.mg_rollout(C.byref(st), n, pvp, 5, 0, 100, K, C.byref(rw), C.byref(out), p(acts), p(stats), 1,
                                  C.byref(rs), s), "rollout")
     nat.check(lib.mg_reset(C.byref(st), n, p(a1), p(obs), C.byref(rs), s), "masked reset")
-    nat.check(lib.mg_record_transitions(p(obs), p(obs), p(term), p(a1), p(a2), p(rew), p(done), p(info), n, 1, 0, 1,
+    nat.check(lib.mg_record_transitions(p(obs), p(obs), p(term), p(a1), p(a2), p(rew), p(done), p(info), None, None, n, 1, 0, 1,
                                         p(ring), 50, p(ids), p(counter), p(scratch), s), "record")
-    nat.check(lib.mg_record_transitions(p(obs), p(obs), None, p(a1), None, p(rew), p(done), p(info), n, 0, 1, 2,
+    nat.check(lib.mg_record_transitions(p(obs), p(obs), None, p(a1), None, p(rew), p(done), p(info), None, None, n, 0, 1, 2,
                                         p(ring), 50, None, p(counter), p(scratch), s), "record log")
-    nat.check(lib.mg_mlp_act(p(obs), None, n, 10, 5, p(w1t), p(b1), p(w2t), p(b2), p(w3), p(b3), p(act_out),
-                             p(q_out), s), "mlp")
+    nat.check(lib.mg_record_transitions(p(obs), p(obs), p(term), p(a1), p(a2), p(rew), p(done), p(info), p(a1), p(a2), n, 0, 2, 1,
+                                        p(ring), 45, None, p(counter), p(scratch), s), "record hdqn rows")
+    for flags in (0, 1):                                        # plain and mirrored (opponent-view) read
+        nat.check(lib.mg_mlp_act(p(obs), None, n, 10, 5, p(w1t), p(b1), p(w2t), p(b2), p(w3), p(b3), p(act_out),
+                                 p(q_out), flags, s), "mlp")
     w2tc = ar.take(4 * 2 * 25 * 14 * 2 * 8 * 4, 0)
-    nat.check(lib.mg_mlp_act_tc(p(obs), None, n, 10, 5, p(w1t), p(b1), p(w2tc), p(b2), p(w3), p(b3), p(act_out),
-                                p(q_out), s), "mlp tc")
+    for flags in (0, 1):
+        nat.check(lib.mg_mlp_act_tc(p(obs), None, n, 10, 5, p(w1t), p(b1), p(w2tc), p(b2), p(w3), p(b3), p(act_out),
+                                    p(q_out), flags, s), "mlp tc")
     torch.cuda.synchronize()
     ar.check()
     assert int(counter.view(torch.int64)[0]) > 0

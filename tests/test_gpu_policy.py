@@ -85,11 +85,31 @@ def test_tensor_core_backend_matches_fp32(mg, in_dim, out_dim, n):
     assert (af == at).float().mean().item() > 0.999
 
 
+@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("in_dim,out_dim", [(10, 5), (11, 5), (10, 3)])
+def test_mirrored_read_equals_opponent_view(mg, backend, in_dim, out_dim):
+    """`mirror=True` (MG_MLP_FLAG_MIRROR): the kernels read every row as the opponent sees it, `state[5:] + state[:5]`
+    (main.py:199; with a goal column: `[goal_op] + state[5:] + state[:5]`, hdqn.py:299) — bit-identical to running
+    them on a materialised `env.opponent_view(obs)`."""
+    n = 3001
+    env = mg.MergeVecEnv(n, seed=2); env.rollout(130)
+    obs = env.step(*env.sample_actions())[0].clone()
+    goal = torch.randint(0, 3, (n,), dtype=torch.uint8, device="cuda") if in_dim == 11 else None
+    pol = mg.MLPPolicy(in_dim, out_dim, seed=9, backend=backend)
+    q1 = torch.empty(n, out_dim, device="cuda"); q2 = torch.empty(n, out_dim, device="cuda")
+    a1 = pol.act(obs, goal=goal, q_out=q1, mirror=True).clone()
+    a2 = pol.act(env.opponent_view(obs).contiguous(), goal=goal, q_out=q2).clone()
+    assert torch.equal(a1, a2) and torch.equal(q1, q2)
+    pol.act(obs, goal=goal, q_out=q2)
+    assert not torch.equal(q1, q2)                                              # and it differs from the unmirrored read
+
+
 def test_tensor_core_backend_is_stable_under_repetition(mg):
-    """The tensor-core kernel is a multi-role pipeline (8 producer warps, two MMA-issuing warps that
-    accumulate into the same TMEM columns, 4 epilogue warps that hand the buffers back zeroed, 20 mbarriers).  A protocol race would
-    show up as an occasional lost update or a stale tile: 150 launches over many tiles per SM
-    (2^17 envs = 1024 tiles on 148 SMs) on changing inputs must all agree with the fp32 kernel."""
+    """The tensor-core kernel is a multi-role pipeline (8 producer warps, an MMA-issuing warp, 4 epilogue warps
+    that hand the accumulator buffers back zeroed, 20 mbarriers).  A protocol race would show up as an occasional lost
+    update or a stale tile: 150 launches over many tiles per SM (2^17 envs = 1024 tiles on 148 SMs) on changing
+    inputs must all agree with the fp32 kernel — and a repeated launch must reproduce its Q-values BIT FOR BIT (the
+    accumulation order in tensor memory is the K-step order; with two issuing warps, MG_TC_MMA_WARPS=2, it is not)."""
     n = 1 << 17
     env = mg.MergeVecEnv(n, seed=11)
     f = mg.MLPPolicy(10, 5, seed=5)
@@ -100,6 +120,9 @@ def test_tensor_core_backend_is_stable_under_repetition(mg):
         obs = env.step(*env.sample_actions())[0]
         f.act(obs, q_out=qf); tc.act(obs, q_out=qt)
         worst = torch.maximum(worst, (qf - qt).abs().max() / qf.abs().max())
+        if t % 10 == 0:
+            q2 = torch.empty_like(qt); tc.act(obs, q_out=q2)
+            assert torch.equal(q2, qt), t
     assert worst.item() < 5e-5                                               # measured 3e-6
 
 
@@ -145,7 +168,7 @@ def test_two_shipped_checkpoints_play_each_other(mg, ckpt, backend):
     T = len(traj["traj_actions"])
     assert len(set(traj["traj_actions"][:, 1].tolist())) == 3
     for t in range(T):
-        a1, a2 = p1.act(obs), p2.act(env.opponent_view(obs))
+        a1, a2 = p1.act(obs), (p2.act(obs, mirror=True) if t % 2 else p2.act(env.opponent_view(obs)))
         assert a1.cpu().tolist() == [int(traj["traj_actions"][t, 0])] * 64, t
         assert a2.cpu().tolist() == [int(traj["traj_actions"][t, 1])] * 64, t
         assert rel_err(obs[0].cpu().numpy(), traj["traj_obs"][t]).max() <= 1e-5, t
