@@ -9,8 +9,10 @@ The package holds only what the hot path needs:
   spaces.py    Discrete(5) / Box(10) stand-ins (gym is not a dependency)
   replay.py    device-resident transition ring (replay rows) and per-episode CSV logs
   policy.py    policy-in-the-loop: the reference's Q-networks as one fused forward+argmax kernel
+  graphed.py   K policy+env(+recorder) steps captured in one CUDA graph
 """
 from ._native import NativeError  # noqa: F401
+from .graphed import GraphedPolicyRollout  # noqa: F401
 from .policy import HDQNPolicy, MLPPolicy, explore, goal_status  # noqa: F401
 from .replay import CsvEpisodeLogger, TransitionRecorder  # noqa: F401
 from .scalar_env import ENV_ID, MergeEnv, make, make_vec, register_gym  # noqa: F401

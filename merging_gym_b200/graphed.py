@@ -1,0 +1,71 @@
+"""K policy-in-the-loop steps per host call ("multi-step rollout with fused greedy policy").
+
+`GraphedPolicyRollout` captures K iterations of
+    a1 = policy1(obs)            [a2 = policy2(opponent's view of obs)]        -> env.step -> [recorder.record]
+into one CUDA graph: a replay advances every env K steps with no host work in between, which is what makes the
+policy loop launch-latency free at small env counts.  The loop body is exactly the reference scripts' inner loop
+(scripts/main.py:194-211, hdqn.py:288-316) with greedy (or `explore`d) actions.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from .vec_env import MergeVecEnv
+
+
+class GraphedPolicyRollout:
+    """`run()` = K env steps.  The env must have been constructed with `out_slots=1` (one fixed observation buffer,
+    so that every captured step reads the buffer the previous one wrote).
+
+    policy1(obs) -> uint8[N] actions of player 1; policy2 (pvp only) receives the same observation buffer and must
+    mirror it itself (`MLPPolicy.act(obs, mirror=True)`).  `after_step(obs_prev, a1, a2, step_out)`, if given, runs
+    inside the graph after every step (e.g. `TransitionRecorder.record`); `obs_prev` is a graph-private copy of the
+    observation the actions were chosen from.
+    """
+
+    def __init__(self, env: MergeVecEnv, policy1: Callable, policy2: Optional[Callable] = None, k_steps: int = 32,
+                 after_step: Optional[Callable] = None, warmup_steps: int = 3):
+        if env.out_slots != 1:
+            raise ValueError("GraphedPolicyRollout needs an env with out_slots=1")
+        if (policy2 is not None) != (env.mode == "pvp"):
+            raise ValueError("policy2 is required for, and only for, a pvp env")
+        self.env, self.k_steps = env, int(k_steps)
+        self._p1, self._p2, self._after = policy1, policy2, after_step
+        n, dev = env.num_envs, env.device
+        self._a1 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._a2 = torch.zeros(n, dtype=torch.uint8, device=dev) if policy2 is not None else None
+        self._prev = torch.empty_like(env.obs_buf[0]) if after_step is not None else None
+        self.last = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # warm-up outside capture (lazy initialisation, autotuning)
+            for _ in range(warmup_steps):
+                self._one_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            for _ in range(self.k_steps):
+                self.last = self._one_step()
+
+    def _one_step(self):
+        env = self.env
+        obs = env.obs_buf[0]
+        if self._prev is not None:
+            self._prev.copy_(obs)
+        self._a1.copy_(self._p1(obs))
+        if self._a2 is not None:
+            self._a2.copy_(self._p2(obs))
+        out = env.step(self._a1, self._a2)
+        if self._after is not None:
+            self._after(self._prev, self._a1, self._a2, out)
+        return out
+
+    def run(self, times: int = 1):
+        """Advance `times * k_steps` steps; returns the (obs, rew, done, info) of the last step (device tensors that
+        alias the env's output buffers).  No host synchronisation."""
+        for _ in range(times):
+            self.graph.replay()
+        return self.last

@@ -288,3 +288,35 @@ def test_examples_run(script, args):
     out = subprocess.run([sys.executable, os.path.join(root, "examples", script), *args], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "episodes" in out.stdout
+
+
+@pytest.mark.parametrize("pvp", [False, True])
+def test_graphed_policy_rollout_equals_the_eager_loop(mg, ckpt, pvp):
+    """`GraphedPolicyRollout`: K steps of policy -> env.step -> recorder.record captured in one CUDA graph and
+    replayed; state, statistics and the recorded replay rows equal the same loop run eagerly."""
+    n, K, R = 2048, 8, 40
+    sd1, _ = ckpt("L2_2133"); sd2, _ = ckpt("L1_2136")
+    def build():
+        env = mg.MergeVecEnv(n, mode="pvp" if pvp else "pve", out_slots=1, seed=1)
+        env.rollout(150)                                        # de-synchronise the envs first
+        env.step(env.sample_actions()[0], env.sample_actions()[1] if pvp else None)
+        p1 = mg.MLPPolicy(10, 5, state_dict=sd1); p2 = mg.MLPPolicy(10, 5, state_dict=sd2) if pvp else None
+        rec = mg.TransitionRecorder(env, 4 * n * K, track_env_ids=True)
+        return env, p1, p2, rec
+    env, p1, p2, rec = build()
+    roll = mg.GraphedPolicyRollout(env, p1, (lambda o: p2.act(o, mirror=True)) if pvp else None, k_steps=K,
+                                   after_step=rec.record, warmup_steps=0)
+    out = roll.run(R)
+    ref, q1, q2, rrec = build()
+    for t in range(K * R):
+        obs = ref.obs_buf[0].clone()
+        a1 = q1.act(obs); a2 = q2.act(obs, mirror=True) if pvp else None
+        rout = ref.step(a1, a2)
+        rrec.record(obs, a1, a2, rout)
+    torch.cuda.synchronize()
+    for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta"):
+        assert torch.equal(getattr(env, k), getattr(ref, k)), k
+    assert env.stats() == ref.stats() and env.stats()["episodes"] > n
+    assert torch.equal(out[0], rout[0]) and torch.equal(rec.counter, rrec.counter)
+    c = min(int(rec.counter.item()), rec.capacity)
+    assert torch.equal(rec.ring[:c], rrec.ring[:c]) and torch.equal(rec.env_ids[:c], rrec.env_ids[:c])
