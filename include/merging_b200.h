@@ -224,7 +224,9 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
 /* ---- "next" rows: device-resident transition writer -----------------------
  * Appends one row per selected env to a ring `ring[capacity][width]` (index = counter % capacity,
  * exactly `DQN.store_transition`, scripts/main.py:115-119), envs in id order, deterministic.
- *   mask_mode 0: every env;  1: `env.winner is not 1` after the step (main.py:209, human_player.py:180)
+ *   mask_mode 0: every env;  1: `env.winner is not 1` after the step (main.py:209, human_player.py:180);
+ *             2: explicit — `info` is then a caller-supplied uint8[n] mask, non-zero = store (used for the h-DQN
+ *                meta-controller's per-option rows, hdqn.py:318)
  *   format 0 (width 22): [s(10), a_p, r_p, s'(10)] for player p (main.py:116);  s' is the stepped
  *                        state's observation: term_obs where done (pass NULL without auto-reset)
  *   format 1 (width 14): [s(10), a1, a2, r1, r2], the CSV row of scripts/human_player.py:111,180-181

@@ -20,8 +20,10 @@ constexpr int kBlock = 256;
 constexpr int kObs = MG_OBS_DIM;
 
 __device__ __forceinline__ bool selected(const uint8_t *info, int64_t e, int mask_mode) {
-    // mask_mode 0: every env; 1: the reference's `env.winner is not 1` (winner AFTER the step)
+    // mask_mode 0: every env; 1: the reference's `env.winner is not 1` (winner AFTER the step);
+    // 2: explicit — `info` is a caller-supplied byte mask, non-zero = store
     if (mask_mode == 0) return true;
+    if (mask_mode == 2) return info[e] != 0u;
     return ((info[e] & MG_INFO_WINNER_MASK) >> MG_INFO_WINNER_SHIFT) != 1u;
 }
 
@@ -213,8 +215,8 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
                                             void *stream) {
     using namespace mg_abi;
     if (n < 0 || capacity <= 0) return fail(MG_ERR_BAD_SIZE, "n < 0 or capacity <= 0");
-    if (mask_mode < 0 || mask_mode > 1 || format < 0 || format > 2 || player < 1 || player > 2)
-        return fail(MG_ERR_BAD_FLAGS, "mask_mode in {0,1}, format in {0,1,2}, player in {1,2}");
+    if (mask_mode < 0 || mask_mode > 2 || format < 0 || format > 2 || player < 1 || player > 2)
+        return fail(MG_ERR_BAD_FLAGS, "mask_mode in {0,1,2}, format in {0,1,2}, player in {1,2}");
     if (n == 0) return MG_OK;
     if (!obs_prev || !obs_next || !a1 || !rew || !done || !info || !ring || !counter || !scratch)
         return fail(MG_ERR_NULL_POINTER, "mg_record_transitions: NULL pointer");

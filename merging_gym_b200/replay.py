@@ -24,6 +24,7 @@ REPLAY_WIDTH = 2 * nat.OBS_DIM + 2      # main.py:92  NUM_STATES * 2 + 2
 LOG_WIDTH = nat.OBS_DIM + 4
 HDQN_WIDTH = 2 * (nat.OBS_DIM + 1) + 2   # hdqn.py:158  (NUM_STATES + 1) * 2 + 2
 _FORMATS = {"replay": (0, REPLAY_WIDTH), "log": (1, LOG_WIDTH), "hdqn": (2, HDQN_WIDTH)}
+_MASKS = {"all": 0, "winner_not_1": 1, "explicit": 2}
 
 # header of scripts/human_player.py:111, verbatim column names
 CSV_HEADER = ["x2 - x1", "y2 - y1", "self.state2['vel'] - self.state1['vel']", "END_POINT - self.state1['pos']",
@@ -44,13 +45,14 @@ class TransitionRecorder:
                      (hdqn.py:180-184,291-316): pass the goals chosen from s and from s' to `record`; the
                      intrinsic reward `1 if g' == goal_status(s) else 0` (hdqn.py:314) is computed on the device.
                      The reference stores these every step: use mask="all".
-    mask "winner_not_1" is the reference's store condition; "all" stores every env every step.
+    mask "winner_not_1" is the reference's store condition; "all" stores every env every step; "explicit"
+    stores the envs selected by the uint8 `select` tensor passed to `record`.
     """
 
     def __init__(self, env, capacity: int, format: str = "replay", player: int = 1,
                  mask: str = "winner_not_1", track_env_ids: bool = False):
-        if format not in _FORMATS or mask not in ("winner_not_1", "all") or player not in (1, 2):
-            raise ValueError("format in {'replay','log','hdqn'}, mask in {'winner_not_1','all'}, player in {1,2}")
+        if format not in _FORMATS or mask not in _MASKS or player not in (1, 2):
+            raise ValueError("format in {'replay','log','hdqn'}, mask in {'winner_not_1','all','explicit'}, player in {1,2}")
         if format != "log" and env.auto_reset and env.terminal_obs is None:
             raise ValueError("replay rows need the terminal observation: create the env with episode_info=True")
         self.env, self.capacity = env, int(capacity)
@@ -64,23 +66,27 @@ class TransitionRecorder:
         self._lib = nat.load()
 
     def record(self, obs_prev: torch.Tensor, a1: torch.Tensor, a2: Optional[torch.Tensor], step_out,
-               goal_prev: Optional[torch.Tensor] = None, goal_next: Optional[torch.Tensor] = None) -> None:
+               goal_prev: Optional[torch.Tensor] = None, goal_next: Optional[torch.Tensor] = None,
+               select: Optional[torch.Tensor] = None) -> None:
         """Append the transitions of one `env.step`: `obs_prev` is the observation the actions were
         chosen from, `step_out` the tuple `env.step` returned.  uint8 actions (and, for format "hdqn",
         uint8 goals chosen from `obs_prev` and from the new observation); no host sync."""
         obs, rew, done, info = step_out
         env = self.env
         term = env.terminal_obs if env.auto_reset else None
-        for t in (a1, a2, goal_prev, goal_next):
+        for t in (a1, a2, goal_prev, goal_next, select):
             if t is not None and t.dtype != torch.uint8:
-                raise TypeError("TransitionRecorder.record expects uint8 action / goal tensors")
+                raise TypeError("TransitionRecorder.record expects uint8 action / goal / select tensors")
+        if (self.mask == "explicit") != (select is not None):
+            raise ValueError("`select` is required for, and only for, mask='explicit'")
         if (self.format == "hdqn") != (goal_prev is not None and goal_next is not None):
             raise ValueError("goal_prev and goal_next are required for, and only for, format 'hdqn'")
         with torch.cuda.device(env.device):
             nat.check(self._lib.mg_record_transitions(
                 _ptr(obs_prev), _ptr(obs), _ptr(term), _ptr(a1), _ptr(a2), _ptr(rew),
-                _ptr(done.view(torch.uint8)), _ptr(info["flags"]), _ptr(goal_prev), _ptr(goal_next), env.num_envs,
-                1 if self.mask == "winner_not_1" else 0, _FORMATS[self.format][0], self.player,
+                _ptr(done.view(torch.uint8)), _ptr(select if select is not None else info["flags"]),
+                _ptr(goal_prev), _ptr(goal_next), env.num_envs,
+                _MASKS[self.mask], _FORMATS[self.format][0], self.player,
                 _ptr(self.ring), self.capacity, _ptr(self.env_ids), _ptr(self.counter), _ptr(self._scratch),
                 C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)), "mg_record_transitions")
 
@@ -100,6 +106,49 @@ class TransitionRecorder:
         """`np.random.choice(MEMORY_CAPACITY, BATCH_SIZE)` (main.py:130) over a full ring, on device."""
         idx = torch.randint(0, self.capacity, (batch_size,), device=self.ring.device, generator=generator)
         return self.ring[idx]
+
+
+class OptionRecorder:
+    """The h-DQN meta-controller's transitions (scripts/hdqn.py:283-320) for N envs on the device.
+
+    An option runs from one goal choice until `done or goal == goal_status(state)` (hdqn.py:316); the reference
+    then stores `upper.store_transition(state, goal, extrinsic_reward, next_state)` (:318) where — because
+    `state = next_state` has already been executed (:315) — BOTH observations are the one the option ended in, `goal`
+    is the goal re-chosen from it, and `extrinsic_reward` is the sum of the ego rewards over the option.  Rows:
+    `[s_end(10), goal, sum_r, s_end(10)]`, 22 floats, appended in env-id order like every other ring here.
+    """
+
+    def __init__(self, env, capacity: int, track_env_ids: bool = False):
+        from .policy import goal_status
+        self._goal_status = goal_status
+        self.env = env
+        self.rec = TransitionRecorder(env, capacity, format="replay", player=1, mask="explicit", track_env_ids=track_env_ids)
+        self.extrinsic = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
+        self._rew = torch.zeros(env.num_envs, 2, dtype=torch.float32, device=env.device)
+
+    @property
+    def ring(self):
+        return self.rec.ring
+
+    @property
+    def counter(self):
+        return self.rec.counter
+
+    def record(self, step_out, goal_next: torch.Tensor) -> torch.Tensor:
+        """Call after every env step with the goal chosen from the NEW state; returns the uint8[N] mask of the
+        envs whose option ended in this step.  No host sync."""
+        obs, rew, done, info = step_out
+        env = self.env
+        s_end = obs
+        if env.auto_reset:                                     # the stepped state's observation, not the reset one
+            s_end = torch.where(done.bool().unsqueeze(1), env.terminal_obs, obs)
+        self.extrinsic += rew[:, 0]
+        ended = (done.bool() | (goal_next == self._goal_status(s_end))).to(torch.uint8)
+        self._rew[:, 0] = self.extrinsic
+        # row = [state, goal, extrinsic_reward, next_state] with state == next_state == s_end (hdqn.py:315-318)
+        self.rec.record(s_end.contiguous(), goal_next, None, (s_end.contiguous(), self._rew, torch.zeros_like(done), info), select=ended)
+        self.extrinsic.masked_fill_(ended.bool(), 0.0)
+        return ended
 
 
 class CsvEpisodeLogger:

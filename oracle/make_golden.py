@@ -294,23 +294,28 @@ def hdqn_fixtures():
                 # the same episode once more through the reference's nested option loop (hdqn.py:276-324) with its own
                 # store_transition calls: the controller's memory rows [g, s, a, r_int, g', s'] (24 floats)
                 lower.memory_counter = 0
+                upper.memory_counter = 0
                 state = env.reset(); done = False
                 with quiet(), torch.no_grad():
                     while not done:
                         goal = upper.choose_goal(state)
+                        extrinsic_reward = 0
                         while not done:
                             goal_state = torch.unsqueeze(torch.FloatTensor([goal] + state), dim=0)
                             action = lower.choose_action(goal_state)
                             next_state, rewards, done, info = env.step(action, None)
                             goal = upper.choose_goal(next_state)
                             next_goal_state = torch.unsqueeze(torch.FloatTensor([goal] + next_state), dim=0)
+                            extrinsic_reward += rewards[0]
                             intrinsic_reward = 1.0 if goal == ref.goal_status(state) else 0.0
                             lower.store_transition(goal_state, action, intrinsic_reward, next_goal_state)
                             state = next_state
                             if done or goal == ref.goal_status(state):
                                 break
-                assert lower.memory_counter == len(rows)
+                        upper.store_transition(state, goal, extrinsic_reward, next_state)      # hdqn.py:318
+                assert lower.memory_counter == len(rows) and upper.memory_counter < ref.GOAL_MEMORY_CAPACITY
                 out[f"{tag}/L0/controller_memory"] = lower.memory[:lower.memory_counter].copy()
+                out[f"{tag}/L0/meta_memory"] = upper.memory[:upper.memory_counter].copy()
             out[f"{tag}/{mode}/traj_obs"] = np.array(obs)
             out[f"{tag}/{mode}/traj"] = np.array(rows, np.uint8)          # goal, action, goal_op, action_op
             out[f"{tag}/{mode}/result"] = np.array([len(rows), env.winner or 0, int(info["collision"]),

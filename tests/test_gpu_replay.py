@@ -183,3 +183,35 @@ def test_hdqn_controller_rows_against_the_reference(mg, seed):
         assert np.array_equal(ring[:, col], mem[:, col]), col
     assert rel_err(ring, mem).max() <= 1e-5
     assert mem[:, 12].sum() == (71 if seed == 36 else 0)
+
+
+@pytest.mark.parametrize("seed", [7, 36])
+def test_hdqn_meta_rows_against_the_reference(mg, seed):
+    """tests/golden/hdqn_policies.npz `meta_memory`: the rows the reference's OWN `Goal_DQN.store_transition`
+    (scripts/hdqn.py:97-101, called at :318 when an option ends: `done or goal == goal_status(state)`, :316) left in
+    `upper.memory` — `[s_end, goal, sum of ego rewards over the option, s_end]`.  `OptionRecorder` driven by
+    HDQNPolicy must leave the same rows (seed 36: 70 options in 225 steps; seed 7: one option = the whole episode)."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "hdqn_policies.npz"))
+    tag = f"seed{seed}"
+    sd = lambda name: {k.split("/")[-1]: z[k] for k in z.files if k.startswith(f"{tag}/{name}/")}
+    mem, steps = z[f"{tag}/L0/meta_memory"], len(z[f"{tag}/L0/controller_memory"])
+    pol = mg.HDQNPolicy(meta_state=sd("meta"), ctrl_state=sd("ctrl"))
+    env = mg.MergeVecEnv(3, mode="pve", auto_reset=False, out_slots=2)
+    opt = mg.OptionRecorder(env, 3 * 200, track_env_ids=True)                    # 3 envs x GOAL_MEMORY_CAPACITY (hdqn.py:22)
+    obs = env.reset().clone()
+    ended_total = 0
+    for t in range(steps):
+        a = pol.act(obs).clone()
+        out = env.step(a, None)
+        g_next = pol.meta.act(out[0]).clone()
+        ended_total += int(opt.record(out, g_next).sum())
+        obs = out[0].clone()
+    assert bool(out[2].all()) and int(opt.counter.item()) == 3 * len(mem) == ended_total
+    ring = opt.ring[:3 * len(mem)].cpu().numpy()
+    for e in range(3):                                                           # three identical envs, rows interleaved
+        rows = ring[e::3]
+        assert np.array_equal(rows[:, 10], mem[:, 10])                           # the goal column, exactly
+        assert rel_err(rows, mem).max() <= 1e-5
+    assert len(mem) == (70 if seed == 36 else 1)
