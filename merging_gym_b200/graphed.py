@@ -22,7 +22,8 @@ class GraphedPolicyRollout:
     policy1(obs) -> uint8[N] actions of player 1; policy2 (pvp only) receives the same observation buffer and must
     mirror it itself (`MLPPolicy.act(obs, mirror=True)`).  `after_step(obs_prev, a1, a2, step_out)`, if given, runs
     inside the graph after every step (e.g. `TransitionRecorder.record`); `obs_prev` is a graph-private copy of the
-    observation the actions were chosen from.
+    observation the actions were chosen from.  Construction runs `warmup_steps` real steps (they advance the env and
+    feed `after_step`) before the capture; pass `warmup_steps=0` once the kernels have been used before.
     """
 
     def __init__(self, env: MergeVecEnv, policy1: Callable, policy2: Optional[Callable] = None, k_steps: int = 32,
