@@ -400,8 +400,8 @@ def run_b200(args):
     e2e_s = float(t.item())
     e2e = {"value": total_envs * E / e2e_s, "unit": UNIT, "steps": E,
            "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": n * (40 + 8 + 1 + 1),
-           "api": "MergeVecEnv.step_host -> mg_step_host (actions in pinned host memory, outputs into pinned host "
-                  "memory, stream synchronised every step)",
+           "api": "MergeVecEnv.step_host -> mg_step_host (actions in pinned host memory, read across PCIe by the step "
+                  "kernel itself; outputs copied into pinned host memory; stream synchronised every step)",
            "pcie_gbs": total_envs / world * 52 * E / e2e_s / 1e9,
            "bound": "PCIe: 52 B/env-step cross the bus (2 up, 50 down); a plain 52 MB device->host copy reaches "
                     "~56 GB/s on this pool (profiles/README.md)"}

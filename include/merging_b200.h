@@ -181,6 +181,8 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
  * host, like the reference scripts): copies h_a1/h_a2 (uint8[n]) to the device scratch actions
  * d_a1/d_a2, runs mg_step, copies obs/rew/done/info back into the h_out arrays and SYNCHRONISES
  * the stream(s).  Optional members of h_out may be NULL.  Pinned host memory is recommended.
+ * d_a1 == NULL: no upload — the kernel reads the actions straight from h_a1 / h_a2, which must then be
+ * pinned (device-accessible) host memory.
  * copy_stream_or_null + chunks > 1: the envs are stepped in `chunks` (<= 16) pieces of whole 256-env
  * blocks and the device-to-host copies of a piece run on copy_stream while the next piece is uploaded
  * and stepped on `stream` (the bus is the bottleneck of this path: 52 bytes per env-step).  Results are

@@ -598,8 +598,11 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
                         void *stream, void *copy_stream, int32_t chunks) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     if (n == 0) return MG_OK;
-    if (!state || !h_a1 || !d_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "state, h_a1, d_a1, d_out or h_out is NULL");
-    if (h_a2 && !d_a2) return fail(MG_ERR_NULL_POINTER, "h_a2 given without d_a2 scratch");
+    if (!state || !h_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "state, h_a1, d_out or h_out is NULL");
+    // d_a1 == NULL: no upload — the kernel reads the actions straight from h_a1 / h_a2, which must then be pinned
+    // (device-accessible) host memory
+    const bool direct = d_a1 == nullptr;
+    if (!direct && h_a2 && !d_a2) return fail(MG_ERR_NULL_POINTER, "h_a2 given without d_a2 scratch");
     if (int rc = check_reset(reset)) return rc;
     cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
     // Chunked pipeline: with a second stream the envs are stepped in `chunks` pieces; the D2H of piece c (copy
@@ -619,8 +622,9 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
         const int64_t m = n - off < piece ? n - off : piece;
         const size_t M = (size_t)m;
         // one upload when the two action vectors sit at the same distance on both sides (single piece only)
-        const bool acts_joined = nch == 1 && h_a2 && d_a2 > d_a1 && (d_a2 - d_a1) == (h_a2 - h_a1) && (size_t)(d_a2 - d_a1) < M + 4096;
-        if (acts_joined) {
+        const bool acts_joined = !direct && nch == 1 && h_a2 && d_a2 > d_a1 && (d_a2 - d_a1) == (h_a2 - h_a1) && (size_t)(d_a2 - d_a1) < M + 4096;
+        if (direct) {
+        } else if (acts_joined) {
             if ((e = cudaMemcpyAsync(d_a1, h_a1, (size_t)(d_a2 - d_a1) + M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D actions");
         } else {
             if ((e = cudaMemcpyAsync(d_a1 + off, h_a1 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a1");
@@ -634,7 +638,9 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
                          d_out->ep_ret ? d_out->ep_ret + off * 2 : nullptr, d_out->ep_len ? d_out->ep_len + off : nullptr};
         MgResetSpec rs = rs0;
         rs.env_id_base += (uint64_t)off;
-        if (int rc = mg_step(&sub, m, d_a1 + off, h_a2 ? d_a2 + off : nullptr, MG_ACT_U8, rewards, &d, stats, flags, &rs, stream)) return rc;
+        const uint8_t *k_a1 = direct ? h_a1 + off : d_a1 + off;
+        const uint8_t *k_a2 = !h_a2 ? nullptr : direct ? h_a2 + off : d_a2 + off;
+        if (int rc = mg_step(&sub, m, k_a1, k_a2, MG_ACT_U8, rewards, &d, stats, flags, &rs, stream)) return rc;
         cudaStream_t out_st = st;
         if (nch > 1) {
             if ((e = cudaEventRecord(ev[c], st))) return cuda_fail(e, "mg_step_host event record");

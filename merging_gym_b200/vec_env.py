@@ -400,10 +400,11 @@ class MergeVecEnv:
         return self._host_np
 
     def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, zero_copy: bool = False,
-                  chunks: int = 1):
+                  chunks: int = 1, direct_actions: bool = True):
         """Drop-in for host-resident callers: uint8 NumPy actions in, NumPy outputs out.
 
-        Default: one `mg_step_host` call = H2D of the actions, the fused step, D2H of
+        Default: one `mg_step_host` call = the fused step reading the actions straight from the pinned
+        staging buffers (`direct_actions=False`: after an explicit H2D copy of them instead), D2H of
         obs/rew/done/info into pinned host buffers, stream synchronise.  `chunks > 1` steps the envs in
         that many pieces so that the device-to-host copy of one piece (on a private copy stream)
         overlaps the upload and the kernel of the next; on a PCIe 5 x16 B200 this does not pay (the
@@ -434,7 +435,8 @@ class MergeVecEnv:
                 self._slot = (self._slot + 1) % self.out_slots
                 nat.check(self._lib.mg_step_host(C.byref(self._state), n, _ptr(h["a1"]),
                                                  _ptr(h["a2"]) if a2 is not None else None,
-                                                 _ptr(self.act1), _ptr(self.act2), C.byref(self._rw),
+                                                 None if direct_actions else _ptr(self.act1),
+                                                 None if direct_actions else _ptr(self.act2), C.byref(self._rw),
                                                  C.byref(self._outs[self._slot]), C.byref(self._host_out),
                                                  _ptr(self.stats_buf), self._flags(), C.byref(self._rs),
                                                  self._stream(), self._copy_stream_ptr(chunks), int(chunks)),

@@ -23,6 +23,7 @@ def timed(fn, iters=30):
 print("pageable actions (staged), 1 piece :", timed(lambda: env.step_host(h1, h2, chunks=1)))
 for c in (1, 2, 4, 8, 16):
     print(f"pinned actions, {c:2d} piece(s)        :", timed(lambda: env.step_host(p1, p2, chunks=c)))
+print("pinned actions read by the kernel   :", timed(lambda: env.step_host(p1, p2, direct_actions=True)))
 print("zero-copy (kernel stores to host)  :", timed(lambda: env.step_host(p1, p2, zero_copy=True)))
 dev = torch.empty(52 << 20, dtype=torch.uint8, device="cuda"); host = torch.empty(52 << 20, dtype=torch.uint8).pin_memory()
 for _ in range(3): host.copy_(dev, non_blocking=True)

@@ -324,7 +324,7 @@ def test_step_host_matches_device_path(mg):
     a = mg.MergeVecEnv(n); b = mg.MergeVecEnv(n)
     for t in range(120):
         act = rng.integers(0, 5, (n, 2)).astype(np.uint8)
-        ho, hr, hd, hi = a.step_host(act[:, 0], act[:, 1])
+        ho, hr, hd, hi = a.step_host(act[:, 0], act[:, 1], direct_actions=bool(t % 2))   # with / without the explicit upload
         o, r, d, i = b.step(act[:, 0], act[:, 1])
         assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy())
         assert np.array_equal(hd, d.cpu().numpy()) and np.array_equal(hi, i["flags"].cpu().numpy())
@@ -351,7 +351,7 @@ def test_step_host_pipeline_pieces(mg, chunks):
     rng = np.random.default_rng(chunks)
     for t in range(260):
         p1[:] = rng.integers(0, 5, n); p2[:] = rng.integers(0, 5, n)
-        ho, hr, hd, hi = a.step_host(p1, p2, chunks=chunks)
+        ho, hr, hd, hi = a.step_host(p1, p2, chunks=chunks, direct_actions=bool((t // 7) % 2))
         o, r, d, i = b.step(p1.copy(), p2.copy())
         if t % 20 == 0 or t > 250:
             assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy())
