@@ -223,6 +223,7 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
                          const float *b2, const float *w3, const float *b3, uint8_t *actions,
                          float *q_out_or_null, uint32_t flags, void *stream);
 
+
 /* ---- "next" rows: device-resident transition writer -----------------------
  * Appends one row per selected env to a ring `ring[capacity][width]` (index = counter % capacity,
  * exactly `DQN.store_transition`, scripts/main.py:115-119), envs in id order, deterministic.
