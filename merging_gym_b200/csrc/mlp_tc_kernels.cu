@@ -217,16 +217,14 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
             off[j] = (uint32_t)((m >> 3) * 256 + (m & 7) * 16);
         }
         float x[4][IN];
-        uint32_t cur = 0xFFFFFFFFu;
+        {
+            const int64_t e0 = (int64_t)blockIdx.x * TM + lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+        }
         for (uint32_t g = (uint32_t)warp; g < total; g += PRODUCER_WARPS) {
             const uint32_t tl = g / KSTEPS, ks = g - tl * KSTEPS;
             MG_TRACE(g_trace_prod, g, 0);
-            if (tl != cur) {                                    // first K-step of this warp in a new tile
-                cur = tl;
-                const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TM + lane;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
-            }
             const int k = 8 * (int)ks;
             const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[k]);
             const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k + 4]);
@@ -248,6 +246,14 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                     acc[j][0] = __ffma2_rn(xx, w01, acc[j][0]); acc[j][1] = __ffma2_rn(xx, w23, acc[j][1]);
                     acc[j][2] = __ffma2_rn(xx, w45, acc[j][2]); acc[j][3] = __ffma2_rn(xx, w67, acc[j][3]);
                 }
+            }
+            // This was the warp's last K-step of the tile and x[] is dead from here on: request the NEXT tile's rows
+            // into it now.  They are needed at this warp's next visit, a store phase and ~2000 cycles away — loaded
+            // there instead, they sit on the critical path of every tile switch (the MMAs consume K-steps in order).
+            if ((g + PRODUCER_WARPS) / KSTEPS != tl) {
+                const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)(tl + 1) * gridDim.x) * TM + lane;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
             }
             // Ring slot s = g % 4 is filled alternately by warps s and s + 4.  A parity wait is only meaningful when
             // the waiter is at most one phase behind the barrier, so every producer warp has its OWN pair of
