@@ -18,9 +18,10 @@
 //
 // Status (B200, 2^18 envs; profiles/README.md): numerically identical to the single-CTA kernel from the first run.
 // 82.1 us with release.cluster arrives / acquire.cluster waits (the remote release-arrive blocks each producer warp
-// for ~900 cycles), 73.5 us with relaxed.cluster arrives, 69.6 us with relaxed arrives and CTA-scope waits — parity
-// with the single-CTA kernel (68.6 us), not a win: the steady-state K-step period drops to 295 cycles, but every
-// hand-over now crosses the cluster (multicast commits, remote arrives) and the tile switch costs ~2500 cycles.
+// for ~900 cycles), 73.5 us with relaxed.cluster arrives, 69.6 us with relaxed arrives and CTA-scope waits — within 3 %
+// of the single-CTA kernel on the same box (69.8 vs 71.9 us traced), not a clear win: the steady-state K-step period
+// drops to 280 cycles, but every hand-over now crosses the cluster (multicast commits, remote arrives) and the tile
+// switch stays expensive.
 // Build: see profiles/exp_tc_pair_trace.cu (which includes this file); -DMG_PAIR_ARRIVE_SEM='".relaxed.cluster"'
 // -DMG_PAIR_ACQ_CTA=1 select the faster, formally weaker synchronisation.
 #include "../merging_gym_b200/csrc/abi_common.h"
@@ -229,18 +230,15 @@ mlp_act_tc_pair_kernel(const float *__restrict__ obs, const uint8_t *__restrict_
             off[j] = (uint32_t)((m >> 3) * 256 + (m & 7) * 16);
         }
         float x[4][IN];
-        uint32_t cur = 0xFFFFFFFFu;
         const int s = warp;
+        {
+            const int64_t e0 = (2 * cid + rank) * TM + lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+        }
         for (uint32_t g = (uint32_t)warp; g < total; g += PRODUCER_WARPS) {
             const uint32_t tl = g / KSTEPS, ks = g - tl * KSTEPS;
             MG_TRACE2(g_trace_prod[rank], g, 0);
-            if (tl != cur) {
-                cur = tl;
-                const int64_t tile = 2 * (cid + (int64_t)tl * n_clusters) + rank;
-                const int64_t e0 = tile * TM + lane;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
-            }
             const int k = 8 * (int)ks;
             const float4 ba = *reinterpret_cast<const float4 *>(&S.b1[k]);
             const float4 bb = *reinterpret_cast<const float4 *>(&S.b1[k + 4]);
@@ -262,6 +260,11 @@ mlp_act_tc_pair_kernel(const float *__restrict__ obs, const uint8_t *__restrict_
                     acc[j][0] = __ffma2_rn(xx, w01, acc[j][0]); acc[j][1] = __ffma2_rn(xx, w23, acc[j][1]);
                     acc[j][2] = __ffma2_rn(xx, w45, acc[j][2]); acc[j][3] = __ffma2_rn(xx, w67, acc[j][3]);
                 }
+            }
+            if ((g + PRODUCER_WARPS) / KSTEPS != tl) {          // last K-step of the tile: x[] is dead, fetch the next tile's rows into it
+                const int64_t e0 = (2 * (cid + (int64_t)(tl + 1) * n_clusters) + rank) * TM + lane;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
             }
             const uint32_t v = g / PRODUCER_WARPS;              // this warp's visit number = use number of its slot
             MG_TRACE2(g_trace_prod[rank], g, 1);
