@@ -231,7 +231,8 @@ class MergeVecEnv:
         """
         m = None
         if mask is not None:
-            m = torch.as_tensor(mask, device=self.device).reshape(-1).to(torch.uint8).contiguous()
+            m = torch.as_tensor(mask, device=self.device).reshape(-1).contiguous()
+            m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)     # bool is one byte: no conversion kernel
             if m.numel() != self.num_envs:
                 raise ValueError("mask must have num_envs elements")
         obs = self.obs_buf[self._slot]
