@@ -10,24 +10,33 @@ uint8 actions (pvp, auto-reset): BASELINE.json configs[2], 2^20 envs per launch 
 Actions are pre-generated on the device (Philox, global env ids), so inputs are HBM-resident.
 L2 rule: one shard's inputs (56.6 MB) would fit the 126 MB L2, so the timed region steps
 `--shards` (4) independent 2^20-env shards round-robin — inputs larger than L2, no flush — and
-every launch reads its state from HBM.  The in-place single-shard figure is reported separately as
-`l2_warm`.  Timed with CUDA events on the launching (current torch) stream, barrier +
-synchronize on both sides, max over ranks.
+every launch reads its state from HBM.  Timed with CUDA events on the launching (current torch)
+stream, barrier + synchronize on both sides, max over ranks.
 
-Extra objects in the JSON line: `roofline` (HBM, algorithmic bytes = 156 B/env-step, see
-DESIGN.md), `cpu_baseline` (the C port of the oracle on this box's host cores, rank 0, N=1),
-`e2e` (the same step through `mg_step_host`: pinned host actions -> H2D -> step -> D2H of
-obs/rewards/done/info, synchronised), `clocks`, `gpu_launches`.
+The JSON line (rank 0) carries, besides the contract keys:
+  roofline       HBM, algorithmic bytes = 156 B/env-step
+  e2e            the same step through the host-buffer API (`MergeVecEnv.step_host_async/_wait`): actions in pinned
+                 host memory, obs/rew/done/info copied back every step; + the synchronous call, the reduced-field
+                 variant and the box's measured device->host copy ceiling
+  sustained      the same measurement at 2000 steps whatever --steps says
+  l2_warm, l2_flushed, overlapped_streams, laned, lean_no_returns, rollout_fused      extra device-side figures
+  policy_in_loop BASELINE configs[4] (2^18 envs, DQN forward in the loop)
+  strong_8m      BASELINE configs[3] (2^23 envs over all ranks, NCCL statistics reduction every 64 steps) with a
+                 digest of the reduced statistics that must be equal for every world size
+  cpu_baseline   (N=1, rank 0) the plain-C oracle port on all host cores, and the reference's OWN unmodified Python
+                 env timed on this box (one process, and one process per core)
 
-`--impl reference` times the reference's CPU implementation of the path.  The reference is
-pure Python and cannot travel to the GPU box (and needs gym/pygame/shapely/qpsolvers, absent
-from the image), so this arm runs the oracle port: the plain-C restatement with all host
-threads (`kind: "port"`).
+`--impl reference` times the reference's CPU implementation of the path on this box's host cores: `value` is the
+plain-C float64 port of the oracle with all host threads (`kind: "port"`, the stronger baseline); the reference's own
+Python `MergeEnv.step` (from the byte-identical copy in baseline/_ref, run against oracle/ref_shims) is timed in the
+same run and printed beside it (`cpu_baseline.reference_python_*`).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
+import math
 import os
 import sys
 import threading
@@ -39,8 +48,20 @@ if ROOT not in sys.path:
 
 ENVS_PER_GPU = 1 << 20
 BYTES_PER_ENV_STEP = 156          # read 54 B + write 102 B (pvp, u8 actions, auto-reset)
+BYTES_PER_ENV_STEP_LEAN = 124     # track_returns=False: the two float64 accumulators are neither read nor written
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
+STRONG_TOTAL_ENVS = 1 << 23       # BASELINE configs[3]
+STRONG_STEPS, STRONG_REDUCE_EVERY = 256, 64
+
+
+def workload_config(n):
+    """The workload, worded identically by both arms (the driver compares the dicts)."""
+    return {"workload": "pvp, 2^20 envs per GPU, auto-reset, uniform-random uint8 actions (BASELINE.json configs[2]); "
+                        "the reference arm steps one 2^20-env shard on the host cores regardless of --gpus",
+            "envs_per_gpu": n, "mode": "pvp", "auto_reset": True, "actions": "uniform-random uint8, pre-generated",
+            "l2": "GPU arm: inputs larger than L2, no flush (4 independent 2^20-env shards per GPU stepped round-robin, "
+                  "218 MB of float64 state: every launch re-reads its shard's state from HBM); CPU arm: not applicable"}
 
 
 def load_peaks():
@@ -117,7 +138,6 @@ class ClockSampler(threading.Thread):
 def cpu_port_throughput(n_envs, min_seconds, threads, warmup_steps=2, max_steps=None, fixed_steps=None):
     """Times the plain-C oracle port (oracle/merge_oracle.c) on host cores.  Checker code used
     as the reported CPU baseline only — never on the product path."""
-    import numpy as np
     from oracle import c_oracle
     env = c_oracle.CVecEnv(n_envs, pvp=True, auto_reset=True, nthreads=threads)
     a1, a2 = c_oracle.philox_actions(n_envs, 0x5EED, 0, 0)
@@ -153,6 +173,59 @@ def python_scalar_port_throughput(seconds=2.0):
     return n / (time.perf_counter() - t0)
 
 
+def _reference_python_worker(args):
+    """One process stepping the reference's OWN `MergeEnv` (unmodified merging_env.py + helper.py, third-party
+    packages replaced by oracle/ref_shims): BASELINE configs[0] workload (random actions, manual reset on done)."""
+    pvp, steps, seed = args
+    import warnings
+    warnings.simplefilter("ignore")
+    import numpy as np
+    from oracle.ref_loader import load_reference_env, quiet
+    env = load_reference_env()
+    acts = np.random.default_rng(seed).integers(0, 5, (steps, 2)).tolist()
+    env.reset()
+    with quiet():                                            # the env prints on every collision (merging_env.py:204)
+        t0 = time.perf_counter()
+        for a1, a2 in acts:
+            _, _, done, _ = env.step(a1, a2 if pvp else None)
+            if done:
+                env.reset()
+        dt = time.perf_counter() - t0
+    return steps / dt
+
+
+def reference_python_throughput(steps=3000, cores=None):
+    """env-steps/s of the unmodified reference env on this box: one process, and one process per core (each its own
+    env, aggregate over the wall clock of the whole pool incl. start-up of the slowest).  None if the reference copy
+    is not present (baseline/_ref is made by baseline/install_ref.py / __graft_entry__.build())."""
+    try:
+        from oracle import ref_loader
+        if not ref_loader.reference_available():
+            return {"unavailable": f"no reference tree at {ref_loader.REFERENCE_ROOT}"}
+    except Exception as e:  # noqa
+        return {"unavailable": repr(e)}
+    import multiprocessing as mp
+    cores = cores or host_threads()
+    out = {"source": ref_loader.REFERENCE_ROOT, "steps_per_process": steps, "cores": cores,
+           "note": "the reference's own merging_env.py + helper.py, byte-identical copy; gym/pygame/shapely/qpsolvers are "
+                   "not installed, so it runs against oracle/ref_shims (lighter than the real packages: this over-estimates "
+                   "the reference's speed)"}
+    try:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(1) as pool:
+            out["pve_1_process"] = pool.map(_reference_python_worker, [(False, steps, 0)])[0]
+            out["pvp_1_process"] = pool.map(_reference_python_worker, [(True, steps, 0)])[0]
+        with ctx.Pool(cores) as pool:
+            pool.map(_reference_python_worker, [(True, 50, s) for s in range(cores)])       # imports done, workers warm
+            for name, pvp in (("pve", False), ("pvp", True)):
+                t0 = time.perf_counter()
+                pool.map(_reference_python_worker, [(pvp, steps, s) for s in range(cores)])
+                out[f"{name}_all_cores"] = cores * steps / (time.perf_counter() - t0)
+    except Exception as e:  # noqa
+        out["error"] = repr(e)
+    return out
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -160,25 +233,37 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_baseline_object(seconds, fixed_steps=None, warmup=2, with_python=True, ref_steps=3000):
+    threads = min(host_threads(), 64)
+    v, steps, dt = cpu_port_throughput(ENVS_PER_GPU, seconds, threads, warmup_steps=warmup, fixed_steps=fixed_steps)
+    cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{ENVS_PER_GPU} envs x {steps} steps in {dt:.1f} s (pvp, auto-reset, pre-generated uint8 actions, "
+                     f"float64, plain-C oracle port, {threads} OpenMP threads)",
+           "ms_per_step": 1e3 * dt / steps}
+    if with_python:
+        cpu["single_thread_value"] = cpu_port_throughput(1 << 16, min(3.0, seconds), 1)[0]
+        cpu["python_scalar_port_value"] = python_scalar_port_throughput(2.0)
+        ref = reference_python_throughput(ref_steps) if ref_steps > 0 else {"unavailable": "--ref-python-steps 0"}
+        cpu["reference_python"] = ref
+        cpu["reference_python_value"] = ref.get("pvp_1_process")
+        cpu["reference_python_all_cores_value"] = ref.get("pvp_all_cores")
+        cpu["note"] = ("value = the C port (the strongest CPU baseline available); reference_python_* = the reference's "
+                       "own Python env on this box (pvp, like the GPU workload; pve = BASELINE configs[0] is inside "
+                       "reference_python); python_scalar_port_value = the oracle's scalar Python restatement")
+    return cpu, dt, steps
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
-    threads = min(host_threads(), 64)
     n = ENVS_PER_GPU
-    val, steps, dt = cpu_port_throughput(n, 0, threads, warmup_steps=args.warmup, fixed_steps=args.steps)
-    sample = f"{n} envs x {steps} steps (pvp, auto-reset, pre-generated uint8 actions), float64, {threads} OpenMP threads"
+    cpu, dt, steps = cpu_baseline_object(0, fixed_steps=args.steps, warmup=args.warmup, ref_steps=args.ref_python_steps)
+    val = cpu["value"]
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "pvp, 2^20 envs, auto-reset, uniform-random uint8 actions (BASELINE.json configs[2]); "
-                                   "CPU sample is one 2^20-env shard regardless of --gpus",
-                       "envs": n},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                             "note": "reference is pure Python needing gym/pygame/shapely/qpsolvers (absent) and "
-                                     "cannot travel to the GPU box; this is the plain-C oracle port, which is "
-                                     "far faster than the reference's ~3e3 steps/s Python loop"},
+            "data": "synthetic", "config": workload_config(n), "cpu_baseline": cpu,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -187,19 +272,21 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import merging_gym_b200 as mg
-    from merging_gym_b200.sharding import init_distributed
+    from merging_gym_b200.affinity import bind_to_gpu
+    from merging_gym_b200.sharding import init_distributed, shard_range
 
     rank, local_rank, world = init_distributed()
     if world != args.gpus and rank == 0:
         print(f"# note: WORLD_SIZE={world} differs from --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    binding = bind_to_gpu(local_rank) if world > 1 else {"bound": False, "note": "single rank: not bound"}
     n = args.envs
     S, R = args.slots, args.shards
-    import math
     # one distinct pre-generated action set per step of the captured graph
     unit = S * R // math.gcd(S, R)
     A = max(unit, (min(args.steps, args.graph_steps) // unit) * unit) if args.action_sets <= 0 else args.action_sets
@@ -221,62 +308,85 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     K, W = args.steps, args.warmup
+    peak, peak_src = load_peaks()
 
-    reducer = mg.AsyncStatsReducer(env) if world > 1 else None
+    # the path's only collective: NCCL all-reduce of the int64 statistics, on a side stream.  Banked: the launching
+    # stream carries no statistics kernel at all (the side stream drains the retired bank).
+    reducer = mg.AsyncStatsReducer(env, banked=True) if world > 1 else None
     if reducer is not None:                               # NCCL communicator set-up happens here, untimed
         reducer.submit()
         reducer.latest()
         torch.cuda.synchronize()
         reducer.submissions = 0
 
-    def timed_region(shards, K, W, sample_clocks, n_streams=1):
-        """W warm-up + K timed mg_step launches round-robin over `shards`; returns (ms, G, eager, clocks).
+    def timed_region(shards, K, W, sample_clocks, n_streams=1, graph_steps=None, lanes=False):
+        """W warm-up + K timed step launches round-robin over `shards`; returns (ms, G, eager, clocks).
         n_streams > 1: shard r is stepped on stream r % n_streams (forked from / joined to the current
-        stream around every batch), so launches of independent shards may overlap."""
+        stream around every batch), so launches of independent shards may overlap.
+        lanes: every shard is a laned env; a step issues one launch per lane, each on the lane's own stream."""
         nsh = len(shards)
         idx = [0]
-        lanes = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else None
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else None
+        gsteps = graph_steps or args.graph_steps
 
         def do_steps(k):
             main = torch.cuda.current_stream()
-            if lanes and k > 0:
-                for ln in lanes:
+            if streams and k > 0:
+                for ln in streams:
                     ln.wait_stream(main)
             for _ in range(k):
                 i = idx[0]
+                sh = shards[i % nsh]
                 if lanes:
-                    with torch.cuda.stream(lanes[(i % nsh) % n_streams]):
-                        shards[i % nsh].step_async(acts1[i % A], acts2[i % A])
+                    for l, sl in enumerate(sh.lane_slices):
+                        sh.step_lane_async(l, acts1[i % A][sl], acts2[i % A][sl])
+                elif streams:
+                    with torch.cuda.stream(streams[(i % nsh) % n_streams]):
+                        sh.step_async(acts1[i % A], acts2[i % A])
                 else:
-                    shards[i % nsh].step_async(acts1[i % A], acts2[i % A])
+                    sh.step_async(acts1[i % A], acts2[i % A])
                 idx[0] = i + 1
-            if lanes and k > 0:
-                for ln in lanes:
+            if streams and k > 0:
+                for ln in streams:
                     main.wait_stream(ln)
+            if lanes and k > 0:
+                for sh in shards:
+                    sh.join_lanes()
+
+        def rewind():
+            idx[0] = 0
+            for e in shards:
+                e._slot = 0
+                e._lane_slot = [0] * e.lanes
 
         do_steps(W)                                       # warm-up, eager
         torch.cuda.synchronize()
-        G, graph = 0, None
+        G, graphs = 0, None
         cyc = S * nsh // math.gcd(S, nsh)
         cyc = cyc * A // math.gcd(cyc, A)                 # slot ring, shard ring and action ring line up
         if not args.no_graph and K >= cyc:
-            G = (min(K, max(args.graph_steps, cyc)) // cyc) * cyc
+            G = (min(K, max(gsteps, cyc)) // cyc) * cyc
+        use_reducer = reducer is not None and sample_clocks and shards[0] is env
         if G > 0:
-            def rewind():
-                idx[0] = 0
-                for e in shards:
-                    e._slot = 0
             rewind()
-            graph = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 do_steps(cyc)                             # warm-up on a side stream before capture
             torch.cuda.current_stream().wait_stream(side)
-            rewind()
-            with torch.cuda.graph(graph):
+            torch.cuda.synchronize()
+
+            def issue():
+                rewind()
                 do_steps(G)
-            graph.replay()                                # one untimed replay
+            if use_reducer:
+                graphs = reducer.capture_per_bank(issue)  # one graph per statistics bank
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    issue()
+                graphs = [g]
+            graphs[0 if not use_reducer else env._stats_active].replay()   # one untimed replay
             torch.cuda.synchronize()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -287,12 +397,14 @@ def run_b200(args):
             sampler.start()
         e0.record()
         done_steps = 0
-        if graph is not None:
+        if graphs is not None:
             for _ in range(K // G):
-                graph.replay()
+                if use_reducer:
+                    reducer.replay(graphs)
+                    reducer.submit()                      # headline region only: async NCCL stats reduce
+                else:
+                    graphs[0].replay()
                 done_steps += G
-                if reducer is not None and sample_clocks:   # headline region only: async NCCL stats reduce
-                    reducer.submit()
         do_steps(K - done_steps)
         e1.record()
         if sampler:
@@ -305,27 +417,71 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), G, K - done_steps, clocks
 
-    ms, G, eager, clocks = timed_region(envs, K, W, True)
     total_envs = n * world                               # envs advanced per step (one launch per GPU)
+
+    def rate(ms, k, bytes_per=BYTES_PER_ENV_STEP):
+        gbs = n * k * bytes_per / (ms * 1e-3) / 1e9
+        return {"value": total_envs * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k, "steps": k,
+                "algorithmic_gbs_per_gpu": gbs, "frac_of_peak": gbs / peak}
+
+    ms, G, eager, clocks = timed_region(envs, K, W, True)
     value = total_envs * K / (ms * 1e-3)
     per_gpu_gbs = n * K * BYTES_PER_ENV_STEP / (ms * 1e-3) / 1e9
-    peak, peak_src = load_peaks()
+    n_reductions = reducer.submissions if reducer else 0
+
+    # ---- sustained: the same region at 2000 steps (graph of 200) whatever --steps says ------------------------
+    sustained = None
+    if args.sustained_steps > 0:
+        if K >= args.sustained_steps:
+            sustained = dict(rate(ms, K), note="the headline region itself")
+        else:
+            ms_s, G_s, _, _ = timed_region(envs, args.sustained_steps, W, False)
+            sustained = dict(rate(ms_s, args.sustained_steps),
+                             note=f"same shards and launches as `value`, {args.sustained_steps} steps as a CUDA graph of {G_s} "
+                                  "replayed; shows what the short driver-run region (--steps) cannot amortise")
     # same kernel, ONE shard stepped in place: its 54.5 MB state is partly L2-resident between steps
-    ms_warm, _, _, _ = timed_region(envs[:1], K, W, False)
+    ms_warm, _, _, _ = timed_region(envs[:1], max(K, 200), W, False)
+    Kw = max(K, 200)
 
     # ---- extra: the same shards on two CUDA streams, so the ramp-up of one shard's launch overlaps the
     #      drain of another's (a forked CUDA graph); whole-GPU throughput, not a per-launch figure -----------
     overlapped = None
+    Ko = max(K, 400)
     if args.overlap_streams > 1 and R % args.overlap_streams == 0:
-        ms_ov, _, _, _ = timed_region(envs, K, W, False, n_streams=args.overlap_streams)
-        ov_gbs = n * K * BYTES_PER_ENV_STEP / (ms_ov * 1e-3) / 1e9
-        overlapped = {"value": total_envs * K / (ms_ov * 1e-3), "unit": UNIT, "streams": args.overlap_streams,
-                      "ms_per_step_effective": ms_ov / K, "algorithmic_gbs_per_gpu": ov_gbs,
-                      "frac_of_peak": ov_gbs / peak,
-                      "note": f"the same {R} shards, shard r on stream r % {args.overlap_streams}: launches of "
-                              "independent shards overlap, which hides the per-launch ramp-up/drain that separates "
-                              "the serialised 2^20-env launch from the copy peak; launches are concurrent, so this "
-                              "is aggregate throughput and is not used for value/roofline"}
+        ms_ov, _, _, _ = timed_region(envs, Ko, W, False, n_streams=args.overlap_streams)
+        overlapped = dict(rate(ms_ov, Ko), streams=args.overlap_streams,
+                          note=f"the same {R} shards, shard r on stream r % {args.overlap_streams}: launches of "
+                               "independent shards overlap, which hides the per-launch ramp-up/drain that separates "
+                               "the serialised 2^20-env launch from the copy peak; launches are concurrent, so this "
+                               "is aggregate throughput and is not used for value/roofline")
+
+    # ---- extra: the product API for that overlap — MergeVecEnv(lanes=2): each 2^20-env shard is two 2^19-env lanes
+    #      on two streams, a lane depending only on its own previous step ------------------------------------------
+    laned = None
+    if args.lanes > 1:
+        lenvs = [mg.MergeVecEnv(n, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=(rank * R + r) * n,
+                                out_slots=S, episode_info=False, track_stats=True, lanes=args.lanes) for r in range(R)]
+        for e in lenvs:
+            e.rollout(args.mix_steps, step0=1000)
+        ms_l, _, _, _ = timed_region(lenvs, Ko, W, False, lanes=True)
+        laned = dict(rate(ms_l, Ko), lanes=args.lanes, launches_per_step=args.lanes,
+                     note=f"MergeVecEnv(lanes={args.lanes}): the same {R} x 2^20-env shards round-robin, each step issued as "
+                          f"{args.lanes} launches of 2^20/{args.lanes} envs on the lanes' own streams (bit-identical results, "
+                          "tests/test_gpu_lanes.py); aggregate throughput of overlapping launches, not used for value/roofline")
+        del lenvs
+
+    # ---- extra: track_returns=False (no float64 return accumulators): 124 B/env-step ------------------------------
+    lean = None
+    if args.lean:
+        nenvs = [mg.MergeVecEnv(n, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=(rank * R + r) * n,
+                                out_slots=S, episode_info=False, track_stats=True, track_returns=False) for r in range(R)]
+        for e in nenvs:
+            e.rollout(args.mix_steps, step0=1000)
+        ms_n, _, _, _ = timed_region(nenvs, Ko, W, False)
+        lean = dict(rate(ms_n, Ko, BYTES_PER_ENV_STEP_LEAN), bytes_per_env_step=BYTES_PER_ENV_STEP_LEAN,
+                    note="MergeVecEnv(track_returns=False): r1_accumulate / r2_accumulate (merging_env.py:191-192) are not "
+                         "kept, 124 instead of 156 B of HBM traffic per env-step; frac_of_peak uses 124 B")
+        del nenvs
 
     # ---- cross-check of the L2 methodology: ONE shard stepped in place with L2 flushed (a 512 MB
     #      buffer overwritten) before every timed launch, each launch bracketed by its own events ------
@@ -360,12 +516,12 @@ def run_b200(args):
         ro = torch.empty(RK, n, 10, device=dev); rr = torch.empty(RK, n, 2, device=dev)
         rd = torch.empty(RK, n, dtype=torch.uint8, device=dev); ri = torch.empty(RK, n, dtype=torch.uint8, device=dev)
         for _ in range(2):
-            env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri)
+            env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri, refresh_obs=False)
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         r0.record()
         for _ in range(8):
-            env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri)
+            env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri, refresh_obs=False)
         r1.record()
         torch.cuda.synchronize()
         rms = r0.elapsed_time(r1) / (8 * RK)
@@ -377,37 +533,151 @@ def run_b200(args):
         rollout = {"value": total_envs / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms, "k_steps_per_launch": RK,
                    "bytes_per_env_step": rb, "achieved_gbs_per_gpu": n * rb / (rms * 1e-3) / 1e9,
                    "note": "mg_rollout: state stays in registers for K steps, actions from in-kernel Philox, "
-                           "obs/rew/done/info written time-major every step; instruction-issue bound, not HBM bound"}
+                           "obs/rew/done/info written time-major every step (the last row is the current observation); "
+                           "instruction-issue bound, not HBM bound"}
         del ro, rr, rd, ri
 
-    # ---- end-to-end through the host-buffer C-ABI entry (mg_step_host) -------------------------
-    import numpy as np
+    # ---- end-to-end through the host-buffer API ------------------------------------------------------------------
     E = max(3, min(K, args.e2e_steps))
-    h1, h2 = env.host_action_buffers()                    # pinned host memory: this step's inputs live here
-    h1[:] = acts1[0].cpu().numpy(); h2[:] = acts2[0].cpu().numpy()
-    for _ in range(2):
-        env.step_host(h1, h2)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(E):
-        env.step_host(h1, h2)                             # synchronises inside
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e = {"value": total_envs * E / e2e_s, "unit": UNIT, "steps": E,
-           "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": n * (40 + 8 + 1 + 1),
-           "api": "MergeVecEnv.step_host -> mg_step_host (actions in pinned host memory, read across PCIe by the step "
-                  "kernel itself; outputs copied into pinned host memory; stream synchronised every step)",
-           "pcie_gbs": total_envs / world * 52 * E / e2e_s / 1e9,
-           "bound": "PCIe: 52 B/env-step cross the bus (2 up, 50 down); a plain 52 MB device->host copy reaches "
-                    "~56 GB/s on this pool (profiles/README.md)"}
+    out_bytes = n * (40 + 8 + 1 + 1)
+    slots = [env.host_action_buffers(0), env.host_action_buffers(1)]   # pinned host memory: the steps' inputs live here
+    for k_, (h1, h2) in enumerate(slots):
+        h1[:] = acts1[k_ % A].cpu().numpy(); h2[:] = acts2[k_ % A].cpu().numpy()
+
+    def e2e_loop(fn, steps):
+        fn(2)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn(steps)
+        s = time.perf_counter() - t0
+        t = torch.tensor([s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sync_steps(k):
+        for _ in range(k):
+            env.step_host(slots[0][0], slots[0][1])          # synchronises inside
+
+    def pipelined(fields):
+        def run(k):
+            for i in range(k):
+                if i >= 2:
+                    env.step_host_wait()                     # the host now owns step i-2's outputs
+                h1, h2 = env.host_action_buffers()           # the pinned slot this step will use (pre-filled above)
+                env.step_host_async(h1, h2, fields=fields)
+            for _ in range(min(k, 2)):
+                env.step_host_wait()
+        return run
+
+    s_sync = e2e_loop(sync_steps, E)
+    s_pipe = e2e_loop(pipelined(None), E)
+    s_small = e2e_loop(pipelined(("rew", "done", "info")), E)
+
+    # what the box moves device->host when every rank copies at once: one plain cudaMemcpyAsync per copy, back to back
+    hbuf = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+
+    def plain_copies(k):
+        for _ in range(k):
+            hbuf.copy_(dbuf, non_blocking=True)
+        torch.cuda.synchronize()
+    s_ceil = e2e_loop(plain_copies, E)
+    ceiling_gbs = world * out_bytes * E / s_ceil / 1e9
+    del hbuf, dbuf
+    e2e = {"value": total_envs * E / s_pipe, "unit": UNIT, "steps": E,
+           "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": out_bytes,
+           "api": "MergeVecEnv.step_host_async / step_host_wait -> mg_step_host_async (two pinned slots: the step kernel "
+                  "reads this step's actions straight from pinned host memory across PCIe, obs|rew|done|info are copied "
+                  "into pinned host memory by one cudaMemcpyAsync on a copy stream; the host waits for step t-2 before it "
+                  "queues step t, all steps have landed when the clock stops)",
+           "pcie_gbs_all_gpus": world * (2 * n + out_bytes) * E / s_pipe / 1e9,
+           "ceiling_gbs": ceiling_gbs,
+           "frac_of_ceiling": world * out_bytes * E / s_pipe / 1e9 / ceiling_gbs,
+           "ceiling_note": f"measured in this run: every rank copies {out_bytes} B device->pinned host {E}x back to back with "
+                           "plain cudaMemcpyAsync, all ranks at once; aggregate GB/s over the slowest rank "
+                           "(profiles/d2h_ceiling.py measures the same stand-alone for N = 1/2/4/8)",
+           "sync_value": total_envs * E / s_sync,
+           "sync_api": "MergeVecEnv.step_host -> mg_step_host (same copies, host synchronises every step; round-1 figure)",
+           "rew_done_info_value": total_envs * E / s_small,
+           "rew_done_info_d2h_bytes_per_step": n * 10,
+           "rew_done_info_note": "fields=('rew','done','info'): for callers whose policy reads the device-resident "
+                                 "observation; NOT the headline (the reference's step returns obs too)",
+           "cpu_binding": binding}
 
     # ---- episode statistics: the one collective on this path (tiny int64 all-reduce over NCCL) --
     stats = env.stats(reduce=world > 1)
+
+    # ---- BASELINE configs[3]: 2^23 envs over all ranks, statistics all-reduced every 64 steps -------------------
+    strong = None
+    if args.strong_envs > 0:
+        base, cnt = shard_range(args.strong_envs, rank, world)
+        senv = mg.MergeVecEnv(cnt, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=base, out_slots=2,
+                              episode_info=False, track_stats=True)
+        SA = 4
+        sa1 = torch.empty(SA, cnt, dtype=torch.uint8, device=dev); sa2 = torch.empty(SA, cnt, dtype=torch.uint8, device=dev)
+        for i in range(SA):
+            a1, a2 = senv.sample_actions(i)
+            sa1[i].copy_(a1); sa2[i].copy_(a2)
+        sred = mg.AsyncStatsReducer(senv, banked=True)
+        ctr = [0]
+
+        def s_issue():
+            senv._slot = 0
+            for i in range(STRONG_REDUCE_EVERY):
+                senv.step_async(sa1[i % SA], sa2[i % SA])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(4):
+                senv.step_async(sa1[i % SA], sa2[i % SA])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        sgraphs = sred.capture_per_bank(s_issue)
+        senv.reset()                                          # the digest run starts from reset, statistics zeroed
+        senv.stats(reset=True)
+        senv._slot = 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(STRONG_STEPS // STRONG_REDUCE_EVERY):
+            sred.replay(sgraphs)
+            sred.submit()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sms = float(t.item())
+        totals = [int(v) for v in sred.latest().cpu().tolist()]
+        strong = {"value": args.strong_envs * STRONG_STEPS / (sms * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "total_envs": args.strong_envs, "envs_per_gpu": cnt, "steps": STRONG_STEPS, "ms_per_step": sms / STRONG_STEPS,
+                  "reductions": sred.submissions, "reduce_every": STRONG_REDUCE_EVERY,
+                  "algorithmic_gbs_per_gpu": cnt * STRONG_STEPS * BYTES_PER_ENV_STEP / (sms * 1e-3) / 1e9,
+                  "stats_totals": totals,
+                  "stats_digest": hashlib.sha256(json.dumps(totals).encode()).hexdigest()[:16],
+                  "note": f"BASELINE configs[3]: {args.strong_envs} envs in total sharded contiguously over the ranks, "
+                          f"{STRONG_STEPS} steps from reset as CUDA graphs of {STRONG_REDUCE_EVERY} mg_step launches, the int64 "
+                          "statistics all-reduced (NCCL, side stream, banked: no statistics kernel on the launching stream) "
+                          "after every graph; stats_digest = sha256 of the reduced totals after the last step — it must be "
+                          "the same at every world size (actions are Philox over GLOBAL env ids)"}
+        del senv, sa1, sa2
+
+    # ---- BASELINE configs[4]: DQN policy forward in the loop, 2^18 envs per GPU --------------------------------------
+    policy = None
+    if args.policy_envs > 0 and rank == 0:
+        import bench_policy
+        policy = {"note": "BASELINE configs[4]: pve, policy forward + arg-max -> mg_step on the device, random starts; "
+                          "graph-timed (bench_policy.measure); rank 0 only"}
+        for be in ("fused", "tf32x3"):
+            try:
+                policy[be] = bench_policy.measure(args.policy_envs, "dqn", be, device=dev)
+            except Exception as e:  # noqa
+                policy[be] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -417,44 +687,35 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = min(host_threads(), 64)
-        v, steps, dt = cpu_port_throughput(ENVS_PER_GPU, args.cpu_seconds, threads)
-        v1, steps1, dt1 = cpu_port_throughput(1 << 16, min(3.0, args.cpu_seconds), 1)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{ENVS_PER_GPU} envs x {steps} steps in {dt:.1f} s (pvp, auto-reset, float64, plain-C oracle port, OpenMP)",
-               "single_thread_value": v1,
-               "python_scalar_port_value": python_scalar_port_throughput(2.0),
-               "note": "python_scalar_port_value is the per-env Python loop the reference itself runs "
-                       "(its QP/pygame/shapely calls replaced by closed forms, so it over-estimates the reference)"}
+        cpu, _, _ = cpu_baseline_object(args.cpu_seconds, ref_steps=args.ref_python_steps)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "pvp, 2^20 envs per GPU, auto-reset, uniform-random uint8 actions "
-                                   "pre-generated on device (BASELINE.json configs[2])",
-                       "envs_per_gpu": n, "total_envs": total_envs, "mode": "pvp", "auto_reset": True,
-                       "envs_per_launch": n, "shards_per_gpu": R,
-                       "launch": (f"CUDA graph of {G} mg_step launches replayed {K // G}x + {eager} eager"
-                                  if G else "eager ctypes launches"),
-                       "l2": f"inputs larger than L2, no flush: {R} independent {n}-env shards per GPU stepped "
-                             f"round-robin ({R * n * 52 / 1e6:.0f} MB of float64 state + {A} action sets "
-                             f"{A * n * 2 / 1e6:.0f} MB, outputs to {R}x{S} ring slots of {n * 50 / 1e6:.0f} MB); "
-                             "each launch re-reads its shard's state from HBM",
-                       "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of 16 int64 "
-                                      f"stats on a side stream every {G or K} steps inside the timed region "
-                                      f"({reducer.submissions if reducer else 0} reductions)"},
+            "dtype": "f64", "data": "synthetic", "config": workload_config(n),
+            "measurement": {"total_envs": total_envs, "envs_per_launch": n, "shards_per_gpu": R,
+                            "launch": (f"CUDA graph of {G} mg_step launches replayed {K // G}x + {eager} eager"
+                                       if G else "eager ctypes launches"),
+                            "state_mb": R * n * 52 / 1e6, "action_sets": A, "ring_slots": S,
+                            "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of 16 int64 "
+                                           f"stats on a side stream after every graph replay inside the timed region "
+                                           f"({n_reductions} reductions; banked: no statistics kernel on the timed stream)"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
                          "frac": per_gpu_gbs / peak, "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
-                         "kernel": "mg::merge_step_kernel<2, uint8_t, true>",
+                         "kernel": "mg::merge_step_kernel<2, uint8_t, true, false, true>",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src,
                          "per": "GPU; achieved = 156 B x envs_per_gpu / (timed ms / steps)"},
-            "l2_warm": {"value": total_envs * K / (ms_warm * 1e-3), "unit": UNIT, "ms_per_step": ms_warm / K,
-                        "note": "one 2^20-env shard stepped in place (the literal 1M-envs/GPU deployment): its "
-                                "54.5 MB state is partly L2-resident between steps, so it runs faster than the "
-                                "HBM roofline allows; not used for value/roofline"},
+            "sustained": sustained,
+            "l2_warm": dict(rate(ms_warm, Kw),
+                            note="one 2^20-env shard stepped in place (the literal 1M-envs/GPU deployment): its "
+                                 "54.5 MB state is partly L2-resident between steps, so it runs faster than the "
+                                 "HBM roofline allows; not used for value/roofline"),
             "l2_flushed": flushed,
             "overlapped_streams": overlapped,
+            "laned": laned,
+            "lean_no_returns": lean,
             "rollout_fused": rollout,
+            "policy_in_loop": policy,
+            "strong_8m": strong,
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "collision_rate", "merge_success_rate",
                                                     "mean_length", "mean_return1", "mean_return2")}}
@@ -480,11 +741,18 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=200)
     ap.add_argument("--mix-steps", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--sustained-steps", type=int, default=2000, help="extra region at this many steps (0 = skip)")
     ap.add_argument("--flush-steps", type=int, default=100, help="launches of the L2-flushed cross-check (0 = skip)")
     ap.add_argument("--rollout-k", type=int, default=32, help="steps per mg_rollout launch for the extra rollout_fused figure (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--overlap-streams", type=int, default=2,
                     help="extra measurement: the shards on this many CUDA streams (0/1 = skip)")
+    ap.add_argument("--lanes", type=int, default=2, help="extra measurement: MergeVecEnv(lanes=L) (0/1 = skip)")
+    ap.add_argument("--lean", type=int, default=1, help="extra measurement: track_returns=False (0 = skip)")
+    ap.add_argument("--strong-envs", type=int, default=STRONG_TOTAL_ENVS, help="configs[3] total envs (0 = skip)")
+    ap.add_argument("--policy-envs", type=int, default=1 << 18, help="configs[4] envs per GPU (0 = skip)")
+    ap.add_argument("--ref-python-steps", type=int, default=3000,
+                    help="steps per process when timing the reference's own Python env (0 = skip)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

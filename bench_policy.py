@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""bench_policy.py — BASELINE.json configs[4]: pve rollout with the DQN policy forward in the loop,
+"""bench_policy.py — BASELINE.json configs[4]: pve rollout with the DQN / h-DQN policy forward in the loop,
 2^18 envs per GPU, observations and actions handed over on the device (no host round-trip).
 
     python bench_policy.py [--envs 262144] [--steps 400] [--policy dqn|hdqn] [--backend fused|tf32x3|torch]
 
-One step = fused Q-network forward + arg-max (`mg_mlp_act`) -> `mg_step` (pve, auto-reset), captured
-in a CUDA graph.  Prints one JSON line with env-steps/s and the share of the step spent in the env
-kernel vs the policy kernel (each timed separately with CUDA events).  Not the headline bench
-(`bench.py`); weights are the reference's shipped DQN checkpoint when the fixture is present,
-random-init (the reference's `uniform_(0,1)` init) otherwise — h-DQN weights were never shipped.
+One step = fused Q-network forward + arg-max (`mg_mlp_act` / `mg_mlp_act_tc`) -> `mg_step` (pve, auto-reset, RANDOM
+starts so that the envs de-synchronise: with the fixed start and a greedy policy all envs would run in lockstep).
+Everything is timed as CUDA-graph replays: graph A holds K x (policy + env step), graph B the same K policy launches
+alone; the env kernel's share of a step is (A - B) / A, free of Python launch latency.  `measure()` is what
+`bench.py` puts into its `policy_in_loop` object.  Weights: the reference's shipped DQN checkpoint from the committed
+fixture `tests/golden/dqn_policies.npz` (h-DQN weights were never shipped: the reference's `uniform_(0,1)` init).
 """
 import argparse
 import json
@@ -22,18 +23,71 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import merging_gym_b200 as mg  # noqa: E402
 
+DQN_FLOPS = 2 * (10 * 200 + 200 * 100 + 100 * 5)
+HDQN_FLOPS = 2 * (10 * 200 + 200 * 100 + 100 * 3) + 2 * (11 * 200 + 200 * 100 + 100 * 5)
 
-def timed(fn, iters, warmup=5):
-    for _ in range(warmup):
-        fn()
+
+def graph_ms(fn, k, replays=5):
+    """ms per call of `fn`, measured as `replays` replays of a CUDA graph of k calls."""
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(k):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(replays):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    return e0.elapsed_time(e1) / (k * replays)
+
+
+def load_policy(policy, backend, device="cuda"):
+    if policy == "dqn":
+        fx = os.path.join(ROOT, "tests", "golden", "dqn_policies.npz")
+        sd, weights = None, "random-init (reference init)"
+        if os.path.exists(fx):
+            z = np.load(fx)
+            sd = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith("L1_1445/") and "traj" not in k and "result" not in k}
+            weights = "test_params/dqn/2022--03--31 14:45:59.../eval.pth (tests/golden/dqn_policies.npz)"
+        return mg.MLPPolicy(10, 5, device=device, state_dict=sd, backend=backend), DQN_FLOPS, weights
+    return mg.HDQNPolicy(device=device, backend=backend), HDQN_FLOPS, "random-init (reference init; no h-DQN weights ship)"
+
+
+def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="cuda", reset_mode="random", mix_steps=300):
+    env = mg.MergeVecEnv(n, mode="pve", device=device, auto_reset=True, episode_info=False, reset_mode=reset_mode)
+    pol, flops, weights = load_policy(policy, backend, device)
+    act = torch.empty(n, dtype=torch.uint8, device=device)
+    obs = env.obs_buf[0]                           # out_slots=1: one fixed observation buffer, replayable
+
+    def policy_only():
+        pol.act(obs, out=act)
+
+    def one_step():
+        pol.act(obs, out=act)
+        env.step_async(act, None)
+
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                  # warm-up (module loading) and episode mixing outside any capture
+        for _ in range(mix_steps):
+            one_step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    env.stats(reset=True)
+    ms_step = graph_ms(one_step, k, replays)
+    st = env.stats()
+    ms_pol = graph_ms(policy_only, k, replays)
+    return {"value": n / (ms_step * 1e-3), "unit": "env-steps/s per GPU", "envs": n, "policy": policy, "backend": backend,
+            "ms_per_step": ms_step, "policy_ms": ms_pol, "env_ms": ms_step - ms_pol,
+            "env_share": (ms_step - ms_pol) / ms_step,
+            "policy_tflops": n * flops / (ms_pol * 1e-3) / 1e12, "weights": weights,
+            "launch": f"CUDA graph of {k} x (policy forward+argmax, mg_step) vs a graph of {k} policy launches alone; "
+                      "env_ms is the difference", "reset_mode": reset_mode,
+            "episode_stats": {q: st[q] for q in ("episodes", "collision_rate", "win_rate_p1", "mean_length", "mean_return1")}}
 
 
 def main():
@@ -42,50 +96,15 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--policy", default="dqn", choices=["dqn", "hdqn"])
     ap.add_argument("--backend", default="fused", choices=["fused", "tf32x3", "torch"])
+    ap.add_argument("--reset-mode", default="random", choices=["fixed", "random"])
     args = ap.parse_args()
-    n = args.envs
-    env = mg.MergeVecEnv(n, mode="pve", auto_reset=True, episode_info=False)
-    weights = "random-init (reference init)"
-    if args.policy == "dqn":
-        fx = os.path.join(ROOT, "tests", "golden", "dqn_policies.npz")
-        sd = None
-        if os.path.exists(fx):
-            z = np.load(fx)
-            sd = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith("L1_1445/") and "traj" not in k and "result" not in k}
-            weights = "test_params/dqn/2022--03--31 14:45:59.../eval.pth"
-        pol = mg.MLPPolicy(10, 5, state_dict=sd, backend=args.backend)
-        flops = 2 * (10 * 200 + 200 * 100 + 100 * 5)
-    else:
-        pol = mg.HDQNPolicy(backend=args.backend)
-        flops = 2 * (10 * 200 + 200 * 100 + 100 * 3) + 2 * (11 * 200 + 200 * 100 + 100 * 5)
-    act = torch.empty(n, dtype=torch.uint8, device="cuda")
-    obs0 = env.reset()
-
-    def one_step(obs):
-        pol.act(obs, out=act)
-        return env.step(act, None)[0]
-
-    obs = obs0
-    for _ in range(20):
-        obs = one_step(obs)
-    torch.cuda.synchronize()
-    # with out_slots=1 the obs buffer is fixed, so a captured step can be replayed indefinitely
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        one_step(env.obs_buf[0])
-    ms_step = timed(g.replay, args.steps)
-    ms_pol = timed(lambda: pol.act(env.obs_buf[0], out=act), 50)
-    ms_env = timed(lambda: env.step(act, None), 50)
-    st = env.stats()
-    line = {"metric": "env_steps_per_sec", "value": n / (ms_step * 1e-3), "unit": "env-steps/s", "n_gpus": 1,
-            "steps": args.steps, "ms_per_step": ms_step, "dtype": "f64 env / f32 policy", "data": "synthetic",
-            "config": {"workload": f"pve, {n} envs, {args.policy} greedy policy in the loop, auto-reset "
-                                   "(BASELINE.json configs[4])", "backend": args.backend, "weights": weights,
-                       "launch": "CUDA graph of one policy+env step"},
-            "policy_kernel_ms": ms_pol, "env_kernel_ms": ms_env,
-            "env_share": ms_env / (ms_env + ms_pol),
-            "policy_tflops": n * flops / (ms_pol * 1e-3) / 1e12,
-            "episode_stats": {k: st[k] for k in ("episodes", "collision_rate", "win_rate_p1", "mean_length", "mean_return1")}}
+    k = 50
+    r = measure(args.envs, args.policy, args.backend, k=k, replays=max(1, args.steps // k), reset_mode=args.reset_mode)
+    line = {"metric": "env_steps_per_sec", "unit": "env-steps/s", "n_gpus": 1, "steps": args.steps,
+            "dtype": "f64 env / f32 policy", "data": "synthetic",
+            "config": {"workload": f"pve, {args.envs} envs, {args.policy} greedy policy in the loop, auto-reset, "
+                                   f"{args.reset_mode} starts (BASELINE.json configs[4])"}}
+    line.update(r)
     print(json.dumps(line))
 
 

@@ -37,7 +37,7 @@ extern "C" {
 #define MG_API __attribute__((visibility("default")))
 #endif
 
-#define MG_ABI_VERSION 3
+#define MG_ABI_VERSION 4
 #define MG_OBS_DIM 10      /* merging_env.py:75,118-132 */
 #define MG_NUM_ACTIONS 5   /* merging_env.py:101-102   */
 
@@ -56,6 +56,11 @@ typedef enum MgActionDtype { MG_ACT_U8 = 0, MG_ACT_I32 = 1, MG_ACT_I64 = 2 } MgA
 /* mg_step / mg_rollout flags */
 #define MG_FLAG_AUTO_RESET 0x1u /* gym-0.20 SyncVectorEnv convention: a finished env is reset in
                                    the same call and returns its reset observation           */
+
+#define MG_FLAG_NO_RETURNS 0x2u /* the env keeps no r1_accumulate / r2_accumulate (merging_env.py:191-192, read only by
+                                   human_player.py:189-193 and render): MgState.ret1/ret2 are not touched and may be
+                                   NULL, MgOut.ep_ret must be NULL, the return columns of `stats` stay 0.  Cuts the
+                                   step's traffic from 156 to 124 bytes per env-step.                             */
 
 /* info byte, one per env per step (merging_env.py:144,187 `info["collision"]`, :164-181
  * `self.winner`, :142 time limit, :143/:171/:181/:184 `self.done`). */
@@ -105,7 +110,7 @@ typedef struct MgState {
 typedef struct MgOut {
     float *obs;       /* [n,10] row-major; merging_env.py:122-131 order                          */
     float *rew;       /* [n,2]  (reward1, reward2), merging_env.py:189                           */
-    uint8_t *done;    /* [n]    0/1                                                              */
+    uint8_t *done;    /* [n]    0/1; may be NULL (the same bit is MG_INFO_DONE of `info`)                */
     uint8_t *info;    /* [n]    MG_INFO_* bit-field                                              */
     float *term_obs;  /* [n,10] or NULL: written ONLY for envs that finished in this step        */
     float *ep_ret;    /* [n,2]  or NULL: finished episode's (r1_accumulate, r2_accumulate), ditto */
@@ -192,6 +197,31 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
                         const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out,
                         int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
                         void *stream, void *copy_stream_or_null, int32_t chunks);
+
+/* Output fields a host-buffer step copies back (mg_step_host_async `fields`): the tuple members of
+ * `return obs, rewards, done, info` (merging_env.py:195).  A caller that needs only rewards / done / info moves
+ * 10 bytes per env-step across PCIe instead of 50. */
+#define MG_FIELD_OBS 0x1u
+#define MG_FIELD_REW 0x2u
+#define MG_FIELD_DONE 0x4u
+#define MG_FIELD_INFO 0x8u
+#define MG_FIELD_ALL 0xFu
+
+/* Pipelined host-buffer step, the asynchronous half of mg_step_host (same role: `MergeEnv.step` for callers whose
+ * actions / results live in host memory, merging_env.py:138-195):
+ *   stream:      [wait ev_done] -> mg_step (reads h_a1 / h_a2 straight from PINNED host memory) -> record ev_stepped
+ *   copy_stream: [wait ev_stepped] -> cudaMemcpyAsync of the selected `fields` d_out -> h_out -> record ev_done
+ * and returns without synchronising.  mg_step_host_wait(ev_done) blocks the host until the copies of that call have
+ * landed.  Events and streams are the caller's (cudaEvent_t / cudaStream_t as void*; the library creates nothing).
+ * With two (d_out, h_out, h_a1/h_a2, ev_done) sets used alternately, the kernel and action fetch of call t+1 run
+ * under the device-to-host copies of call t, so the bus never idles; h_a1 / h_a2 of a call may be overwritten once
+ * its ev_done has completed.  Selected fields that sit back to back at equal offsets in d_out and h_out travel in
+ * one copy. */
+MG_API int mg_step_host_async(const MgState *state, int64_t n, const uint8_t *h_a1, const uint8_t *h_a2_or_null,
+                              const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out, uint32_t fields,
+                              int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
+                              void *stream, void *copy_stream, void *ev_stepped, void *ev_done);
+MG_API int mg_step_host_wait(void *ev_done);
 
 #define MG_MLP_FLAG_MIRROR 0x1u /* evaluate the network on the OPPONENT's view of each observation row,
                                    `state[5:] + state[:5]` (scripts/main.py:199, hdqn.py:285,299): the half-swap

@@ -10,7 +10,7 @@ import os
 
 from ._paths import LIB_PATH
 
-MG_ABI_VERSION = 3
+MG_ABI_VERSION = 4
 OBS_DIM = 10
 NUM_ACTIONS = 5
 STATS_ROWS = 1024
@@ -18,6 +18,9 @@ STATS_COLS = 16
 
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 FLAG_AUTO_RESET = 0x1
+FLAG_NO_RETURNS = 0x2
+FIELD_OBS, FIELD_REW, FIELD_DONE, FIELD_INFO, FIELD_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
+FIELD_BITS = {"obs": FIELD_OBS, "rew": FIELD_REW, "done": FIELD_DONE, "info": FIELD_INFO}
 
 INFO_COLLISION = 0x01
 INFO_WINNER_SHIFT = 1
@@ -97,6 +100,9 @@ def load():
                                C.POINTER(MgRewards), C.POINTER(MgOut), vp, vp, u32, rsp, vp]
     lib.mg_step_host.argtypes = [C.POINTER(MgState), i64, vp, vp, vp, vp, C.POINTER(MgRewards),
                                  C.POINTER(MgOut), C.POINTER(MgOut), vp, u32, rsp, vp, vp, i32]
+    lib.mg_step_host_async.argtypes = [C.POINTER(MgState), i64, vp, vp, C.POINTER(MgRewards), C.POINTER(MgOut),
+                                       C.POINTER(MgOut), u32, vp, u32, rsp, vp, vp, vp, vp]
+    lib.mg_step_host_wait.argtypes = [vp]
     lib.mg_mlp_act.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]
     lib.mg_mlp_act.restype = C.c_int
     lib.mg_mlp_act_tc.argtypes = lib.mg_mlp_act.argtypes
@@ -104,7 +110,8 @@ def load():
     lib.mg_record_transitions.argtypes = [vp] * 10 + [i64, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.mg_record_transitions.restype = C.c_int
     for f in (lib.mg_get_constants, lib.mg_default_rewards, lib.mg_reset, lib.mg_step,
-              lib.mg_sample_actions, lib.mg_rollout, lib.mg_step_host):
+              lib.mg_sample_actions, lib.mg_rollout, lib.mg_step_host, lib.mg_step_host_async,
+              lib.mg_step_host_wait):
         f.restype = C.c_int
     if lib.mg_version() != MG_ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {lib.mg_version()} != binding {MG_ABI_VERSION}")

@@ -38,7 +38,7 @@ constexpr float kResetRemaining = 900.0f;
 
 // ---- x / d for a compile-time divisor, bit-identical to IEEE division -----------------------
 // q = RN(x*y), r = x - d*q (exact in one FMA), q' = RN(q + r*y)  with y = RN(1/d)
-// (Markstein's correction).  oracle/merge_oracle.c::mgo_check_div and tests/test_arith.py
+// (Markstein's correction).  oracle/merge_oracle.c::mgo_check_div and tests/test_oracle_c.py
 // confirm q' == x/d bit for bit for d = 3 and d = 30000 over the ranges the env reaches.
 __device__ __forceinline__ double div_const(double x, double d, double y) {
     const double q = __dmul_rn(x, y);
@@ -227,7 +227,7 @@ __device__ __forceinline__ void reset_env(EnvRegs &e, const MgResetSpec &rs, uin
 // and roundings per env as the scalar reference; batching only lets the compiler share constants
 // and interleave independent float64 chains).  a1/a2 already validated into 0..4 (bad -> info
 // bit).  PVP=false: `action2 is None` -> acc2 = 0 (merging_env.py:152).
-template <bool PVP, int E>
+template <bool PVP, int E, bool RET = true>
 __device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1)[E], const int (&a2)[E],
                                                const bool (&bad_action)[E], const MgRewards &rw,
                                                StepResult (&out)[E]) {
@@ -304,8 +304,10 @@ __device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1
         r1 = collided ? __dadd_rn(r1, rw.r_collision) : r1;
         r2 = collided ? __dadd_rn(r2, rw.r_collision) : r2;
         // :191-192
-        e.R1 = __dadd_rn(e.R1, r1);
-        e.R2 = __dadd_rn(e.R2, r2);
+        if (RET) {                       // RET = false: MG_FLAG_NO_RETURNS, the accumulators do not exist
+            e.R1 = __dadd_rn(e.R1, r1);
+            e.R2 = __dadd_rn(e.R2, r2);
+        }
         e.meta = (e.meta & ~((1u << MG_META_RESETS_SHIFT) - 1u)) | steps[i] | (w << MG_META_WINNER_SHIFT) |
                  (dn ? MG_META_DONE : 0u);
 
@@ -322,7 +324,7 @@ __device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1
 
 // ---- per-thread episode statistics, packed so that one warp reduction covers several ---------
 struct StatAcc {
-    uint32_t a = 0;   // episodes | collisions<<8 | wins_p1<<16 | wins_p2<<24   (<= 128 each per warp)
+    uint32_t a = 0;   // episodes | collisions<<8 | wins_p1<<16 | wins_p2<<24   (8-bit fields: <= 255 events per warp and flush)
     uint32_t b = 0;   // timeouts | merges_ok<<8 | bad_actions<<16
     uint32_t len = 0; // sum of finished episode lengths
     long long fx1 = 0, fx2 = 0;   // sum of finished returns, fixed point 2^24

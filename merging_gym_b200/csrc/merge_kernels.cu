@@ -34,6 +34,7 @@ namespace mg {
 #ifndef MG_MIN_BLOCKS
 #define MG_MIN_BLOCKS 8   // __launch_bounds__ min resident blocks per SM: caps the step kernel at 64 registers
 #endif
+static_assert(32 * MG_EPT <= 255, "StatAcc packs per-warp event counts into 8-bit fields (merge_device.cuh)");
 constexpr int kBlock = MG_BLOCK;
 constexpr int kWarps = kBlock / 32;
 
@@ -110,7 +111,7 @@ __device__ __forceinline__ void write_episode_outputs(const MgOut &o, int64_t e,
 //   grid = ceil(n / (kBlock*EPT)), block = kBlock.  A warp owns 32*EPT consecutive envs.
 //   Full warps take the vector path; the (at most one) ragged warp takes the scalar path.
 // =================================================================================================
-template <int EPT, typename ActT, bool PVP, bool RR>
+template <int EPT, typename ActT, bool PVP, bool RR, bool RET>
 __global__ void __launch_bounds__(kBlock, MG_MIN_BLOCKS)
 merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
                   const ActT *__restrict__ a2g, const int64_t n, const MgRewards rw,
@@ -142,7 +143,11 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
         uint32_t m[EPT];
         ld_pack<double, EPT>(s.pos1 + e0, p1); ld_pack<double, EPT>(s.vel1 + e0, v1);
         ld_pack<double, EPT>(s.pos2 + e0, p2); ld_pack<double, EPT>(s.vel2 + e0, v2);
-        ld_pack<double, EPT>(s.ret1 + e0, R1); ld_pack<double, EPT>(s.ret2 + e0, R2);
+        if (RET) { ld_pack<double, EPT>(s.ret1 + e0, R1); ld_pack<double, EPT>(s.ret2 + e0, R2); }
+        else {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) R1[j] = R2[j] = 0.0;
+        }
         ld_pack<uint32_t, EPT>(s.meta + e0, m);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
@@ -159,7 +164,7 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
             valid[j] = e < n;
             bad[j] = false;
             if (valid[j]) {
-                env[j] = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], s.ret1[e], s.ret2[e], s.meta[e]};
+                env[j] = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], RET ? s.ret1[e] : 0.0, RET ? s.ret2[e] : 0.0, s.meta[e]};
                 act1[j] = clamp_action((long long)a1g[e], bad[j]);
                 act2[j] = PVP ? clamp_action((long long)a2g[e], bad[j]) : 0;
             } else {
@@ -176,7 +181,7 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
     float *my_stage = &stage[warp][lane * EPT * MG_OBS_DIM];
 
     StepResult res[EPT];
-    env_step_batch<PVP, EPT>(env, act1, act2, bad, rw, res);
+    env_step_batch<PVP, EPT, RET>(env, act1, act2, bad, rw, res);
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
         StepResult &r = res[j];
@@ -206,14 +211,14 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
         _Pragma("unroll") for (int j = 0; j < EPT; ++j) t[j] = env[j].field; \
         st_pack<double, EPT>(arr + e0, t);
         MG_ST(p1, s.pos1) MG_ST(v1, s.vel1) MG_ST(p2, s.pos2) MG_ST(v2, s.vel2)
-        MG_ST(R1, s.ret1) MG_ST(R2, s.ret2)
+        if (RET) { MG_ST(R1, s.ret1) MG_ST(R2, s.ret2) }
 #undef MG_ST
         uint32_t m[EPT];
 #pragma unroll
         for (int j = 0; j < EPT; ++j) m[j] = env[j].meta;
         st_pack<uint32_t, EPT>(s.meta + e0, m);
         st_pack_stream<float, 2 * EPT>(o.rew + 2 * e0, rew);
-        st_pack_stream<uint8_t, EPT>(o.done + e0, done8);
+        if (o.done) st_pack_stream<uint8_t, EPT>(o.done + e0, done8);     // NULL: the caller reads MG_INFO_DONE instead
         st_pack_stream<uint8_t, EPT>(o.info + e0, info8);
         // obs rows of this warp are one contiguous, 16-byte aligned span of 32*EPT*40 bytes
 #if MG_TMA_OBS
@@ -242,9 +247,11 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
             const int64_t e = e0 + j;
             if (!valid[j]) continue;
             s.pos1[e] = env[j].p1; s.vel1[e] = env[j].v1; s.pos2[e] = env[j].p2; s.vel2[e] = env[j].v2;
-            s.ret1[e] = env[j].R1; s.ret2[e] = env[j].R2; s.meta[e] = env[j].meta;
+            if (RET) { s.ret1[e] = env[j].R1; s.ret2[e] = env[j].R2; }
+            s.meta[e] = env[j].meta;
             o.rew[2 * e] = rew[2 * j]; o.rew[2 * e + 1] = rew[2 * j + 1];
-            o.done[e] = done8[j]; o.info[e] = info8[j];
+            if (o.done) o.done[e] = done8[j];
+            o.info[e] = info8[j];
         }
     }
 
@@ -264,7 +271,7 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 #ifndef MG_ROLLOUT_MIN_BLOCKS
 #define MG_ROLLOUT_MIN_BLOCKS 4
 #endif
-template <bool PVP, bool RR>
+template <bool PVP, bool RR, bool RET>
 __global__ void __launch_bounds__(kBlock, MG_ROLLOUT_MIN_BLOCKS)
 merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actions_out, const int64_t n,
                      const uint64_t seed, const uint64_t env_id_base, const uint64_t step0,
@@ -286,7 +293,7 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
     for (int j = 0; j < EPT; ++j) {
         const int64_t e = e0 + j;
         valid[j] = e < n;
-        if (valid[j]) env[j] = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], s.ret1[e], s.ret2[e], s.meta[e]};
+        if (valid[j]) env[j] = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], RET ? s.ret1[e] : 0.0, RET ? s.ret2[e] : 0.0, s.meta[e]};
         else reset_regs(env[j]);
     }
     unsigned long long *stats_row = stats ? stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS : nullptr;
@@ -301,7 +308,7 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
         for (int j = 0; j < EPT; ++j)
             philox_actions(seed, env_id_base + (uint64_t)(e0 + j), step0 + (uint64_t)t, act1[j], act2[j]);
         StepResult res[EPT];
-        env_step_batch<PVP, EPT>(env, act1, act2, nobad, rw, res);
+        env_step_batch<PVP, EPT, RET>(env, act1, act2, nobad, rw, res);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             const int64_t e = e0 + j;
@@ -345,7 +352,8 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
         const int64_t e = e0 + j;
         if (!valid[j]) continue;
         s.pos1[e] = env[j].p1; s.vel1[e] = env[j].v1; s.pos2[e] = env[j].p2; s.vel2[e] = env[j].v2;
-        s.ret1[e] = env[j].R1; s.ret2[e] = env[j].R2; s.meta[e] = env[j].meta;
+        if (RET) { s.ret1[e] = env[j].R1; s.ret2[e] = env[j].R2; }
+        s.meta[e] = env[j].meta;
     }
 }
 
@@ -369,7 +377,8 @@ merge_reset_kernel(const MgState s, const int64_t n, const uint8_t *__restrict__
         if (rs.mode == MG_RESET_RANDOM) reset_env<true>(r, rs, (uint64_t)e, ob);
         else reset_env<false>(r, rs, (uint64_t)e, ob);
         s.pos1[e] = r.p1; s.vel1[e] = r.v1; s.pos2[e] = r.p2; s.vel2[e] = r.v2;
-        s.ret1[e] = 0.0; s.ret2[e] = 0.0; s.meta[e] = r.meta;
+        if (s.ret1) { s.ret1[e] = 0.0; s.ret2[e] = 0.0; }      // NULL: the env keeps no return accumulators
+        s.meta[e] = r.meta;
     } else {
         if (valid) { r.p1 = s.pos1[e]; r.v1 = s.vel1[e]; r.p2 = s.pos2[e]; r.v2 = s.vel2[e]; }
         observe(r, ob);
@@ -415,10 +424,11 @@ using mg_abi::aligned16;
 using mg_abi::cuda_fail;
 using mg_abi::fail;
 
-int check_state(const MgState *s) {
+int check_state(const MgState *s, bool returns = true) {
     if (!s) return fail(MG_ERR_NULL_POINTER, "state is NULL");
-    const void *ptrs[] = {s->pos1, s->vel1, s->pos2, s->vel2, s->ret1, s->ret2, s->meta};
-    for (const void *p : ptrs) {
+    const void *ptrs[] = {s->pos1, s->vel1, s->pos2, s->vel2, s->meta, s->ret1, s->ret2};
+    for (int i = 0; i < (returns ? 7 : 5); ++i) {
+        const void *p = ptrs[i];
         if (!p) return fail(MG_ERR_NULL_POINTER, "a state array pointer is NULL");
         if (!aligned16(p)) return fail(MG_ERR_ALIGNMENT, "state arrays must be 16-byte aligned");
     }
@@ -426,8 +436,8 @@ int check_state(const MgState *s) {
 }
 int check_out(const MgOut *o, bool all_required) {
     if (!o) return fail(MG_ERR_NULL_POINTER, "out is NULL");
-    if (all_required && (!o->obs || !o->rew || !o->done || !o->info))
-        return fail(MG_ERR_NULL_POINTER, "out.obs/rew/done/info must be non-NULL");
+    if (all_required && (!o->obs || !o->rew || !o->info))
+        return fail(MG_ERR_NULL_POINTER, "out.obs/rew/info must be non-NULL");
     const void *ptrs[] = {o->obs, o->rew, o->done, o->info, o->term_obs, o->ep_ret, o->ep_len};
     for (const void *p : ptrs)
         if (p && !aligned16(p)) return fail(MG_ERR_ALIGNMENT, "output arrays must be 16-byte aligned");
@@ -457,7 +467,10 @@ cudaEvent_t *host_chunk_events() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
     if (!ready[dev]) {
         for (int i = 0; i < kMaxHostChunks; ++i)
-            if (cudaEventCreateWithFlags(&ev[dev][i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&ev[dev][i], cudaEventDisableTiming) != cudaSuccess) {
+                while (--i >= 0) cudaEventDestroy(ev[dev][i]);     // nothing half-made is kept
+                return nullptr;
+            }
         ready[dev] = true;
     }
     return ev[dev];
@@ -478,6 +491,7 @@ cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const 
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
     const bool rr = rs.mode == MG_RESET_RANDOM;
+    const bool ret = (flags & MG_FLAG_NO_RETURNS) == 0u;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(mg::kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -485,9 +499,11 @@ cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = MG_PDL ? 1 : 0;
     cudaError_t le = cudaSuccess;
-#define MG_LAUNCH(PVP, RR, A2)                                                              \
-    le = cudaLaunchKernelEx(&cfg, mg::merge_step_kernel<EPT, ActT, PVP, RR>, s, o, (const ActT *)a1, \
-                            (const ActT *)(A2), n, rw, flags, rs, stp)
+#define MG_LAUNCH(PVP, RR, A2)                                                                        \
+    le = ret ? cudaLaunchKernelEx(&cfg, mg::merge_step_kernel<EPT, ActT, PVP, RR, true>, s, o, (const ActT *)a1,  \
+                                  (const ActT *)(A2), n, rw, flags, rs, stp)                            \
+             : cudaLaunchKernelEx(&cfg, mg::merge_step_kernel<EPT, ActT, PVP, RR, false>, s, o, (const ActT *)a1, \
+                                  (const ActT *)(A2), n, rw, flags, rs, stp)
     if (a2) { if (rr) MG_LAUNCH(true, true, a2); else MG_LAUNCH(true, false, a2); }
     else    { if (rr) MG_LAUNCH(false, true, nullptr); else MG_LAUNCH(false, false, nullptr); }
 #undef MG_LAUNCH
@@ -523,7 +539,7 @@ MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask, float 
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     if (int rc = check_reset(reset)) return rc;
     if (n == 0) return MG_OK;
-    if (int rc = check_state(state)) return rc;
+    if (int rc = check_state(state, state && (state->ret1 || state->ret2))) return rc;
     const unsigned grid = (unsigned)((n + mg::kBlock - 1) / mg::kBlock);
     mg::merge_reset_kernel<<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(*state, n, mask, obs, reset ? *reset : kFixedReset);
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_reset launch");
@@ -535,12 +551,13 @@ MG_API int mg_step(const MgState *state, int64_t n, const void *a1, const void *
                    const MgResetSpec *reset, void *stream) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     if (int rc = check_reset(reset)) return rc;
-    if (flags & ~MG_FLAG_AUTO_RESET) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
     if (act_dtype < MG_ACT_U8 || act_dtype > MG_ACT_I64)
         return fail(MG_ERR_BAD_DTYPE, "act_dtype must be MG_ACT_U8, MG_ACT_I32 or MG_ACT_I64");
     if (n == 0) return MG_OK;
-    if (int rc = check_state(state)) return rc;
+    if (int rc = check_state(state, !(flags & MG_FLAG_NO_RETURNS))) return rc;
     if (int rc = check_out(out, true)) return rc;
+    if ((flags & MG_FLAG_NO_RETURNS) && out->ep_ret) return fail(MG_ERR_BAD_FLAGS, "out.ep_ret needs the return accumulators (MG_FLAG_NO_RETURNS is set)");
     if (!a1) return fail(MG_ERR_NULL_POINTER, "a1 is NULL");
     const MgRewards rw = rewards ? *rewards : kDefaultRewards;
     const MgResetSpec rs = reset ? *reset : kFixedReset;
@@ -573,18 +590,24 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
     if (int rc = check_reset(reset)) return rc;
     const MgResetSpec rs = reset ? *reset : kFixedReset;
     if (n < 0 || k_steps < 0) return fail(MG_ERR_BAD_SIZE, "n < 0 or k_steps < 0");
-    if (flags & ~MG_FLAG_AUTO_RESET) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
     if (n == 0 || k_steps == 0) return MG_OK;
-    if (int rc = check_state(state)) return rc;
+    const bool ret = (flags & MG_FLAG_NO_RETURNS) == 0u;
+    if (int rc = check_state(state, ret)) return rc;
     if (int rc = check_out(out, false)) return rc;
+    if (!ret && out->ep_ret) return fail(MG_ERR_BAD_FLAGS, "out.ep_ret needs the return accumulators (MG_FLAG_NO_RETURNS is set)");
     const MgRewards rw = rewards ? *rewards : kDefaultRewards;
     const int64_t per_block = (int64_t)mg::kBlock * 2;
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
     const bool rr = rs.mode == MG_RESET_RANDOM;
-#define MG_LAUNCH(PVP, RR)                                                                       \
-    mg::merge_rollout_kernel<PVP, RR><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(            \
-        *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, rs, stp)
+#define MG_LAUNCH(PVP, RR)                                                                             \
+    do {                                                                                               \
+        if (ret) mg::merge_rollout_kernel<PVP, RR, true><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(   \
+            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
+        else mg::merge_rollout_kernel<PVP, RR, false><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(      \
+            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
+    } while (0)
     if (pvp) { if (rr) MG_LAUNCH(true, true); else MG_LAUNCH(true, false); }
     else     { if (rr) MG_LAUNCH(false, true); else MG_LAUNCH(false, false); }
 #undef MG_LAUNCH
@@ -609,11 +632,15 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
     // stream) overlaps the H2D + kernel of piece c+1 (main stream), so the bus idles only while the first
     // piece is uploaded and stepped.  Pieces are multiples of 256 envs (whole blocks, every array 16-byte aligned).
     int nch = (copy_stream && copy_stream != stream && chunks > 1) ? (chunks > kMaxHostChunks ? kMaxHostChunks : chunks) : 1;
-    int64_t piece = ((n + nch - 1) / nch + 255) / 256 * 256;
+    constexpr int64_t kPieceAlign = (int64_t)mg::kBlock * MG_EPT;    // whole blocks of the step kernel
+    int64_t piece = ((n + nch - 1) / nch + kPieceAlign - 1) / kPieceAlign * kPieceAlign;
     cudaEvent_t *ev = nullptr;
     if (nch > 1) {
         ev = host_chunk_events();
-        if (!ev) return cuda_fail(cudaGetLastError(), "mg_step_host event");
+        if (!ev) {
+            const cudaError_t ce = cudaGetLastError();
+            return ce ? cuda_fail(ce, "mg_step_host event") : fail(MG_ERR_BAD_SIZE, "mg_step_host: no event set for this device (index >= 32?)");
+        }
     }
     const MgResetSpec rs0 = reset ? *reset : kFixedReset;
     cudaError_t e;
@@ -631,7 +658,8 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
             if (h_a2 && (e = cudaMemcpyAsync(d_a2 + off, h_a2 + off, M, cudaMemcpyHostToDevice, st))) return cuda_fail(e, "H2D a2");
         }
         const MgState sub = {state->pos1 + off, state->vel1 + off, state->pos2 + off, state->vel2 + off,
-                             state->ret1 + off, state->ret2 + off, state->meta + off};
+                             state->ret1 ? state->ret1 + off : nullptr, state->ret2 ? state->ret2 + off : nullptr,
+                             state->meta + off};
         const MgOut d = {d_out->obs ? d_out->obs + off * MG_OBS_DIM : nullptr, d_out->rew ? d_out->rew + off * 2 : nullptr,
                          d_out->done ? d_out->done + off : nullptr, d_out->info ? d_out->info + off : nullptr,
                          d_out->term_obs ? d_out->term_obs + off * MG_OBS_DIM : nullptr,
@@ -663,6 +691,54 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
     }
     if (nch > 1 && (e = cudaStreamSynchronize(cs))) return cuda_fail(e, "mg_step_host copy-stream sync");
     if ((e = cudaStreamSynchronize(st))) return cuda_fail(e, "mg_step_host sync");
+    return MG_OK;
+}
+
+MG_API int mg_step_host_async(const MgState *state, int64_t n, const uint8_t *h_a1, const uint8_t *h_a2,
+                              const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out, uint32_t fields,
+                              int64_t *stats, uint32_t flags, const MgResetSpec *reset, void *stream,
+                              void *copy_stream, void *ev_stepped, void *ev_done) {
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (!state || !h_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "state, h_a1, d_out or h_out is NULL");
+    if (!copy_stream || !ev_stepped || !ev_done || copy_stream == stream)
+        return fail(MG_ERR_NULL_POINTER, "mg_step_host_async needs a copy stream (different from stream) and two events");
+    if (fields & ~MG_FIELD_ALL) return fail(MG_ERR_BAD_FLAGS, "unknown field bits");
+    cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+    cudaEvent_t ek = (cudaEvent_t)ev_stepped, ed = (cudaEvent_t)ev_done;
+    cudaError_t e;
+    // d_out was last read by the copies that recorded ev_done (a never-recorded event completes at once): the
+    // kernel may overwrite the slot only after them.  This wait is the only coupling between consecutive calls,
+    // so with two (d_out, h_out, ev_done) sets the kernel of call t+1 runs under the copies of call t.
+    if ((e = cudaStreamWaitEvent(st, ed, 0))) return cuda_fail(e, "mg_step_host_async slot wait");
+    if (int rc = mg_step(state, n, h_a1, h_a2, MG_ACT_U8, rewards, d_out, stats, flags, reset, stream)) return rc;
+    if ((e = cudaEventRecord(ek, st))) return cuda_fail(e, "mg_step_host_async event record");
+    if ((e = cudaStreamWaitEvent(cs, ek, 0))) return cuda_fail(e, "mg_step_host_async event wait");
+    if (n > 0) {
+        // one cudaMemcpyAsync per run of selected fields that are adjacent (gap < 4 KB) at equal offsets on both sides
+        const size_t M = (size_t)n;
+        const char *dp[4] = {(const char *)d_out->obs, (const char *)d_out->rew, (const char *)d_out->done, (const char *)d_out->info};
+        char *hp[4] = {(char *)h_out->obs, (char *)h_out->rew, (char *)h_out->done, (char *)h_out->info};
+        const size_t sz[4] = {M * MG_OBS_DIM * sizeof(float), M * 2 * sizeof(float), M, M};
+        int i = 0;
+        while (i < 4) {
+            if (!(fields & (1u << i))) { ++i; continue; }
+            if (!dp[i] || !hp[i]) return fail(MG_ERR_NULL_POINTER, "a selected output field is NULL in d_out or h_out");
+            int j = i;
+            while (j + 1 < 4 && (fields & (1u << (j + 1))) && dp[j + 1] && hp[j + 1] &&
+                   dp[j + 1] - dp[i] == hp[j + 1] - hp[i] && dp[j + 1] >= dp[j] + sz[j] && dp[j + 1] - (dp[j] + sz[j]) < 4096)
+                ++j;
+            const size_t span = (size_t)(dp[j] - dp[i]) + sz[j];
+            if ((e = cudaMemcpyAsync(hp[i], dp[i], span, cudaMemcpyDeviceToHost, cs))) return cuda_fail(e, "D2H outputs");
+            i = j + 1;
+        }
+    }
+    if ((e = cudaEventRecord(ed, cs))) return cuda_fail(e, "mg_step_host_async done record");
+    return MG_OK;
+}
+
+MG_API int mg_step_host_wait(void *ev_done) {
+    if (!ev_done) return fail(MG_ERR_NULL_POINTER, "ev_done is NULL");
+    if (cudaError_t e = cudaEventSynchronize((cudaEvent_t)ev_done)) return cuda_fail(e, "mg_step_host_wait");
     return MG_OK;
 }
 

@@ -64,6 +64,7 @@ class TransitionRecorder:
         self.env_ids = torch.full((self.capacity,), -1, dtype=torch.int32, device=dev) if track_env_ids else None
         self._scratch = torch.zeros((env.num_envs + 31) // 32 + 4, dtype=torch.int32, device=dev)
         self._lib = nat.load()
+        self._same_obs_ok = False       # OptionRecorder stores [s_end, goal, sum_r, s_end]: s == s' on purpose
 
     def record(self, obs_prev: torch.Tensor, a1: torch.Tensor, a2: Optional[torch.Tensor], step_out,
                goal_prev: Optional[torch.Tensor] = None, goal_next: Optional[torch.Tensor] = None,
@@ -81,6 +82,14 @@ class TransitionRecorder:
             raise ValueError("`select` is required for, and only for, mask='explicit'")
         if (self.format == "hdqn") != (goal_prev is not None and goal_next is not None):
             raise ValueError("goal_prev and goal_next are required for, and only for, format 'hdqn'")
+        if not (isinstance(obs_prev, torch.Tensor) and obs_prev.dtype == torch.float32 and obs_prev.is_contiguous()
+                and obs_prev.device == env.device and tuple(obs_prev.shape) == (env.num_envs, nat.OBS_DIM)):
+            raise ValueError(f"obs_prev must be a contiguous float32[{env.num_envs}, {nat.OBS_DIM}] tensor on {env.device} "
+                             "(the kernel reads it with 128-bit loads)")
+        if self.format != "log" and not self._same_obs_ok and obs_prev.data_ptr() == obs.data_ptr():
+            # with out_slots=1 `env.step` returns the buffer it was given: s and s' would be the same row
+            raise ValueError("obs_prev aliases the new observation (the env's single output slot was overwritten by this "
+                             "step): create the env with out_slots >= 2 or pass a copy of the previous observation")
         with torch.cuda.device(env.device):
             nat.check(self._lib.mg_record_transitions(
                 _ptr(obs_prev), _ptr(obs), _ptr(term), _ptr(a1), _ptr(a2), _ptr(rew),
@@ -123,6 +132,7 @@ class OptionRecorder:
         self._goal_status = goal_status
         self.env = env
         self.rec = TransitionRecorder(env, capacity, format="replay", player=1, mask="explicit", track_env_ids=track_env_ids)
+        self.rec._same_obs_ok = True
         self.extrinsic = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
         self._rew = torch.zeros(env.num_envs, 2, dtype=torch.float32, device=env.device)
 

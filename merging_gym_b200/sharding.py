@@ -64,32 +64,82 @@ def all_reduce_stats(stats: torch.Tensor, async_op: bool = False):
 
 
 class AsyncStatsReducer:
-    """Periodic, off-critical-path reduction of the episode statistics over all ranks.
+    """Periodic, off-critical-path reduction of the episode statistics over all ranks — the path's only collective.
 
-    `submit()` snapshots this rank's int64[16] totals on the current stream and all-reduces them
-    on a side stream (NCCL on GPUs); the env's launches are never blocked.  `latest()` waits for the
-    most recent submission and returns the reduced totals.  This is the path's only collective.
+    `submit()` takes a snapshot of this rank's int64[16] totals that is consistent with everything launched on the
+    current stream so far, and all-reduces it on a side stream (NCCL on GPUs); the env's launches are never blocked.
+    `latest()` waits for the most recent submission and returns the reduced totals.
+
+    banked=False: the snapshot is one small row-sum kernel on the launching stream.
+    banked=True:  the launching stream carries NO statistics work at all: `submit()` retires the env's active
+        statistics bank (later launches add into the other one), records an event, and the side stream drains the
+        retired bank — row sum into the env's running totals, zero — before the all-reduce.  Launches pick the bank
+        up when they are issued, so a caller that replays CUDA graphs must capture one graph per bank and replay the
+        one that matches `env._stats_active` (bench.py does); eager launches need nothing.
     """
 
-    def __init__(self, env):
+    def __init__(self, env, banked: bool = False):
         self.env = env
+        self.banked = bool(banked)
         self.side = torch.cuda.Stream(device=env.device)
         self._work = None
         self._buf = None
+        self._drained = {}                                  # bank id -> event after which it is empty again
         self.submissions = 0
 
     def submit(self) -> None:
         import torch.distributed as dist
-        snap = self.env.stats_tensor()                      # tiny sum kernel on the current stream
+        env = self.env
+        cur = torch.cuda.current_stream(env.device)
+        if self.banked:
+            retired = env._retire_stats_bank()
+            ev = self._drained.get(id(env.stats_buf))       # the bank that becomes active was drained by an earlier
+            if ev is not None:                              # submit: order its reuse behind that (long finished)
+                cur.wait_event(ev)
+            snap = None
+        else:
+            retired = None
+            snap = env.stats_tensor()                       # tiny sum kernel on the current stream
         ready = torch.cuda.Event()
-        ready.record()
+        ready.record(cur)
         with torch.cuda.stream(self.side):
             self.side.wait_event(ready)
-            snap.record_stream(self.side)
+            if self.banked:
+                env._stats_total += retired.sum(dim=0)
+                retired.zero_()
+                done = torch.cuda.Event()
+                done.record(self.side)
+                self._drained[id(retired)] = done
+                env._stats_side_event = done
+                snap = env._stats_total.clone()
+            else:
+                snap.record_stream(self.side)
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 self._work = dist.all_reduce(snap, op=dist.ReduceOp.SUM, async_op=True)
             self._buf = snap
         self.submissions += 1
+
+    def capture_per_bank(self, issue):
+        """For CUDA-graph callers of a banked reducer: captures `issue()` (a callable that launches this env's steps)
+        once per statistics bank and returns [graph_bank0, graph_bank1]; `replay(graphs)` replays the one whose
+        launches add into the currently active bank.  `issue` must put the env's host-side cursors (output slot,
+        action index) back to the same start itself."""
+        env = self.env
+        if len(env._stats_banks) == 1:
+            env._retire_stats_bank()
+            env._retire_stats_bank()
+        keep, graphs = env._stats_active, []
+        for b in (0, 1):
+            env._stats_active = b
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                issue()
+            graphs.append(g)
+        env._stats_active = keep
+        return graphs
+
+    def replay(self, graphs) -> None:
+        graphs[self.env._stats_active if self.banked else 0].replay()
 
     def latest(self) -> torch.Tensor:
         if self._buf is None:

@@ -106,18 +106,35 @@ class MergeVecEnv:
     reset_mode    "fixed": pos=50, vel=20 (merging_env.py:216-217, the live code); "random": the
                   reference's commented-out random start (:219-221) drawn per (reset_seed, global
                   env id, reset count) with Philox + Box-Muller, for explicit and automatic resets.
+    track_returns False drops the float64 `r1_accumulate` / `r2_accumulate` state (merging_env.py:191-192;
+                  only human_player.py:189-193 and `render` read them): 124 instead of 156 bytes of HBM
+                  traffic per env-step.  `episode_return`, the return statistics and the two attributes
+                  are then unavailable.
+    host_slots    pinned host buffer sets of the host-buffer path (`step_host_async` keeps up to this
+                  many steps in flight).
+    lanes         L > 1 splits the envs into L contiguous sub-shards ("lanes", whole 256-env blocks), each
+                  stepped by its own launch on its own CUDA stream: `step_lane_async(l, ...)` /
+                  `step_lane_wait(l)`.  A lane depends only on its own previous step, so the launch of one
+                  lane starts while another lane's launch drains — that overlap is what separates the
+                  serialised 2^20-env launch (0.91 of the HBM copy peak) from the peak.  Results are
+                  bit-identical to the single-lane env; `step()` steps all lanes and joins them.
     """
 
     def __init__(self, num_envs: int, mode: str = "pvp", device="cuda", auto_reset: bool = True,
                  seed: int = ACTION_SEED_DEFAULT, env_id_base: int = 0, out_slots: int = 1,
                  episode_info: bool = True, track_stats: bool = True, rewards: Optional[dict] = None,
-                 validate_actions: bool = False, reset_mode: str = "fixed", reset_seed: Optional[int] = None):
+                 validate_actions: bool = False, reset_mode: str = "fixed", reset_seed: Optional[int] = None,
+                 track_returns: bool = True, host_slots: int = 2, lanes: int = 1):
         if mode not in ("pvp", "pve"):
             raise ValueError("mode must be 'pvp' or 'pve'")
         if num_envs < 0 or out_slots < 1:
             raise ValueError("num_envs must be >= 0 and out_slots >= 1")
         if reset_mode not in ("fixed", "random"):
             raise ValueError("reset_mode must be 'fixed' or 'random'")
+        if host_slots < 1:
+            raise ValueError("host_slots must be >= 1")
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
         self._lib = nat.load()                       # raises if the CUDA library is not built
         if not torch.cuda.is_available():
             raise nat.NativeError("merging_gym_b200 needs a CUDA device (no CPU fallback exists)")
@@ -134,6 +151,8 @@ class MergeVecEnv:
         self._rs = nat.MgResetSpec(nat.RESET_RANDOM if reset_mode == "random" else nat.RESET_FIXED, 0,
                                    int(seed if reset_seed is None else reset_seed), int(env_id_base))
         self.out_slots = int(out_slots)
+        self.track_returns = bool(track_returns)
+        self.host_slots = int(host_slots)
         self._slot = 0
         self.step_count = 0                          # Philox step counter for sample_actions/rollout
         self.closed = False
@@ -153,7 +172,9 @@ class MergeVecEnv:
         f = self._state_block[:n32 * 48].view(torch.float64).view(6, n32)
         self.pos1, self.vel1, self.pos2, self.vel2, self.ret1, self.ret2 = (f[i, :n] for i in range(6))
         self.meta = self._state_block[n32 * 48:].view(torch.int32)[:n]
-        self._state = nat.MgState(*[t.data_ptr() for t in
+        if not self.track_returns:
+            self.ret1 = self.ret2 = None
+        self._state = nat.MgState(*[None if t is None else t.data_ptr() for t in
                                     (self.pos1, self.vel1, self.pos2, self.vel2, self.ret1, self.ret2, self.meta)])
         K = self.out_slots
         n_pad = (n + 15) // 16 * 16                  # keeps every slot's base pointer 16-byte aligned
@@ -164,11 +185,11 @@ class MergeVecEnv:
         self._extras = {}
         if episode_info:
             self.terminal_obs = torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, device=dev)
-            self.episode_return = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+            self.episode_return = torch.zeros(n, 2, dtype=torch.float32, device=dev) if self.track_returns else None
             self.episode_length = torch.zeros(n, dtype=torch.int32, device=dev)
-            self._extras = {"terminal_observation": self.terminal_obs,
-                            "episode_return": self.episode_return,
-                            "episode_length": self.episode_length}
+            self._extras = {"terminal_observation": self.terminal_obs, "episode_length": self.episode_length}
+            if self.track_returns:
+                self._extras["episode_return"] = self.episode_return
         else:
             self.terminal_obs = self.episode_return = self.episode_length = None
         self._outs = [nat.MgOut(self.obs_buf[k].data_ptr(), self.rew_buf[k].data_ptr(),
@@ -176,27 +197,53 @@ class MergeVecEnv:
                                 *[None if t is None else t.data_ptr() for t in
                                   (self.terminal_obs, self.episode_return, self.episode_length)])
                       for k in range(K)]
-        self.stats_buf = (torch.zeros(nat.STATS_ROWS, nat.STATS_COLS, dtype=torch.int64, device=dev)
-                          if track_stats else None)
+        # Episode statistics: the kernels add into the ACTIVE bank of per-block partial rows.  A banked
+        # `AsyncStatsReducer` retires the active bank and drains it (row sum into `_stats_total`, zero) on its side
+        # stream, so the launching stream never runs a statistics kernel; without one, bank 0 is all there is.
+        self._stats_banks = ([torch.zeros(nat.STATS_ROWS, nat.STATS_COLS, dtype=torch.int64, device=dev)]
+                             if track_stats else None)
+        self._stats_active = 0
+        self._stats_total = torch.zeros(nat.STATS_COLS, dtype=torch.int64, device=dev) if track_stats else None
+        self._stats_side_event = None                # last work a reducer queued on its side stream
         self._act_block = torch.zeros(2 * n_pad, dtype=torch.uint8, device=dev)   # sample_actions / step_host scratch
         self.act1, self.act2 = self._act_block[:n], self._act_block[n_pad:n_pad + n]
         self._host = None
+        self._hslots = None
+        self._hfly = []                              # host slots with a step in flight, oldest first
+        self._hnext = 0
         self._copy_stream = None
         self._pending = None
+        self._zero_mask = None
+        self._init_lanes(int(lanes))
 
         self.single_observation_space: Box = merge_observation_space()
         self.single_action_space: Discrete = merge_action_space()
-        self.observation_space = Box(np.tile(self.single_observation_space.low, (n, 1)),
-                                     np.tile(self.single_observation_space.high, (n, 1)), dtype=np.float16)
-        self.action_space = MultiDiscrete(np.full(n, nat.NUM_ACTIONS))
+        self._batched_spaces = None
         self.reset()
+
+    @property
+    def observation_space(self) -> Box:
+        """Batched Box[N,10] (gym 0.20 `VectorEnv.observation_space`); the bounds are broadcast views, O(1) memory."""
+        return self._spaces()[0]
+
+    @property
+    def action_space(self) -> MultiDiscrete:
+        return self._spaces()[1]
+
+    def _spaces(self):
+        if self._batched_spaces is None:
+            n, so = self.num_envs, self.single_observation_space
+            self._batched_spaces = (Box(np.broadcast_to(so.low, (n,) + so.low.shape), np.broadcast_to(so.high, (n,) + so.high.shape),
+                                        dtype=np.float16),
+                                    MultiDiscrete(np.broadcast_to(np.int64(nat.NUM_ACTIONS), (n,))))
+        return self._batched_spaces
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _flags(self):
-        return nat.FLAG_AUTO_RESET if self.auto_reset else 0
+        return (nat.FLAG_AUTO_RESET if self.auto_reset else 0) | (0 if self.track_returns else nat.FLAG_NO_RETURNS)
 
     def _as_action(self, a, name):
         if not isinstance(a, torch.Tensor):
@@ -236,17 +283,119 @@ class MergeVecEnv:
             if m.numel() != self.num_envs:
                 raise ValueError("mask must have num_envs elements")
         obs = self.obs_buf[self._slot]
+        self._join_lanes()
         with torch.cuda.device(self.device):
             nat.check(self._lib.mg_reset(C.byref(self._state), self.num_envs, _ptr(m), _ptr(obs),
                                          C.byref(self._rs), self._stream()), "mg_reset")
         return obs
 
+    # ------------------------------------------------------------------ lanes
+    def _init_lanes(self, L: int) -> None:
+        n = self.num_envs
+        per = ((n + L - 1) // L + 255) // 256 * 256 if L > 1 else n       # whole blocks: every sub-array stays 16-byte aligned
+        bounds = [(min(l * per, n), min((l + 1) * per, n)) for l in range(L)]
+        self.lane_bounds = [b for b in bounds if b[1] > b[0]] or [(0, n)]
+        self.lanes = len(self.lane_bounds)
+        self.lane_slices = [slice(lo, hi) for lo, hi in self.lane_bounds]
+        self._lane_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.lanes)] if self.lanes > 1 else []
+        self._lane_ev = [None] * self.lanes          # event after the lane's last launch (None: nothing outstanding)
+        self._lane_slot = [0] * self.lanes
+        self._lane_pending = [None] * self.lanes
+        if self.lanes == 1:
+            return
+        st = (self.pos1, self.vel1, self.pos2, self.vel2, self.ret1, self.ret2, self.meta)
+        self._lane_state, self._lane_outs, self._lane_rs = [], [], []
+        for lo, hi in self.lane_bounds:
+            self._lane_state.append(nat.MgState(*[None if t is None else t[lo:hi].data_ptr() for t in st]))
+            self._lane_outs.append([nat.MgOut(self.obs_buf[k, lo:hi].data_ptr(), self.rew_buf[k, lo:hi].data_ptr(),
+                                              self.done_buf[k, lo:hi].data_ptr(), self.info_buf[k, lo:hi].data_ptr(),
+                                              *[None if t is None else t[lo:hi].data_ptr() for t in
+                                                (self.terminal_obs, self.episode_return, self.episode_length)])
+                                    for k in range(self.out_slots)])
+            self._lane_rs.append(nat.MgResetSpec(self._rs.mode, 0, self._rs.seed, self.env_id_base + lo))
+
+    def join_lanes(self) -> None:
+        """Order the current stream behind every outstanding lane launch (call before reading `env.pos1` etc. after
+        `step_lane_async`; the env's own whole-env calls do it themselves)."""
+        self._join_lanes()
+
+    def _join_lanes(self) -> None:
+        cur = None
+        for l, ev in enumerate(self._lane_ev):
+            if ev is not None:
+                cur = cur or torch.cuda.current_stream(self.device)
+                cur.wait_event(ev)
+                self._lane_ev[l] = None
+
+    def step_lane_async(self, lane: int, a1, a2=None) -> None:
+        """`step` for the envs of one lane (`lane_slices[lane]`), launched on the lane's own stream behind
+        everything queued on the current stream so far (so actions computed there are visible)."""
+        if self.lanes == 1:
+            return self.step_async(a1, a2)
+        lo, hi = self.lane_bounds[lane]
+        a1 = self._as_lane_action(a1, hi - lo, "action1")
+        if a2 is not None:
+            a2 = self._as_lane_action(a2, hi - lo, "action2")
+            if a2.dtype != a1.dtype:
+                wide = a1.dtype if a1.element_size() >= a2.element_size() else a2.dtype
+                a1, a2 = a1.to(wide), a2.to(wide)
+        k = self._lane_slot[lane] = (self._lane_slot[lane] + 1) % self.out_slots
+        cur, ls = torch.cuda.current_stream(self.device), self._lane_streams[lane]
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        ls.wait_event(fork)
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_step(C.byref(self._lane_state[lane]), hi - lo, _ptr(a1), _ptr(a2),
+                                        self._ACT_DTYPE[a1.dtype], C.byref(self._rw), C.byref(self._lane_outs[lane][k]),
+                                        _ptr(self.stats_buf), self._flags(), C.byref(self._lane_rs[lane]),
+                                        C.c_void_p(ls.cuda_stream)), "mg_step (lane)")
+        ev = torch.cuda.Event()
+        ev.record(ls)
+        self._lane_ev[lane] = ev
+        self._lane_pending[lane] = k
+
+    def step_lane_wait(self, lane: int):
+        """Orders the current stream behind the lane's last launch and returns that step's
+        (obs, rewards, done, info) for the lane's envs (views of the env-wide output slot)."""
+        if self.lanes == 1:
+            return self.step_wait()
+        k = self._lane_pending[lane]
+        if k is None:
+            raise RuntimeError("step_lane_wait() called without step_lane_async()")
+        self._lane_pending[lane] = None
+        if self._lane_ev[lane] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._lane_ev[lane])
+            self._lane_ev[lane] = None
+        sl = self.lane_slices[lane]
+        extras = {q: t[sl] for q, t in self._extras.items()}
+        return (self.obs_buf[k, sl], self.rew_buf[k, sl], self.done_buf[k, sl].view(torch.bool),
+                StepInfo(self.info_buf[k, sl], extras))
+
+    def _as_lane_action(self, a, m, name):
+        if not isinstance(a, torch.Tensor) or a.device != self.device or a.dtype not in self._ACT_DTYPE:
+            raise TypeError(f"{name}: lane actions must be uint8 / int32 / int64 tensors on {self.device}")
+        a = a.reshape(-1)
+        if a.numel() != m:
+            raise ValueError(f"{name}: expected {m} actions for this lane, got {a.numel()}")
+        if not a.is_contiguous() or a.data_ptr() % 16:
+            a = a.contiguous().clone() if a.data_ptr() % 16 else a.contiguous()
+        return a
+
     def step_async(self, a1, a2=None) -> None:
         a1 = self._as_action(a1, "action1")
         if a2 is not None:
             a2 = self._as_action(a2, "action2")
-            if a2.dtype != a1.dtype:
-                a2 = a2.to(a1.dtype)
+            if a2.dtype != a1.dtype:                 # one element type per launch: widen, never narrow (256 must stay bad)
+                wide = a1.dtype if a1.element_size() >= a2.element_size() else a2.dtype
+                a1, a2 = a1.to(wide), a2.to(wide)
+        if self.lanes > 1:
+            # lane slots advance together here, so the env-wide views of slot k are whole
+            for l, sl in enumerate(self.lane_slices):
+                self._lane_slot[l] = self._slot
+                self.step_lane_async(l, a1[sl], None if a2 is None else a2[sl])
+            self._slot = self._lane_slot[0]
+            self._pending = self._slot
+            return
         self._slot = (self._slot + 1) % self.out_slots
         k = self._slot
         with torch.cuda.device(self.device):
@@ -261,6 +410,9 @@ class MergeVecEnv:
         if k is None:
             raise RuntimeError("step_wait() called without step_async()")
         self._pending = None
+        if self.lanes > 1:
+            self._join_lanes()
+            self._lane_pending = [None] * self.lanes
         return (self.obs_buf[k], self.rew_buf[k], self.done_buf[k].view(torch.bool),
                 StepInfo(self.info_buf[k], self._extras))
 
@@ -310,10 +462,14 @@ class MergeVecEnv:
 
     @property
     def r1_accumulate(self) -> torch.Tensor:
+        if self.ret1 is None:
+            raise AttributeError("r1_accumulate: the env was created with track_returns=False")
         return self.ret1
 
     @property
     def r2_accumulate(self) -> torch.Tensor:
+        if self.ret2 is None:
+            raise AttributeError("r2_accumulate: the env was created with track_returns=False")
         return self.ret2
 
     @staticmethod
@@ -340,12 +496,15 @@ class MergeVecEnv:
 
     def rollout(self, k_steps: int, obs: Optional[torch.Tensor] = None, rew: Optional[torch.Tensor] = None,
                 done: Optional[torch.Tensor] = None, info: Optional[torch.Tensor] = None,
-                actions: Optional[torch.Tensor] = None, step0: Optional[int] = None):
+                actions: Optional[torch.Tensor] = None, step0: Optional[int] = None, refresh_obs: bool = True):
         """`k_steps` random-action steps in ONE launch (state stays in registers between steps).
 
         Time-major output tensors are optional: obs f32[k,N,10], rew f32[k,N,2], done u8[k,N],
         info u8[k,N], actions u8[k,N,2].  The action stream equals `sample_actions` at steps
         step0..step0+k-1, so `rollout(k)` and k x (`sample_actions` + `step`) give identical results.
+        `refresh_obs`: afterwards write the observation of the final state into the env's current
+        observation buffer (`observe()`, one extra small launch), so that `env.obs_buf[slot]` is what a
+        policy should act on next; pass False when only the time-major outputs are used.
         """
         n, k = self.num_envs, int(k_steps)
         if step0 is None:
@@ -363,29 +522,69 @@ class MergeVecEnv:
         chk(actions, (k, n, 2), torch.uint8, "actions")
         out = nat.MgOut(*[None if t is None else t.data_ptr() for t in
                           (obs, rew, done, info, self.terminal_obs, self.episode_return, self.episode_length)])
+        self._join_lanes()
         with torch.cuda.device(self.device):
             nat.check(self._lib.mg_rollout(C.byref(self._state), n, int(self.mode == "pvp"), self.philox_seed,
                                            self.env_id_base, int(step0), k, C.byref(self._rw),
                                            C.byref(out), _ptr(actions), _ptr(self.stats_buf),
                                            self._flags(), C.byref(self._rs), self._stream()), "mg_rollout")
+        if refresh_obs and k > 0:
+            self.refresh_observation()
+
+    def refresh_observation(self) -> torch.Tensor:
+        """`observe()` (merging_env.py:118-132) of the current state into the current observation buffer: an
+        `mg_reset` with an all-zero mask resets nothing and writes every env's observation."""
+        if self._zero_mask is None:
+            self._zero_mask = torch.zeros(max(self.num_envs, 1), dtype=torch.uint8, device=self.device)
+        obs = self.obs_buf[self._slot]
+        self._join_lanes()
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_reset(C.byref(self._state), self.num_envs, _ptr(self._zero_mask), _ptr(obs),
+                                         C.byref(self._rs), self._stream()), "mg_reset (observe)")
+        return obs
 
     # ------------------------------------------------------------------ host-buffer path
     def _host_buffers(self) -> dict:
-        if self._host is None:
-            # pinned mirrors with the device layout (actions: [a1 | a2]; outputs: [obs | rew | done | info]), so that
-            # mg_step_host needs one copy per direction
-            n = self.num_envs
+        """Pinned mirrors of host slot 0 (the synchronous `step_host` path uses only this one)."""
+        return self._host_slots()[0]
+
+    def _host_slots(self) -> list:
+        if self._hslots is None:
+            # Per host slot: pinned mirrors with the device layout (actions: [a1 | a2]; outputs: [obs | rew | done |
+            # info]) so that one copy per direction suffices, a device output block of its own (the asynchronous
+            # path's kernel may run while the env's regular output slots are still being read), and two events.
+            n, H, dev = self.num_envs, self.host_slots, self.device
             n_pad = (n + 15) // 16 * 16
-            acts = torch.zeros(2 * n_pad, dtype=torch.uint8, pin_memory=True)
-            outs = torch.zeros(n_pad * 50, dtype=torch.uint8, pin_memory=True)
-            obs, rew, done, info = _slot_views(outs, 1, n, n_pad)
-            self._host = dict(a1=acts[:n], a2=acts[n_pad:n_pad + n], obs=obs[0], rew=rew[0], done=done[0], info=info[0],
-                              _blocks=(acts, outs))
-            h = self._host
-            self._host_np = (h["a1"].numpy(), h["a2"].numpy())
-            self._host_out = nat.MgOut(h["obs"].data_ptr(), h["rew"].data_ptr(), h["done"].data_ptr(),
+            self._hd_block = torch.zeros(H * n_pad * 50, dtype=torch.uint8, device=dev)
+            d_obs, d_rew, d_done, d_info = _slot_views(self._hd_block, H, n, n_pad)
+            self._copy_stream = self._copy_stream or torch.cuda.Stream(device=dev)
+            slots = []
+            for k in range(H):
+                acts = torch.zeros(2 * n_pad, dtype=torch.uint8, pin_memory=True)
+                outs = torch.zeros(n_pad * 50, dtype=torch.uint8, pin_memory=True)
+                obs, rew, done, info = _slot_views(outs, 1, n, n_pad)
+                h = dict(a1=acts[:n], a2=acts[n_pad:n_pad + n], obs=obs[0], rew=rew[0], done=done[0], info=info[0],
+                         _blocks=(acts, outs))
+                h["np_acts"] = (h["a1"].numpy(), h["a2"].numpy())
+                h["np_out"] = (h["obs"].numpy(), h["rew"].numpy(), h["done"].numpy().view(np.bool_), h["info"].numpy())
+                h["h_out"] = nat.MgOut(h["obs"].data_ptr(), h["rew"].data_ptr(), h["done"].data_ptr(),
                                        h["info"].data_ptr(), None, None, None)
-        return self._host
+                h["d_out"] = nat.MgOut(d_obs[k].data_ptr(), d_rew[k].data_ptr(), d_done[k].data_ptr(), d_info[k].data_ptr(),
+                                       *[None if t is None else t.data_ptr() for t in
+                                         (self.terminal_obs, self.episode_return, self.episode_length)])
+                ev = (torch.cuda.Event(), torch.cuda.Event())
+                with torch.cuda.device(dev):
+                    for e in ev:                     # torch creates the CUDA event lazily, on its first record
+                        e.record(self._copy_stream)
+                h["ev"] = ev
+                h["fields"] = nat.FIELD_ALL
+                slots.append(h)
+            self._copy_stream.synchronize()
+            self._hslots = slots
+            self._host = slots[0]
+            self._host_np = slots[0]["np_acts"]
+            self._host_out = slots[0]["h_out"]
+        return self._hslots
 
     def _copy_stream_ptr(self, chunks: int):
         if chunks <= 1:
@@ -394,22 +593,83 @@ class MergeVecEnv:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         return C.c_void_p(self._copy_stream.cuda_stream)
 
-    def host_action_buffers(self):
-        """(a1, a2): uint8[N] NumPy views of the PINNED staging buffers `step_host` uploads from.  A caller that
-        writes its actions into them and passes them back to `step_host` saves the extra host-side copy."""
-        self._host_buffers()
-        return self._host_np
+    def host_action_buffers(self, slot: Optional[int] = None):
+        """(a1, a2): uint8[N] NumPy views of the PINNED staging buffers the step kernel reads its actions from.  A
+        caller that writes its actions into them and passes them back to `step_host` / `step_host_async` saves the
+        extra host-side copy.  `slot=None`: the slot the next `step_host_async` (or `step_host`) call will use."""
+        slots = self._host_slots()
+        return slots[self._hnext if slot is None else slot]["np_acts"]
+
+    @staticmethod
+    def _field_mask(fields) -> int:
+        if fields is None:
+            return nat.FIELD_ALL
+        m = 0
+        for f in ([fields] if isinstance(fields, str) else fields):
+            if f not in nat.FIELD_BITS:
+                raise ValueError(f"unknown field {f!r}: choose from {sorted(nat.FIELD_BITS)}")
+            m |= nat.FIELD_BITS[f]
+        if not m:
+            raise ValueError("fields must name at least one of obs / rew / done / info")
+        return m
+
+    def step_host_async(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, fields=None) -> None:
+        """Pipelined host-buffer step (`mg_step_host_async`): queues the fused step — the kernel reads the uint8
+        actions straight from this slot's pinned buffers — and the device-to-host copies of the selected `fields`
+        (any of "obs", "rew", "done", "info"; default all four) on a private copy stream, and returns at once.
+        Up to `host_slots` steps may be in flight; `step_host_wait()` hands back the oldest.  With two slots the
+        kernel and action fetch of step t+1 run under the copies of step t, so the PCIe link never idles.
+        The reference's contract per call is `return obs, rewards, done, info` (merging_env.py:195): a caller that
+        only logs rewards / dones (its policy reading the device-resident observation) moves 10 B per env instead of 50.
+        """
+        slots = self._host_slots()
+        self._join_lanes()
+        if len(self._hfly) >= self.host_slots:
+            raise RuntimeError(f"{self.host_slots} host steps already in flight: call step_host_wait() first")
+        k = self._hnext
+        h = slots[k]
+        mask = self._field_mask(fields)
+        npa = h["np_acts"]
+        # actions written in place into `host_action_buffers()` are used as they are; anything else is staged
+        # into those pinned buffers first (an extra host copy of n bytes per player)
+        if a1 is not npa[0]:
+            npa[0][:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
+        if a2 is not None and a2 is not npa[1]:
+            npa[1][:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_step_host_async(C.byref(self._state), self.num_envs, _ptr(h["a1"]),
+                                                   _ptr(h["a2"]) if a2 is not None else None, C.byref(self._rw),
+                                                   C.byref(h["d_out"]), C.byref(h["h_out"]), mask, _ptr(self.stats_buf),
+                                                   self._flags(), C.byref(self._rs), self._stream(),
+                                                   C.c_void_p(self._copy_stream.cuda_stream),
+                                                   C.c_void_p(h["ev"][0].cuda_event), C.c_void_p(h["ev"][1].cuda_event)),
+                      "mg_step_host_async")
+        h["fields"] = mask
+        self._hfly.append(k)
+        self._hnext = (k + 1) % self.host_slots
+
+    def step_host_wait(self):
+        """Blocks until the oldest in-flight `step_host_async` has landed in host memory; returns
+        (obs, rewards, done, info_flags) as NumPy views of that slot's pinned buffers — None for fields that were
+        not requested.  The views are overwritten when the slot is reused, `host_slots` calls later."""
+        if not self._hfly:
+            raise RuntimeError("step_host_wait() called without step_host_async()")
+        h = self._hslots[self._hfly.pop(0)]
+        nat.check(self._lib.mg_step_host_wait(C.c_void_p(h["ev"][1].cuda_event)), "mg_step_host_wait")
+        m = h["fields"]
+        return tuple(v if m & (1 << i) else None for i, v in enumerate(h["np_out"]))
 
     def step_host(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, zero_copy: bool = False,
-                  chunks: int = 1, direct_actions: bool = True):
+                  chunks: int = 1, direct_actions: bool = True, fields=None):
         """Drop-in for host-resident callers: uint8 NumPy actions in, NumPy outputs out.
 
         Default: one `mg_step_host` call = the fused step reading the actions straight from the pinned
         staging buffers (`direct_actions=False`: after an explicit H2D copy of them instead), D2H of
-        obs/rew/done/info into pinned host buffers, stream synchronise.  `chunks > 1` steps the envs in
-        that many pieces so that the device-to-host copy of one piece (on a private copy stream)
-        overlaps the upload and the kernel of the next; on a PCIe 5 x16 B200 this does not pay (the
-        upload + kernel it can hide are 0.07 ms of 1.04 ms, the extra small copies cost more:
+        obs/rew/done/info into pinned host buffers, stream synchronise.  `fields` (any of "obs", "rew",
+        "done", "info") restricts the copy-back; it is served by `step_host_async` + `step_host_wait`.
+        `chunks > 1` steps the envs in that many pieces so that the device-to-host copy of one piece (on a
+        private copy stream) overlaps the upload and the kernel of the next; on a PCIe 5 x16 B200 this does
+        not pay (the upload + kernel it can hide are 0.07 ms of 1.04 ms, the extra small copies cost more:
         `profiles/e2e_paths.py`), so the default is one piece.
         `zero_copy=True`: `mg_step` is handed the pinned host buffers themselves (pinned memory is
         device-addressable under UVA), so the kernel reads the actions and streams its outputs
@@ -417,10 +677,17 @@ class MergeVecEnv:
         Returns (obs, rewards, done, info_flags) as NumPy views of the pinned buffers (overwritten
         by the next call).
         """
+        if self._hfly:
+            raise RuntimeError("step_host() while step_host_async() calls are in flight: call step_host_wait() first")
+        if fields is not None:
+            self._hnext = 0
+            self.step_host_async(a1, a2, fields)
+            self._hnext = 0
+            return self.step_host_wait()
         n = self.num_envs
         h = self._host_buffers()
-        # actions written in place into `host_action_buffers()` are used as they are; anything else is
-        # staged into those pinned buffers first (an extra host copy of n bytes per player)
+        self._join_lanes()
+        self._hnext = 0
         if a1 is not self._host_np[0]:
             self._host_np[0][:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
         if a2 is not None and a2 is not self._host_np[1]:
@@ -442,14 +709,35 @@ class MergeVecEnv:
                                                  _ptr(self.stats_buf), self._flags(), C.byref(self._rs),
                                                  self._stream(), self._copy_stream_ptr(chunks), int(chunks)),
                           "mg_step_host")
-        return h["obs"].numpy(), h["rew"].numpy(), h["done"].numpy().view(np.bool_), h["info"].numpy()
+        return h["np_out"]
 
     # ------------------------------------------------------------------ statistics
+    @property
+    def stats_buf(self) -> Optional[torch.Tensor]:
+        """int64[1024,16] partial rows the kernels launched from now on add into (the active bank)."""
+        return None if self._stats_banks is None else self._stats_banks[self._stats_active]
+
+    def _retire_stats_bank(self) -> torch.Tensor:
+        """Make the other bank active and return the retired one (banked `AsyncStatsReducer` only).  Kernels already
+        queued — and CUDA graphs captured earlier — keep adding into the bank that was active when they were launched
+        or captured."""
+        if len(self._stats_banks) == 1:
+            self._stats_banks.append(torch.zeros_like(self._stats_banks[0]))
+        retired = self._stats_banks[self._stats_active]
+        self._stats_active ^= 1
+        return retired
+
     def stats_tensor(self) -> torch.Tensor:
-        """int64[16] device totals (sum of the per-block partial rows); no host sync."""
-        if self.stats_buf is None:
+        """int64[16] device totals (retired banks' totals + the sum of every bank's partial rows); no host sync."""
+        if self._stats_banks is None:
             raise RuntimeError("track_stats=False")
-        return self.stats_buf.sum(dim=0)
+        self._join_lanes()
+        if self._stats_side_event is not None:       # a reducer may still be draining a bank on its side stream
+            torch.cuda.current_stream(self.device).wait_event(self._stats_side_event)
+        t = self._stats_total.clone()
+        for b in self._stats_banks:
+            t += b.sum(dim=0)
+        return t
 
     def stats(self, reduce: bool = False, reset: bool = False) -> dict:
         """Episode statistics as a dict (host sync).  `reduce=True` sums over all ranks first."""
@@ -459,25 +747,50 @@ class MergeVecEnv:
             t = all_reduce_stats(t)
         d = stats_to_dict(t.cpu().numpy(), self.constants.return_fixed_point_scale)
         if reset:
-            self.stats_buf.zero_()
+            self._stats_total.zero_()
+            for b in self._stats_banks:
+                b.zero_()
         return d
 
     # ------------------------------------------------------------------ checkpoint
     _STATE_KEYS = ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta")
 
     def state_dict(self) -> dict:
-        d = {k: getattr(self, k).clone() for k in self._STATE_KEYS}
+        """Everything a bit-exact continuation needs: the env state arrays, the Philox step counter and keys (action
+        stream, random starts), the first global env id, and the statistics partials."""
+        self._join_lanes()
+        d = {k: getattr(self, k).clone() for k in self._STATE_KEYS if getattr(self, k) is not None}
         d["step_count"] = self.step_count
-        if self.stats_buf is not None:
-            d["stats"] = self.stats_buf.clone()
+        d["philox_seed"], d["reset_seed"], d["env_id_base"] = self.philox_seed, int(self._rs.seed), self.env_id_base
+        d["reset_mode"] = self.reset_mode
+        if self._stats_banks is not None:
+            st = self._stats_banks[0].clone()
+            for b in self._stats_banks[1:]:
+                st += b
+            st[0] += self._stats_total
+            d["stats"] = st
         return d
 
     def load_state_dict(self, d: dict) -> None:
+        """Restores `state_dict()` and re-derives the current observation (`observe()` of the loaded state) into
+        the current observation buffer."""
+        self._join_lanes()
         for k in self._STATE_KEYS:
-            getattr(self, k).copy_(d[k])
+            if getattr(self, k) is not None:
+                getattr(self, k).copy_(d[k])
         self.step_count = int(d.get("step_count", 0))
-        if self.stats_buf is not None and "stats" in d:
+        self.philox_seed = int(d.get("philox_seed", self.philox_seed))
+        self.env_id_base = int(d.get("env_id_base", self.env_id_base))
+        if d.get("reset_mode", self.reset_mode) != self.reset_mode:
+            raise ValueError(f"state_dict was saved with reset_mode={d['reset_mode']!r}, this env has {self.reset_mode!r}")
+        self._rs.seed = int(d.get("reset_seed", self._rs.seed))
+        self._rs.env_id_base = self.env_id_base
+        if self._stats_banks is not None and "stats" in d:
+            self._stats_total.zero_()
+            for b in self._stats_banks:
+                b.zero_()
             self.stats_buf.copy_(d["stats"])
+        self.refresh_observation()
 
     def __repr__(self):
         return (f"MergeVecEnv(num_envs={self.num_envs}, mode={self.mode!r}, device={self.device}, "

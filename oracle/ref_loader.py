@@ -1,11 +1,12 @@
 """TEST INFRASTRUCTURE — loads the UNMODIFIED reference env for golden-vector generation.
 
-Only usable in the build container, where `/root/reference` exists.  Puts
+Uses `/root/reference` where it exists (the build container), else the byte-identical copy that
+`baseline/install_ref.py` left in the git-ignored `baseline/_ref/` (the GPU box).  Puts
 `oracle/ref_shims/` (stand-ins for gym/pygame/shapely/qpsolvers/matplotlib, all
 absent from the image) plus `/root/reference` and `/root/reference/scripts` on
 `sys.path`, then imports `merging_gym` exactly as the reference scripts do
-(scripts/main.py:1-2,20).  Never imported by the product package, by `-m gpu`
-tests, by `smoke()` or by `bench.py`.
+(scripts/main.py:1-2,20).  Never imported by the product package; `bench.py` uses it only in its CPU-baseline legs
+(to time the reference's own `MergeEnv.step` on the box's host cores).
 """
 import contextlib
 import io
@@ -13,12 +14,29 @@ import os
 import sys
 import warnings
 
-REFERENCE_ROOT = os.environ.get("MERGING_GYM_REFERENCE", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "ref_shims")
+# The unmodified copy made by baseline/install_ref.py (git-ignored; it travels to the GPU box, /root/reference does not)
+TRAVELLING_COPY = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _has_env(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "merging_gym", "envs", "merging_env.py")) and \
+        os.path.isfile(os.path.join(root, "scripts", "helper.py"))
+
+
+def _pick_root() -> str:
+    env = os.environ.get("MERGING_GYM_REFERENCE")
+    if env:
+        return env
+    return "/root/reference" if _has_env("/root/reference") else TRAVELLING_COPY
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "merging_gym", "envs", "merging_env.py"))
+    return _has_env(REFERENCE_ROOT)
 
 
 def load_reference_env():

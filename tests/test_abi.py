@@ -30,8 +30,8 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     assert declared_symbols() == sorted([
         "mg_version", "mg_last_error", "mg_get_constants", "mg_default_rewards", "mg_reset",
-        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_mlp_act", "mg_mlp_act_tc",
-        "mg_record_transitions"])
+        "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_step_host_async", "mg_step_host_wait",
+        "mg_mlp_act", "mg_mlp_act_tc", "mg_record_transitions"])
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -72,7 +72,9 @@ def test_header_macros_match_binding():
                  ("MG_INFO_DONE", nat.INFO_DONE), ("MG_INFO_BAD_ACTION", nat.INFO_BAD_ACTION),
                  ("MG_INFO_WINNER_MASK", nat.INFO_WINNER_MASK), ("MG_META_DONE", nat.META_DONE),
                  ("MG_META_STEPS_MASK", nat.META_STEPS_MASK), ("MG_FLAG_AUTO_RESET", nat.FLAG_AUTO_RESET),
-                 ("MG_META_RESETS_SHIFT", nat.META_RESETS_SHIFT)]:
+                 ("MG_META_RESETS_SHIFT", nat.META_RESETS_SHIFT), ("MG_FLAG_NO_RETURNS", nat.FLAG_NO_RETURNS),
+                 ("MG_FIELD_OBS", nat.FIELD_OBS), ("MG_FIELD_REW", nat.FIELD_REW), ("MG_FIELD_DONE", nat.FIELD_DONE),
+                 ("MG_FIELD_INFO", nat.FIELD_INFO), ("MG_FIELD_ALL", nat.FIELD_ALL)]:
         assert macro(n) == v, n
     # and with the oracle's copy of the info bits
     assert (nat.INFO_COLLISION, nat.INFO_TIMEOUT, nat.INFO_DONE, nat.INFO_BAD_ACTION) == \
@@ -110,6 +112,13 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mg_mlp_act_tc(None, None, 8, 10, 5, None, None, None, None, None, None, None, None, 0x10, None) == -4
     assert lib.mg_record_transitions(*([None] * 10), 8, 0, 3, 1, None, 16, None, None, None, None) == -4
     assert lib.mg_step_host(None, 8, *([None] * 8), 0, None, None, None, 1) == -1
+    assert lib.mg_step_host_async(None, 8, *([None] * 5), 0xF, None, 0, None, None, None, None, None) == -1
+    assert lib.mg_step_host_wait(None) == -1
+    # the lean state: MG_FLAG_NO_RETURNS accepts NULL ret1/ret2 but refuses an episode-return output
+    lean = nat.MgState(0x1000, 0x1000, 0x1000, 0x1000, None, None, 0x1000)
+    o2 = nat.MgOut(0x1000, 0x1000, None, 0x1000, None, 0x1000, None)
+    assert lib.mg_step(C.byref(lean), 8, None, None, 0, C.byref(rw), C.byref(o2), None, nat.FLAG_NO_RETURNS, None, None) == -4
+    assert lib.mg_step(C.byref(lean), 8, None, None, 0, C.byref(rw), C.byref(o2), None, 0, None, None) == -1      # ret1 NULL without the flag
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

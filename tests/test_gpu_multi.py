@@ -38,7 +38,7 @@ rank, local, world = mg.init_distributed()
 total, K = 1 << 16, 260
 base, count = mg.shard_range(total, rank, world)
 env = mg.MergeVecEnv(count, device=f"cuda:{local}", seed=11, env_id_base=base)
-red = mg.AsyncStatsReducer(env)
+red = mg.AsyncStatsReducer(env, banked=bool(int(os.environ["MG_BANKED"])))
 for t in range(K):
     env.step(*env.sample_actions())
     if t % 64 == 63:
@@ -53,11 +53,13 @@ torch.distributed.barrier(); torch.distributed.destroy_process_group()
 
 
 @needs2
-def test_torchrun_nccl_stats_are_world_size_invariant(tmp_path):
+@pytest.mark.parametrize("banked", [0, 1])
+def test_torchrun_nccl_stats_are_world_size_invariant(tmp_path, banked):
+    """banked=1: the launching stream carries no statistics kernel (the side stream drains the retired bank)."""
     import merging_gym_b200 as mg
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MG_ROOT=ROOT)
+    env = dict(os.environ, MG_ROOT=ROOT, MG_BANKED=str(banked))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
