@@ -208,19 +208,26 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1,
 #define MG_FIELD_ALL 0xFu
 
 /* Pipelined host-buffer step, the asynchronous half of mg_step_host (same role: `MergeEnv.step` for callers whose
- * actions / results live in host memory, merging_env.py:138-195):
- *   stream:      [wait ev_done] -> mg_step (reads h_a1 / h_a2 straight from PINNED host memory) -> record ev_stepped
+ * actions / results live in host memory, merging_env.py:138-195).  One MgHostSlot = the buffers and events of one step
+ * in flight; everything in it belongs to the caller (cudaEvent_t / cudaStream_t as void*; the library creates nothing).
+ *   upload_stream (optional): cudaMemcpyAsync h_a1|h_a2 -> d_a1|d_a2 -> record ev_uploaded
+ *   stream:      [wait ev_uploaded] [wait ev_done] -> mg_step -> record ev_stepped
+ *                (upload_stream == NULL: the kernel reads h_a1 / h_a2 straight from PINNED host memory instead)
  *   copy_stream: [wait ev_stepped] -> cudaMemcpyAsync of the selected `fields` d_out -> h_out -> record ev_done
- * and returns without synchronising.  mg_step_host_wait(ev_done) blocks the host until the copies of that call have
- * landed.  Events and streams are the caller's (cudaEvent_t / cudaStream_t as void*; the library creates nothing).
- * With two (d_out, h_out, h_a1/h_a2, ev_done) sets used alternately, the kernel and action fetch of call t+1 run
- * under the device-to-host copies of call t, so the bus never idles; h_a1 / h_a2 of a call may be overwritten once
- * its ev_done has completed.  Selected fields that sit back to back at equal offsets in d_out and h_out travel in
- * one copy. */
-MG_API int mg_step_host_async(const MgState *state, int64_t n, const uint8_t *h_a1, const uint8_t *h_a2_or_null,
-                              const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out, uint32_t fields,
-                              int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
-                              void *stream, void *copy_stream, void *ev_stepped, void *ev_done);
+ * and returns without synchronising.  mg_step_host_wait(slot->ev_done) blocks the host until the copies of that call
+ * have landed.  With two slots used alternately, the upload and the kernel of call t+1 run under the device-to-host
+ * copies of call t, so the bus never idles; h_a1 / h_a2 of a slot may be overwritten once its ev_done has completed.
+ * Selected fields that sit back to back at equal offsets in d_out and h_out travel in one copy, and so do [a1 | a2]. */
+typedef struct MgHostSlot {
+    const uint8_t *h_a1, *h_a2; /* pinned host actions of this step; h_a2 NULL = pve                       */
+    uint8_t *d_a1, *d_a2;       /* device scratch for the uploaded actions (only with an upload stream)     */
+    MgOut d_out, h_out;         /* device outputs of the step / their pinned host mirrors                   */
+    void *ev_uploaded, *ev_stepped, *ev_done; /* cudaEvent_t, created by the caller (timing disabled)       */
+} MgHostSlot;
+MG_API int mg_step_host_async(const MgState *state, int64_t n, const MgHostSlot *slot, uint32_t fields,
+                              const MgRewards *rewards, int64_t *stats_or_null, uint32_t flags,
+                              const MgResetSpec *reset_or_null, void *stream, void *copy_stream,
+                              void *upload_stream_or_null);
 MG_API int mg_step_host_wait(void *ev_done);
 
 #define MG_MLP_FLAG_MIRROR 0x1u /* evaluate the network on the OPPONENT's view of each observation row,

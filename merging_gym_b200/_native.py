@@ -48,6 +48,12 @@ class MgOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("obs", "rew", "done", "info", "term_obs", "ep_ret", "ep_len")]
 
 
+class MgHostSlot(C.Structure):
+    _fields_ = [("h_a1", C.c_void_p), ("h_a2", C.c_void_p), ("d_a1", C.c_void_p), ("d_a2", C.c_void_p),
+                ("d_out", MgOut), ("h_out", MgOut),
+                ("ev_uploaded", C.c_void_p), ("ev_stepped", C.c_void_p), ("ev_done", C.c_void_p)]
+
+
 class MgRewards(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("r_first", "r_second", "r_collision", "vel_penalty", "time_penalty")]
 
@@ -100,8 +106,8 @@ def load():
                                C.POINTER(MgRewards), C.POINTER(MgOut), vp, vp, u32, rsp, vp]
     lib.mg_step_host.argtypes = [C.POINTER(MgState), i64, vp, vp, vp, vp, C.POINTER(MgRewards),
                                  C.POINTER(MgOut), C.POINTER(MgOut), vp, u32, rsp, vp, vp, i32]
-    lib.mg_step_host_async.argtypes = [C.POINTER(MgState), i64, vp, vp, C.POINTER(MgRewards), C.POINTER(MgOut),
-                                       C.POINTER(MgOut), u32, vp, u32, rsp, vp, vp, vp, vp]
+    lib.mg_step_host_async.argtypes = [C.POINTER(MgState), i64, C.POINTER(MgHostSlot), u32, C.POINTER(MgRewards), vp,
+                                       u32, rsp, vp, vp, vp]
     lib.mg_step_host_wait.argtypes = [vp]
     lib.mg_mlp_act.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]
     lib.mg_mlp_act.restype = C.c_int

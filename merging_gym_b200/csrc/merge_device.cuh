@@ -101,7 +101,10 @@ __device__ __forceinline__ void sincos_poly(const double (&x)[M], double (&s)[M]
 // finished env without auto-reset) leave the polynomial's range: one rarely-taken branch for the
 // whole batch then uses the CUDA library sincos.
 constexpr double kPolyMaxLon = 24000.0;   // |atan2(H,R) - lon/R| <= 0.767 < pi/4 for 0 <= lon <= 24000
-template <int M>
+// CHECK_RANGE = false: the caller guarantees 0 <= lon <= kPolyMaxLon (the rollout kernel with auto-reset: a car moves
+// at most 8 per step and the time limit resets the env after 2501 steps, so lon < 50 + 5 sigma + 20008 — it checks
+// the loaded state once instead of every step).
+template <int M, bool CHECK_RANGE = true>
 __device__ __forceinline__ void lon2coord_batch(const double (&lon)[M], const double (&sign)[M],
                                                 double (&x)[M], double (&y)[M]) {
     double ang[M], s[M], c[M];
@@ -109,9 +112,9 @@ __device__ __forceinline__ void lon2coord_batch(const double (&lon)[M], const do
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         ang[i] = __dsub_rn(kAngle0, div_const(lon[i], kR, kInvR));
-        wild |= !(lon[i] >= 0.0 && lon[i] <= kPolyMaxLon);
+        if (CHECK_RANGE) wild |= !(lon[i] >= 0.0 && lon[i] <= kPolyMaxLon);
     }
-    if (wild) {
+    if (CHECK_RANGE && wild) {
 #pragma unroll
         for (int i = 0; i < M; ++i) sincos(ang[i], &s[i], &c[i]);
     } else {
@@ -169,13 +172,16 @@ __device__ __forceinline__ void reset_regs(EnvRegs &e) {   // merging_env.py:208
     e.R1 = 0.0; e.R2 = 0.0; e.meta = 0u;
 }
 
-__device__ __forceinline__ void write_obs(double x1, double y1, double x2, double y2, const EnvRegs &e,
-                                          float *obs) {                    // merging_env.py:122-131
-    const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1), dv = __dsub_rn(e.v2, e.v1);
+__device__ __forceinline__ void write_obs(double x1, double y1, double x2, double y2, double p1, double v1,
+                                          double p2, double v2, float *obs) {      // merging_env.py:122-131
+    const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1), dv = __dsub_rn(v2, v1);
     obs[0] = (float)dx;  obs[1] = (float)dy;  obs[2] = (float)dv;
-    obs[3] = (float)__dsub_rn(kEnd, e.p1);  obs[4] = (float)e.v1;
+    obs[3] = (float)__dsub_rn(kEnd, p1);  obs[4] = (float)v1;
     obs[5] = (float)-dx; obs[6] = (float)-dy; obs[7] = (float)-dv;   // a-b == -(b-a) exactly
-    obs[8] = (float)__dsub_rn(kEnd, e.p2);  obs[9] = (float)e.v2;
+    obs[8] = (float)__dsub_rn(kEnd, p2);  obs[9] = (float)v2;
+}
+__device__ __forceinline__ void write_obs(double x1, double y1, double x2, double y2, const EnvRegs &e, float *obs) {
+    write_obs(x1, y1, x2, y2, e.p1, e.v1, e.p2, e.v2, obs);
 }
 
 __device__ __forceinline__ void observe(const EnvRegs &e, float *obs) {   // merging_env.py:118-132
@@ -225,61 +231,66 @@ __device__ __forceinline__ void reset_env(EnvRegs &e, const MgResetSpec &rs, uin
 
 // merging_env.py:138-195 for E envs held by one thread, evaluated in lock-step (same operations
 // and roundings per env as the scalar reference; batching only lets the compiler share constants
-// and interleave independent float64 chains).  a1/a2 already validated into 0..4 (bad -> info
-// bit).  PVP=false: `action2 is None` -> acc2 = 0 (merging_env.py:152).
-template <bool PVP, int E, bool RET = true>
-__device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1)[E], const int (&a2)[E],
-                                               const bool (&bad_action)[E], const MgRewards &rw,
-                                               StepResult (&out)[E]) {
-    uint32_t steps[E], winner[E];
-    bool was_done[E], timeout[E], done[E];
+// and interleave independent float64 chains).  a1/a2 already validated into 0..4.
+// PVP=false: `action2 is None` -> acc2 = 0 (merging_env.py:152).
+//
+// The core works on the UNPACKED bookkeeping of an env — steps since reset, winner (0 = None), sticky done — so that a
+// caller that keeps envs in registers over many steps (the rollout kernel) packs / unpacks the meta word once per
+// launch, not once per step.  `collided` / `timeout` come back as flags; the caller assembles the info byte.
+struct StepFlags {
+    bool done;        // done flag returned for this step
+    bool finished;    // done became true in this step (0 -> 1 transition)
+    bool collided, timeout;
+};
+
+template <bool PVP, int E, bool RET, bool CHECK_RANGE = true>
+__device__ __forceinline__ void env_step_core(double (&p1)[E], double (&v1)[E], double (&p2)[E], double (&v2)[E],
+                                              double (&R1)[E], double (&R2)[E], uint32_t (&steps)[E],
+                                              uint32_t (&winner)[E], bool (&sticky)[E], const int (&a1)[E],
+                                              const int (&a2)[E], const MgRewards &rw, float (&obs)[E][MG_OBS_DIM],
+                                              float (&rew1)[E], float (&rew2)[E], StepFlags (&fl)[E]) {
     double lon[2 * E], sign[2 * E], x[2 * E], y[2 * E];
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-        EnvRegs &e = env[i];
         // :141-143  time_stamp += dT; > 500 first holds at step 2501 -> integer step counter
-        steps[i] = min((e.meta & MG_META_STEPS_MASK) + 1u, (uint32_t)MG_META_STEPS_MASK);
-        was_done[i] = (e.meta & MG_META_DONE) != 0u;
-        timeout[i] = steps[i] >= (uint32_t)kMaxSteps;
-        done[i] = was_done[i] | timeout[i];
-        winner[i] = (e.meta >> MG_META_WINNER_SHIFT) & 3u;
+        steps[i] = min(steps[i] + 1u, (uint32_t)MG_META_STEPS_MASK);
         // :147-150  player 1: acc = mpc_1d(...) == (vt - v)/3; vel = max(0, vel + acc*dT); pos += vel*dT
         {
             const double vt = kActionDv * (double)a1[i];
-            const double acc = div_const(__dsub_rn(vt, e.v1), kPredT, kInvPredT);
-            const double v = __dadd_rn(e.v1, __dmul_rn(acc, kDT));
-            e.v1 = (v > 0.0) ? v : 0.0;
-            e.p1 = __dadd_rn(e.p1, __dmul_rn(e.v1, kDT));
+            const double acc = div_const(__dsub_rn(vt, v1[i]), kPredT, kInvPredT);
+            const double v = __dadd_rn(v1[i], __dmul_rn(acc, kDT));
+            v1[i] = (v > 0.0) ? v : 0.0;
+            p1[i] = __dadd_rn(p1[i], __dmul_rn(v1[i], kDT));
         }
         // :152-154  player 2
         if (PVP) {
             const double vt = kActionDv * (double)a2[i];
-            const double acc = div_const(__dsub_rn(vt, e.v2), kPredT, kInvPredT);
-            const double v = __dadd_rn(e.v2, __dmul_rn(acc, kDT));
-            e.v2 = (v > 0.0) ? v : 0.0;
+            const double acc = div_const(__dsub_rn(vt, v2[i]), kPredT, kInvPredT);
+            const double v = __dadd_rn(v2[i], __dmul_rn(acc, kDT));
+            v2[i] = (v > 0.0) ? v : 0.0;
         } else {
-            e.v2 = (e.v2 > 0.0) ? e.v2 : 0.0;          // max(0, vel + 0*dT)
+            v2[i] = (v2[i] > 0.0) ? v2[i] : 0.0;          // max(0, vel + 0*dT)
         }
-        e.p2 = __dadd_rn(e.p2, __dmul_rn(e.v2, kDT));
-        lon[2 * i] = e.p1; sign[2 * i] = 1.0;
-        lon[2 * i + 1] = e.p2; sign[2 * i + 1] = -1.0;
+        p2[i] = __dadd_rn(p2[i], __dmul_rn(v2[i], kDT));
+        lon[2 * i] = p1[i]; sign[2 * i] = 1.0;
+        lon[2 * i + 1] = p2[i]; sign[2 * i + 1] = -1.0;
     }
     // :156, :118-132, :48-58  geometry once per car (the reference recomputes it in is_collided)
-    lon2coord_batch<2 * E>(lon, sign, x, y);
+    lon2coord_batch<2 * E, CHECK_RANGE>(lon, sign, x, y);
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-        EnvRegs &e = env[i];
         const double x1 = x[2 * i], y1 = y[2 * i], x2 = x[2 * i + 1], y2 = y[2 * i + 1];
-        write_obs(x1, y1, x2, y2, e, out[i].obs);
+        write_obs(x1, y1, x2, y2, p1[i], v1[i], p2[i], v2[i], obs[i]);
 
         // :158-159  reward_i = -time_penalty - vel_penalty*|v_i - 20|
-        double r1 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v1, 20.0))));
-        double r2 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(e.v2, 20.0))));
+        double r1 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(v1[i], 20.0))));
+        double r2 = __dsub_rn(-rw.time_penalty, __dmul_rn(rw.vel_penalty, fabs(__dsub_rn(v2[i], 20.0))));
         uint32_t w = winner[i];
-        bool dn = done[i];
+        const bool to = steps[i] >= (uint32_t)kMaxSteps;
+        bool dn = sticky[i] | to;
         // :163-171  player 1 crosses with strict '>' and is evaluated first (branch-free selects)
         {
-            const bool f = e.p1 > kEnd;
+            const bool f = p1[i] > kEnd;
             const double bonus = (w == 0u) ? rw.r_first : rw.r_second;
             const double r_cross = (w == 1u) ? 0.0 : __dadd_rn(r1, bonus);
             r1 = f ? r_cross : r1;
@@ -288,7 +299,7 @@ __device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1
         }
         // :173-181  player 2 crosses with '>='
         {
-            const bool f = e.p2 >= kEnd;
+            const bool f = p2[i] >= kEnd;
             const double bonus = (w == 0u) ? rw.r_first : rw.r_second;
             const double r_cross = (w == 2u) ? 0.0 : __dadd_rn(r2, bonus);
             r2 = f ? r_cross : r2;
@@ -305,20 +316,58 @@ __device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1
         r2 = collided ? __dadd_rn(r2, rw.r_collision) : r2;
         // :191-192
         if (RET) {                       // RET = false: MG_FLAG_NO_RETURNS, the accumulators do not exist
-            e.R1 = __dadd_rn(e.R1, r1);
-            e.R2 = __dadd_rn(e.R2, r2);
+            R1[i] = __dadd_rn(R1[i], r1);
+            R2[i] = __dadd_rn(R2[i], r2);
         }
-        e.meta = (e.meta & ~((1u << MG_META_RESETS_SHIFT) - 1u)) | steps[i] | (w << MG_META_WINNER_SHIFT) |
-                 (dn ? MG_META_DONE : 0u);
+        rew1[i] = (float)r1;
+        rew2[i] = (float)r2;
+        fl[i].done = dn;
+        fl[i].finished = dn & !sticky[i];
+        fl[i].collided = collided;
+        fl[i].timeout = to;
+        winner[i] = w;
+        sticky[i] = dn;
+    }
+}
 
-        out[i].r1 = (float)r1;
-        out[i].r2 = (float)r2;
+__device__ __forceinline__ uint32_t info_byte(const StepFlags &f, uint32_t winner, bool bad_action) {
+    return (f.collided ? MG_INFO_COLLISION : 0u) | (winner << MG_INFO_WINNER_SHIFT) | (f.timeout ? MG_INFO_TIMEOUT : 0u) |
+           (f.done ? MG_INFO_DONE : 0u) | (bad_action ? MG_INFO_BAD_ACTION : 0u);
+}
+
+// The packed-meta front end the single-step kernel uses: unpack, core, pack.
+template <bool PVP, int E, bool RET = true>
+__device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1)[E], const int (&a2)[E],
+                                               const bool (&bad_action)[E], const MgRewards &rw,
+                                               StepResult (&out)[E]) {
+    double p1[E], v1[E], p2[E], v2[E], R1[E], R2[E];
+    uint32_t steps[E], winner[E];
+    bool sticky[E];
+    float obs[E][MG_OBS_DIM], rew1[E], rew2[E];
+    StepFlags fl[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const EnvRegs &e = env[i];
+        p1[i] = e.p1; v1[i] = e.v1; p2[i] = e.p2; v2[i] = e.v2; R1[i] = e.R1; R2[i] = e.R2;
+        steps[i] = e.meta & MG_META_STEPS_MASK;
+        winner[i] = (e.meta >> MG_META_WINNER_SHIFT) & 3u;
+        sticky[i] = (e.meta & MG_META_DONE) != 0u;
+    }
+    env_step_core<PVP, E, RET>(p1, v1, p2, v2, R1, R2, steps, winner, sticky, a1, a2, rw, obs, rew1, rew2, fl);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        EnvRegs &e = env[i];
+        e.p1 = p1[i]; e.v1 = v1[i]; e.p2 = p2[i]; e.v2 = v2[i]; e.R1 = R1[i]; e.R2 = R2[i];
+        e.meta = (e.meta & ~((1u << MG_META_RESETS_SHIFT) - 1u)) | steps[i] | (winner[i] << MG_META_WINNER_SHIFT) |
+                 (fl[i].done ? MG_META_DONE : 0u);
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM; ++k) out[i].obs[k] = obs[i][k];
+        out[i].r1 = rew1[i];
+        out[i].r2 = rew2[i];
         out[i].steps = steps[i];
-        out[i].done = dn;
-        out[i].finished = dn & !was_done[i];
-        out[i].info = (collided ? MG_INFO_COLLISION : 0u) | (w << MG_INFO_WINNER_SHIFT) |
-                      (timeout[i] ? MG_INFO_TIMEOUT : 0u) | (dn ? MG_INFO_DONE : 0u) |
-                      (bad_action[i] ? MG_INFO_BAD_ACTION : 0u);
+        out[i].done = fl[i].done;
+        out[i].finished = fl[i].finished;
+        out[i].info = info_byte(fl[i], winner[i], bad_action[i]);
     }
 }
 

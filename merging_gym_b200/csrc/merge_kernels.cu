@@ -263,18 +263,62 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 }
 
 // =================================================================================================
-// merge_rollout_kernel: k consecutive steps with in-kernel Philox actions; state stays in
-// registers, outputs are time-major.  One env per thread element, EPT=2 vector state I/O.
+// merge_rollout_kernel: k consecutive steps with in-kernel Philox actions; the envs stay in registers
+// (bookkeeping unpacked: steps / winner / done / reset count) for the whole launch, outputs are time-major.
+// One thread owns 2 consecutive envs.  Two loop bodies:
+//   FAST  — a full warp (64 envs), n even (every time-major row 16-byte aligned) and all four outputs
+//           obs | rew | done | info requested (or none at all): no per-env validity tests, no per-output
+//           pointer tests, running output pointers (no 64-bit index arithmetic per step), one 128-bit
+//           reward store per thread, Philox round keys from the parameter bank, statistics flushed every
+//           32 steps instead of every step.
+//   SLOW  — the ragged last warp, odd n, or a partial output selection / the action log: the general code.
+// The round-2 profile (profiles/r02_rollout_*.md) showed the kernel at 70 % of its issue slots with
+// 764 warp-instructions per 2 env-steps, only 238 of them float64 arithmetic or conversions; FAST is the diet.
 // =================================================================================================
-// 4 resident blocks per SM (120 registers, no spills): the rollout is latency-bound (FP64 chains), so 16 warps per SM
-// beat 12 at 158 registers (15.5 vs 16.1 us per 2^20-env step with all outputs); 5 and 6 blocks spill and tie, 8 loses.
 #ifndef MG_ROLLOUT_MIN_BLOCKS
 #define MG_ROLLOUT_MIN_BLOCKS 4
 #endif
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };          // key schedule of Philox4x32-10: k + r * Weyl constant
+struct RollEnv {                                         // two envs of one thread
+    double p1[2], v1[2], p2[2], v2[2], R1[2], R2[2];
+    uint32_t steps[2], winner[2], resets[2];
+    bool sticky[2];
+};
+
+__device__ __forceinline__ void philox_actions_keyed(const PhiloxKeys &K, uint64_t env_id, uint32_t s_lo, uint32_t s_hi,
+                                                     int &a1, int &a2) {
+    uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = s_lo, c3 = s_hi;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ K.k0[r], n2 = hi0 ^ c3 ^ K.k1[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    a1 = (int)__umulhi(c0, 5u);
+    a2 = (int)__umulhi(c1, 5u);
+}
+
+template <bool RR>
+__device__ __forceinline__ void roll_reset(RollEnv &e, int j, const MgResetSpec &rs, uint64_t local_id, float *obs) {
+    if (RR) {
+        EnvRegs t;
+        random_start(t, rs.seed, rs.env_id_base + local_id, e.resets[j]);
+        e.p1[j] = t.p1; e.v1[j] = t.v1; e.p2[j] = t.p2; e.v2[j] = t.v2;
+        observe(t, obs);
+    } else {
+        e.p1[j] = kStart; e.v1[j] = kInitVel; e.p2[j] = kStart; e.v2[j] = kInitVel;
+        reset_obs_fixed(obs);
+    }
+    e.R1[j] = 0.0; e.R2[j] = 0.0;
+    e.steps[j] = 0u; e.winner[j] = 0u; e.sticky[j] = false;
+    e.resets[j] += 1u;
+}
+
 template <bool PVP, bool RR, bool RET>
 __global__ void __launch_bounds__(kBlock, MG_ROLLOUT_MIN_BLOCKS)
 merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actions_out, const int64_t n,
-                     const uint64_t seed, const uint64_t env_id_base, const uint64_t step0,
+                     const PhiloxKeys keys, const uint64_t env_id_base, const uint64_t step0,
                      const int k_steps, const MgRewards rw, const uint32_t flags, const MgResetSpec rs,
                      unsigned long long *__restrict__ stats) {
     constexpr int EPT = 2;
@@ -282,78 +326,160 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
     if (warp_base >= n) return;
-    // time-major obs rows start at t*n*40 bytes: 16-byte aligned for every t only if n is even
-    const bool full = (warp_base + 32 * EPT <= n) && ((n & 1) == 0);
     const int64_t e0 = warp_base + (int64_t)lane * EPT;
     const bool auto_reset = (flags & MG_FLAG_AUTO_RESET) != 0u;
+    const bool all_out = o.obs && o.rew && o.done && o.info, no_out = !o.obs && !o.rew && !o.done && !o.info;
+    // time-major rows start at t*n*{40,8,1} bytes: aligned for the vector stores at every t only if n is even
+    const bool full = (warp_base + 32 * EPT <= n) && ((n & 1) == 0);
 
-    EnvRegs env[EPT];
+    RollEnv env;
     bool valid[EPT];
+    bool in_range = true;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
         const int64_t e = e0 + j;
         valid[j] = e < n;
-        if (valid[j]) env[j] = EnvRegs{s.pos1[e], s.vel1[e], s.pos2[e], s.vel2[e], RET ? s.ret1[e] : 0.0, RET ? s.ret2[e] : 0.0, s.meta[e]};
-        else reset_regs(env[j]);
+        uint32_t m = 0u;
+        if (valid[j]) {
+            env.p1[j] = s.pos1[e]; env.v1[j] = s.vel1[e]; env.p2[j] = s.pos2[e]; env.v2[j] = s.vel2[e];
+            env.R1[j] = RET ? s.ret1[e] : 0.0; env.R2[j] = RET ? s.ret2[e] : 0.0;
+            m = s.meta[e];
+        } else {
+            env.p1[j] = kStart; env.v1[j] = kInitVel; env.p2[j] = kStart; env.v2[j] = kInitVel;
+            env.R1[j] = env.R2[j] = 0.0;
+        }
+        env.steps[j] = m & MG_META_STEPS_MASK;
+        env.winner[j] = (m >> MG_META_WINNER_SHIFT) & 3u;
+        env.sticky[j] = (m & MG_META_DONE) != 0u;
+        env.resets[j] = m >> MG_META_RESETS_SHIFT;
+        // the in-range polynomial needs 0 <= lon <= 24000 for the whole launch: true with auto-reset when it holds now
+        // (<= 8 per step, time limit after 2501 steps); random starts draw p1 from N(50, 5)
+        in_range &= env.p1[j] >= 0.0 && env.p1[j] <= 3000.0 && env.p2[j] >= 0.0 && env.p2[j] <= 3000.0 &&
+                    env.steps[j] <= (uint32_t)kMaxSteps;
     }
     unsigned long long *stats_row = stats ? stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS : nullptr;
     float *my_stage = &stage[warp][lane * EPT * MG_OBS_DIM];
+    const uint64_t gid0 = env_id_base + (uint64_t)e0;
+    const bool fast = full && (all_out || no_out) && !actions_out && auto_reset && !RR &&
+                      __all_sync(0xFFFFFFFFu, in_range);
 
-    for (int t = 0; t < k_steps; ++t) {
+    if (fast) {
+        // ---------------- FAST loop ----------------
+        float4 *obs_p = all_out ? reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM) + lane : nullptr;
+        float4 *rew_p = all_out ? reinterpret_cast<float4 *>(o.rew + 2 * e0) : nullptr;
+        uchar2 *done_p = all_out ? reinterpret_cast<uchar2 *>(o.done + e0) : nullptr;
+        uchar2 *info_p = all_out ? reinterpret_cast<uchar2 *>(o.info + e0) : nullptr;
+        const int64_t obs_stride = n * MG_OBS_DIM / 4, rew_stride = n / 2, byte_stride = n / 2;    // per step, in elements
         StatAcc st;
-        const int64_t toff = (int64_t)t * n;
-        int act1[EPT], act2[EPT];
-        const bool nobad[EPT] = {};
+        uint64_t step = step0;
+        for (int t = 0; t < k_steps; ++t, ++step) {
+            int act1[EPT], act2[EPT];
 #pragma unroll
-        for (int j = 0; j < EPT; ++j)
-            philox_actions(seed, env_id_base + (uint64_t)(e0 + j), step0 + (uint64_t)t, act1[j], act2[j]);
-        StepResult res[EPT];
-        env_step_batch<PVP, EPT, RET>(env, act1, act2, nobad, rw, res);
+            for (int j = 0; j < EPT; ++j)
+                philox_actions_keyed(keys, gid0 + (uint64_t)j, (uint32_t)step, (uint32_t)(step >> 32), act1[j], act2[j]);
+            float obs[EPT][MG_OBS_DIM], r1[EPT], r2[EPT];
+            StepFlags fl[EPT];
+            env_step_core<PVP, EPT, RET, false>(env.p1, env.v1, env.p2, env.v2, env.R1, env.R2, env.steps, env.winner,
+                                                env.sticky, act1, act2, rw, obs, r1, r2, fl);
+            uint32_t info[EPT];
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const int64_t e = e0 + j;
-            const int a1 = act1[j], a2 = act2[j];
-            StepResult &r = res[j];
-            if (valid[j]) {
-                if (stats) st.add(r, env[j].R1, env[j].R2);
-                if (r.finished) write_episode_outputs(o, e, r, env[j].R1, env[j].R2);
-            }
-            if (r.done && auto_reset) reset_env<RR>(env[j], rs, (uint64_t)e, r.obs);
-            if (valid[j]) {
-                if (o.rew) __stcs(reinterpret_cast<float2 *>(o.rew + 2 * (toff + e)), make_float2(r.r1, r.r2));
-                if (o.done) __stcs(o.done + toff + e, (uint8_t)(r.done ? 1 : 0));
-                if (o.info) __stcs(o.info + toff + e, (uint8_t)r.info);
-                if (actions_out) __stcs(reinterpret_cast<uchar2 *>(actions_out + 2 * (toff + e)),
-                                        make_uchar2((uint8_t)a1, (uint8_t)(PVP ? a2 : 0)));
-            }
-            if (o.obs) {
-                if (full) {
+            for (int j = 0; j < EPT; ++j) {
+                info[j] = info_byte(fl[j], env.winner[j], false);
+                if (fl[j].done) {                       // rare: ~0.5 % of envs per step
+                    StepResult r;
+                    r.info = info[j]; r.steps = env.steps[j]; r.finished = fl[j].finished; r.done = true;
+                    if (stats) st.add(r, env.R1[j], env.R2[j]);
+                    if (o.term_obs || o.ep_ret || o.ep_len) {
 #pragma unroll
-                    for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = r.obs[k];
-                } else if (valid[j]) {
-                    float *row = o.obs + (toff + e) * MG_OBS_DIM;
-#pragma unroll
-                    for (int k = 0; k < MG_OBS_DIM; ++k) row[k] = r.obs[k];
+                        for (int k = 0; k < MG_OBS_DIM; ++k) r.obs[k] = obs[j][k];
+                        write_episode_outputs(o, e0 + j, r, env.R1[j], env.R2[j]);
+                    }
+                    roll_reset<false>(env, j, rs, (uint64_t)(e0 + j), obs[j]);
                 }
             }
-        }
-        if (o.obs && full) {
-            __syncwarp();
-            const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
-            float4 *dst = reinterpret_cast<float4 *>(o.obs + (toff + warp_base) * MG_OBS_DIM);
+            if (all_out) {
 #pragma unroll
-            for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
-            __syncwarp();
+                for (int j = 0; j < EPT; ++j)
+#pragma unroll
+                    for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = obs[j][k];
+                __stcs(rew_p, make_float4(r1[0], r2[0], r1[1], r2[1]));
+                __stcs(reinterpret_cast<unsigned short *>(done_p),
+                       (unsigned short)((fl[0].done ? 1u : 0u) | (fl[1].done ? 0x100u : 0u)));
+                __stcs(reinterpret_cast<unsigned short *>(info_p), (unsigned short)(info[0] | (info[1] << 8)));
+                __syncwarp();
+                const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]) + lane;
+#pragma unroll
+                for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(obs_p + 32 * k, src[32 * k]);
+                __syncwarp();
+                obs_p += obs_stride; rew_p += rew_stride; done_p += byte_stride; info_p += byte_stride;
+            }
+            if (stats && ((t & 31) == 31)) { flush_stats(st, stats_row, 0xFFFFFFFFu, lane); st = StatAcc(); }
         }
         if (stats) flush_stats(st, stats_row, 0xFFFFFFFFu, lane);
+    } else {
+        // ---------------- SLOW loop: any n, any output selection ----------------
+        for (int t = 0; t < k_steps; ++t) {
+            StatAcc st;
+            const int64_t toff = (int64_t)t * n;
+            const uint64_t step = step0 + (uint64_t)t;
+            int act1[EPT], act2[EPT];
+#pragma unroll
+            for (int j = 0; j < EPT; ++j)
+                philox_actions_keyed(keys, gid0 + (uint64_t)j, (uint32_t)step, (uint32_t)(step >> 32), act1[j], act2[j]);
+            float obs[EPT][MG_OBS_DIM], r1[EPT], r2[EPT];
+            StepFlags fl[EPT];
+            env_step_core<PVP, EPT, RET, true>(env.p1, env.v1, env.p2, env.v2, env.R1, env.R2, env.steps, env.winner,
+                                               env.sticky, act1, act2, rw, obs, r1, r2, fl);
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                const int64_t e = e0 + j;
+                const uint32_t info = info_byte(fl[j], env.winner[j], false);
+                if (valid[j] && (fl[j].finished || stats)) {
+                    StepResult r;
+                    r.info = info; r.steps = env.steps[j]; r.finished = fl[j].finished; r.done = fl[j].done;
+#pragma unroll
+                    for (int k = 0; k < MG_OBS_DIM; ++k) r.obs[k] = obs[j][k];
+                    if (stats) st.add(r, env.R1[j], env.R2[j]);
+                    if (fl[j].finished) write_episode_outputs(o, e, r, env.R1[j], env.R2[j]);
+                }
+                if (fl[j].done && auto_reset) roll_reset<RR>(env, j, rs, (uint64_t)e, obs[j]);
+                if (valid[j]) {
+                    if (o.rew) __stcs(reinterpret_cast<float2 *>(o.rew + 2 * (toff + e)), make_float2(r1[j], r2[j]));
+                    if (o.done) __stcs(o.done + toff + e, (uint8_t)(fl[j].done ? 1 : 0));
+                    if (o.info) __stcs(o.info + toff + e, (uint8_t)info);
+                    if (actions_out) __stcs(reinterpret_cast<uchar2 *>(actions_out + 2 * (toff + e)),
+                                            make_uchar2((uint8_t)act1[j], (uint8_t)(PVP ? act2[j] : 0)));
+                }
+                if (o.obs) {
+                    if (full) {
+#pragma unroll
+                        for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = obs[j][k];
+                    } else if (valid[j]) {
+                        float *row = o.obs + (toff + e) * MG_OBS_DIM;
+#pragma unroll
+                        for (int k = 0; k < MG_OBS_DIM; ++k) row[k] = obs[j][k];
+                    }
+                }
+            }
+            if (o.obs && full) {
+                __syncwarp();
+                const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
+                float4 *dst = reinterpret_cast<float4 *>(o.obs + (toff + warp_base) * MG_OBS_DIM);
+#pragma unroll
+                for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+                __syncwarp();
+            }
+            if (stats) flush_stats(st, stats_row, 0xFFFFFFFFu, lane);
+        }
     }
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
         const int64_t e = e0 + j;
         if (!valid[j]) continue;
-        s.pos1[e] = env[j].p1; s.vel1[e] = env[j].v1; s.pos2[e] = env[j].p2; s.vel2[e] = env[j].v2;
-        if (RET) { s.ret1[e] = env[j].R1; s.ret2[e] = env[j].R2; }
-        s.meta[e] = env[j].meta;
+        s.pos1[e] = env.p1[j]; s.vel1[e] = env.v1[j]; s.pos2[e] = env.p2[j]; s.vel2[e] = env.v2[j];
+        if (RET) { s.ret1[e] = env.R1[j]; s.ret2[e] = env.R2[j]; }
+        s.meta[e] = env.steps[j] | (env.winner[j] << MG_META_WINNER_SHIFT) | (env.sticky[j] ? MG_META_DONE : 0u) |
+                    (env.resets[j] << MG_META_RESETS_SHIFT);
     }
 }
 
@@ -601,12 +727,17 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
     const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
     const bool rr = rs.mode == MG_RESET_RANDOM;
+    mg::PhiloxKeys keys;
+    for (int r = 0; r < 10; ++r) {
+        keys.k0[r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        keys.k1[r] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
 #define MG_LAUNCH(PVP, RR)                                                                             \
     do {                                                                                               \
         if (ret) mg::merge_rollout_kernel<PVP, RR, true><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(   \
-            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
+            *state, *out, actions_out, n, keys, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
         else mg::merge_rollout_kernel<PVP, RR, false><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(      \
-            *state, *out, actions_out, n, seed, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
+            *state, *out, actions_out, n, keys, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
     } while (0)
     if (pvp) { if (rr) MG_LAUNCH(true, true); else MG_LAUNCH(true, false); }
     else     { if (rr) MG_LAUNCH(false, true); else MG_LAUNCH(false, false); }
@@ -694,28 +825,47 @@ MG_API int mg_step_host(const MgState *state, int64_t n, const uint8_t *h_a1, co
     return MG_OK;
 }
 
-MG_API int mg_step_host_async(const MgState *state, int64_t n, const uint8_t *h_a1, const uint8_t *h_a2,
-                              const MgRewards *rewards, const MgOut *d_out, const MgOut *h_out, uint32_t fields,
-                              int64_t *stats, uint32_t flags, const MgResetSpec *reset, void *stream,
-                              void *copy_stream, void *ev_stepped, void *ev_done) {
+MG_API int mg_step_host_async(const MgState *state, int64_t n, const MgHostSlot *slot, uint32_t fields,
+                              const MgRewards *rewards, int64_t *stats, uint32_t flags, const MgResetSpec *reset,
+                              void *stream, void *copy_stream, void *upload_stream) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
-    if (!state || !h_a1 || !h_out || !d_out) return fail(MG_ERR_NULL_POINTER, "state, h_a1, d_out or h_out is NULL");
-    if (!copy_stream || !ev_stepped || !ev_done || copy_stream == stream)
-        return fail(MG_ERR_NULL_POINTER, "mg_step_host_async needs a copy stream (different from stream) and two events");
+    if (!state || !slot || !slot->h_a1) return fail(MG_ERR_NULL_POINTER, "state, slot or slot.h_a1 is NULL");
+    if (!copy_stream || !slot->ev_stepped || !slot->ev_done || copy_stream == stream)
+        return fail(MG_ERR_NULL_POINTER, "mg_step_host_async needs a copy stream (different from stream) and the slot's events");
     if (fields & ~MG_FIELD_ALL) return fail(MG_ERR_BAD_FLAGS, "unknown field bits");
-    cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
-    cudaEvent_t ek = (cudaEvent_t)ev_stepped, ed = (cudaEvent_t)ev_done;
+    const bool upload = upload_stream != nullptr;
+    if (upload && (!slot->d_a1 || (slot->h_a2 && !slot->d_a2) || !slot->ev_uploaded || upload_stream == stream))
+        return fail(MG_ERR_NULL_POINTER, "upload_stream given: the slot needs d_a1 (d_a2) scratch and ev_uploaded, and a stream of its own");
+    cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream, us = (cudaStream_t)upload_stream;
+    cudaEvent_t ek = (cudaEvent_t)slot->ev_stepped, ed = (cudaEvent_t)slot->ev_done, eu = (cudaEvent_t)slot->ev_uploaded;
+    const MgOut *d_out = &slot->d_out, *h_out = &slot->h_out;
+    const size_t M = (size_t)n;
     cudaError_t e;
+    const uint8_t *k_a1 = slot->h_a1, *k_a2 = slot->h_a2;
+    if (upload && n > 0) {
+        // the actions travel by copy engine on a stream of their own (under the previous call's device-to-host copies,
+        // the other direction of the link); one copy when [a1 | a2] sit at the same distance on both sides
+        const bool joined = slot->h_a2 && slot->d_a2 > slot->d_a1 && (slot->d_a2 - slot->d_a1) == (slot->h_a2 - slot->h_a1) &&
+                            (size_t)(slot->d_a2 - slot->d_a1) < M + 4096;
+        if (joined) {
+            if ((e = cudaMemcpyAsync(slot->d_a1, slot->h_a1, (size_t)(slot->d_a2 - slot->d_a1) + M, cudaMemcpyHostToDevice, us))) return cuda_fail(e, "H2D actions");
+        } else {
+            if ((e = cudaMemcpyAsync(slot->d_a1, slot->h_a1, M, cudaMemcpyHostToDevice, us))) return cuda_fail(e, "H2D a1");
+            if (slot->h_a2 && (e = cudaMemcpyAsync(slot->d_a2, slot->h_a2, M, cudaMemcpyHostToDevice, us))) return cuda_fail(e, "H2D a2");
+        }
+        if ((e = cudaEventRecord(eu, us))) return cuda_fail(e, "mg_step_host_async upload record");
+        if ((e = cudaStreamWaitEvent(st, eu, 0))) return cuda_fail(e, "mg_step_host_async upload wait");
+        k_a1 = slot->d_a1; k_a2 = slot->h_a2 ? slot->d_a2 : nullptr;
+    }
     // d_out was last read by the copies that recorded ev_done (a never-recorded event completes at once): the
     // kernel may overwrite the slot only after them.  This wait is the only coupling between consecutive calls,
-    // so with two (d_out, h_out, ev_done) sets the kernel of call t+1 runs under the copies of call t.
+    // so with two slots the kernel of call t+1 runs under the copies of call t.
     if ((e = cudaStreamWaitEvent(st, ed, 0))) return cuda_fail(e, "mg_step_host_async slot wait");
-    if (int rc = mg_step(state, n, h_a1, h_a2, MG_ACT_U8, rewards, d_out, stats, flags, reset, stream)) return rc;
+    if (int rc = mg_step(state, n, k_a1, k_a2, MG_ACT_U8, rewards, d_out, stats, flags, reset, stream)) return rc;
     if ((e = cudaEventRecord(ek, st))) return cuda_fail(e, "mg_step_host_async event record");
     if ((e = cudaStreamWaitEvent(cs, ek, 0))) return cuda_fail(e, "mg_step_host_async event wait");
     if (n > 0) {
         // one cudaMemcpyAsync per run of selected fields that are adjacent (gap < 4 KB) at equal offsets on both sides
-        const size_t M = (size_t)n;
         const char *dp[4] = {(const char *)d_out->obs, (const char *)d_out->rew, (const char *)d_out->done, (const char *)d_out->info};
         char *hp[4] = {(char *)h_out->obs, (char *)h_out->rew, (char *)h_out->done, (char *)h_out->info};
         const size_t sz[4] = {M * MG_OBS_DIM * sizeof(float), M * 2 * sizeof(float), M, M};

@@ -558,6 +558,7 @@ class MergeVecEnv:
             self._hd_block = torch.zeros(H * n_pad * 50, dtype=torch.uint8, device=dev)
             d_obs, d_rew, d_done, d_info = _slot_views(self._hd_block, H, n, n_pad)
             self._copy_stream = self._copy_stream or torch.cuda.Stream(device=dev)
+            self._upload_stream = torch.cuda.Stream(device=dev)
             slots = []
             for k in range(H):
                 acts = torch.zeros(2 * n_pad, dtype=torch.uint8, pin_memory=True)
@@ -572,11 +573,17 @@ class MergeVecEnv:
                 h["d_out"] = nat.MgOut(d_obs[k].data_ptr(), d_rew[k].data_ptr(), d_done[k].data_ptr(), d_info[k].data_ptr(),
                                        *[None if t is None else t.data_ptr() for t in
                                          (self.terminal_obs, self.episode_return, self.episode_length)])
-                ev = (torch.cuda.Event(), torch.cuda.Event())
+                h["d_acts"] = torch.zeros(2 * n_pad, dtype=torch.uint8, device=dev)    # [a1 | a2] like the pinned side
+                ev = (torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event())
                 with torch.cuda.device(dev):
                     for e in ev:                     # torch creates the CUDA event lazily, on its first record
                         e.record(self._copy_stream)
                 h["ev"] = ev
+                h["slot"] = nat.MgHostSlot(h["a1"].data_ptr(), h["a2"].data_ptr(), h["d_acts"].data_ptr(),
+                                           h["d_acts"][n_pad:].data_ptr(), h["d_out"], h["h_out"],
+                                           ev[0].cuda_event, ev[1].cuda_event, ev[2].cuda_event)
+                h["slot_pve"] = nat.MgHostSlot(h["a1"].data_ptr(), None, h["d_acts"].data_ptr(), None, h["d_out"], h["h_out"],
+                                               ev[0].cuda_event, ev[1].cuda_event, ev[2].cuda_event)
                 h["fields"] = nat.FIELD_ALL
                 slots.append(h)
             self._copy_stream.synchronize()
@@ -613,9 +620,11 @@ class MergeVecEnv:
             raise ValueError("fields must name at least one of obs / rew / done / info")
         return m
 
-    def step_host_async(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, fields=None) -> None:
-        """Pipelined host-buffer step (`mg_step_host_async`): queues the fused step — the kernel reads the uint8
-        actions straight from this slot's pinned buffers — and the device-to-host copies of the selected `fields`
+    def step_host_async(self, a1: np.ndarray, a2: Optional[np.ndarray] = None, fields=None, upload: bool = True) -> None:
+        """Pipelined host-buffer step (`mg_step_host_async`): queues the upload of the uint8 actions from this slot's
+        pinned buffers (one cudaMemcpyAsync on a private upload stream; `upload=False`: the kernel reads them straight
+        from pinned host memory instead, which costs the concurrent device-to-host copy 1-3 % on the boxes measured,
+        `profiles/e2e_pipeline_probe.py`), the fused step, and the device-to-host copies of the selected `fields`
         (any of "obs", "rew", "done", "info"; default all four) on a private copy stream, and returns at once.
         Up to `host_slots` steps may be in flight; `step_host_wait()` hands back the oldest.  With two slots the
         kernel and action fetch of step t+1 run under the copies of step t, so the PCIe link never idles.
@@ -637,12 +646,11 @@ class MergeVecEnv:
         if a2 is not None and a2 is not npa[1]:
             npa[1][:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
         with torch.cuda.device(self.device):
-            nat.check(self._lib.mg_step_host_async(C.byref(self._state), self.num_envs, _ptr(h["a1"]),
-                                                   _ptr(h["a2"]) if a2 is not None else None, C.byref(self._rw),
-                                                   C.byref(h["d_out"]), C.byref(h["h_out"]), mask, _ptr(self.stats_buf),
-                                                   self._flags(), C.byref(self._rs), self._stream(),
-                                                   C.c_void_p(self._copy_stream.cuda_stream),
-                                                   C.c_void_p(h["ev"][0].cuda_event), C.c_void_p(h["ev"][1].cuda_event)),
+            nat.check(self._lib.mg_step_host_async(C.byref(self._state), self.num_envs,
+                                                   C.byref(h["slot"] if a2 is not None else h["slot_pve"]), mask,
+                                                   C.byref(self._rw), _ptr(self.stats_buf), self._flags(), C.byref(self._rs),
+                                                   self._stream(), C.c_void_p(self._copy_stream.cuda_stream),
+                                                   C.c_void_p(self._upload_stream.cuda_stream) if upload else None),
                       "mg_step_host_async")
         h["fields"] = mask
         self._hfly.append(k)
@@ -655,7 +663,7 @@ class MergeVecEnv:
         if not self._hfly:
             raise RuntimeError("step_host_wait() called without step_host_async()")
         h = self._hslots[self._hfly.pop(0)]
-        nat.check(self._lib.mg_step_host_wait(C.c_void_p(h["ev"][1].cuda_event)), "mg_step_host_wait")
+        nat.check(self._lib.mg_step_host_wait(C.c_void_p(h["ev"][2].cuda_event)), "mg_step_host_wait")
         m = h["fields"]
         return tuple(v if m & (1 << i) else None for i, v in enumerate(h["np_out"]))
 
@@ -681,7 +689,7 @@ class MergeVecEnv:
             raise RuntimeError("step_host() while step_host_async() calls are in flight: call step_host_wait() first")
         if fields is not None:
             self._hnext = 0
-            self.step_host_async(a1, a2, fields)
+            self.step_host_async(a1, a2, fields, upload=not direct_actions)
             self._hnext = 0
             return self.step_host_wait()
         n = self.num_envs

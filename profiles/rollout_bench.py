@@ -33,6 +33,6 @@ res = {}
 for name, kw in [("all_outputs", dict(obs=obs, rew=rew, done=done, info=info)),
                  ("all_outputs+actions", dict(obs=obs, rew=rew, done=done, info=info, actions=acts)),
                  ("no_outputs", {}), ("obs_only", dict(obs=obs))]:
-    ms = timed(lambda: env.rollout(K, **kw))
+    ms = timed(lambda: env.rollout(K, refresh_obs=False, **kw))
     res[name] = {"us_per_step": 1e3 * ms / K, "env_steps_per_s": n * K / (ms * 1e-3)}
 print(json.dumps({"K": K, "envs": n, "lib": os.environ.get("MERGING_B200_LIB", "default"), **res}))

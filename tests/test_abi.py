@@ -84,6 +84,7 @@ def test_header_macros_match_binding():
 def test_struct_sizes():
     assert C.sizeof(nat.MgState) == 7 * 8 and C.sizeof(nat.MgOut) == 7 * 8
     assert C.sizeof(nat.MgRewards) == 5 * 8 and C.sizeof(nat.MgResetSpec) == 24
+    assert C.sizeof(nat.MgHostSlot) == 4 * 8 + 2 * 7 * 8 + 3 * 8
     assert C.sizeof(nat.MgConstants) == 9 * 8 + 7 * 4 + 4 + 8      # 4 bytes padding before the double
 
 
@@ -112,7 +113,11 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mg_mlp_act_tc(None, None, 8, 10, 5, None, None, None, None, None, None, None, None, 0x10, None) == -4
     assert lib.mg_record_transitions(*([None] * 10), 8, 0, 3, 1, None, 16, None, None, None, None) == -4
     assert lib.mg_step_host(None, 8, *([None] * 8), 0, None, None, None, 1) == -1
-    assert lib.mg_step_host_async(None, 8, *([None] * 5), 0xF, None, 0, None, None, None, None, None) == -1
+    assert lib.mg_step_host_async(None, 8, None, 0xF, None, None, 0, None, None, None, None) == -1
+    slot = nat.MgHostSlot()
+    slot.h_a1 = 0x1000
+    assert lib.mg_step_host_async(C.byref(nat.MgState()), 8, C.byref(slot), 0xF, None, None, 0, None, None, None, None) == -1  # no copy stream
+    assert lib.mg_step_host_async(C.byref(nat.MgState()), 8, C.byref(slot), 0x1F, None, None, 0, None, None, 0x10, None) == -1  # no events
     assert lib.mg_step_host_wait(None) == -1
     # the lean state: MG_FLAG_NO_RETURNS accepts NULL ret1/ret2 but refuses an episode-return output
     lean = nat.MgState(0x1000, 0x1000, 0x1000, 0x1000, None, None, 0x1000)

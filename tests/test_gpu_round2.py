@@ -111,7 +111,9 @@ def test_lanes_inside_a_cuda_graph(mg):
 
 
 # ---------------------------------------------------------------------------------------------- host-buffer pipeline
-def test_step_host_async_pipeline_matches_device_path(mg):
+@pytest.mark.parametrize("upload", [True, False])
+def test_step_host_async_pipeline_matches_device_path(mg, upload):
+    """upload=True: the actions travel by cudaMemcpyAsync on an upload stream; False: the kernel reads the pinned buffers."""
     n, T = 3000, 40
     dev = mg.MergeVecEnv(n, seed=4)
     env = mg.MergeVecEnv(n, seed=4)
@@ -126,7 +128,7 @@ def test_step_host_async_pipeline_matches_device_path(mg):
             got.append([x.copy() for x in env.step_host_wait()])
         h1, h2 = env.host_action_buffers()                   # written in place: no staging copy
         h1[:] = acts[t][0]; h2[:] = acts[t][1]
-        env.step_host_async(h1, h2)
+        env.step_host_async(h1, h2, upload=upload)
     with pytest.raises(RuntimeError, match="in flight"):
         env.step_host_async(acts[0][0], acts[0][1])
     with pytest.raises(RuntimeError, match="in flight"):
