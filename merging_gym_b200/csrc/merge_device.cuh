@@ -101,9 +101,7 @@ __device__ __forceinline__ void sincos_poly(const double (&x)[M], double (&s)[M]
 // finished env without auto-reset) leave the polynomial's range: one rarely-taken branch for the
 // whole batch then uses the CUDA library sincos.
 constexpr double kPolyMaxLon = 24000.0;   // |atan2(H,R) - lon/R| <= 0.767 < pi/4 for 0 <= lon <= 24000
-// CHECK_RANGE = false: the caller guarantees 0 <= lon <= kPolyMaxLon (the rollout kernel with auto-reset: a car moves
-// at most 8 per step and the time limit resets the env after 2501 steps, so lon < 50 + 5 sigma + 20008 — it checks
-// the loaded state once instead of every step).
+// CHECK_RANGE = false: the caller guarantees lon <= kPolyMaxLon.
 template <int M, bool CHECK_RANGE = true>
 __device__ __forceinline__ void lon2coord_batch(const double (&lon)[M], const double (&sign)[M],
                                                 double (&x)[M], double (&y)[M]) {
@@ -112,7 +110,9 @@ __device__ __forceinline__ void lon2coord_batch(const double (&lon)[M], const do
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         ang[i] = __dsub_rn(kAngle0, div_const(lon[i], kR, kInvR));
-        if (CHECK_RANGE) wild |= !(lon[i] >= 0.0 && lon[i] <= kPolyMaxLon);
+        // one compare per car: catches lon beyond the polynomial's range and NaN.  Negative longitudes need no test: a
+        // car never moves backwards (vel >= 0), and even lon = -20000 keeps the angle below pi/4.
+        if (CHECK_RANGE) wild |= !(lon[i] <= kPolyMaxLon);
     }
     if (CHECK_RANGE && wild) {
 #pragma unroll

@@ -315,172 +315,195 @@ __device__ __forceinline__ void roll_reset(RollEnv &e, int j, const MgResetSpec 
     e.resets[j] += 1u;
 }
 
+__device__ __forceinline__ void roll_load(const MgState &s, int64_t e, bool valid, bool ret, RollEnv &env, int j) {
+    uint32_t m = 0u;
+    if (valid) {
+        env.p1[j] = s.pos1[e]; env.v1[j] = s.vel1[e]; env.p2[j] = s.pos2[e]; env.v2[j] = s.vel2[e];
+        env.R1[j] = ret ? s.ret1[e] : 0.0; env.R2[j] = ret ? s.ret2[e] : 0.0;
+        m = s.meta[e];
+    } else {
+        env.p1[j] = kStart; env.v1[j] = kInitVel; env.p2[j] = kStart; env.v2[j] = kInitVel;
+        env.R1[j] = env.R2[j] = 0.0;
+    }
+    env.steps[j] = m & MG_META_STEPS_MASK;
+    env.winner[j] = (m >> MG_META_WINNER_SHIFT) & 3u;
+    env.sticky[j] = (m & MG_META_DONE) != 0u;
+    env.resets[j] = m >> MG_META_RESETS_SHIFT;
+}
+__device__ __forceinline__ void roll_store(const MgState &s, int64_t e, bool ret, const RollEnv &env, int j) {
+    s.pos1[e] = env.p1[j]; s.vel1[e] = env.v1[j]; s.pos2[e] = env.p2[j]; s.vel2[e] = env.v2[j];
+    if (ret) { s.ret1[e] = env.R1[j]; s.ret2[e] = env.R2[j]; }
+    s.meta[e] = env.steps[j] | (env.winner[j] << MG_META_WINNER_SHIFT) | (env.sticky[j] ? MG_META_DONE : 0u) |
+                (env.resets[j] << MG_META_RESETS_SHIFT);
+}
+
+// FAST: whole warps only (the host launches it on the first n_fast = 64 * floor(n / 64) envs), auto-reset with the fixed
+// start, outputs either all four (OUT, n even) or none.
+#ifndef MG_ROLLOUT_FAST_MIN_BLOCKS
+#define MG_ROLLOUT_FAST_MIN_BLOCKS 6   // 80 registers (40 B spilled): 11.9 us per 2^20-env step against 12.15 at 4 blocks / 120 registers, 12.0 at 5, 14.0 at 8
+#endif
+template <bool PVP, bool RET, bool OUT>
+__global__ void __launch_bounds__(kBlock, MG_ROLLOUT_FAST_MIN_BLOCKS)
+merge_rollout_fast_kernel(const MgState s, const MgOut o, const int64_t n, const int64_t n_fast, const PhiloxKeys keys,
+                          const uint64_t env_id_base, const uint64_t step0, const int k_steps, const MgRewards rw,
+                          const MgResetSpec rs, unsigned long long *__restrict__ stats) {
+    constexpr int EPT = 2;
+    __shared__ __align__(16) float stage[OUT ? kWarps : 1][32 * EPT * MG_OBS_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
+    if (warp_base >= n_fast) return;
+    const int64_t e0 = warp_base + (int64_t)lane * EPT;
+    RollEnv env;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) roll_load(s, e0 + j, true, RET, env, j);
+    unsigned long long *stats_row = stats ? stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS : nullptr;
+    const uint64_t gid0 = env_id_base + (uint64_t)e0;
+    const bool episode_out = o.term_obs || o.ep_ret || o.ep_len;
+
+    float4 *obs_p = nullptr, *rew_p = nullptr;
+    unsigned short *done_p = nullptr, *info_p = nullptr;
+    float *my_stage = nullptr;
+    if (OUT) {
+        obs_p = reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM) + lane;
+        rew_p = reinterpret_cast<float4 *>(o.rew + 2 * e0);
+        done_p = reinterpret_cast<unsigned short *>(o.done + e0);
+        info_p = reinterpret_cast<unsigned short *>(o.info + e0);
+        my_stage = &stage[warp][lane * EPT * MG_OBS_DIM];
+    }
+    const int64_t obs_stride = n * MG_OBS_DIM / 4, half_n = n / 2;    // per step, in float4 / 2-env elements
+    StatAcc st;
+    uint64_t step = step0;
+    for (int t = 0; t < k_steps; ++t, ++step) {
+        int act1[EPT], act2[EPT];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j)
+            philox_actions_keyed(keys, gid0 + (uint64_t)j, (uint32_t)step, (uint32_t)(step >> 32), act1[j], act2[j]);
+        float obs[EPT][MG_OBS_DIM], r1[EPT], r2[EPT];
+        StepFlags fl[EPT];
+        env_step_core<PVP, EPT, RET>(env.p1, env.v1, env.p2, env.v2, env.R1, env.R2, env.steps, env.winner,
+                                     env.sticky, act1, act2, rw, obs, r1, r2, fl);
+        uint32_t info[EPT];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            info[j] = info_byte(fl[j], env.winner[j], false);
+            if (fl[j].done) {                       // rare: ~0.5 % of envs per step
+                StepResult r;
+                r.info = info[j]; r.steps = env.steps[j]; r.finished = true; r.done = true;
+                if (stats) st.add(r, env.R1[j], env.R2[j]);
+                if (episode_out) {
+#pragma unroll
+                    for (int k = 0; k < MG_OBS_DIM; ++k) r.obs[k] = obs[j][k];
+                    write_episode_outputs(o, e0 + j, r, env.R1[j], env.R2[j]);
+                }
+                roll_reset<false>(env, j, rs, (uint64_t)(e0 + j), obs[j]);   // gym-0.20: the step returns the reset obs
+            }
+        }
+        if (OUT) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j)
+#pragma unroll
+                for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = obs[j][k];
+            __stcs(rew_p, make_float4(r1[0], r2[0], r1[1], r2[1]));
+            __stcs(done_p, (unsigned short)((fl[0].done ? 1u : 0u) | (fl[1].done ? 0x100u : 0u)));
+            __stcs(info_p, (unsigned short)(info[0] | (info[1] << 8)));
+            __syncwarp();
+            const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]) + lane;
+#pragma unroll
+            for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(obs_p + 32 * k, src[32 * k]);
+            __syncwarp();
+            obs_p += obs_stride; rew_p += half_n; done_p += half_n; info_p += half_n;
+        }
+        if (stats && ((t & 31) == 31)) { flush_stats(st, stats_row, 0xFFFFFFFFu, lane); st = StatAcc(); }
+    }
+    if (stats) flush_stats(st, stats_row, 0xFFFFFFFFu, lane);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) roll_store(s, e0 + j, RET, env, j);
+}
+
+// SLOW: envs [e_begin, n) — the ragged tail behind the FAST launch, or everything when FAST does not apply.
 template <bool PVP, bool RR, bool RET>
 __global__ void __launch_bounds__(kBlock, MG_ROLLOUT_MIN_BLOCKS)
 merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actions_out, const int64_t n,
-                     const PhiloxKeys keys, const uint64_t env_id_base, const uint64_t step0,
+                     const int64_t e_begin, const PhiloxKeys keys, const uint64_t env_id_base, const uint64_t step0,
                      const int k_steps, const MgRewards rw, const uint32_t flags, const MgResetSpec rs,
                      unsigned long long *__restrict__ stats) {
     constexpr int EPT = 2;
     __shared__ __align__(16) float stage[kWarps][32 * EPT * MG_OBS_DIM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
+    const int64_t warp_base = e_begin + ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
     if (warp_base >= n) return;
     const int64_t e0 = warp_base + (int64_t)lane * EPT;
     const bool auto_reset = (flags & MG_FLAG_AUTO_RESET) != 0u;
-    const bool all_out = o.obs && o.rew && o.done && o.info, no_out = !o.obs && !o.rew && !o.done && !o.info;
-    // time-major rows start at t*n*{40,8,1} bytes: aligned for the vector stores at every t only if n is even
-    const bool full = (warp_base + 32 * EPT <= n) && ((n & 1) == 0);
+    // time-major obs rows start at t*n*40 bytes: 16-byte aligned for every t only if n is even
+    const bool full = (warp_base + 32 * EPT <= n) && ((n & 1) == 0) && ((warp_base & 1) == 0);
 
     RollEnv env;
     bool valid[EPT];
-    bool in_range = true;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-        const int64_t e = e0 + j;
-        valid[j] = e < n;
-        uint32_t m = 0u;
-        if (valid[j]) {
-            env.p1[j] = s.pos1[e]; env.v1[j] = s.vel1[e]; env.p2[j] = s.pos2[e]; env.v2[j] = s.vel2[e];
-            env.R1[j] = RET ? s.ret1[e] : 0.0; env.R2[j] = RET ? s.ret2[e] : 0.0;
-            m = s.meta[e];
-        } else {
-            env.p1[j] = kStart; env.v1[j] = kInitVel; env.p2[j] = kStart; env.v2[j] = kInitVel;
-            env.R1[j] = env.R2[j] = 0.0;
-        }
-        env.steps[j] = m & MG_META_STEPS_MASK;
-        env.winner[j] = (m >> MG_META_WINNER_SHIFT) & 3u;
-        env.sticky[j] = (m & MG_META_DONE) != 0u;
-        env.resets[j] = m >> MG_META_RESETS_SHIFT;
-        // the in-range polynomial needs 0 <= lon <= 24000 for the whole launch: true with auto-reset when it holds now
-        // (<= 8 per step, time limit after 2501 steps); random starts draw p1 from N(50, 5)
-        in_range &= env.p1[j] >= 0.0 && env.p1[j] <= 3000.0 && env.p2[j] >= 0.0 && env.p2[j] <= 3000.0 &&
-                    env.steps[j] <= (uint32_t)kMaxSteps;
+        valid[j] = e0 + j < n;
+        roll_load(s, e0 + j, valid[j], RET, env, j);
     }
     unsigned long long *stats_row = stats ? stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS : nullptr;
     float *my_stage = &stage[warp][lane * EPT * MG_OBS_DIM];
     const uint64_t gid0 = env_id_base + (uint64_t)e0;
-    const bool fast = full && (all_out || no_out) && !actions_out && auto_reset && !RR &&
-                      __all_sync(0xFFFFFFFFu, in_range);
 
-    if (fast) {
-        // ---------------- FAST loop ----------------
-        float4 *obs_p = all_out ? reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM) + lane : nullptr;
-        float4 *rew_p = all_out ? reinterpret_cast<float4 *>(o.rew + 2 * e0) : nullptr;
-        uchar2 *done_p = all_out ? reinterpret_cast<uchar2 *>(o.done + e0) : nullptr;
-        uchar2 *info_p = all_out ? reinterpret_cast<uchar2 *>(o.info + e0) : nullptr;
-        const int64_t obs_stride = n * MG_OBS_DIM / 4, rew_stride = n / 2, byte_stride = n / 2;    // per step, in elements
+    for (int t = 0; t < k_steps; ++t) {
         StatAcc st;
-        uint64_t step = step0;
-        for (int t = 0; t < k_steps; ++t, ++step) {
-            int act1[EPT], act2[EPT];
+        const int64_t toff = (int64_t)t * n;
+        const uint64_t step = step0 + (uint64_t)t;
+        int act1[EPT], act2[EPT];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j)
-                philox_actions_keyed(keys, gid0 + (uint64_t)j, (uint32_t)step, (uint32_t)(step >> 32), act1[j], act2[j]);
-            float obs[EPT][MG_OBS_DIM], r1[EPT], r2[EPT];
-            StepFlags fl[EPT];
-            env_step_core<PVP, EPT, RET, false>(env.p1, env.v1, env.p2, env.v2, env.R1, env.R2, env.steps, env.winner,
-                                                env.sticky, act1, act2, rw, obs, r1, r2, fl);
-            uint32_t info[EPT];
+        for (int j = 0; j < EPT; ++j)
+            philox_actions_keyed(keys, gid0 + (uint64_t)j, (uint32_t)step, (uint32_t)(step >> 32), act1[j], act2[j]);
+        float obs[EPT][MG_OBS_DIM], r1[EPT], r2[EPT];
+        StepFlags fl[EPT];
+        env_step_core<PVP, EPT, RET>(env.p1, env.v1, env.p2, env.v2, env.R1, env.R2, env.steps, env.winner,
+                                     env.sticky, act1, act2, rw, obs, r1, r2, fl);
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                info[j] = info_byte(fl[j], env.winner[j], false);
-                if (fl[j].done) {                       // rare: ~0.5 % of envs per step
-                    StepResult r;
-                    r.info = info[j]; r.steps = env.steps[j]; r.finished = fl[j].finished; r.done = true;
-                    if (stats) st.add(r, env.R1[j], env.R2[j]);
-                    if (o.term_obs || o.ep_ret || o.ep_len) {
+        for (int j = 0; j < EPT; ++j) {
+            const int64_t e = e0 + j;
+            const uint32_t info = info_byte(fl[j], env.winner[j], false);
+            if (valid[j] && (fl[j].finished || stats)) {
+                StepResult r;
+                r.info = info; r.steps = env.steps[j]; r.finished = fl[j].finished; r.done = fl[j].done;
 #pragma unroll
-                        for (int k = 0; k < MG_OBS_DIM; ++k) r.obs[k] = obs[j][k];
-                        write_episode_outputs(o, e0 + j, r, env.R1[j], env.R2[j]);
-                    }
-                    roll_reset<false>(env, j, rs, (uint64_t)(e0 + j), obs[j]);
-                }
+                for (int k = 0; k < MG_OBS_DIM; ++k) r.obs[k] = obs[j][k];
+                if (stats) st.add(r, env.R1[j], env.R2[j]);
+                if (fl[j].finished) write_episode_outputs(o, e, r, env.R1[j], env.R2[j]);
             }
-            if (all_out) {
-#pragma unroll
-                for (int j = 0; j < EPT; ++j)
+            if (fl[j].done && auto_reset) roll_reset<RR>(env, j, rs, (uint64_t)e, obs[j]);
+            if (valid[j]) {
+                if (o.rew) __stcs(reinterpret_cast<float2 *>(o.rew + 2 * (toff + e)), make_float2(r1[j], r2[j]));
+                if (o.done) __stcs(o.done + toff + e, (uint8_t)(fl[j].done ? 1 : 0));
+                if (o.info) __stcs(o.info + toff + e, (uint8_t)info);
+                if (actions_out) __stcs(reinterpret_cast<uchar2 *>(actions_out + 2 * (toff + e)),
+                                        make_uchar2((uint8_t)act1[j], (uint8_t)(PVP ? act2[j] : 0)));
+            }
+            if (o.obs) {
+                if (full) {
 #pragma unroll
                     for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = obs[j][k];
-                __stcs(rew_p, make_float4(r1[0], r2[0], r1[1], r2[1]));
-                __stcs(reinterpret_cast<unsigned short *>(done_p),
-                       (unsigned short)((fl[0].done ? 1u : 0u) | (fl[1].done ? 0x100u : 0u)));
-                __stcs(reinterpret_cast<unsigned short *>(info_p), (unsigned short)(info[0] | (info[1] << 8)));
-                __syncwarp();
-                const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]) + lane;
+                } else if (valid[j]) {
+                    float *row = o.obs + (toff + e) * MG_OBS_DIM;
 #pragma unroll
-                for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(obs_p + 32 * k, src[32 * k]);
-                __syncwarp();
-                obs_p += obs_stride; rew_p += rew_stride; done_p += byte_stride; info_p += byte_stride;
+                    for (int k = 0; k < MG_OBS_DIM; ++k) row[k] = obs[j][k];
+                }
             }
-            if (stats && ((t & 31) == 31)) { flush_stats(st, stats_row, 0xFFFFFFFFu, lane); st = StatAcc(); }
+        }
+        if (o.obs && full) {
+            __syncwarp();
+            const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
+            float4 *dst = reinterpret_cast<float4 *>(o.obs + (toff + warp_base) * MG_OBS_DIM);
+#pragma unroll
+            for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+            __syncwarp();
         }
         if (stats) flush_stats(st, stats_row, 0xFFFFFFFFu, lane);
-    } else {
-        // ---------------- SLOW loop: any n, any output selection ----------------
-        for (int t = 0; t < k_steps; ++t) {
-            StatAcc st;
-            const int64_t toff = (int64_t)t * n;
-            const uint64_t step = step0 + (uint64_t)t;
-            int act1[EPT], act2[EPT];
-#pragma unroll
-            for (int j = 0; j < EPT; ++j)
-                philox_actions_keyed(keys, gid0 + (uint64_t)j, (uint32_t)step, (uint32_t)(step >> 32), act1[j], act2[j]);
-            float obs[EPT][MG_OBS_DIM], r1[EPT], r2[EPT];
-            StepFlags fl[EPT];
-            env_step_core<PVP, EPT, RET, true>(env.p1, env.v1, env.p2, env.v2, env.R1, env.R2, env.steps, env.winner,
-                                               env.sticky, act1, act2, rw, obs, r1, r2, fl);
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                const int64_t e = e0 + j;
-                const uint32_t info = info_byte(fl[j], env.winner[j], false);
-                if (valid[j] && (fl[j].finished || stats)) {
-                    StepResult r;
-                    r.info = info; r.steps = env.steps[j]; r.finished = fl[j].finished; r.done = fl[j].done;
-#pragma unroll
-                    for (int k = 0; k < MG_OBS_DIM; ++k) r.obs[k] = obs[j][k];
-                    if (stats) st.add(r, env.R1[j], env.R2[j]);
-                    if (fl[j].finished) write_episode_outputs(o, e, r, env.R1[j], env.R2[j]);
-                }
-                if (fl[j].done && auto_reset) roll_reset<RR>(env, j, rs, (uint64_t)e, obs[j]);
-                if (valid[j]) {
-                    if (o.rew) __stcs(reinterpret_cast<float2 *>(o.rew + 2 * (toff + e)), make_float2(r1[j], r2[j]));
-                    if (o.done) __stcs(o.done + toff + e, (uint8_t)(fl[j].done ? 1 : 0));
-                    if (o.info) __stcs(o.info + toff + e, (uint8_t)info);
-                    if (actions_out) __stcs(reinterpret_cast<uchar2 *>(actions_out + 2 * (toff + e)),
-                                            make_uchar2((uint8_t)act1[j], (uint8_t)(PVP ? act2[j] : 0)));
-                }
-                if (o.obs) {
-                    if (full) {
-#pragma unroll
-                        for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = obs[j][k];
-                    } else if (valid[j]) {
-                        float *row = o.obs + (toff + e) * MG_OBS_DIM;
-#pragma unroll
-                        for (int k = 0; k < MG_OBS_DIM; ++k) row[k] = obs[j][k];
-                    }
-                }
-            }
-            if (o.obs && full) {
-                __syncwarp();
-                const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
-                float4 *dst = reinterpret_cast<float4 *>(o.obs + (toff + warp_base) * MG_OBS_DIM);
-#pragma unroll
-                for (int k = 0; k < EPT * MG_OBS_DIM / 4; ++k) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
-                __syncwarp();
-            }
-            if (stats) flush_stats(st, stats_row, 0xFFFFFFFFu, lane);
-        }
     }
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const int64_t e = e0 + j;
-        if (!valid[j]) continue;
-        s.pos1[e] = env.p1[j]; s.vel1[e] = env.v1[j]; s.pos2[e] = env.p2[j]; s.vel2[e] = env.v2[j];
-        if (RET) { s.ret1[e] = env.R1[j]; s.ret2[e] = env.R2[j]; }
-        s.meta[e] = env.steps[j] | (env.winner[j] << MG_META_WINNER_SHIFT) | (env.sticky[j] ? MG_META_DONE : 0u) |
-                    (env.resets[j] << MG_META_RESETS_SHIFT);
-    }
+    for (int j = 0; j < EPT; ++j)
+        if (valid[j]) roll_store(s, e0 + j, RET, env, j);
 }
 
 // =================================================================================================
@@ -724,7 +747,6 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
     if (!ret && out->ep_ret) return fail(MG_ERR_BAD_FLAGS, "out.ep_ret needs the return accumulators (MG_FLAG_NO_RETURNS is set)");
     const MgRewards rw = rewards ? *rewards : kDefaultRewards;
     const int64_t per_block = (int64_t)mg::kBlock * 2;
-    const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
     const bool rr = rs.mode == MG_RESET_RANDOM;
     mg::PhiloxKeys keys;
@@ -732,16 +754,37 @@ MG_API int mg_rollout(const MgState *state, int64_t n, int pvp, uint64_t seed, u
         keys.k0[r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
         keys.k1[r] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
+    cudaStream_t cst = (cudaStream_t)stream;
+    // FAST kernel on the whole warps when it applies (see merge_rollout_fast_kernel), SLOW kernel on the rest
+    const bool all_out = out->obs && out->rew && out->done && out->info;
+    const bool no_out = !out->obs && !out->rew && !out->done && !out->info;
+    const bool fast_ok = (flags & MG_FLAG_AUTO_RESET) && !rr && !actions_out && (no_out || (all_out && (n & 1) == 0));
+    const int64_t n_fast = fast_ok ? n / 64 * 64 : 0;
+    if (n_fast > 0) {
+        const unsigned grid = (unsigned)((n_fast + per_block - 1) / per_block);
+#define MG_FAST(PVP, RET, OUT)                                                                            \
+        mg::merge_rollout_fast_kernel<PVP, RET, OUT><<<grid, mg::kBlock, 0, cst>>>(                      \
+            *state, *out, n, n_fast, keys, env_id_base, step0, k_steps, rw, rs, stp)
+        if (pvp) { if (ret) { if (all_out) MG_FAST(true, true, true); else MG_FAST(true, true, false); }
+                   else     { if (all_out) MG_FAST(true, false, true); else MG_FAST(true, false, false); } }
+        else     { if (ret) { if (all_out) MG_FAST(false, true, true); else MG_FAST(false, true, false); }
+                   else     { if (all_out) MG_FAST(false, false, true); else MG_FAST(false, false, false); } }
+#undef MG_FAST
+        if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_rollout launch (fast)");
+    }
+    if (n_fast < n) {
+        const unsigned grid = (unsigned)((n - n_fast + per_block - 1) / per_block);
 #define MG_LAUNCH(PVP, RR)                                                                             \
     do {                                                                                               \
-        if (ret) mg::merge_rollout_kernel<PVP, RR, true><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(   \
-            *state, *out, actions_out, n, keys, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
-        else mg::merge_rollout_kernel<PVP, RR, false><<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(      \
-            *state, *out, actions_out, n, keys, env_id_base, step0, k_steps, rw, flags, rs, stp);      \
+        if (ret) mg::merge_rollout_kernel<PVP, RR, true><<<grid, mg::kBlock, 0, cst>>>(                \
+            *state, *out, actions_out, n, n_fast, keys, env_id_base, step0, k_steps, rw, flags, rs, stp);  \
+        else mg::merge_rollout_kernel<PVP, RR, false><<<grid, mg::kBlock, 0, cst>>>(                   \
+            *state, *out, actions_out, n, n_fast, keys, env_id_base, step0, k_steps, rw, flags, rs, stp);  \
     } while (0)
-    if (pvp) { if (rr) MG_LAUNCH(true, true); else MG_LAUNCH(true, false); }
-    else     { if (rr) MG_LAUNCH(false, true); else MG_LAUNCH(false, false); }
+        if (pvp) { if (rr) MG_LAUNCH(true, true); else MG_LAUNCH(true, false); }
+        else     { if (rr) MG_LAUNCH(false, true); else MG_LAUNCH(false, false); }
 #undef MG_LAUNCH
+    }
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_rollout launch");
     return MG_OK;
 }
