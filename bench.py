@@ -266,7 +266,7 @@ def run_reference(args):
             "data": "synthetic", "config": workload_config(n), "cpu_baseline": cpu,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     return 0
 
 
@@ -296,6 +296,13 @@ def run_b200(args):
                            env_id_base=(rank * R + r) * n, out_slots=S, episode_info=False, track_stats=True)
             for r in range(R)]
     env = envs[0]
+    laned_headline = args.headline == "laned" and args.lanes > 1
+    lenvs = None
+    if args.lanes > 1:
+        # the product API for overlapping launches: each 2^20-env shard is L lanes of 2^20/L envs on L streams
+        lenvs = [mg.MergeVecEnv(n, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=(rank * R + r) * n,
+                                out_slots=S, episode_info=False, track_stats=True, lanes=args.lanes) for r in range(R)]
+    henvs = lenvs if laned_headline else envs
     # pre-generated, HBM-resident action sets (Philox over global env ids), cycled over steps
     acts1 = torch.empty(A, n, dtype=torch.uint8, device=dev)
     acts2 = torch.empty(A, n, dtype=torch.uint8, device=dev)
@@ -303,7 +310,7 @@ def run_b200(args):
         a1, a2 = envs[i % R].sample_actions(i)
         acts1[i].copy_(a1); acts2[i].copy_(a2)
     # de-synchronise episodes so the timed region sees the steady-state reset rate (~1/210 per step)
-    for e in envs:
+    for e in envs + (lenvs or []):
         e.rollout(args.mix_steps, step0=1000)
     torch.cuda.synchronize()
 
@@ -312,12 +319,15 @@ def run_b200(args):
 
     # the path's only collective: NCCL all-reduce of the int64 statistics, on a side stream.  Banked: the launching
     # stream carries no statistics kernel at all (the side stream drains the retired bank).
-    reducer = mg.AsyncStatsReducer(env, banked=True) if world > 1 else None
+    reducer = mg.AsyncStatsReducer(henvs[0], banked=True) if world > 1 else None
     if reducer is not None:                               # NCCL communicator set-up happens here, untimed
         reducer.submit()
         reducer.latest()
         torch.cuda.synchronize()
         reducer.submissions = 0
+
+    gate_hz = 1e3 * float(getattr(torch.cuda.get_device_properties(dev), "clock_rate", 1.9e6))   # kHz -> Hz
+    last_host_ms = [0.0]
 
     def timed_region(shards, K, W, sample_clocks, n_streams=1, graph_steps=None, lanes=False):
         """W warm-up + K timed step launches round-robin over `shards`; returns (ms, G, eager, clocks).
@@ -366,7 +376,7 @@ def run_b200(args):
         cyc = cyc * A // math.gcd(cyc, A)                 # slot ring, shard ring and action ring line up
         if not args.no_graph and K >= cyc:
             G = (min(K, max(gsteps, cyc)) // cyc) * cyc
-        use_reducer = reducer is not None and sample_clocks and shards[0] is env
+        use_reducer = reducer is not None and sample_clocks and shards[0] is reducer.env
         if G > 0:
             rewind()
             side = torch.cuda.Stream()
@@ -395,18 +405,25 @@ def run_b200(args):
         torch.cuda.synchronize()
         if sampler:
             sampler.start()
+        # Gate: a spin kernel keeps the stream busy for ~args.gate_ms while the host queues the whole region behind
+        # it, so the events time the DEVICE executing K back-to-back launches and not how fast this host thread
+        # (one of N ranks sharing the box's cores) issues a graph launch / an NCCL call.  Device time only either way.
+        if args.gate_ms > 0:
+            torch.cuda._sleep(int(args.gate_ms * 1e-3 * gate_hz))
+        h0 = time.perf_counter()
         e0.record()
         done_steps = 0
         if graphs is not None:
             for _ in range(K // G):
                 if use_reducer:
-                    reducer.replay(graphs)
-                    reducer.submit()                      # headline region only: async NCCL stats reduce
+                    reducer.submit()                      # headline region only: the async NCCL statistics reduce of
+                    reducer.replay(graphs)                # everything so far runs on its side stream UNDER these launches
                 else:
                     graphs[0].replay()
                 done_steps += G
         do_steps(K - done_steps)
         e1.record()
+        host_ms = 1e3 * (time.perf_counter() - h0)
         if sampler:
             sampler.sample_now()                          # the queue is still draining: a sample under load
         torch.cuda.synchronize()
@@ -415,6 +432,7 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        last_host_ms[0] = host_ms
         return float(t.item()), G, K - done_steps, clocks
 
     total_envs = n * world                               # envs advanced per step (one launch per GPU)
@@ -424,10 +442,16 @@ def run_b200(args):
         return {"value": total_envs * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k, "steps": k,
                 "algorithmic_gbs_per_gpu": gbs, "frac_of_peak": gbs / peak}
 
-    ms, G, eager, clocks = timed_region(envs, K, W, True)
+    ms, G, eager, clocks = timed_region(henvs, K, W, True, lanes=laned_headline)
+    host_issue_ms = last_host_ms[0]
     value = total_envs * K / (ms * 1e-3)
     per_gpu_gbs = n * K * BYTES_PER_ENV_STEP / (ms * 1e-3) / 1e9
     n_reductions = reducer.submissions if reducer else 0
+    # the other launch scheme over the same K steps, reported beside the headline
+    other = None
+    if lenvs is not None:
+        ms_o, G_o, _, _ = timed_region(envs if laned_headline else lenvs, K, W, False, lanes=not laned_headline)
+        other = dict(rate(ms_o, K), launch=f"CUDA graph of {G_o} steps" if G_o else "eager")
 
     # ---- sustained: the same region at 2000 steps (graph of 200) whatever --steps says ------------------------
     sustained = None
@@ -435,7 +459,7 @@ def run_b200(args):
         if K >= args.sustained_steps:
             sustained = dict(rate(ms, K), note="the headline region itself")
         else:
-            ms_s, G_s, _, _ = timed_region(envs, args.sustained_steps, W, False)
+            ms_s, G_s, _, _ = timed_region(henvs, args.sustained_steps, W, False, lanes=laned_headline)
             sustained = dict(rate(ms_s, args.sustained_steps),
                              note=f"same shards and launches as `value`, {args.sustained_steps} steps as a CUDA graph of {G_s} "
                                   "replayed; shows what the short driver-run region (--steps) cannot amortise")
@@ -455,21 +479,17 @@ def run_b200(args):
                                "the serialised 2^20-env launch from the copy peak; launches are concurrent, so this "
                                "is aggregate throughput and is not used for value/roofline")
 
-    # ---- extra: the product API for that overlap — MergeVecEnv(lanes=2): each 2^20-env shard is two 2^19-env lanes
-    #      on two streams, a lane depending only on its own previous step ------------------------------------------
-    laned = None
-    if args.lanes > 1:
-        lenvs = [mg.MergeVecEnv(n, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=(rank * R + r) * n,
-                                out_slots=S, episode_info=False, track_stats=True, lanes=args.lanes) for r in range(R)]
-        for e in lenvs:
-            e.rollout(args.mix_steps, step0=1000)
-        ms_l, _, _, _ = timed_region(lenvs, Ko, W, False, lanes=True)
-        laned = dict(rate(ms_l, Ko), lanes=args.lanes, launches_per_step=args.lanes,
-                     note=f"MergeVecEnv(lanes={args.lanes}): the same {R} x 2^20-env shards round-robin, each step issued as "
-                          f"{args.lanes} launches of 2^20/{args.lanes} envs on the lanes' own streams (bit-identical results, "
-                          "tests/test_gpu_lanes.py); aggregate throughput of overlapping launches, not used for value/roofline")
-        del lenvs
-
+    # ---- extra: the other launch scheme at the longer step count -------------------------------------------------
+    laned = serialized = None
+    if lenvs is not None:
+        ms_l, _, _, _ = timed_region(envs if laned_headline else lenvs, Ko, W, False, lanes=not laned_headline)
+        o = dict(rate(ms_l, Ko), at_headline_steps=other)
+        if laned_headline:
+            serialized = dict(o, note="one mg_step launch per 2^20-env step, all on ONE stream (round 1's headline): each launch "
+                                      "pays its own ramp-up and drain")
+        else:
+            laned = dict(o, lanes=args.lanes, launches_per_step=args.lanes,
+                         note=f"MergeVecEnv(lanes={args.lanes}): each step issued as {args.lanes} launches on the lanes' streams")
     # ---- extra: track_returns=False (no float64 return accumulators): 124 B/env-step ------------------------------
     lean = None
     if args.lean:
@@ -685,6 +705,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return 0
 
+    LPS = henvs[0].lanes
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _, _ = cpu_baseline_object(args.cpu_seconds, ref_steps=args.ref_python_steps)
@@ -692,18 +713,33 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(n),
-            "measurement": {"total_envs": total_envs, "envs_per_launch": n, "shards_per_gpu": R,
-                            "launch": (f"CUDA graph of {G} mg_step launches replayed {K // G}x + {eager} eager"
+            "measurement": {"total_envs": total_envs, "envs_per_step": n, "launches_per_step": LPS,
+                            "envs_per_launch": n // LPS, "shards_per_gpu": R,
+                            "scheme": (f"MergeVecEnv(lanes={LPS}): a step of a 2^20-env shard = {LPS} mg_step launches of "
+                                       f"{n // LPS} envs, lane l on its own CUDA stream and ordered only behind lane l's previous "
+                                       "step, so one lane's launch ramps up while the other's drains (bit-identical to one "
+                                       "launch: tests/test_gpu_round2.py); `serialized` = one launch per step on one stream"
+                                       if laned_headline else "one mg_step launch per step on one stream"),
+                            "launch": (f"CUDA graph of {G} steps ({G * LPS} mg_step launches) replayed {K // G}x + {eager} eager steps"
                                        if G else "eager ctypes launches"),
+                            "gate": (f"a {args.gate_ms} ms spin kernel precedes the start event, so the host has queued the region "
+                                     "before the device starts it" if args.gate_ms > 0 else "none"),
+                            "host_issue_ms": host_issue_ms,
                             "state_mb": R * n * 52 / 1e6, "action_sets": A, "ring_slots": S,
                             "parallelism": f"env-sharded x{world}, no data-path collective; NCCL all-reduce of 16 int64 "
-                                           f"stats on a side stream after every graph replay inside the timed region "
-                                           f"({n_reductions} reductions; banked: no statistics kernel on the timed stream)"},
+                                           f"stats on a side stream before every graph replay inside the timed region, running "
+                                           f"under the step launches ({n_reductions} reductions; banked: no statistics kernel "
+                                           "on the timed streams)"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
                          "frac": per_gpu_gbs / peak, "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
                          "kernel": "mg::merge_step_kernel<2, uint8_t, true, false, true>",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src,
-                         "per": "GPU; achieved = 156 B x envs_per_gpu / (timed ms / steps)"},
+                         "per": ("GPU; achieved = 156 B x envs stepped in the timed region / its duration (CUDA events); with "
+                                 f"{LPS} lanes the launches overlap, so this is the rate of the kernel over the region, not of "
+                                 "one isolated launch (that one is `serialized`); traffic = ncu DRAM bytes of one 2^20-env launch"
+                                 if laned_headline else
+                                 "GPU; achieved = 156 B x envs_per_gpu / (timed ms / steps)")},
+            "serialized": serialized,
             "sustained": sustained,
             "l2_warm": dict(rate(ms_warm, Kw),
                             note="one 2^20-env shard stepped in place (the literal 1M-envs/GPU deployment): its "
@@ -716,16 +752,35 @@ def run_b200(args):
             "rollout_fused": rollout,
             "policy_in_loop": policy,
             "strong_8m": strong,
-            "e2e": e2e, "gpu_launches": K, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": K * LPS, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "collision_rate", "merge_success_rate",
                                                     "mean_length", "mean_return1", "mean_return2")}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line there.  Everything but `emit()`
+    goes to stderr from here on."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def main():
@@ -753,11 +808,18 @@ def main():
     ap.add_argument("--policy-envs", type=int, default=1 << 18, help="configs[4] envs per GPU (0 = skip)")
     ap.add_argument("--ref-python-steps", type=int, default=3000,
                     help="steps per process when timing the reference's own Python env (0 = skip)")
+    ap.add_argument("--gate-ms", type=float, default=4.0,
+                    help="spin-kernel gate in front of every timed region so that the host has queued the region before "
+                         "the device starts it (0 = none)")
+    ap.add_argument("--headline", default="laned", choices=["laned", "serialized"],
+                    help="what `value` measures: MergeVecEnv(lanes=L) (each step = L launches on L streams) or one "
+                         "launch per step on one stream; the other one is reported beside it")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
