@@ -70,6 +70,12 @@ def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="c
         pol.act(obs, out=act)
         env.step_async(act, None)
 
+    def one_step_fused():                          # mg_policy_step: forward + arg-max + env step in ONE launch
+        if policy == "dqn":
+            env.policy_step(pol)
+        else:
+            pol.step(env)
+
     side = torch.cuda.Stream(device=device)
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):                  # warm-up (module loading) and episode mixing outside any capture
@@ -81,7 +87,15 @@ def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="c
     ms_step = graph_ms(one_step, k, replays)
     st = env.stats()
     ms_pol = graph_ms(policy_only, k, replays)
-    return {"value": n / (ms_step * 1e-3), "unit": "env-steps/s per GPU", "envs": n, "policy": policy, "backend": backend,
+    fused = None
+    if backend in ("fused", "tf32x3"):
+        for _ in range(3):
+            one_step_fused()
+        ms_f = graph_ms(one_step_fused, k, replays)
+        fused = {"value": n / (ms_f * 1e-3), "ms_per_step": ms_f, "launches_per_step": 1 if policy == "dqn" else 2,
+                 "note": "mg_policy_step: the env step is the epilogue of the policy kernel (no action array, no second "
+                         "launch); bit-identical to the separate launches (tests/test_gpu_fused_policy.py)"}
+    return {"value": n / (ms_step * 1e-3), "fused_step": fused, "unit": "env-steps/s per GPU", "envs": n, "policy": policy, "backend": backend,
             "ms_per_step": ms_step, "policy_ms": ms_pol, "env_ms": ms_step - ms_pol,
             "env_share": (ms_step - ms_pol) / ms_step,
             "policy_tflops": n * flops / (ms_pol * 1e-3) / 1e12, "weights": weights,

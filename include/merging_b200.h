@@ -37,7 +37,7 @@ extern "C" {
 #define MG_API __attribute__((visibility("default")))
 #endif
 
-#define MG_ABI_VERSION 4
+#define MG_ABI_VERSION 5
 #define MG_OBS_DIM 10      /* merging_env.py:75,118-132 */
 #define MG_NUM_ACTIONS 5   /* merging_env.py:101-102   */
 
@@ -260,6 +260,49 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
                          const float *b2, const float *w3, const float *b3, uint8_t *actions,
                          float *q_out_or_null, uint32_t flags, void *stream);
 
+
+/* ---- "next" row 8f-4 / 8f-1: one policy-in-the-loop iteration per launch ------------------------------------
+ * The reference scripts' inner loop (scripts/main.py:194-211, scripts/hdqn.py:288-316)
+ *     action = dqn.choose_action(state)                     # Net forward + torch.max, or a random action
+ *     next_state, rewards, done, info = env.step(action, action_op)
+ * for n envs in ONE kernel: the Q-network forward + arg-max of mg_mlp_act (backend 0, fp32 FFMA: the reference's
+ * arithmetic) or mg_mlp_act_tc (backend 1, tcgen05 3xTF32) with MergeEnv.step as its epilogue — the thread that
+ * finishes env e's arg-max also owns env e's state, applies the exploration rule, steps the env and writes the next
+ * observation row where the next launch's layer-1 read expects it.  Bit-identical to mg_mlp_act[_tc] followed by
+ * mg_step on the same inputs.
+ *   obs_in          float[n,10]: the observation the policy acts on (observe() of `state`); out->obs may alias it
+ *   goal_or_null    uint8[n]: the h-DQN controller's `[goal] + state` input column (hdqn.py:291); network input 11
+ *   w1t..b3         as mg_mlp_act (backend 0: w2 = w2p) or mg_mlp_act_tc (backend 1: w2 = w2_tc); out_dim is 5
+ *   a2_or_null      uint8[n] actions of player 2 (pvp), NULL = `action_op = None` (pve)
+ *   flags           MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE (MG_FLAG_NO_RETURNS is implied by state->ret1 == NULL)
+ *   explore         the scripts' rule `np.random.randn() <= EPISILO ? greedy : np.random.randint(0, 5)` (main.py:103-110):
+ *                   randn() <= t has probability Phi(t), so keep_u32 = floor(Phi(t) * 2^32) and the greedy action is
+ *                   kept iff a Philox u32 < keep_u32; the draws are Philox4x32-10 keyed by seed ^ ('EXPL' << 32) with
+ *                   counter (global env id = reset->env_id_base + e, step ^ env clock), the env clock being the env's meta word
+ *                   without its done bit (reset count, winner, steps since reset — never repeats for an env): sharding- and
+ *                   launch-invariant, and a CUDA graph replaying identical parameters still draws fresh numbers
+ *   actions_out     uint8[n] or NULL: the action taken (what `store_transition` records, main.py:207)
+ *   q_out_or_null   float[n,5] Q-values */
+#define MG_POLICY_FLAG_EXPLORE 0x100u
+#define MG_POLICY_BACKEND_FP32 0
+#define MG_POLICY_BACKEND_TF32X3 1
+typedef struct MgExplore {
+    uint64_t seed, step;
+    uint32_t keep_u32, reserved;
+} MgExplore;
+MG_API int mg_policy_step(const MgState *state, int64_t n, const float *obs_in, const uint8_t *goal_or_null,
+                          int32_t backend, const float *w1t, const float *b1, const float *w2, const float *b2,
+                          const float *w3, const float *b3, const uint8_t *a2_or_null, const MgRewards *rewards,
+                          const MgOut *out, int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
+                          const MgExplore *explore_or_null, uint8_t *actions_out_or_null, float *q_out_or_null,
+                          void *stream);
+
+/* The exploration rule alone, for callers that keep policy and env in separate launches: overwrites greedy actions /
+ * goals in place (`num_choices` = 5 actions, main.py:103-110, or 3 goals, hdqn.py:84-92).  Same Philox stream as
+ * mg_policy_step when `salt` is 0; the h-DQN meta-controller uses salt 1 so that goal and action draws differ. */
+MG_API int mg_explore(uint8_t *choices, int64_t n, int32_t num_choices, const MgExplore *explore,
+                      const uint32_t *meta_or_null /* MgState.meta: the env clock, see above */, uint64_t env_id_base,
+                      uint32_t salt, void *stream);
 
 /* ---- "next" rows: device-resident transition writer -----------------------
  * Appends one row per selected env to a ring `ring[capacity][width]` (index = counter % capacity,

@@ -13,7 +13,7 @@ The package holds only what the hot path needs:
 """
 from ._native import NativeError  # noqa: F401
 from .graphed import GraphedPolicyRollout  # noqa: F401
-from .policy import HDQNPolicy, MLPPolicy, explore, goal_status  # noqa: F401
+from .policy import Exploration, HDQNPolicy, MLPPolicy, explore, goal_status  # noqa: F401
 from .replay import CsvEpisodeLogger, OptionRecorder, TransitionRecorder  # noqa: F401
 from .scalar_env import ENV_ID, MergeEnv, make, make_vec, register_gym  # noqa: F401
 from .sharding import AsyncStatsReducer, all_reduce_stats, init_distributed, shard_range  # noqa: F401

@@ -10,7 +10,7 @@ import os
 
 from ._paths import LIB_PATH
 
-MG_ABI_VERSION = 4
+MG_ABI_VERSION = 5
 OBS_DIM = 10
 NUM_ACTIONS = 5
 STATS_ROWS = 1024
@@ -19,6 +19,8 @@ STATS_COLS = 16
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 FLAG_AUTO_RESET = 0x1
 FLAG_NO_RETURNS = 0x2
+POLICY_FLAG_EXPLORE = 0x100
+POLICY_BACKEND_FP32, POLICY_BACKEND_TF32X3 = 0, 1
 FIELD_OBS, FIELD_REW, FIELD_DONE, FIELD_INFO, FIELD_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 FIELD_BITS = {"obs": FIELD_OBS, "rew": FIELD_REW, "done": FIELD_DONE, "info": FIELD_INFO}
 
@@ -60,6 +62,10 @@ class MgRewards(C.Structure):
 
 class MgResetSpec(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("reserved", C.c_uint32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+
+
+class MgExplore(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("step", C.c_uint64), ("keep_u32", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class MgConstants(C.Structure):
@@ -113,6 +119,11 @@ def load():
     lib.mg_mlp_act.restype = C.c_int
     lib.mg_mlp_act_tc.argtypes = lib.mg_mlp_act.argtypes
     lib.mg_mlp_act_tc.restype = C.c_int
+    lib.mg_policy_step.argtypes = [C.POINTER(MgState), i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(MgRewards),
+                                   C.POINTER(MgOut), vp, u32, rsp, C.POINTER(MgExplore), vp, vp, vp]
+    lib.mg_policy_step.restype = C.c_int
+    lib.mg_explore.argtypes = [vp, i64, i32, C.POINTER(MgExplore), vp, u64, u32, vp]
+    lib.mg_explore.restype = C.c_int
     lib.mg_record_transitions.argtypes = [vp] * 10 + [i64, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.mg_record_transitions.restype = C.c_int
     for f in (lib.mg_get_constants, lib.mg_default_rewards, lib.mg_reset, lib.mg_step,

@@ -199,7 +199,7 @@ __device__ __forceinline__ void reset_obs_fixed(float *obs) {
 // MergeEnv.reset() for one env (merging_env.py:208-230): fixed start (:216-217) or the commented-out
 // random start (:219-221).  Keeps and advances the env's reset count (meta bits 15-31), which is the
 // Philox counter of the random draw.  Writes the reset observation.
-__device__ __noinline__ void random_start(EnvRegs &e, uint64_t seed, uint64_t env_id, uint32_t count) {
+static __device__ __noinline__ void random_start(EnvRegs &e, uint64_t seed, uint64_t env_id, uint32_t count) {
     uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = count, c3 = 0u;
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x52535445u);
     const double k32 = 1.0 / 4294967296.0;
@@ -369,6 +369,27 @@ __device__ __forceinline__ void env_step_batch(EnvRegs (&env)[E], const int (&a1
         out[i].finished = fl[i].finished;
         out[i].info = info_byte(fl[i], winner[i], bad_action[i]);
     }
+}
+
+template <typename ActT>
+__device__ __forceinline__ int load_action(const ActT *p, int64_t i) { return (int)p[i]; }
+
+// validate into 0..4 (the reference raises KeyError from action_dict[a], merging_env.py:147)
+__device__ __forceinline__ int clamp_action(long long a, bool &bad) {
+    if (a < 0 || a >= MG_NUM_ACTIONS) { bad = true; a = a < 0 ? 0 : MG_NUM_ACTIONS - 1; }
+    return (int)a;
+}
+
+// Scatter the optional "finished episode" outputs (rare: ~0.5 % of envs per step).
+__device__ __forceinline__ void write_episode_outputs(const MgOut &o, int64_t e, const StepResult &r,
+                                                      double R1, double R2) {
+    if (o.term_obs) {
+        float *t = o.term_obs + e * MG_OBS_DIM;
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM; ++k) t[k] = r.obs[k];
+    }
+    if (o.ep_ret) { o.ep_ret[2 * e] = (float)R1; o.ep_ret[2 * e + 1] = (float)R2; }
+    if (o.ep_len) o.ep_len[e] = (int32_t)r.steps;
 }
 
 // ---- per-thread episode statistics, packed so that one warp reduction covers several ---------

@@ -85,27 +85,6 @@ __device__ __forceinline__ void st_pack_stream(T *__restrict__ p, const T (&in)[
     }
 }
 
-template <typename ActT>
-__device__ __forceinline__ int load_action(const ActT *p, int64_t i) { return (int)p[i]; }
-
-// validate into 0..4 (the reference raises KeyError from action_dict[a], merging_env.py:147)
-__device__ __forceinline__ int clamp_action(long long a, bool &bad) {
-    if (a < 0 || a >= MG_NUM_ACTIONS) { bad = true; a = a < 0 ? 0 : MG_NUM_ACTIONS - 1; }
-    return (int)a;
-}
-
-// Scatter the optional "finished episode" outputs (rare: ~0.5 % of envs per step).
-__device__ __forceinline__ void write_episode_outputs(const MgOut &o, int64_t e, const StepResult &r,
-                                                      double R1, double R2) {
-    if (o.term_obs) {
-        float *t = o.term_obs + e * MG_OBS_DIM;
-#pragma unroll
-        for (int k = 0; k < MG_OBS_DIM; ++k) t[k] = r.obs[k];
-    }
-    if (o.ep_ret) { o.ep_ret[2 * e] = (float)R1; o.ep_ret[2 * e + 1] = (float)R2; }
-    if (o.ep_len) o.ep_len[e] = (int32_t)r.steps;
-}
-
 // =================================================================================================
 // merge_step_kernel: one MergeEnv.step() for n envs.
 //   grid = ceil(n / (kBlock*EPT)), block = kBlock.  A warp owns 32*EPT consecutive envs.

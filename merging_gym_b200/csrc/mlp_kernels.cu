@@ -26,6 +26,7 @@
 #include <cstring>
 
 #include "abi_common.h"
+#include "policy_env.cuh"
 
 namespace mgmlp {
 
@@ -48,12 +49,15 @@ struct Smem {
     float w1[IN][H1];
     float w3[OUT][H2];
     float b1[H1], b2[H2], b3[MAX_OUT];
+    uint8_t act_tile[TM];          // ENV: the tile's greedy actions, handed from the arg-max lanes to one thread per env
 };
 
 // one env's input row [goal] + obs straight from global memory into registers (40-byte rows, 8-byte
 // aligned; a warp covers one contiguous 1280-byte span)
-template <int IN, bool MIRROR>
-__device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal,
+// COHERENT: the fused env epilogue writes observation rows in the same launch (possibly into the buffer being read), so
+// the rows must not travel through the non-coherent (ld.global.nc) path.
+template <int IN, bool MIRROR, bool COHERENT = false>
+__device__ __forceinline__ void load_row(const float *obs, const uint8_t *__restrict__ goal,
                                          int64_t e, int64_t n, int obs_dim, float (&x)[IN]) {
     constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
     (void)obs_dim;
@@ -63,12 +67,15 @@ __device__ __forceinline__ void load_row(const float *__restrict__ obs, const ui
             const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
             for (int i = 0; i < MG_OBS_DIM / 2; ++i) {          // obs_dim is 10: five float2
-                const float2 v = __ldg(src + i);
+                const float2 v = COHERENT ? __ldcg(src + i) : __ldg(src + i);
                 x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
             }
         } else {                                                // the opponent's view: state[5:] + state[:5] (main.py:199)
 #pragma unroll
-            for (int i = 0; i < MG_OBS_DIM; ++i) x[off + i] = __ldg(obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM);
+            for (int i = 0; i < MG_OBS_DIM; ++i) {
+                const float *q = obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM;
+                x[off + i] = COHERENT ? __ldcg(q) : __ldg(q);
+            }
         }
     } else {
 #pragma unroll
@@ -76,12 +83,17 @@ __device__ __forceinline__ void load_row(const float *__restrict__ obs, const ui
     }
 }
 
-template <int IN, int OUT, bool MIRROR>
+// ENV: `mg_policy_step` — the env step runs as this kernel's epilogue (policy_env.cuh): the arg-max lanes drop the
+// tile's 256 actions into shared memory and every thread steps one env of the tile.  (A ninth warp that owns the env,
+// as in the tensor-core kernel, would cap this kernel at 168 registers — ptxas sizes the budget for 384 threads — and
+// spill the layer-2 register tile; here the env costs 6 450 of a tile's 67 000 cycles.)
+// ENV: 0 = policy only, 1 = + env step pve, 2 = + env step pvp
+template <int IN, int OUT, bool MIRROR, int ENV>
 __global__ void __launch_bounds__(TM, 1)
-mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
+mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
                const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2p,
                const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
-               uint8_t *__restrict__ act, float *__restrict__ q_out) {
+               uint8_t *__restrict__ act, float *__restrict__ q_out, const mgpe::Args P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<IN, OUT> &S = *reinterpret_cast<Smem<IN, OUT> *>(smem_raw);
     const int t = threadIdx.x;
@@ -94,7 +106,7 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
     // first tile's input rows are requested before the weights so the two latencies overlap
     float xr[LR][IN];
 #pragma unroll
-    for (int r = 0; r < LR; ++r) load_row<IN, MIRROR>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
+    for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
 
     // ---- weights -> shared memory, once per (persistent) CTA: straight 128-bit copies -------------
     {
@@ -189,7 +201,7 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
         }
         // next tile's input rows: issued now, consumed after the epilogue
 #pragma unroll
-        for (int r = 0; r < LR; ++r) load_row<IN, MIRROR>(obs, goal, (tile + gridDim.x) * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
+        for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (tile + gridDim.x) * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
 
         // ---- layer 3 + arg-max ---------------------------------------------------------------------
         float q[4][OUT];
@@ -231,7 +243,9 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
                     if (q[e][o] > bv) { bv = q[e][o]; best = o; }   // first maximum, like torch.max
                 a4[e] = (uint8_t)best;
             }
-            if (e0 + 4 <= n) {
+            if (ENV) {
+                *reinterpret_cast<uchar4 *>(&S.act_tile[4 * eg]) = make_uchar4(a4[0], a4[1], a4[2], a4[3]);
+            } else if (e0 + 4 <= n) {
                 uchar4 v = make_uchar4(a4[0], a4[1], a4[2], a4[3]);
                 *reinterpret_cast<uchar4 *>(act + e0) = v;
             } else {
@@ -246,14 +260,25 @@ mlp_act_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, 
                         for (int o = 0; o < OUT; ++o) q_out[(e0 + e) * OUT + o] = q[e][o];
             }
         }
+        if (ENV) {
+            // ---- env step of the tile: thread t owns env base + t (coalesced state access) -------------------
+            __syncthreads();                   // the tile's actions are in shared memory
+            mg::StatAcc st;
+            mgpe::Loaded x;
+            mgpe::load_env<ENV == 2>(P, base + t, n, x);
+            mgpe::step_loaded<ENV == 2>(P, base + t, x, (int)S.act_tile[t], st);
+            if (P.stats)
+                mg::flush_stats(st, P.stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS, 0xFFFFFFFFu, t & 31);
+            // act_tile is rewritten only after the next tile's chunk barriers
+        }
     }
 }
 
-template <int IN, int OUT, bool MIRROR>
+template <int IN, int OUT, bool MIRROR, int ENV = 0>
 cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t,
                    const float *b1, const float *w2t, const float *b2, const float *w3, const float *b3,
-                   uint8_t *act, float *q_out, cudaStream_t st) {
-    auto kern = mlp_act_kernel<IN, OUT, MIRROR>;
+                   uint8_t *act, float *q_out, cudaStream_t st, const mgpe::Args &P = mgpe::Args{}) {
+    auto kern = mlp_act_kernel<IN, OUT, MIRROR, ENV>;
     const size_t smem = sizeof(Smem<IN, OUT>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
@@ -262,7 +287,7 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    kern<<<grid, TM, smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2t, b2, w3, b3, act, q_out);
+    kern<<<grid, TM, smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2t, b2, w3, b3, act, q_out, P);
     return cudaGetLastError();
 }
 
@@ -292,5 +317,83 @@ extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, 
     MG_MLP_CASE(10, 5) MG_MLP_CASE(10, 3) MG_MLP_CASE(11, 5) MG_MLP_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_MLP_CASE
     if (e) return cuda_fail(e, "mg_mlp_act launch");
+    return MG_OK;
+}
+
+// ---- mg_policy_step: policy forward + arg-max + exploration + MergeEnv.step in one launch ------------------------
+cudaError_t mg_policy_step_tc_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const float *w1t,
+                                     const float *b1, const float *w2_tc, const float *b2, const float *w3, const float *b3,
+                                     float *q_out, cudaStream_t st, const mgpe::Args &P);
+
+namespace mgmlp {
+__global__ void __launch_bounds__(256)
+explore_kernel(uint8_t *__restrict__ choices, const uint32_t *__restrict__ meta, const int64_t n, const int num_choices,
+               const mgpe::Args P) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e < n) choices[e] = (uint8_t)mgpe::explore(P, e, (int)choices[e], num_choices, meta ? meta[e] : 0u);
+}
+}  // namespace mgmlp
+
+extern "C" MG_API int mg_policy_step(const MgState *state, int64_t n, const float *obs_in, const uint8_t *goal_or_null,
+                                     int32_t backend, const float *w1t, const float *b1, const float *w2, const float *b2,
+                                     const float *w3, const float *b3, const uint8_t *a2_or_null, const MgRewards *rewards,
+                                     const MgOut *out, int64_t *stats_or_null, uint32_t flags, const MgResetSpec *reset_or_null,
+                                     const MgExplore *explore_or_null, uint8_t *actions_out_or_null, float *q_out_or_null,
+                                     void *stream) {
+    using namespace mg_abi;
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS | MG_POLICY_FLAG_EXPLORE)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (backend != MG_POLICY_BACKEND_FP32 && backend != MG_POLICY_BACKEND_TF32X3)
+        return fail(MG_ERR_BAD_FLAGS, "backend must be MG_POLICY_BACKEND_FP32 or MG_POLICY_BACKEND_TF32X3");
+    if ((flags & MG_POLICY_FLAG_EXPLORE) && !explore_or_null) return fail(MG_ERR_NULL_POINTER, "MG_POLICY_FLAG_EXPLORE without an MgExplore");
+    if (reset_or_null && reset_or_null->mode > MG_RESET_RANDOM) return fail(MG_ERR_BAD_FLAGS, "MgResetSpec.mode must be MG_RESET_FIXED or MG_RESET_RANDOM");
+    if (n == 0) return MG_OK;
+    if (!state || !out || !obs_in || !w1t || !b1 || !w2 || !b2 || !w3 || !b3) return fail(MG_ERR_NULL_POINTER, "mg_policy_step: NULL pointer");
+    if (!state->pos1 || !state->vel1 || !state->pos2 || !state->vel2 || !state->meta) return fail(MG_ERR_NULL_POINTER, "a state array pointer is NULL");
+    if (!out->obs || !out->rew || !out->info) return fail(MG_ERR_NULL_POINTER, "out.obs/rew/info must be non-NULL");
+    const bool ret = state->ret1 && state->ret2 && !(flags & MG_FLAG_NO_RETURNS);
+    if (!ret && out->ep_ret) return fail(MG_ERR_BAD_FLAGS, "out.ep_ret needs the return accumulators");
+    if (!aligned16(obs_in) || !aligned16(out->obs) || !aligned16(out->rew) || !aligned16(w1t) || !aligned16(w2) || !aligned16(b1))
+        return fail(MG_ERR_ALIGNMENT, "obs, out and weight arrays must be 16-byte aligned");
+    mgpe::Args P{};
+    P.s = *state;
+    if (!ret) P.s.ret1 = P.s.ret2 = nullptr;
+    P.o = *out;
+    P.a2 = a2_or_null;
+    P.actions = actions_out_or_null;
+    P.stats = reinterpret_cast<unsigned long long *>(stats_or_null);
+    if (rewards) P.rw = *rewards; else mg_default_rewards(&P.rw);
+    P.rs = reset_or_null ? *reset_or_null : MgResetSpec{MG_RESET_FIXED, 0u, 0ull, 0ull};
+    P.flags = flags;
+    if (explore_or_null) { P.explore_seed = explore_or_null->seed; P.explore_step = explore_or_null->step; P.explore_keep = explore_or_null->keep_u32; }
+    const int in_dim = MG_OBS_DIM + (goal_or_null ? 1 : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (backend == MG_POLICY_BACKEND_TF32X3)
+        e = mg_policy_step_tc_launch(in_dim, obs_in, goal_or_null, n, w1t, b1, w2, b2, w3, b3, q_out_or_null, st, P);
+    else if (in_dim == 10)
+        e = a2_or_null ? mgmlp::launch<10, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P)
+                       : mgmlp::launch<10, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P);
+    else
+        e = a2_or_null ? mgmlp::launch<11, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P)
+                       : mgmlp::launch<11, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P);
+    if (e) return cuda_fail(e, "mg_policy_step launch");
+    return MG_OK;
+}
+
+extern "C" MG_API int mg_explore(uint8_t *choices, int64_t n, int32_t num_choices, const MgExplore *explore,
+                                 const uint32_t *meta_or_null, uint64_t env_id_base, uint32_t salt, void *stream) {
+    using namespace mg_abi;
+    if (n < 0 || num_choices < 1 || num_choices > 255) return fail(MG_ERR_BAD_SIZE, "n < 0 or num_choices outside 1..255");
+    if (n == 0) return MG_OK;
+    if (!choices || !explore) return fail(MG_ERR_NULL_POINTER, "mg_explore: NULL pointer");
+    mgpe::Args P{};
+    P.flags = MG_POLICY_FLAG_EXPLORE;
+    P.rs.env_id_base = env_id_base;
+    P.explore_seed = explore->seed ^ ((uint64_t)salt << 20);
+    P.explore_step = explore->step;
+    P.explore_keep = explore->keep_u32;
+    mgmlp::explore_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(choices, meta_or_null, n, num_choices, P);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_explore launch");
     return MG_OK;
 }

@@ -28,6 +28,7 @@
 // timeline is measured by profiles/exp_tc_trace.cu (-DMG_TC_TRACE=1).
 // Every mbarrier wait is bounded and traps instead of hanging.
 #include "abi_common.h"
+#include "policy_env.cuh"
 
 // 1 = a single MMA-issuing warp with its K loop fully unrolled: accumulation order in TMEM is the K-step order, the
 //     kernel is bitwise reproducible (69.6 us per 2^18 envs);
@@ -65,6 +66,8 @@ constexpr int TMEM_COLS = 512;                // 2 accumulator buffers x 256 col
 constexpr int PRODUCER_WARPS = 8;             // thread = 4 envs x one K-step
 constexpr int MMA_WARPS = MG_TC_MMA_WARPS;     // warps 12.. issue the MMAs, K-steps interleaved
 constexpr int NUM_THREADS = 384 + 32 * MMA_WARPS;   // 8 producer warps + 4 epilogue warps + the MMA warps
+constexpr int ENV_WARP0 = 12 + MMA_WARPS;           // mg_policy_step only: ENV_WARPS more warps that own the env step
+constexpr int ENV_WARPS = 2;                        // 480 threads: ptxas still budgets 128 registers (512-thread granule)
 constexpr int MAX_OUT = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -78,6 +81,7 @@ struct Smem {
     float b1[H1], b2[H2 + 12], b3[MAX_OUT];
     unsigned long long full[PRODUCER_WARPS], empty[PRODUCER_WARPS], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
+    mgpe::Handoff<TM, ENV_WARPS> env;                    // ENV: the tile's actions, epilogue warps -> env warp
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,8 +130,10 @@ __device__ __forceinline__ uint32_t mbar_test(unsigned long long *b, uint32_t pa
     return done;
 }
 
-template <int IN, bool MIRROR>
-__device__ __forceinline__ void load_row(const float *__restrict__ obs, const uint8_t *__restrict__ goal, int64_t e,
+// COHERENT: the fused env epilogue writes observation rows in the same launch (possibly into the buffer being read), so
+// the rows must not travel through the non-coherent (ld.global.nc) path.
+template <int IN, bool MIRROR, bool COHERENT = false>
+__device__ __forceinline__ void load_row(const float *obs, const uint8_t *__restrict__ goal, int64_t e,
                                          int64_t n, int obs_dim, float (&x)[IN]) {
     constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
     (void)obs_dim;
@@ -137,12 +143,15 @@ __device__ __forceinline__ void load_row(const float *__restrict__ obs, const ui
             const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
             for (int i = 0; i < MG_OBS_DIM / 2; ++i) {          // obs_dim is 10: five float2
-                const float2 v = __ldg(src + i);
+                const float2 v = COHERENT ? __ldcg(src + i) : __ldg(src + i);
                 x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
             }
         } else {                                                // the opponent's view: state[5:] + state[:5] (main.py:199)
 #pragma unroll
-            for (int i = 0; i < MG_OBS_DIM; ++i) x[off + i] = __ldg(obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM);
+            for (int i = 0; i < MG_OBS_DIM; ++i) {
+                const float *q = obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM;
+                x[off + i] = COHERENT ? __ldcg(q) : __ldg(q);
+            }
         }
     } else {
 #pragma unroll
@@ -150,12 +159,16 @@ __device__ __forceinline__ void load_row(const float *__restrict__ obs, const ui
     }
 }
 
-template <int IN, int OUT, bool MIRROR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
+// ENV: `mg_policy_step` — the epilogue threads drop the tile's actions into shared memory and one extra warp steps the
+// tile's envs (policy_env.cuh) while the other warps are on the next tile.  (Stepping the env in the epilogue threads
+// themselves doubled the tile period: the epilogue warps have no slack, profiles/r02_policy_step_*.)
+// ENV: 0 = policy only, 1 = + env step pve, 2 = + env step pvp
+template <int IN, int OUT, bool MIRROR, int ENV>
+__global__ void __launch_bounds__(NUM_THREADS + (ENV ? 32 * ENV_WARPS : 0), 1)
+mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
                   const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2_tc,
                   const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
-                  uint8_t *__restrict__ act, float *__restrict__ q_out) {
+                  uint8_t *__restrict__ act, float *__restrict__ q_out, const mgpe::Args P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem<IN, OUT> &S = *reinterpret_cast<Smem<IN, OUT> *>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -165,21 +178,22 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
     {
         const float4 *src = reinterpret_cast<const float4 *>(w2_tc);          // already in the canonical layout
         float4 *dst = reinterpret_cast<float4 *>(S.b_cat);
-        for (int i = t; i < B_BYTES / 16; i += NUM_THREADS) dst[i] = __ldg(src + i);
+        for (int i = t; i < B_BYTES / 16; i += (int)blockDim.x) dst[i] = __ldg(src + i);
         const float4 *s1 = reinterpret_cast<const float4 *>(w1t);
         float4 *d1 = reinterpret_cast<float4 *>(&S.w1[0][0]);
-        for (int i = t; i < IN * H1 / 4; i += NUM_THREADS) d1[i] = __ldg(s1 + i);
-        for (int i = t; i < OUT * H2P; i += NUM_THREADS) {
+        for (int i = t; i < IN * H1 / 4; i += (int)blockDim.x) d1[i] = __ldg(s1 + i);
+        for (int i = t; i < OUT * H2P; i += (int)blockDim.x) {
             const int o = i / H2P, c = i - o * H2P;
             S.w3[o][c] = c < H2 ? w3[o * H2 + c] : 0.f;
         }
-        for (int i = t; i < H1; i += NUM_THREADS) S.b1[i] = b1[i];
-        for (int i = t; i < H2 + 12; i += NUM_THREADS) S.b2[i] = i < H2 ? b2[i] : 0.f;
+        for (int i = t; i < H1; i += (int)blockDim.x) S.b1[i] = b1[i];
+        for (int i = t; i < H2 + 12; i += (int)blockDim.x) S.b2[i] = i < H2 ? b2[i] : 0.f;
         if (t < OUT) S.b3[t] = b3[t];
     }
     if (t == 0) {
         for (int s = 0; s < PRODUCER_WARPS; ++s) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], MMA_WARPS); mbar_init(&S.tmem_empty[b], TM); }
+        if (ENV) mgpe::handoff_init(S.env, TM);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W2 hi/lo written by the generic proxy
@@ -220,7 +234,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         {
             const int64_t e0 = (int64_t)blockIdx.x * TM + lane;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR, ENV != 0>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
         }
         for (uint32_t g = (uint32_t)warp; g < total; g += PRODUCER_WARPS) {
             const uint32_t tl = g / KSTEPS, ks = g - tl * KSTEPS;
@@ -253,7 +267,7 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
             if ((g + PRODUCER_WARPS) / KSTEPS != tl) {
                 const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)(tl + 1) * gridDim.x) * TM + lane;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR, ENV != 0>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
             }
             // Ring slot s = g % 4 is filled alternately by warps s and s + 4.  A parity wait is only meaningful when
             // the waiter is at most one phase behind the barrier, so every producer warp has its OWN pair of
@@ -283,6 +297,10 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
             mbar_arrive(&S.full[warp]);
             MG_TRACE(g_trace_prod, g, 4);
         }
+    } else if (ENV && warp >= ENV_WARP0) {
+        // =================================== ENV WARPS: MergeEnv.step of the tiles the epilogue has finished ==========
+        mgpe::env_warp_loop<TM, ENV_WARPS, ENV == 2>(P, S.env, warp - ENV_WARP0, blockIdx.x, gridDim.x, n_tiles, n, lane,
+                                                     (int)(blockIdx.x % MG_STATS_ROWS));
     } else if (warp >= 12) {
         // =================================== MMA ISSUERS =========================================
         // The issuing warp runs its loop whole-warp and issues by PREDICATION from one elected lane (inside an
@@ -416,17 +434,22 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
                 mine[o] = (t0 == 0 ? q[0][o] : t0 == 1 ? q[1][o] : t0 == 2 ? q[2][o] : q[3][o]) + S.b3[o];
             }
             const int64_t e = tile * TM + q4 * 32 + t1 + 8 * t0;
-            if (e < n) {
-                int best = 0;
-                float bv = mine[0];
+            int best = 0;
+            float bv = mine[0];
 #pragma unroll
-                for (int o = 1; o < OUT; ++o)
-                    if (mine[o] > bv) { bv = mine[o]; best = o; }   // first maximum, like torch.max
-                act[e] = (uint8_t)best;
+            for (int o = 1; o < OUT; ++o)
+                if (mine[o] > bv) { bv = mine[o]; best = o; }       // first maximum, like torch.max
+            if (e < n) {
+                if (!ENV) act[e] = (uint8_t)best;
                 if (q_out) {
 #pragma unroll
                     for (int o = 0; o < OUT; ++o) q_out[e * OUT + o] = mine[o];
                 }
+            }
+            if (ENV) {                                          // hand the action to the env warp
+                uint8_t *tile_act = mgpe::handoff_acquire(S.env, tl);
+                tile_act[q4 * 32 + t1 + 8 * t0] = (uint8_t)best;
+                mgpe::handoff_publish(S.env, tl);
             }
         }
     }
@@ -437,11 +460,11 @@ mlp_act_tc_kernel(const float *__restrict__ obs, const uint8_t *__restrict__ goa
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
 }
 
-template <int IN, int OUT, bool MIRROR>
+template <int IN, int OUT, bool MIRROR, int ENV = 0>
 cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t, const float *b1,
                    const float *w2_tc, const float *b2, const float *w3, const float *b3, uint8_t *act, float *q_out,
-                   cudaStream_t st) {
-    auto kern = mlp_act_tc_kernel<IN, OUT, MIRROR>;
+                   cudaStream_t st, const mgpe::Args &P = mgpe::Args{}) {
+    auto kern = mlp_act_tc_kernel<IN, OUT, MIRROR, ENV>;
     const size_t smem = sizeof(Smem<IN, OUT>) + 1024;           // slack for the 1024-byte alignment of the base
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
@@ -450,11 +473,24 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    kern<<<grid, NUM_THREADS, smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, act, q_out);
+    kern<<<grid, NUM_THREADS + (ENV ? 32 * ENV_WARPS : 0), smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, act, q_out, P);
     return cudaGetLastError();
 }
 
 }  // namespace mgtc
+
+// the fused policy + env step on the tensor-core backend (called by mg_policy_step in mlp_kernels.cu)
+cudaError_t mg_policy_step_tc_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const float *w1t,
+                                     const float *b1, const float *w2_tc, const float *b2, const float *w3, const float *b3,
+                                     float *q_out, cudaStream_t st, const mgpe::Args &P) {
+    const bool pvp = P.a2 != nullptr;
+#define MG_TC_ENV(I) (pvp ? mgtc::launch<I, 5, false, 2>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P) \
+                          : mgtc::launch<I, 5, false, 1>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P))
+    if (in_dim == 10) return MG_TC_ENV(10);
+    if (in_dim == 11) return MG_TC_ENV(11);
+#undef MG_TC_ENV
+    return cudaErrorInvalidValue;
+}
 
 extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                                     int32_t out_dim, const float *w1t, const float *b1, const float *w2_tc,

@@ -17,7 +17,14 @@ from .vec_env import MergeVecEnv
 
 class GraphedPolicyRollout:
     """`run()` = K env steps.  The env must have been constructed with `out_slots=1` (one fixed observation buffer,
-    so that every captured step reads the buffer the previous one wrote).
+    so that every captured step reads the buffer the previous one wrote) — or, with `fused=True`, any `out_slots`
+    that divides K.
+
+    fused=True: player 1's step is ONE launch, `MergeVecEnv.policy_step` (`mg_policy_step`: forward + arg-max +
+    exploration + env step), instead of policy launch + action copy + `mg_step`; `policy1` must then be an `MLPPolicy`
+    (backend "fused" or "tf32x3") or an `HDQNPolicy` (two launches: goal, then controller + env).  `explore` (an
+    `Exploration`) applies the scripts' `randn() <= EPISILO` rule on the device.  With `after_step` the env needs
+    `out_slots >= 2`, so that the observation the actions were chosen from is still intact when the recorder reads it.
 
     policy1(obs) -> uint8[N] actions of player 1; policy2 (pvp only) receives the same observation buffer and must
     mirror it itself (`MLPPolicy.act(obs, mirror=True)`).  `after_step(obs_prev, a1, a2, step_out)`, if given, runs
@@ -27,9 +34,19 @@ class GraphedPolicyRollout:
     """
 
     def __init__(self, env: MergeVecEnv, policy1: Callable, policy2: Optional[Callable] = None, k_steps: int = 32,
-                 after_step: Optional[Callable] = None, warmup_steps: int = 3):
-        if env.out_slots != 1:
+                 after_step: Optional[Callable] = None, warmup_steps: int = 3, fused: bool = False, explore=None):
+        self.fused, self.explore = bool(fused), explore
+        if fused:
+            if int(k_steps) % env.out_slots:
+                raise ValueError("fused GraphedPolicyRollout: k_steps must be a multiple of env.out_slots")
+            if after_step is not None and env.out_slots < 2:
+                raise ValueError("fused GraphedPolicyRollout with after_step needs an env with out_slots >= 2")
+            if explore is not None and not hasattr(explore, "spec"):
+                raise ValueError("explore must be a merging_gym_b200.Exploration")
+        elif env.out_slots != 1:
             raise ValueError("GraphedPolicyRollout needs an env with out_slots=1")
+        elif explore is not None:
+            raise ValueError("explore is applied by the fused step: pass fused=True")
         if (policy2 is not None) != (env.mode == "pvp"):
             raise ValueError("policy2 is required for, and only for, a pvp env")
         self.env, self.k_steps = env, int(k_steps)
@@ -37,7 +54,9 @@ class GraphedPolicyRollout:
         n, dev = env.num_envs, env.device
         self._a1 = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._a2 = torch.zeros(n, dtype=torch.uint8, device=dev) if policy2 is not None else None
-        self._prev = torch.empty_like(env.obs_buf[0]) if after_step is not None else None
+        self._prev = torch.empty_like(env.obs_buf[0]) if after_step is not None and not fused else None
+        if fused and warmup_steps % env.out_slots:
+            warmup_steps += env.out_slots - warmup_steps % env.out_slots     # the slot ring is back at its start for the capture
         self.last = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -53,6 +72,18 @@ class GraphedPolicyRollout:
 
     def _one_step(self):
         env = self.env
+        if self.fused:
+            obs = env.obs_buf[env._slot]
+            if self._a2 is not None:
+                self._a2.copy_(self._p2(obs))
+            want = self._a1 if self._after is not None else None
+            if hasattr(self._p1, "ctrl"):                       # HDQNPolicy: goal launch + fused controller/env launch
+                out = self._p1.step(env, a2=self._a2, explore=self.explore, actions_out=want)
+            else:
+                out = env.policy_step(self._p1, a2=self._a2, explore=self.explore, actions_out=want)
+            if self._after is not None:
+                self._after(obs, self._a1, self._a2, out)
+            return out
         obs = env.obs_buf[0]
         if self._prev is not None:
             self._prev.copy_(obs)

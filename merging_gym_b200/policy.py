@@ -27,6 +27,7 @@ from . import _native as nat
 
 EPISILO = 0.7          # scripts/main.py:16, hdqn.py:20
 HIDDEN1, HIDDEN2 = 200, 100
+POLICY_BACKENDS = {"fused": nat.POLICY_BACKEND_FP32, "tf32x3": nat.POLICY_BACKEND_TF32X3}
 
 
 def _ptr(t):
@@ -148,10 +149,52 @@ class MLPPolicy:
     __call__ = act
 
 
+class Exploration:
+    """The scripts' exploration rule as device code (main.py:103-110, hdqn.py:84-92,168-176):
+        `if np.random.randn() <= EPISILO:` greedy choice `else:` `np.random.randint(0, num_choices)`.
+    `randn() <= t` holds with probability Phi(t) (0.758 for t = 0.7 — NOT epsilon-greedy with 0.7), so per env and step
+    one Philox uniform is compared with Phi(t) and a second one picks the random choice; the counter is (global env
+    id, step), so the draws do not depend on sharding or launch shape.  `step` advances by one per `spec()` /
+    `apply()` call unless given."""
+
+    def __init__(self, threshold: float = EPISILO, seed: int = 0, step: int = 0):
+        import math
+        self.threshold, self.seed, self.step = float(threshold), int(seed), int(step)
+        self.keep_prob = 0.5 * (1.0 + math.erf(self.threshold / math.sqrt(2.0)))
+        self.keep_u32 = min(int(self.keep_prob * 4294967296.0), 0xFFFFFFFF)
+
+    def spec(self, step: Optional[int] = None) -> "nat.MgExplore":
+        """The launch parameter block.  The device XORs `step` with each env's own clock (its meta word: reset count,
+        winner, steps since reset), so `step` only has to change where envs' clocks can coincide — it does not have to
+        advance inside a CUDA graph.  `self.step` is used (and NOT advanced) unless `step` is given."""
+        return nat.MgExplore(self.seed, int(self.step if step is None else step), self.keep_u32, 0)
+
+    def apply(self, choices: torch.Tensor, num_choices: int, env=None, env_id_base: int = 0, salt: int = 0,
+              step: Optional[int] = None) -> torch.Tensor:
+        """In place on a uint8 device tensor of greedy choices (`mg_explore`, one small kernel).  `env` (a MergeVecEnv)
+        supplies the env clocks and the global env id base.  salt 0 is the stream `MergeVecEnv.policy_step(explore=...)`
+        uses for actions; the h-DQN meta-controller's goals use salt 1."""
+        if not (choices.is_cuda and choices.dtype == torch.uint8 and choices.is_contiguous()):
+            raise ValueError("choices must be a contiguous uint8 CUDA tensor")
+        ex = self.spec(step)
+        meta = None
+        if env is not None:
+            meta, env_id_base = env.meta, env.env_id_base
+        with torch.cuda.device(choices.device):
+            nat.check(nat.load().mg_explore(_ptr(choices), choices.numel(), int(num_choices), C.byref(ex), _ptr(meta),
+                                            int(env_id_base), int(salt),
+                                            C.c_void_p(torch.cuda.current_stream(choices.device).cuda_stream)), "mg_explore")
+        return choices
+
+
 def explore(greedy: torch.Tensor, num_actions: int, generator: Optional[torch.Generator] = None,
-            threshold: float = EPISILO) -> torch.Tensor:
-    """The scripts' exploration rule, batched: keep the greedy action where randn() <= 0.7, else a
-    uniform random action (main.py:103-110).  Device-side, no host sync."""
+            threshold: float = EPISILO, exploration: Optional[Exploration] = None, env=None) -> torch.Tensor:
+    """The scripts' exploration rule, batched: keep the greedy action where randn() <= 0.7, else a uniform random
+    action (main.py:103-110).  With `exploration` (an `Exploration`) the draw is the hand-written Philox kernel
+    (`mg_explore`, in place on a uint8 tensor); without it, the plain PyTorch restatement of the same rule on torch's
+    generator, kept as the reference the kernel's distribution is tested against."""
+    if exploration is not None:
+        return exploration.apply(greedy, num_actions, env)
     n, dev = greedy.shape[0], greedy.device
     keep = torch.randn(n, device=dev, generator=generator) <= threshold
     rnd = torch.randint(0, num_actions, (n,), device=dev, generator=generator, dtype=torch.int64).to(greedy.dtype)
@@ -183,3 +226,16 @@ class HDQNPolicy:
         return self.ctrl.act(obs, goal=self.goal, out=out)      # hdqn.py:291-292  [goal] + state
 
     __call__ = act
+
+    def step(self, env, a2: Optional[torch.Tensor] = None, explore: Optional[Exploration] = None,
+             actions_out: Optional[torch.Tensor] = None):
+        """One iteration of the h-DQN loop (hdqn.py:288-303) in two launches: `choose_goal(state)` (meta forward +
+        arg-max [+ exploration, salt 1]) and `mg_policy_step` with the controller on `[goal] + state` — forward,
+        arg-max, exploration and `env.step` fused.  Returns the step tuple; `self.goal` holds the goals acted on."""
+        obs = env.obs_buf[env._slot]
+        if self.goal is None or self.goal.shape[0] != obs.shape[0]:
+            self.goal = torch.empty(obs.shape[0], dtype=torch.uint8, device=obs.device)
+        self.meta.act(obs, out=self.goal)
+        if explore is not None:
+            explore.apply(self.goal, self.meta.out_dim, env, salt=1)
+        return env.policy_step(self.ctrl, goal=self.goal, a2=a2, explore=explore, actions_out=actions_out)

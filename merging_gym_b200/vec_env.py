@@ -245,6 +245,10 @@ class MergeVecEnv:
     def _flags(self):
         return (nat.FLAG_AUTO_RESET if self.auto_reset else 0) | (0 if self.track_returns else nat.FLAG_NO_RETURNS)
 
+    def lane_stream(self, lane: int):
+        """The CUDA stream lane `lane`'s launches run on (the current stream for a single-lane env)."""
+        return self._lane_streams[lane] if self.lanes > 1 else torch.cuda.current_stream(self.device)
+
     def _as_action(self, a, name):
         if not isinstance(a, torch.Tensor):
             a = torch.as_tensor(np.asarray(a))
@@ -425,6 +429,60 @@ class MergeVecEnv:
         """
         self.step_async(a1, a2)
         return self.step_wait()
+
+    # ------------------------------------------------------------------ policy in the loop, one launch per step
+    def policy_step(self, policy, goal: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
+                    explore=None, actions_out: Optional[torch.Tensor] = None, q_out: Optional[torch.Tensor] = None):
+        """One iteration of the reference scripts' inner loop (scripts/main.py:194-211, hdqn.py:288-316)
+            action = policy(obs)  [exploration rule]  ->  obs, rewards, done, info = env.step(action, a2)
+        in ONE kernel (`mg_policy_step`): the Q-network forward + arg-max with `MergeEnv.step` as its epilogue.  The
+        policy reads the env's current observation buffer; the next observation goes into the next output slot
+        (with `out_slots=1`: in place).  Bit-identical to `policy.act(obs)` followed by `step(...)`.
+
+        policy       an `MLPPolicy` with 5 outputs and backend "fused" (fp32) or "tf32x3" (tensor cores)
+        goal         uint8[N]: the h-DQN controller's `[goal] + state` column (`MLPPolicy(11, 5)`, hdqn.py:291)
+        a2           uint8[N] actions of player 2, None = pve (the constant-speed opponent, merging_env.py:152)
+        explore      None = greedy; a `policy.Exploration` = the scripts' `randn() <= EPISILO` rule (main.py:103-110)
+                     drawn on the device from Philox over (seed, global env id, step)
+        actions_out  uint8[N]: receives the action taken (what `store_transition` records)
+        Returns (obs, rewards, done, info) like `step`.
+        """
+        from .policy import POLICY_BACKENDS
+        if policy.out_dim != nat.NUM_ACTIONS or policy.backend not in POLICY_BACKENDS:
+            raise ValueError("policy_step needs an MLPPolicy with 5 outputs and backend 'fused' or 'tf32x3'")
+        if policy.in_dim != nat.OBS_DIM + (0 if goal is None else 1):
+            raise ValueError("policy input width does not match obs (+ goal)")
+        n = self.num_envs
+
+        def u8(t, name):
+            if t is None:
+                return None
+            if not (isinstance(t, torch.Tensor) and t.dtype == torch.uint8 and t.device == self.device
+                    and t.is_contiguous() and t.numel() == n):
+                raise ValueError(f"{name} must be a contiguous uint8 tensor of {n} elements on {self.device}")
+            return t
+        goal, a2, actions_out = u8(goal, "goal"), u8(a2, "a2"), u8(actions_out, "actions_out")
+        if q_out is not None and (tuple(q_out.shape) != (n, nat.NUM_ACTIONS) or q_out.dtype != torch.float32
+                                  or not q_out.is_contiguous() or q_out.device != self.device):
+            raise ValueError("q_out must be a contiguous float32 [N,5] tensor on the env's device")
+        self._join_lanes()
+        obs_in = self.obs_buf[self._slot]
+        self._slot = (self._slot + 1) % self.out_slots
+        k = self._slot
+        flags = self._flags()
+        ex = None
+        if explore is not None:
+            ex = explore.spec()
+            flags |= nat.POLICY_FLAG_EXPLORE
+        w2 = policy.w2_tc if policy.backend == "tf32x3" else policy.w2_p
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.mg_policy_step(C.byref(self._state), n, _ptr(obs_in), _ptr(goal), POLICY_BACKENDS[policy.backend],
+                                               _ptr(policy.w1_t), _ptr(policy.b1), _ptr(w2), _ptr(policy.b2), _ptr(policy.w3),
+                                               _ptr(policy.b3), _ptr(a2), C.byref(self._rw), C.byref(self._outs[k]),
+                                               _ptr(self.stats_buf), flags, C.byref(self._rs),
+                                               None if ex is None else C.byref(ex), _ptr(actions_out), _ptr(q_out),
+                                               self._stream()), "mg_policy_step")
+        return (self.obs_buf[k], self.rew_buf[k], self.done_buf[k].view(torch.bool), StepInfo(self.info_buf[k], self._extras))
 
     def close(self):
         self.closed = True

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One kernel at bench size, a few launches — the command ncu captures (`-k regex:<name>`).
 
-    python profiles/ncu_target.py rollout|step|step_lean|mlp_tc|mlp|record [--envs N]
+    python profiles/ncu_target.py rollout|step|step_lean|mlp_tc|mlp|policy_step|policy_step_tc|record [--envs N]
 """
 import os
 import sys
@@ -36,6 +36,12 @@ elif what in ("mlp", "mlp_tc"):
     out = torch.empty(n, dtype=torch.uint8, device=dev)
     for _ in range(4):
         pol.act(env.obs_buf[0], out=out)
+elif what in ("policy_step", "policy_step_tc"):
+    env = mg.MergeVecEnv(n, mode="pve", episode_info=False, reset_mode="random")
+    env.rollout(200)
+    pol = mg.MLPPolicy(10, 5, seed=1, backend="tf32x3" if what == "policy_step_tc" else "fused")
+    for _ in range(4):
+        env.policy_step(pol)
 elif what == "record":
     env = mg.MergeVecEnv(n, out_slots=2)
     env.rollout(215)
