@@ -57,9 +57,13 @@ def load_policy(policy, backend, device="cuda"):
     return mg.HDQNPolicy(device=device, backend=backend), HDQN_FLOPS, "random-init (reference init; no h-DQN weights ship)"
 
 
-def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="cuda", reset_mode="random", mix_steps=300):
+def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="cuda", reset_mode="random", mix_steps=300,
+            pdl=True):
     env = mg.MergeVecEnv(n, mode="pve", device=device, auto_reset=True, episode_info=False, reset_mode=reset_mode)
     pol, flops, weights = load_policy(policy, backend, device)
+    for q in (pol, getattr(pol, "meta", None), getattr(pol, "ctrl", None)):    # rollout loop: the kernel before a policy
+        if hasattr(q, "pdl"):                                                  # kernel is the env step -> PDL is valid
+            q.pdl = pdl
     act = torch.empty(n, dtype=torch.uint8, device=device)
     obs = env.obs_buf[0]                           # out_slots=1: one fixed observation buffer, replayable
 
@@ -99,7 +103,7 @@ def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="c
             "ms_per_step": ms_step, "policy_ms": ms_pol, "env_ms": ms_step - ms_pol,
             "env_share": (ms_step - ms_pol) / ms_step,
             "policy_tflops": n * flops / (ms_pol * 1e-3) / 1e12, "weights": weights,
-            "launch": f"CUDA graph of {k} x (policy forward+argmax, mg_step) vs a graph of {k} policy launches alone; "
+            "pdl": pdl, "launch": f"CUDA graph of {k} x (policy forward+argmax, mg_step) vs a graph of {k} policy launches alone; "
                       "env_ms is the difference", "reset_mode": reset_mode,
             "episode_stats": {q: st[q] for q in ("episodes", "collision_rate", "win_rate_p1", "mean_length", "mean_return1")}}
 
@@ -111,9 +115,10 @@ def main():
     ap.add_argument("--policy", default="dqn", choices=["dqn", "hdqn"])
     ap.add_argument("--backend", default="fused", choices=["fused", "tf32x3", "torch"])
     ap.add_argument("--reset-mode", default="random", choices=["fixed", "random"])
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the policy kernels (0/1)")
     args = ap.parse_args()
     k = 50
-    r = measure(args.envs, args.policy, args.backend, k=k, replays=max(1, args.steps // k), reset_mode=args.reset_mode)
+    r = measure(args.envs, args.policy, args.backend, k=k, replays=max(1, args.steps // k), reset_mode=args.reset_mode, pdl=bool(args.pdl))
     line = {"metric": "env_steps_per_sec", "unit": "env-steps/s", "n_gpus": 1, "steps": args.steps,
             "dtype": "f64 env / f32 policy", "data": "synthetic",
             "config": {"workload": f"pve, {args.envs} envs, {args.policy} greedy policy in the loop, auto-reset, "

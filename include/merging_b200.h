@@ -234,6 +234,12 @@ MG_API int mg_step_host_wait(void *ev_done);
                                    `state[5:] + state[:5]` (scripts/main.py:199, hdqn.py:285,299): the half-swap
                                    is done while the row is read, no mirrored copy is materialised */
 
+#define MG_MLP_FLAG_PDL 0x2u    /* programmatic dependent launch: the kernel's prologue (weight staging, barrier and tensor-
+                                   memory set-up — it reads nothing but the weights) may run while the previous kernel
+                                   of the stream is still draining; observations are read only after that kernel has
+                                   completed.  Set it when the previous kernel does not write this policy's weights
+                                   (in a rollout loop it is the env step).                                           */
+
 /* ---- "next" row: policy in the loop -------------------------------------------
  * Fused forward + arg-max of the reference's Q-network `Net(in, out)`:
  * Linear(in,200)-ReLU-Linear(200,100)-ReLU-Linear(100,out) in fp32 followed by
@@ -274,7 +280,8 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
  *   goal_or_null    uint8[n]: the h-DQN controller's `[goal] + state` input column (hdqn.py:291); network input 11
  *   w1t..b3         as mg_mlp_act (backend 0: w2 = w2p) or mg_mlp_act_tc (backend 1: w2 = w2_tc); out_dim is 5
  *   a2_or_null      uint8[n] actions of player 2 (pvp), NULL = `action_op = None` (pve)
- *   flags           MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE (MG_FLAG_NO_RETURNS is implied by state->ret1 == NULL)
+ *   flags           MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE | MG_POLICY_FLAG_PDL (MG_FLAG_NO_RETURNS is implied by
+ *                   state->ret1 == NULL)
  *   explore         the scripts' rule `np.random.randn() <= EPISILO ? greedy : np.random.randint(0, 5)` (main.py:103-110):
  *                   randn() <= t has probability Phi(t), so keep_u32 = floor(Phi(t) * 2^32) and the greedy action is
  *                   kept iff a Philox u32 < keep_u32; the draws are Philox4x32-10 keyed by seed ^ ('EXPL' << 32) with
@@ -284,6 +291,7 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
  *   actions_out     uint8[n] or NULL: the action taken (what `store_transition` records, main.py:207)
  *   q_out_or_null   float[n,5] Q-values */
 #define MG_POLICY_FLAG_EXPLORE 0x100u
+#define MG_POLICY_FLAG_PDL 0x200u     /* as MG_MLP_FLAG_PDL: the previous kernel of the stream does not write the weights */
 #define MG_POLICY_BACKEND_FP32 0
 #define MG_POLICY_BACKEND_TF32X3 1
 typedef struct MgExplore {

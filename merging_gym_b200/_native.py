@@ -20,6 +20,8 @@ ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 FLAG_AUTO_RESET = 0x1
 FLAG_NO_RETURNS = 0x2
 POLICY_FLAG_EXPLORE = 0x100
+POLICY_FLAG_PDL = 0x200
+MLP_FLAG_MIRROR, MLP_FLAG_PDL = 0x1, 0x2
 POLICY_BACKEND_FP32, POLICY_BACKEND_TF32X3 = 0, 1
 FIELD_OBS, FIELD_REW, FIELD_DONE, FIELD_INFO, FIELD_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 FIELD_BITS = {"obs": FIELD_OBS, "rew": FIELD_REW, "done": FIELD_DONE, "info": FIELD_INFO}

@@ -199,7 +199,10 @@ __device__ __forceinline__ void reset_obs_fixed(float *obs) {
 // MergeEnv.reset() for one env (merging_env.py:208-230): fixed start (:216-217) or the commented-out
 // random start (:219-221).  Keeps and advances the env's reset count (meta bits 15-31), which is the
 // Philox counter of the random draw.  Writes the reset observation.
-static __device__ __noinline__ void random_start(EnvRegs &e, uint64_t seed, uint64_t env_id, uint32_t count) {
+// Returned by value (pos1, vel1, pos2, vel2): a reference parameter of a non-inlined function would force the caller's
+// env registers into local memory.
+struct StartState { double p1, v1, p2, v2; };
+static __device__ __noinline__ StartState random_start_state(uint64_t seed, uint64_t env_id, uint32_t count) {
     uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = count, c3 = 0u;
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x52535445u);
     const double k32 = 1.0 / 4294967296.0;
@@ -208,10 +211,16 @@ static __device__ __noinline__ void random_start(EnvRegs &e, uint64_t seed, uint
     const double r = sqrt(-2.0 * log(u1));
     double sn, cs;
     sincospi(2.0 * u2, &sn, &cs);
-    e.p1 = kStart + (r * cs) * 5.0;                         // START_POINT + np.random.randn() * 5
-    e.v1 = kInitVel + (r * sn) * 3.0;                       // 20.0 + np.random.randn() * 3
-    e.p2 = kStart + (-4.0 + 8.0 * (((double)c2 + 0.5) * k32));     // + uniform(-VEHICLE_H/2, VEHICLE_H/2)
-    e.v2 = kInitVel + (-5.0 + 15.0 * (((double)c3 + 0.5) * k32));  // 20.0 + uniform(-5, 10)
+    StartState st;
+    st.p1 = kStart + (r * cs) * 5.0;                        // START_POINT + np.random.randn() * 5
+    st.v1 = kInitVel + (r * sn) * 3.0;                      // 20.0 + np.random.randn() * 3
+    st.p2 = kStart + (-4.0 + 8.0 * (((double)c2 + 0.5) * k32));     // + uniform(-VEHICLE_H/2, VEHICLE_H/2)
+    st.v2 = kInitVel + (-5.0 + 15.0 * (((double)c3 + 0.5) * k32));  // 20.0 + uniform(-5, 10)
+    return st;
+}
+__device__ __forceinline__ void random_start(EnvRegs &e, uint64_t seed, uint64_t env_id, uint32_t count) {
+    const StartState st = random_start_state(seed, env_id, count);
+    e.p1 = st.p1; e.v1 = st.v1; e.p2 = st.p2; e.v2 = st.v2;
 }
 
 // RANDOM is a compile-time switch: the fixed-start kernels carry none of the random-start code.

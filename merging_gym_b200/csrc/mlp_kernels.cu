@@ -100,14 +100,10 @@ mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t
     const int ng = t & 3, eg = t >> 2;
     const int64_t n_tiles = (n + TM - 1) / TM;
 
-    // layer-1 mapping: thread = env pair {e0, e0 + 128} x one half of the K-chunk's units, so that every weight
-    // read from shared memory (a warp-uniform LDS.128, 2.4 wavefronts) feeds two envs instead of one
+    // layer-1 mapping: thread = LR envs {e0 + r * TM/LR} x one LR-th of the K-chunk's units, so that every weight read
+    // from shared memory (a warp-uniform LDS.128, 2.4 wavefronts) feeds LR envs instead of one
     const int e0 = t & (TM / LR - 1), uh = t / (TM / LR);
-    // first tile's input rows are requested before the weights so the two latencies overlap
     float xr[LR][IN];
-#pragma unroll
-    for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
-
     // ---- weights -> shared memory, once per (persistent) CTA: straight 128-bit copies -------------
     {
         const float4 *src = reinterpret_cast<const float4 *>(w2p);
@@ -122,6 +118,12 @@ mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t
         for (int i = t; i < H2; i += TM) S.b2[i] = b2[i];
         if (t < OUT) S.b3[t] = b3[t];
     }
+    // The weight staging above reads nothing the previous kernel of the stream can have written: under programmatic
+    // dependent launch (MG_MLP_FLAG_PDL) it overlaps that kernel's drain.  Observations are read from here on.
+    cudaGridDependencySynchronize();
+    if (ENV) cudaTriggerProgrammaticLaunchCompletion();
+#pragma unroll
+    for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
     __syncthreads();
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -277,7 +279,7 @@ mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t
 template <int IN, int OUT, bool MIRROR, int ENV = 0>
 cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t,
                    const float *b1, const float *w2t, const float *b2, const float *w3, const float *b3,
-                   uint8_t *act, float *q_out, cudaStream_t st, const mgpe::Args &P = mgpe::Args{}) {
+                   uint8_t *act, float *q_out, cudaStream_t st, const mgpe::Args &P = mgpe::Args{}, bool pdl = false) {
     auto kern = mlp_act_kernel<IN, OUT, MIRROR, ENV>;
     const size_t smem = sizeof(Smem<IN, OUT>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -287,8 +289,14 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    kern<<<grid, TM, smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2t, b2, w3, b3, act, q_out, P);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TM); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_dim, w1t, b1, w2t, b2, w3, b3, act, q_out, P);
+    return e ? e : cudaGetLastError();
 }
 
 }  // namespace mgmlp
@@ -299,8 +307,8 @@ extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, 
                                  float *q_out_or_null, uint32_t flags, void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
-    if (flags & ~MG_MLP_FLAG_MIRROR) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
-    const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u;
+    if (flags & ~(MG_MLP_FLAG_MIRROR | MG_MLP_FLAG_PDL)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u, pdl = (flags & MG_MLP_FLAG_PDL) != 0u;
     const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
     if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
         return fail(MG_ERR_BAD_SIZE, "mg_mlp_act supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs "
@@ -313,7 +321,7 @@ extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #define MG_MLP_CASE(I, O) \
-    if (in_dim == I && out_dim == O) e = mirror ? mgmlp::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st) : mgmlp::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st); else
+    if (in_dim == I && out_dim == O) e = mirror ? mgmlp::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl) : mgmlp::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl); else
     MG_MLP_CASE(10, 5) MG_MLP_CASE(10, 3) MG_MLP_CASE(11, 5) MG_MLP_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_MLP_CASE
     if (e) return cuda_fail(e, "mg_mlp_act launch");
@@ -342,7 +350,8 @@ extern "C" MG_API int mg_policy_step(const MgState *state, int64_t n, const floa
                                      void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
-    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS | MG_POLICY_FLAG_EXPLORE)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS | MG_POLICY_FLAG_EXPLORE | MG_POLICY_FLAG_PDL)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    const bool pdl = (flags & MG_POLICY_FLAG_PDL) != 0u;
     if (backend != MG_POLICY_BACKEND_FP32 && backend != MG_POLICY_BACKEND_TF32X3)
         return fail(MG_ERR_BAD_FLAGS, "backend must be MG_POLICY_BACKEND_FP32 or MG_POLICY_BACKEND_TF32X3");
     if ((flags & MG_POLICY_FLAG_EXPLORE) && !explore_or_null) return fail(MG_ERR_NULL_POINTER, "MG_POLICY_FLAG_EXPLORE without an MgExplore");
@@ -372,11 +381,11 @@ extern "C" MG_API int mg_policy_step(const MgState *state, int64_t n, const floa
     if (backend == MG_POLICY_BACKEND_TF32X3)
         e = mg_policy_step_tc_launch(in_dim, obs_in, goal_or_null, n, w1t, b1, w2, b2, w3, b3, q_out_or_null, st, P);
     else if (in_dim == 10)
-        e = a2_or_null ? mgmlp::launch<10, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P)
-                       : mgmlp::launch<10, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P);
+        e = a2_or_null ? mgmlp::launch<10, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl)
+                       : mgmlp::launch<10, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl);
     else
-        e = a2_or_null ? mgmlp::launch<11, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P)
-                       : mgmlp::launch<11, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P);
+        e = a2_or_null ? mgmlp::launch<11, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl)
+                       : mgmlp::launch<11, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl);
     if (e) return cuda_fail(e, "mg_policy_step launch");
     return MG_OK;
 }

@@ -80,6 +80,7 @@ struct Smem {
     float w3[OUT][H2P];
     float b1[H1], b2[H2 + 12], b3[MAX_OUT];
     unsigned long long full[PRODUCER_WARPS], empty[PRODUCER_WARPS], tmem_full[2], tmem_empty[2];
+    unsigned long long w2_ready;              // completes when the bulk copies of b_cat have landed
     uint32_t tmem_base;
     mgpe::Handoff<TM, ENV_WARPS> env;                    // ENV: the tile's actions, epilogue warps -> env warp
 };
@@ -174,11 +175,27 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int64_t n_tiles = (n + TM - 1) / TM;
 
-    // ---- one-time setup: weights -> smem, barriers, TMEM -------------------------------------------
+    // ---- one-time setup: barriers, weights -> smem, TMEM ---------------------------------------------
+    // Nothing in this prologue reads anything but the weights, so under programmatic dependent launch (MG_MLP_FLAG_PDL)
+    // it runs while the previous kernel of the stream is still draining.  W2 (179 KB, already in the canonical UMMA
+    // layout) comes by bulk-copy engine: one thread issues five cp.async.bulk and only the MMA warp ever waits for
+    // them, so layer 1 of the first tile starts while the copy is in flight (staging it with LDG/STS through all
+    // threads cost ~4 of the kernel's ~10 us of fixed time, profiles/r02_policy_lane_probe.json).
+    if (t == 0) {
+        for (int s = 0; s < PRODUCER_WARPS; ++s) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], MMA_WARPS); mbar_init(&S.tmem_empty[b], TM); }
+        mbar_init(&S.w2_ready, 1);
+        if (ENV) mgpe::handoff_init(S.env, TM, ENV_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        constexpr uint32_t kChunk = B_BYTES / 5;      // 35 840 B, a multiple of 16
+        static_assert(kChunk * 5 == B_BYTES && kChunk % 16 == 0, "W2 is copied in five equal 16-byte-aligned pieces");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.w2_ready)), "r"((uint32_t)B_BYTES) : "memory");
+        for (uint32_t c = 0; c < 5; ++c)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(S.b_cat + c * kChunk)), "l"(reinterpret_cast<const unsigned char *>(w2_tc) + c * kChunk),
+                            "r"(kChunk), "r"(smem_u32(&S.w2_ready)) : "memory");
+    }
     {
-        const float4 *src = reinterpret_cast<const float4 *>(w2_tc);          // already in the canonical layout
-        float4 *dst = reinterpret_cast<float4 *>(S.b_cat);
-        for (int i = t; i < B_BYTES / 16; i += (int)blockDim.x) dst[i] = __ldg(src + i);
         const float4 *s1 = reinterpret_cast<const float4 *>(w1t);
         float4 *d1 = reinterpret_cast<float4 *>(&S.w1[0][0]);
         for (int i = t; i < IN * H1 / 4; i += (int)blockDim.x) d1[i] = __ldg(s1 + i);
@@ -190,13 +207,6 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
         for (int i = t; i < H2 + 12; i += (int)blockDim.x) S.b2[i] = i < H2 ? b2[i] : 0.f;
         if (t < OUT) S.b3[t] = b3[t];
     }
-    if (t == 0) {
-        for (int s = 0; s < PRODUCER_WARPS; ++s) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], MMA_WARPS); mbar_init(&S.tmem_empty[b], TM); }
-        if (ENV) mgpe::handoff_init(S.env, TM);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // W2 hi/lo written by the generic proxy
     if (warp == 12) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
                      "r"((uint32_t)TMEM_COLS));
@@ -216,6 +226,11 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // From here on observations and env state are read: wait for the previous kernel of the stream (a no-op without
+    // the PDL launch attribute), and let the NEXT launch start its own prologue right away.
+    cudaGridDependencySynchronize();
+    if (ENV) cudaTriggerProgrammaticLaunchCompletion();        // the next fused launch can only land on other SMs anyway
+                                                               // (an early trigger in front of mg_step made that step slower)
 
     if (warp < PRODUCER_WARPS) {
         // =================================== PRODUCERS: layer 1 ===================================
@@ -299,7 +314,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
         }
     } else if (ENV && warp >= ENV_WARP0) {
         // =================================== ENV WARPS: MergeEnv.step of the tiles the epilogue has finished ==========
-        mgpe::env_warp_loop<TM, ENV_WARPS, ENV == 2>(P, S.env, warp - ENV_WARP0, blockIdx.x, gridDim.x, n_tiles, n, lane,
+        mgpe::env_warp_loop<TM, ENV_WARPS, ENV_WARPS, ENV == 2>(P, S.env, warp - ENV_WARP0, blockIdx.x, gridDim.x, n_tiles, n, lane,
                                                      (int)(blockIdx.x % MG_STATS_ROWS));
     } else if (warp >= 12) {
         // =================================== MMA ISSUERS =========================================
@@ -315,6 +330,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
         // low descriptor words: (address >> 4) | (LBO >> 4) << 16; stepping an operand = adding (bytes >> 4)
         const uint32_t b_cat = (uint32_t)make_desc(smem_u32(S.b_cat)), a_hi0 = (uint32_t)make_desc(smem_u32(S.a_hi[0])),
                        a_lo0 = (uint32_t)make_desc(smem_u32(S.a_lo[0]));
+        mbar_wait(&S.w2_ready, 0u);                            // the bulk copies of W2 have landed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             const uint32_t buf = tl & 1u;
             mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);                // epilogue drained (and zeroed) this buffer
@@ -376,7 +392,11 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int o = 0; o < OUT; ++o) q[r][o] = 0.f;
-#pragma unroll
+            // NOT unrolled: fully unrolled, this loop is 1 000 instructions that each epilogue warp runs once per tile
+            // between two producer warps on its scheduler — 62 % of the epilogue's samples were instruction-fetch
+            // stalls (profiles/r02_policy_step_tc_v3: stall_no_inst 623 of 1 002); as a 7-trip loop the body stays
+            // in the instruction cache.
+#pragma unroll 1
             for (int cb = 0; cb < UN / 16; ++cb) {
                 uint32_t a[2][8], l[2][8];
 #pragma unroll
@@ -463,7 +483,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
 template <int IN, int OUT, bool MIRROR, int ENV = 0>
 cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t, const float *b1,
                    const float *w2_tc, const float *b2, const float *w3, const float *b3, uint8_t *act, float *q_out,
-                   cudaStream_t st, const mgpe::Args &P = mgpe::Args{}) {
+                   cudaStream_t st, const mgpe::Args &P = mgpe::Args{}, bool pdl = false) {
     auto kern = mlp_act_tc_kernel<IN, OUT, MIRROR, ENV>;
     const size_t smem = sizeof(Smem<IN, OUT>) + 1024;           // slack for the 1024-byte alignment of the base
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -473,8 +493,14 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    kern<<<grid, NUM_THREADS + (ENV ? 32 * ENV_WARPS : 0), smem, st>>>(obs, goal, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, act, q_out, P);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS + (ENV ? 32 * ENV_WARPS : 0)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, act, q_out, P);
+    return e ? e : cudaGetLastError();
 }
 
 }  // namespace mgtc
@@ -483,9 +509,9 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
 cudaError_t mg_policy_step_tc_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const float *w1t,
                                      const float *b1, const float *w2_tc, const float *b2, const float *w3, const float *b3,
                                      float *q_out, cudaStream_t st, const mgpe::Args &P) {
-    const bool pvp = P.a2 != nullptr;
-#define MG_TC_ENV(I) (pvp ? mgtc::launch<I, 5, false, 2>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P) \
-                          : mgtc::launch<I, 5, false, 1>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P))
+    const bool pvp = P.a2 != nullptr, pdl = (P.flags & MG_POLICY_FLAG_PDL) != 0u;
+#define MG_TC_ENV(I) (pvp ? mgtc::launch<I, 5, false, 2>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P, pdl) \
+                          : mgtc::launch<I, 5, false, 1>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P, pdl))
     if (in_dim == 10) return MG_TC_ENV(10);
     if (in_dim == 11) return MG_TC_ENV(11);
 #undef MG_TC_ENV
@@ -498,8 +524,8 @@ extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_nul
                                     float *q_out_or_null, uint32_t flags, void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
-    if (flags & ~MG_MLP_FLAG_MIRROR) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
-    const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u;
+    if (flags & ~(MG_MLP_FLAG_MIRROR | MG_MLP_FLAG_PDL)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u, pdl = (flags & MG_MLP_FLAG_PDL) != 0u;
     const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
     if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
         return fail(MG_ERR_BAD_SIZE, "mg_mlp_act_tc supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs");
@@ -511,7 +537,7 @@ extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_nul
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #define MG_TC_CASE(I, O) \
-    if (in_dim == I && out_dim == O) e = mirror ? mgtc::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st) : mgtc::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st); else
+    if (in_dim == I && out_dim == O) e = mirror ? mgtc::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl) : mgtc::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl); else
     MG_TC_CASE(10, 5) MG_TC_CASE(10, 3) MG_TC_CASE(11, 5) MG_TC_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_TC_CASE
     if (e) return cuda_fail(e, "mg_mlp_act_tc launch");

@@ -108,10 +108,10 @@ __device__ __forceinline__ void step_loaded(const Args &A, int64_t e, Loaded &x,
 // ---- the hand-over between the policy warps and the env warps: NB action tiles in shared memory ----------------------
 // The tensor-core policy kernel is bound by its matrix pipeline and its epilogue warps have no slack (ncu,
 // profiles/r02_policy_step_tc_*): an env step run BY the epilogue threads lengthened the tile period from 9 200 to
-// 18 400 cycles.  NB extra warps therefore own the env: the arg-max threads drop tile tl's actions into tile[tl % NB]
-// and arrive on full[tl % NB]; env warp tl % NB steps the tile's envs — one env per lane, four rounds of the same small
-// loop body, the next round's state requested before the current one is computed — while the policy warps are already
-// on the following tiles, and hands the buffer back through empty[].  mbarrier arrive / try_wait carry release /
+// 18 400 cycles.  Extra warps therefore own the env: the arg-max threads drop tile tl's actions into tile[tl % NB]
+// and arrive on full[tl % NB]; the env warps step the tile's envs — one env per lane, rounds of the same small loop
+// body, the next round's state requested before the current one is computed — while the policy warps are already
+// on the following tiles, and hand the buffer back through empty[].  mbarrier arrive / try_wait carry release /
 // acquire semantics at CTA scope.
 template <int TM, int NB>
 struct Handoff {
@@ -133,10 +133,11 @@ __device__ __forceinline__ void hs_wait(unsigned long long *b, uint32_t parity) 
                      : "=r"(done) : "r"(hs_u32(b)), "r"(parity) : "memory");
     if (!done) __trap();                              // never hang the GPU on a protocol bug
 }
-// init by one thread before the CTA-wide barrier that precedes the role split; `writers` threads arrive on full[]
+// init by one thread before the CTA-wide barrier that precedes the role split; `writers` threads arrive on full[],
+// `readers` (one lane per env warp) on empty[]
 template <int TM, int NB>
-__device__ __forceinline__ void handoff_init(Handoff<TM, NB> &H, uint32_t writers) {
-    for (int b = 0; b < NB; ++b) { hs_init(&H.full[b], writers); hs_init(&H.empty[b], 1); }
+__device__ __forceinline__ void handoff_init(Handoff<TM, NB> &H, uint32_t writers, uint32_t readers) {
+    for (int b = 0; b < NB; ++b) { hs_init(&H.full[b], writers); hs_init(&H.empty[b], readers); }
 }
 // policy side, tile number tl (0, 1, ...) of this CTA: wait until the env warp has released the buffer, then the caller
 // stores its actions into the returned tile and calls handoff_publish
@@ -148,29 +149,31 @@ __device__ __forceinline__ uint8_t *handoff_acquire(Handoff<TM, NB> &H, uint32_t
 template <int TM, int NB>
 __device__ __forceinline__ void handoff_publish(Handoff<TM, NB> &H, uint32_t tl) { hs_arrive(&H.full[tl % NB]); }
 
-// env warp w of NB: this CTA's tiles tl = w, w + NB, ... (global tile = first_tile + tl * tile_stride), TM envs each
-template <int TM, int NB, bool PVP>
+// env warp w of NW: rounds w, w + NW, ... (32 envs each) of EVERY tile of this CTA (global tile = first_tile + tl *
+// tile_stride, TM envs): the warps share a tile so that what is left to do after the policy warps' last tile — the only
+// part of the env work that is not hidden — is 1/NW of a tile per warp.  empty[] therefore counts NW arrivals.
+template <int TM, int NB, int NW, bool PVP>
 __device__ __forceinline__ void env_warp_loop(const Args &A, Handoff<TM, NB> &H, int w, int64_t first_tile, int64_t tile_stride,
                                               int64_t n_tiles, int64_t n, int lane, int stats_row) {
     static_assert(TM % 32 == 0, "a tile is a whole number of warp rounds");
     constexpr int ROUNDS = TM / 32;
-    for (uint32_t tl = (uint32_t)w;; tl += NB) {
-        const int64_t tile = first_tile + (int64_t)tl * tile_stride;
-        if (tile >= n_tiles) break;
+    uint32_t tl = 0;
+    for (int64_t tile = first_tile; tile < n_tiles; tile += tile_stride, ++tl) {
+        const uint32_t buf = tl % NB;
         const int64_t e0 = tile * TM + lane;
         Loaded cur, nxt;
-        load_env<PVP>(A, e0, n, nxt);                     // the state does not depend on the actions: ask for it first
-        hs_wait(&H.full[w], (tl / NB) & 1u);
+        load_env<PVP>(A, e0 + 32 * w, n, nxt);            // the state does not depend on the actions: ask for it first
+        hs_wait(&H.full[buf], (tl / NB) & 1u);
         mg::StatAcc st;
 #pragma unroll 1
-        for (int r = 0; r < ROUNDS; ++r) {
+        for (int r = w; r < ROUNDS; r += NW) {
             cur = nxt;
-            if (r + 1 < ROUNDS) load_env<PVP>(A, e0 + 32 * (r + 1), n, nxt);
-            step_loaded<PVP>(A, e0 + 32 * r, cur, (int)H.tile[w][32 * r + lane], st);
+            if (r + NW < ROUNDS) load_env<PVP>(A, e0 + 32 * (r + NW), n, nxt);
+            step_loaded<PVP>(A, e0 + 32 * r, cur, (int)H.tile[buf][32 * r + lane], st);
         }
         if (A.stats) mg::flush_stats(st, A.stats + (size_t)stats_row * MG_STATS_COLS, 0xFFFFFFFFu, lane);
         __syncwarp();
-        if (lane == 0) hs_arrive(&H.empty[w]);
+        if (lane == 0) hs_arrive(&H.empty[buf]);
     }
 }
 

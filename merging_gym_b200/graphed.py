@@ -50,6 +50,10 @@ class GraphedPolicyRollout:
         if (policy2 is not None) != (env.mode == "pvp"):
             raise ValueError("policy2 is required for, and only for, a pvp env")
         self.env, self.k_steps = env, int(k_steps)
+        for p in (policy1, policy2):        # inside this loop the kernel before a policy kernel is the env step (or the
+            for q in (p, getattr(p, "meta", None), getattr(p, "ctrl", None)):   # recorder): the weights are not written
+                if hasattr(q, "pdl"):
+                    q.pdl = True
         self._p1, self._p2, self._after = policy1, policy2, after_step
         n, dev = env.num_envs, env.device
         self._a1 = torch.zeros(n, dtype=torch.uint8, device=dev)

@@ -43,6 +43,7 @@ class MLPPolicy:
             raise ValueError("backend must be 'fused', 'tf32x3' or 'torch'")
         self.in_dim, self.out_dim, self.backend = int(in_dim), int(out_dim), backend
         self.device = torch.device(device)
+        self.pdl = False                     # see act(): set True when no kernel that writes the weights precedes act()
         if state_dict is None:
             # the reference's init: weights uniform_(0,1), biases nn.Linear default (main.py:34-39)
             g = torch.Generator().manual_seed(0 if seed is None else seed)
@@ -109,10 +110,13 @@ class MLPPolicy:
         return torch.addmm(self.b3, h, self.w3.t())
 
     def act(self, obs: torch.Tensor, goal: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-            q_out: Optional[torch.Tensor] = None, mirror: bool = False) -> torch.Tensor:
+            q_out: Optional[torch.Tensor] = None, mirror: bool = False, pdl: Optional[bool] = None) -> torch.Tensor:
         """Greedy actions uint8[N] = argmax_a Q(obs)[a] (first maximum wins, as torch.max does).
         `mirror=True` evaluates the network on the opponent's view `state[5:] + state[:5]` (main.py:199) of every
-        row; the fused kernels swap the halves while they read the row."""
+        row; the fused kernels swap the halves while they read the row.
+        `pdl` (default `self.pdl`): programmatic dependent launch — the kernel stages its weights while the previous
+        kernel of the stream is still draining (`MG_MLP_FLAG_PDL`).  Only valid when that kernel does not write this
+        policy's weights; in a rollout loop it is the env step, so `GraphedPolicyRollout` and `bench_policy` turn it on."""
         n = obs.shape[0]
         if mirror and self.backend == "torch":
             obs = torch.cat([obs[:, 5:], obs[:, :5]], dim=1)
@@ -133,16 +137,17 @@ class MLPPolicy:
         if goal is not None and not (goal.dtype == torch.uint8 and goal.is_contiguous()):
             raise ValueError("goal must be a contiguous uint8 tensor")
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        flags = (nat.MLP_FLAG_MIRROR if mirror else 0) | (nat.MLP_FLAG_PDL if (self.pdl if pdl is None else pdl) else 0)
         with torch.cuda.device(self.device):
             if self.backend == "tf32x3":
                 nat.check(lib.mg_mlp_act_tc(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
                                             _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_tc), _ptr(self.b2),
-                                            _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), 1 if mirror else 0, stream),
+                                            _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), flags, stream),
                           "mg_mlp_act_tc")
             else:
                 nat.check(lib.mg_mlp_act(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
                                          _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_p), _ptr(self.b2),
-                                         _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), 1 if mirror else 0, stream),
+                                         _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), flags, stream),
                           "mg_mlp_act")
         return out
 

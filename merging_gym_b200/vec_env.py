@@ -474,6 +474,8 @@ class MergeVecEnv:
         if explore is not None:
             ex = explore.spec()
             flags |= nat.POLICY_FLAG_EXPLORE
+        if policy.pdl:
+            flags |= nat.POLICY_FLAG_PDL
         w2 = policy.w2_tc if policy.backend == "tf32x3" else policy.w2_p
         with torch.cuda.device(self.device):
             nat.check(self._lib.mg_policy_step(C.byref(self._state), n, _ptr(obs_in), _ptr(goal), POLICY_BACKENDS[policy.backend],
