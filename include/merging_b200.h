@@ -336,6 +336,17 @@ MG_API int mg_record_transitions(const float *obs_prev, const float *obs_next,
                                  int32_t *env_ids_or_null, uint64_t *counter, uint32_t *scratch,
                                  void *stream);
 
+/* The h-DQN meta-controller's per-step bookkeeping (scripts/hdqn.py:283-320) for n envs in one launch: an option runs
+ * until `done or goal == goal_status(state)` (:316) while `extrinsic_reward += reward` (:312); the meta-controller then
+ * stores `[state, goal, extrinsic_reward, next_state]` with state == next_state == the observation the option ended in
+ * (:315-318).  Per env: s_end = done ? term_obs : obs (the stepped state's observation; term_obs NULL = no auto-reset),
+ * sum = extrinsic + rew[e][0], ended = done || goal_next == goal_status(s_end) (goal_status: hdqn.py:223-236);
+ * writes s_end_out[n,10], rew_out[n,2] = (sum, 0), ended_out[n], and extrinsic = ended ? 0 : sum.  Feed s_end_out /
+ * rew_out / ended_out to mg_record_transitions (format 0, mask_mode 2) to append the rows. */
+MG_API int mg_option_update(const float *obs, const float *term_obs_or_null, const float *rew, const uint8_t *done,
+                            const uint8_t *goal_next, int64_t n, float *extrinsic, float *s_end_out, float *rew_out,
+                            uint8_t *ended_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ The package holds only what the hot path needs:
   replay.py    device-resident transition ring (replay rows) and per-episode CSV logs
   policy.py    policy-in-the-loop: the reference's Q-networks as one fused forward+argmax kernel
   graphed.py   K policy+env(+recorder) steps captured in one CUDA graph
+  tracing.py   optional NVTX ranges around the launches
 """
 from ._native import NativeError  # noqa: F401
 from .graphed import GraphedPolicyRollout  # noqa: F401
@@ -18,6 +19,7 @@ from .replay import CsvEpisodeLogger, OptionRecorder, TransitionRecorder  # noqa
 from .scalar_env import ENV_ID, MergeEnv, make, make_vec, register_gym  # noqa: F401
 from .sharding import AsyncStatsReducer, all_reduce_stats, init_distributed, shard_range  # noqa: F401
 from .spaces import Box, Discrete, MultiDiscrete  # noqa: F401
+from .tracing import enable as enable_nvtx, nvtx_range  # noqa: F401
 from .vec_env import MergeVecEnv, StepInfo  # noqa: F401
 
 __version__ = "0.1.0"

@@ -126,6 +126,8 @@ def load():
     lib.mg_policy_step.restype = C.c_int
     lib.mg_explore.argtypes = [vp, i64, i32, C.POINTER(MgExplore), vp, u64, u32, vp]
     lib.mg_explore.restype = C.c_int
+    lib.mg_option_update.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.mg_option_update.restype = C.c_int
     lib.mg_record_transitions.argtypes = [vp] * 10 + [i64, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.mg_record_transitions.restype = C.c_int
     for f in (lib.mg_get_constants, lib.mg_default_rewards, lib.mg_reset, lib.mg_step,

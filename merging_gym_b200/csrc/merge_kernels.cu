@@ -90,22 +90,16 @@ __device__ __forceinline__ void st_pack_stream(T *__restrict__ p, const T (&in)[
 //   grid = ceil(n / (kBlock*EPT)), block = kBlock.  A warp owns 32*EPT consecutive envs.
 //   Full warps take the vector path; the (at most one) ragged warp takes the scalar path.
 // =================================================================================================
-template <int EPT, typename ActT, bool PVP, bool RR, bool RET>
-__global__ void __launch_bounds__(kBlock, MG_MIN_BLOCKS)
-merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
-                  const ActT *__restrict__ a2g, const int64_t n, const MgRewards rw,
-                  const uint32_t flags, const MgResetSpec rs, unsigned long long *__restrict__ stats) {
-    __shared__ __align__(16) float stage[kWarps][32 * EPT * MG_OBS_DIM];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * (32 * EPT);
-#if MG_PDL
-    // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the
-    // stream drains; nothing of global memory is touched before the previous grid has completed
-    // and flushed.  Triggering right away lets the NEXT launch pre-stage the same way.
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
+#ifndef MG_STEP_PERSISTENT
+#define MG_STEP_PERSISTENT 0   // 1: grid = SMs x MG_MIN_BLOCKS blocks that loop over the 256-env tiles (experiment, profiles/r02_variant_sweep.md)
 #endif
+template <int EPT, typename ActT, bool PVP, bool RR, bool RET>
+__device__ __forceinline__ void step_block(const int64_t blk, float (*stage)[32 * EPT * MG_OBS_DIM], const MgState &s, const MgOut &o,
+                                           const ActT *__restrict__ a1g, const ActT *__restrict__ a2g, const int64_t n,
+                                           const MgRewards &rw, const uint32_t flags, const MgResetSpec &rs,
+                                           unsigned long long *__restrict__ stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_base = (blk * kWarps + warp) * (32 * EPT);
     if (warp_base >= n) return;
     const bool full = warp_base + 32 * EPT <= n;
     const int64_t e0 = warp_base + (int64_t)lane * EPT;
@@ -234,10 +228,34 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
         }
     }
 
-    if (stats) flush_stats(st, stats + (size_t)(blockIdx.x % MG_STATS_ROWS) * MG_STATS_COLS, 0xFFFFFFFFu, lane);
+    if (stats) flush_stats(st, stats + (size_t)(blk % MG_STATS_ROWS) * MG_STATS_COLS, 0xFFFFFFFFu, lane);
 #if MG_TMA_OBS
     // the staging tile must stay intact until the bulk copy has read it
     if (full && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+
+template <int EPT, typename ActT, bool PVP, bool RR, bool RET>
+__global__ void __launch_bounds__(kBlock, MG_MIN_BLOCKS)
+merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
+                  const ActT *__restrict__ a2g, const int64_t n, const MgRewards rw,
+                  const uint32_t flags, const MgResetSpec rs, unsigned long long *__restrict__ stats) {
+    __shared__ __align__(16) float stage[kWarps][32 * EPT * MG_OBS_DIM];
+#if MG_PDL
+    // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the
+    // stream drains; nothing of global memory is touched before the previous grid has completed
+    // and flushed.  Triggering right away lets the NEXT launch pre-stage the same way.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+#endif
+#if MG_STEP_PERSISTENT
+    const int64_t n_blocks = (n + (int64_t)kBlock * EPT - 1) / ((int64_t)kBlock * EPT);
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        step_block<EPT, ActT, PVP, RR, RET>(blk, stage, s, o, a1g, a2g, n, rw, flags, rs, stats);
+        __syncwarp();                                  // the warp's staging tile is reused by the next trip
+    }
+#else
+    step_block<EPT, ActT, PVP, RR, RET>((int64_t)blockIdx.x, stage, s, o, a1g, a2g, n, rw, flags, rs, stats);
 #endif
 }
 
@@ -616,7 +634,15 @@ cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const 
                         const MgRewards &rw, uint32_t flags, const MgResetSpec &rs, int64_t *stats, cudaStream_t st) {
     constexpr int EPT = MG_EPT;
     const int64_t per_block = (int64_t)mg::kBlock * EPT;
-    const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
+    unsigned grid = (unsigned)((n + per_block - 1) / per_block);
+#if MG_STEP_PERSISTENT
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (grid > (unsigned)(sms * MG_MIN_BLOCKS)) grid = (unsigned)(sms * MG_MIN_BLOCKS);
+    }
+#endif
     auto *stp = reinterpret_cast<unsigned long long *>(stats);
     const bool rr = rs.mode == MG_RESET_RANDOM;
     const bool ret = (flags & MG_FLAG_NO_RETURNS) == 0u;

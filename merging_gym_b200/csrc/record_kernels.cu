@@ -245,3 +245,51 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_record_transitions launch");
     return MG_OK;
 }
+
+// ---- h-DQN meta-controller bookkeeping (scripts/hdqn.py:283-320), one thread per env -------------------------------
+// An option runs from one goal choice until `done or goal == goal_status(state)` (hdqn.py:316); on the way the ego
+// rewards are summed into `extrinsic_reward` (:312).  Per env and step this kernel (1) picks the observation the option
+// would end in — the stepped state's: the terminal observation where the env finished and was auto-reset —, (2) adds
+// the step's ego reward to the running sum, (3) decides whether the option ended, (4) hands the recorder what
+// `upper.store_transition(state, goal, extrinsic_reward, next_state)` (:318) needs: the row's observation, the sum in
+// column 0 of a reward pair, the ended mask; and (5) restarts the sum of an ended option.
+namespace mgrec {
+__global__ void __launch_bounds__(kBlock)
+option_update_kernel(const float *__restrict__ obs, const float *__restrict__ term_obs, const float *__restrict__ rew,
+                     const uint8_t *__restrict__ done, const uint8_t *__restrict__ goal_next, const int64_t n,
+                     float *__restrict__ extrinsic, float *__restrict__ s_end, float *__restrict__ rew_out,
+                     uint8_t *__restrict__ ended) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= n) return;
+    const bool dn = done[e] != 0;
+    const float2 *src = reinterpret_cast<const float2 *>((dn && term_obs ? term_obs : obs) + e * kObs);
+    float2 *dst = reinterpret_cast<float2 *>(s_end + e * kObs);
+    float2 row[kObs / 2];
+#pragma unroll
+    for (int k = 0; k < kObs / 2; ++k) { row[k] = src[k]; dst[k] = row[k]; }
+    const float dx1 = row[0].x, v2 = row[kObs / 2 - 1].y;                       // goal_status, hdqn.py:223-236
+    const uint8_t status = dx1 < -0.5f * v2 ? 0 : dx1 < 0.5f * v2 ? 1 : 2;
+    const float sum = extrinsic[e] + rew[2 * e];                                // extrinsic_reward += reward (:312)
+    const bool end = dn || goal_next[e] == status;                              // :316
+    *reinterpret_cast<float2 *>(rew_out + 2 * e) = make_float2(sum, 0.f);
+    ended[e] = end ? 1 : 0;
+    extrinsic[e] = end ? 0.f : sum;
+}
+}  // namespace mgrec
+
+extern "C" MG_API int mg_option_update(const float *obs, const float *term_obs_or_null, const float *rew, const uint8_t *done,
+                                       const uint8_t *goal_next, int64_t n, float *extrinsic, float *s_end_out,
+                                       float *rew_out, uint8_t *ended_out, void *stream) {
+    using namespace mg_abi;
+    if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if (n == 0) return MG_OK;
+    if (!obs || !rew || !done || !goal_next || !extrinsic || !s_end_out || !rew_out || !ended_out)
+        return fail(MG_ERR_NULL_POINTER, "mg_option_update: NULL pointer");
+    if (!aligned16(obs) || !aligned16(s_end_out) || !aligned16(rew_out) || (term_obs_or_null && !aligned16(term_obs_or_null)))
+        return fail(MG_ERR_ALIGNMENT, "observation and reward arrays must be 16-byte aligned");
+    const unsigned grid = (unsigned)((n + mgrec::kBlock - 1) / mgrec::kBlock);
+    mgrec::option_update_kernel<<<grid, mgrec::kBlock, 0, (cudaStream_t)stream>>>(obs, term_obs_or_null, rew, done, goal_next, n,
+                                                                                  extrinsic, s_end_out, rew_out, ended_out);
+    if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_option_update launch");
+    return MG_OK;
+}

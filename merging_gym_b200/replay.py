@@ -19,6 +19,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _native as nat
+from .tracing import nvtx_range
 
 REPLAY_WIDTH = 2 * nat.OBS_DIM + 2      # main.py:92  NUM_STATES * 2 + 2
 LOG_WIDTH = nat.OBS_DIM + 4
@@ -90,7 +91,7 @@ class TransitionRecorder:
             # with out_slots=1 `env.step` returns the buffer it was given: s and s' would be the same row
             raise ValueError("obs_prev aliases the new observation (the env's single output slot was overwritten by this "
                              "step): create the env with out_slots >= 2 or pass a copy of the previous observation")
-        with torch.cuda.device(env.device):
+        with torch.cuda.device(env.device), nvtx_range("mg.record"):
             nat.check(self._lib.mg_record_transitions(
                 _ptr(obs_prev), _ptr(obs), _ptr(term), _ptr(a1), _ptr(a2), _ptr(rew),
                 _ptr(done.view(torch.uint8)), _ptr(select if select is not None else info["flags"]),
@@ -128,13 +129,15 @@ class OptionRecorder:
     """
 
     def __init__(self, env, capacity: int, track_env_ids: bool = False):
-        from .policy import goal_status
-        self._goal_status = goal_status
         self.env = env
         self.rec = TransitionRecorder(env, capacity, format="replay", player=1, mask="explicit", track_env_ids=track_env_ids)
         self.rec._same_obs_ok = True
-        self.extrinsic = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
-        self._rew = torch.zeros(env.num_envs, 2, dtype=torch.float32, device=env.device)
+        n, dev = env.num_envs, env.device
+        self.extrinsic = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._rew = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+        self._s_end = torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, device=dev)
+        self._ended = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._not_done = torch.zeros(n, dtype=torch.uint8, device=dev)
 
     @property
     def ring(self):
@@ -146,19 +149,23 @@ class OptionRecorder:
 
     def record(self, step_out, goal_next: torch.Tensor) -> torch.Tensor:
         """Call after every env step with the goal chosen from the NEW state; returns the uint8[N] mask of the
-        envs whose option ended in this step.  No host sync."""
+        envs whose option ended in this step (a buffer that the next call overwrites).  Two launches —
+        `mg_option_update` (end-of-option test, reward sum, row observation) and the ring append — no host sync."""
         obs, rew, done, info = step_out
         env = self.env
-        s_end = obs
-        if env.auto_reset:                                     # the stepped state's observation, not the reset one
-            s_end = torch.where(done.bool().unsqueeze(1), env.terminal_obs, obs)
-        self.extrinsic += rew[:, 0]
-        ended = (done.bool() | (goal_next == self._goal_status(s_end))).to(torch.uint8)
-        self._rew[:, 0] = self.extrinsic
+        if goal_next.dtype != torch.uint8 or not goal_next.is_contiguous():
+            raise TypeError("goal_next must be a contiguous uint8 tensor")
+        term = env.terminal_obs if env.auto_reset else None      # the stepped state's observation, not the reset one
+        with torch.cuda.device(env.device):
+            nat.check(self.rec._lib.mg_option_update(_ptr(obs), _ptr(term), _ptr(rew), _ptr(done.view(torch.uint8)),
+                                                     _ptr(goal_next), env.num_envs, _ptr(self.extrinsic), _ptr(self._s_end),
+                                                     _ptr(self._rew), _ptr(self._ended),
+                                                     C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)),
+                      "mg_option_update")
         # row = [state, goal, extrinsic_reward, next_state] with state == next_state == s_end (hdqn.py:315-318)
-        self.rec.record(s_end.contiguous(), goal_next, None, (s_end.contiguous(), self._rew, torch.zeros_like(done), info), select=ended)
-        self.extrinsic.masked_fill_(ended.bool(), 0.0)
-        return ended
+        self.rec.record(self._s_end, goal_next, None, (self._s_end, self._rew, self._not_done.view(torch.bool), info),
+                        select=self._ended)
+        return self._ended
 
 
 class CsvEpisodeLogger:

@@ -28,6 +28,7 @@ import torch
 
 from . import _native as nat
 from .spaces import Box, Discrete, MultiDiscrete, merge_action_space, merge_observation_space
+from .tracing import nvtx_range
 
 ACTION_SEED_DEFAULT = 0x5EED
 
@@ -288,7 +289,7 @@ class MergeVecEnv:
                 raise ValueError("mask must have num_envs elements")
         obs = self.obs_buf[self._slot]
         self._join_lanes()
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("mg.reset"):
             nat.check(self._lib.mg_reset(C.byref(self._state), self.num_envs, _ptr(m), _ptr(obs),
                                          C.byref(self._rs), self._stream()), "mg_reset")
         return obs
@@ -348,7 +349,7 @@ class MergeVecEnv:
         fork = torch.cuda.Event()
         fork.record(cur)
         ls.wait_event(fork)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("mg.step[lane]"):
             nat.check(self._lib.mg_step(C.byref(self._lane_state[lane]), hi - lo, _ptr(a1), _ptr(a2),
                                         self._ACT_DTYPE[a1.dtype], C.byref(self._rw), C.byref(self._lane_outs[lane][k]),
                                         _ptr(self.stats_buf), self._flags(), C.byref(self._lane_rs[lane]),
@@ -402,7 +403,7 @@ class MergeVecEnv:
             return
         self._slot = (self._slot + 1) % self.out_slots
         k = self._slot
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("mg.step"):
             nat.check(self._lib.mg_step(C.byref(self._state), self.num_envs, _ptr(a1), _ptr(a2),
                                         self._ACT_DTYPE[a1.dtype], C.byref(self._rw),
                                         C.byref(self._outs[k]), _ptr(self.stats_buf), self._flags(),
@@ -477,7 +478,7 @@ class MergeVecEnv:
         if policy.pdl:
             flags |= nat.POLICY_FLAG_PDL
         w2 = policy.w2_tc if policy.backend == "tf32x3" else policy.w2_p
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("mg.policy_step"):
             nat.check(self._lib.mg_policy_step(C.byref(self._state), n, _ptr(obs_in), _ptr(goal), POLICY_BACKENDS[policy.backend],
                                                _ptr(policy.w1_t), _ptr(policy.b1), _ptr(w2), _ptr(policy.b2), _ptr(policy.w3),
                                                _ptr(policy.b3), _ptr(a2), C.byref(self._rw), C.byref(self._outs[k]),
@@ -583,7 +584,7 @@ class MergeVecEnv:
         out = nat.MgOut(*[None if t is None else t.data_ptr() for t in
                           (obs, rew, done, info, self.terminal_obs, self.episode_return, self.episode_length)])
         self._join_lanes()
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range(f"mg.rollout[{k}]"):
             nat.check(self._lib.mg_rollout(C.byref(self._state), n, int(self.mode == "pvp"), self.philox_seed,
                                            self.env_id_base, int(step0), k, C.byref(self._rw),
                                            C.byref(out), _ptr(actions), _ptr(self.stats_buf),
@@ -705,7 +706,7 @@ class MergeVecEnv:
             npa[0][:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
         if a2 is not None and a2 is not npa[1]:
             npa[1][:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("mg.step_host_async"):
             nat.check(self._lib.mg_step_host_async(C.byref(self._state), self.num_envs,
                                                    C.byref(h["slot"] if a2 is not None else h["slot_pve"]), mask,
                                                    C.byref(self._rw), _ptr(self.stats_buf), self._flags(), C.byref(self._rs),
@@ -760,7 +761,7 @@ class MergeVecEnv:
             self._host_np[0][:] = np.asarray(a1, dtype=np.uint8).reshape(-1)
         if a2 is not None and a2 is not self._host_np[1]:
             self._host_np[1][:] = np.asarray(a2, dtype=np.uint8).reshape(-1)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("mg.step_host"):
             if zero_copy:
                 nat.check(self._lib.mg_step(C.byref(self._state), n, _ptr(h["a1"]),
                                             _ptr(h["a2"]) if a2 is not None else None, nat.ACT_U8,

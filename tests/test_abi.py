@@ -31,7 +31,7 @@ def test_header_declares_expected_entry_points():
     assert declared_symbols() == sorted([
         "mg_version", "mg_last_error", "mg_get_constants", "mg_default_rewards", "mg_reset",
         "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_step_host_async", "mg_step_host_wait",
-        "mg_mlp_act", "mg_mlp_act_tc", "mg_record_transitions", "mg_policy_step", "mg_explore"])
+        "mg_mlp_act", "mg_mlp_act_tc", "mg_record_transitions", "mg_policy_step", "mg_explore", "mg_option_update"])
 
 
 def test_library_exports_every_declared_symbol(lib):

@@ -78,7 +78,9 @@ def test_gpu_arm_contract_line():
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert abs(r["achieved"] - 156 * n / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
     assert 0.3 < r["frac"] < 1.05
-    assert d["gpu_launches"] == 48
+    m = d["measurement"]
+    assert m["launches_per_step"] == 2 and d["gpu_launches"] == 48 * 2           # headline: MergeVecEnv(lanes=2)
+    assert d["serialized"]["value"] > 0 and d["serialized"]["at_headline_steps"]["steps"] == 48
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 2 * n and e["d2h_bytes_per_step"] == 50 * n and 0 < e["value"] < d["value"]
     cb = d["cpu_baseline"]
@@ -86,9 +88,10 @@ def test_gpu_arm_contract_line():
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert "l2" in d["config"] and "workload" in d["config"]
     assert d["overlapped_streams"]["value"] > 0 and d["l2_warm"]["value"] > 0
-    assert d["sustained"]["steps"] == 200 and d["laned"]["value"] > 0 and d["lean_no_returns"]["bytes_per_env_step"] == 124
+    assert d["sustained"]["steps"] == 200 and d["lean_no_returns"]["bytes_per_env_step"] == 124
     assert e["sync_value"] > 0 and e["rew_done_info_value"] > e["value"] and 0 < e["frac_of_ceiling"] <= 1.05
     st = d["strong_8m"]
     assert st["total_envs"] == 65536 and st["steps"] == 256 and len(st["stats_digest"]) == 16 and st["stats_totals"][0] > 0
     assert d["policy_in_loop"]["fused"]["value"] > 0 and 0 < d["policy_in_loop"]["tf32x3"]["env_share"] < 1
+    assert d["policy_in_loop"]["tf32x3"]["fused_step"]["value"] > 0 and d["policy_in_loop"]["tf32x3_4096_envs"]["value"] > 0
     assert cb["reference_python_value"] > 0

@@ -105,6 +105,42 @@ def test_golden_vec16_from_reference_file(mg):
             assert rel_err(info["terminal_observation"].cpu().numpy()[m], tr["step_obs"][t][m]).max() <= TOL
 
 
+@pytest.mark.parametrize("name,pvp", [("config1_pve_trace.npz", False), ("pvp_trace.npz", True)])
+def test_cuda_path_replays_the_reference_traces(mg, golden, name, pvp):
+    """BASELINE.json configs[0] straight on the CUDA path: the 10 000-step pve trace (and the 6 000-step pvp trace) that
+    the UNMODIFIED reference env produced — random actions, `env.reset()` after every `done` — replayed through `mg_step` /
+    `mg_reset` with the recorded actions: done / collision / winner bit-exact at every step, observations, rewards and
+    the float64 return accumulators within 1e-5 relative.  70 envs replay the same trace (two full warps of the
+    vector path and a ragged tail of the scalar path); envs 0, 63 and 69 are checked."""
+    tr = golden(name)
+    assert bool(tr["pvp"]) == pvp
+    n, probe = 70, [0, 63, 69]
+    env = mg.MergeVecEnv(n, mode="pvp" if pvp else "pve", auto_reset=False, episode_info=False)
+    obs0 = env.reset().cpu().numpy()
+    assert rel_err(obs0[probe], np.broadcast_to(tr["reset_obs"], (3, 10))).max() <= TOL
+    T = len(tr["done"])
+    acts = torch.as_tensor(tr["actions"]).cuda()                       # [T, 2] uint8
+    ones = torch.ones(n, dtype=torch.uint8, device="cuda")
+    episodes = 0
+    for t in range(T):
+        a1 = ones * acts[t, 0]
+        a2 = ones * acts[t, 1] if pvp else None
+        obs, rew, done, info = env.step(a1, a2)
+        d = done[probe].cpu().numpy()
+        assert d.tolist() == [bool(tr["done"][t])] * 3, f"done differs at step {t}"
+        assert info["collision"][probe].cpu().tolist() == [bool(tr["collision"][t])] * 3, f"collision differs at step {t}"
+        assert info["winner"][probe].cpu().tolist() == [int(tr["winner"][t])] * 3, f"winner differs at step {t}"
+        if t % 7 == 0 or d[0]:                                         # continuous outputs: every 7th step and every terminal step
+            assert rel_err(obs[probe].cpu().numpy(), np.broadcast_to(tr["obs"][t], (3, 10))).max() <= TOL, t
+            assert rel_err(rew[probe].cpu().numpy(), np.broadcast_to(tr["rewards"][t], (3, 2))).max() <= TOL, t
+            ret = torch.stack([env.r1_accumulate[probe], env.r2_accumulate[probe]], 1).cpu().numpy()
+            assert rel_err(ret, np.broadcast_to(tr["returns"][t], (3, 2))).max() <= TOL, t
+        if d[0]:
+            env.reset()
+            episodes += 1
+    assert episodes == int(tr["done"].sum()) > 10
+
+
 def test_known_answer_episodes_sticky_done(mg):
     """All scripted KAT episodes side by side in one launch, auto_reset off, run to 2600 steps
     (covers the 2501-step time limit, '>=' vs '>', truncation vs rounding, winner-keeps-driving)."""
