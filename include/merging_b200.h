@@ -37,7 +37,7 @@ extern "C" {
 #define MG_API __attribute__((visibility("default")))
 #endif
 
-#define MG_ABI_VERSION 5
+#define MG_ABI_VERSION 6
 #define MG_OBS_DIM 10      /* merging_env.py:75,118-132 */
 #define MG_NUM_ACTIONS 5   /* merging_env.py:101-102   */
 
@@ -61,6 +61,21 @@ typedef enum MgActionDtype { MG_ACT_U8 = 0, MG_ACT_I32 = 1, MG_ACT_I64 = 2 } MgA
                                    human_player.py:189-193 and render): MgState.ret1/ret2 are not touched and may be
                                    NULL, MgOut.ep_ret must be NULL, the return columns of `stats` stay 0.  Cuts the
                                    step's traffic from 156 to 124 bytes per env-step.                             */
+
+/* Observation layouts (SURVEY.md 7.4 / 8b `obs_layout`).  The reference's observation is a Python list that its callers
+ * slice and concatenate (`state[5:] + state[:5]`, `[goal] + state`: scripts/hdqn.py:285,291,299); on the device the same
+ * ten values can be laid out for their consumer:
+ *   default             obs[n][10]        the gym-shaped rows (40-byte rows; staged per warp, linear 128-bit stores)
+ *   MG_FLAG_OBS_SOA     obs[10][S]        S = MG_OBS_SOA_STRIDE(n): one column per feature, every access of a warp is one
+ *                                         contiguous span — the layout a fused policy consumer reads best
+ *   MG_FLAG_OBS_GOAL_SLOT obs[n][11]      rows `[goal] + state` (hdqn.py:291): slots 1..10 are the observation, slot 0
+ *                                         belongs to the goal policy (mg_mlp_act* with MG_MLP_FLAG_WRITE_GOAL writes its
+ *                                         arg-max there); the env never touches slot 0
+ * accepted by mg_reset, mg_step (uint8 actions, with return accumulators) and mg_policy_step; the policy kernels read
+ * all three (MG_MLP_FLAG_OBS_*).  mg_rollout, mg_step_host* and mg_record_transitions work on the default rows only. */
+#define MG_FLAG_OBS_SOA 0x10u
+#define MG_FLAG_OBS_GOAL_SLOT 0x20u
+#define MG_OBS_SOA_STRIDE(n) (((n) + 15) & ~(int64_t)15)
 
 /* info byte, one per env per step (merging_env.py:144,187 `info["collision"]`, :164-181
  * `self.winner`, :142 time limit, :143/:171/:181/:184 `self.done`). */
@@ -155,6 +170,7 @@ MG_API int mg_default_rewards(MgRewards *out); /* merging_env.py:28-32 / show_re
  * Writes the state and, if obs != NULL, obs[n,10] for ALL envs (masked-out rows get their
  * current observation, i.e. `observe()`, merging_env.py:118-132). */
 MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask_or_null, float *obs_or_null,
+                    uint32_t flags /* 0 | MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT: layout of obs */,
                     const MgResetSpec *reset_or_null /* NULL = MG_RESET_FIXED */, void *stream);
 
 /* MergeEnv.step(action1, action2)  (merging_env.py:138-195) for n envs in one fused launch:
@@ -234,6 +250,12 @@ MG_API int mg_step_host_wait(void *ev_done);
                                    `state[5:] + state[:5]` (scripts/main.py:199, hdqn.py:285,299): the half-swap
                                    is done while the row is read, no mirrored copy is materialised */
 
+#define MG_MLP_FLAG_OBS_SOA 0x4u       /* obs is [10][MG_OBS_SOA_STRIDE(n)] (MG_FLAG_OBS_SOA)                                  */
+#define MG_MLP_FLAG_OBS_GOAL_SLOT 0x8u /* obs is [n][11] rows `[goal] + state` (MG_FLAG_OBS_GOAL_SLOT): a 10-input network
+                                          reads slots 1..10, an 11-input network (goal pointer NULL) the whole row       */
+#define MG_MLP_FLAG_WRITE_GOAL 0x10u   /* with MG_MLP_FLAG_OBS_GOAL_SLOT: also store the arg-max, as a float, into slot 0
+                                          of every row — `goal = upper.choose_goal(state)` feeding `[goal] + state`
+                                          (hdqn.py:283,291,303) without a separate goal array                           */
 #define MG_MLP_FLAG_PDL 0x2u    /* programmatic dependent launch: the kernel's prologue (weight staging, barrier and tensor-
                                    memory set-up — it reads nothing but the weights) may run while the previous kernel
                                    of the stream is still draining; observations are read only after that kernel has
@@ -280,7 +302,8 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
  *   goal_or_null    uint8[n]: the h-DQN controller's `[goal] + state` input column (hdqn.py:291); network input 11
  *   w1t..b3         as mg_mlp_act (backend 0: w2 = w2p) or mg_mlp_act_tc (backend 1: w2 = w2_tc); out_dim is 5
  *   a2_or_null      uint8[n] actions of player 2 (pvp), NULL = `action_op = None` (pve)
- *   flags           MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE | MG_POLICY_FLAG_PDL (MG_FLAG_NO_RETURNS is implied by
+ *   flags           MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE | MG_POLICY_FLAG_PDL | MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT
+ *                   (the layout of obs_in AND out->obs) | MG_POLICY_FLAG_GOAL_IN_SLOT (MG_FLAG_NO_RETURNS is implied by
  *                   state->ret1 == NULL)
  *   explore         the scripts' rule `np.random.randn() <= EPISILO ? greedy : np.random.randint(0, 5)` (main.py:103-110):
  *                   randn() <= t has probability Phi(t), so keep_u32 = floor(Phi(t) * 2^32) and the greedy action is
@@ -291,6 +314,7 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
  *   actions_out     uint8[n] or NULL: the action taken (what `store_transition` records, main.py:207)
  *   q_out_or_null   float[n,5] Q-values */
 #define MG_POLICY_FLAG_EXPLORE 0x100u
+#define MG_POLICY_FLAG_GOAL_IN_SLOT 0x400u /* the network has 11 inputs and reads its goal from slot 0 of the MG_FLAG_OBS_GOAL_SLOT rows */
 #define MG_POLICY_FLAG_PDL 0x200u     /* as MG_MLP_FLAG_PDL: the previous kernel of the stream does not write the weights */
 #define MG_POLICY_BACKEND_FP32 0
 #define MG_POLICY_BACKEND_TF32X3 1

@@ -10,7 +10,7 @@ import os
 
 from ._paths import LIB_PATH
 
-MG_ABI_VERSION = 5
+MG_ABI_VERSION = 6
 OBS_DIM = 10
 NUM_ACTIONS = 5
 STATS_ROWS = 1024
@@ -21,7 +21,18 @@ FLAG_AUTO_RESET = 0x1
 FLAG_NO_RETURNS = 0x2
 POLICY_FLAG_EXPLORE = 0x100
 POLICY_FLAG_PDL = 0x200
+POLICY_FLAG_GOAL_IN_SLOT = 0x400
 MLP_FLAG_MIRROR, MLP_FLAG_PDL = 0x1, 0x2
+MLP_FLAG_OBS_SOA, MLP_FLAG_OBS_GOAL_SLOT, MLP_FLAG_WRITE_GOAL = 0x4, 0x8, 0x10
+FLAG_OBS_SOA, FLAG_OBS_GOAL_SLOT = 0x10, 0x20
+OBS_LAYOUTS = ("aos", "soa", "goal_slot")
+OBS_LAYOUT_FLAG = {"aos": 0, "soa": FLAG_OBS_SOA, "goal_slot": FLAG_OBS_GOAL_SLOT}
+MLP_LAYOUT_FLAG = {"aos": 0, "soa": MLP_FLAG_OBS_SOA, "goal_slot": MLP_FLAG_OBS_GOAL_SLOT}
+
+
+def soa_stride(n: int) -> int:
+    """MG_OBS_SOA_STRIDE: elements per column of the [10][stride] observation layout."""
+    return (int(n) + 15) & ~15
 POLICY_BACKEND_FP32, POLICY_BACKEND_TF32X3 = 0, 1
 FIELD_OBS, FIELD_REW, FIELD_DONE, FIELD_INFO, FIELD_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 FIELD_BITS = {"obs": FIELD_OBS, "rew": FIELD_REW, "done": FIELD_DONE, "info": FIELD_INFO}
@@ -106,7 +117,7 @@ def load():
     lib.mg_get_constants.argtypes = [C.POINTER(MgConstants)]
     lib.mg_default_rewards.argtypes = [C.POINTER(MgRewards)]
     rsp = C.POINTER(MgResetSpec)
-    lib.mg_reset.argtypes = [C.POINTER(MgState), i64, vp, vp, rsp, vp]
+    lib.mg_reset.argtypes = [C.POINTER(MgState), i64, vp, vp, u32, rsp, vp]
     lib.mg_step.argtypes = [C.POINTER(MgState), i64, vp, vp, C.c_int, C.POINTER(MgRewards),
                             C.POINTER(MgOut), vp, u32, rsp, vp]
     lib.mg_sample_actions.argtypes = [vp, vp, i64, u64, u64, u64, vp]

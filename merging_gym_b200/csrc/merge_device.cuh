@@ -401,6 +401,29 @@ __device__ __forceinline__ void write_episode_outputs(const MgOut &o, int64_t e,
     if (o.ep_len) o.ep_len[e] = (int32_t)r.steps;
 }
 
+// ---- observation layouts (MG_FLAG_OBS_*): where the ten values of env e go / come from ------------------------------
+enum : uint32_t { kObsAos = 0u, kObsSoa = 1u, kObsGoalSlot = 2u };
+__host__ __device__ __forceinline__ uint32_t obs_layout_of(uint32_t flags) {
+    return (flags & MG_FLAG_OBS_SOA) ? kObsSoa : (flags & MG_FLAG_OBS_GOAL_SLOT) ? kObsGoalSlot : kObsAos;
+}
+// one env's observation into any layout (the step kernel's full warps have their own staged path for the default rows)
+__device__ __forceinline__ void store_obs(float *__restrict__ obs, uint32_t layout, int64_t e, int64_t n,
+                                          const float (&o)[MG_OBS_DIM]) {
+    if (layout == kObsAos) {
+        float2 *row = reinterpret_cast<float2 *>(obs + e * MG_OBS_DIM);          // 40-byte rows: 8-byte aligned
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM / 2; ++k) row[k] = make_float2(o[2 * k], o[2 * k + 1]);
+    } else if (layout == kObsSoa) {
+        const int64_t stride = MG_OBS_SOA_STRIDE(n);
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM; ++k) obs[k * stride + e] = o[k];
+    } else {
+        float *row = obs + e * (MG_OBS_DIM + 1) + 1;                             // slot 0 is the goal policy's
+#pragma unroll
+        for (int k = 0; k < MG_OBS_DIM; ++k) row[k] = o[k];
+    }
+}
+
 // ---- per-thread episode statistics, packed so that one warp reduction covers several ---------
 struct StatAcc {
     uint32_t a = 0;   // episodes | collisions<<8 | wins_p1<<16 | wins_p2<<24   (8-bit fields: <= 255 events per warp and flush)

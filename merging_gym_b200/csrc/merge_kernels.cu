@@ -12,6 +12,7 @@
 //   write 6*8 + 4 (state) + 40 (obs) + 8 (rew) + 1 + 1    = 102 B        total 156 B
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "abi_common.h"
 #include "merge_device.cuh"
@@ -93,7 +94,8 @@ __device__ __forceinline__ void st_pack_stream(T *__restrict__ p, const T (&in)[
 #ifndef MG_STEP_PERSISTENT
 #define MG_STEP_PERSISTENT 0   // 1: grid = SMs x MG_MIN_BLOCKS blocks that loop over the 256-env tiles (experiment, profiles/r02_variant_sweep.md)
 #endif
-template <int EPT, typename ActT, bool PVP, bool RR, bool RET>
+// LAYOUT: 0 = the default obs[n][10] rows (staged per warp), 1 = MG_FLAG_OBS_SOA, 2 = MG_FLAG_OBS_GOAL_SLOT.
+template <int EPT, typename ActT, bool PVP, bool RR, bool RET, int LAYOUT = 0>
 __device__ __forceinline__ void step_block(const int64_t blk, float (*stage)[32 * EPT * MG_OBS_DIM], const MgState &s, const MgOut &o,
                                            const ActT *__restrict__ a1g, const ActT *__restrict__ a2g, const int64_t n,
                                            const MgRewards &rw, const uint32_t flags, const MgResetSpec &rs,
@@ -167,7 +169,18 @@ __device__ __forceinline__ void step_block(const int64_t blk, float (*stage)[32 
         }
         if (r.done && auto_reset)            // gym-0.20 vector convention: return the reset obs
             reset_env<RR>(env[j], rs, (uint64_t)(e0 + j), r.obs);
-        if (full) {
+        if (LAYOUT != 0) {
+            if (LAYOUT == 1 && full && EPT == 2) {
+                if (j == 1) {                       // the thread's two envs are neighbours in every column: one 64-bit store
+                    const int64_t stride = MG_OBS_SOA_STRIDE(n);
+#pragma unroll
+                    for (int k = 0; k < MG_OBS_DIM; ++k)
+                        __stcs(reinterpret_cast<float2 *>(o.obs + k * stride + e0), make_float2(res[0].obs[k], r.obs[k]));
+                }
+            } else if (valid[j]) {
+                store_obs(o.obs, (uint32_t)LAYOUT, e0 + j, n, r.obs);
+            }
+        } else if (full) {
 #pragma unroll
             for (int k = 0; k < MG_OBS_DIM; ++k) my_stage[j * MG_OBS_DIM + k] = r.obs[k];
         } else if (valid[j]) {
@@ -206,13 +219,15 @@ __device__ __forceinline__ void step_block(const int64_t blk, float (*stage)[32 
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
 #else
-        __syncwarp();
-        const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
-        float4 *dst = reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM);
-        constexpr int kVec = 32 * EPT * MG_OBS_DIM / 4;   // float4 per warp
+        if (LAYOUT == 0) {
+            __syncwarp();
+            const float4 *src = reinterpret_cast<const float4 *>(&stage[warp][0]);
+            float4 *dst = reinterpret_cast<float4 *>(o.obs + warp_base * MG_OBS_DIM);
+            constexpr int kVec = 32 * EPT * MG_OBS_DIM / 4;   // float4 per warp
 #pragma unroll
-        for (int k = 0; k < (kVec + 31) / 32; ++k)
-            if (kVec % 32 == 0 || lane + 32 * k < kVec) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+            for (int k = 0; k < (kVec + 31) / 32; ++k)
+                if (kVec % 32 == 0 || lane + 32 * k < kVec) __stcs(dst + lane + 32 * k, src[lane + 32 * k]);
+        }
 #endif
     } else {
 #pragma unroll
@@ -235,7 +250,7 @@ __device__ __forceinline__ void step_block(const int64_t blk, float (*stage)[32 
 #endif
 }
 
-template <int EPT, typename ActT, bool PVP, bool RR, bool RET>
+template <int EPT, typename ActT, bool PVP, bool RR, bool RET, int LAYOUT = 0>
 __global__ void __launch_bounds__(kBlock, MG_MIN_BLOCKS)
 merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
                   const ActT *__restrict__ a2g, const int64_t n, const MgRewards rw,
@@ -251,11 +266,11 @@ merge_step_kernel(const MgState s, const MgOut o, const ActT *__restrict__ a1g,
 #if MG_STEP_PERSISTENT
     const int64_t n_blocks = (n + (int64_t)kBlock * EPT - 1) / ((int64_t)kBlock * EPT);
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        step_block<EPT, ActT, PVP, RR, RET>(blk, stage, s, o, a1g, a2g, n, rw, flags, rs, stats);
+        step_block<EPT, ActT, PVP, RR, RET, LAYOUT>(blk, stage, s, o, a1g, a2g, n, rw, flags, rs, stats);
         __syncwarp();                                  // the warp's staging tile is reused by the next trip
     }
 #else
-    step_block<EPT, ActT, PVP, RR, RET>((int64_t)blockIdx.x, stage, s, o, a1g, a2g, n, rw, flags, rs, stats);
+    step_block<EPT, ActT, PVP, RR, RET, LAYOUT>((int64_t)blockIdx.x, stage, s, o, a1g, a2g, n, rw, flags, rs, stats);
 #endif
 }
 
@@ -508,7 +523,7 @@ merge_rollout_kernel(const MgState s, const MgOut o, uint8_t *__restrict__ actio
 // =================================================================================================
 __global__ void __launch_bounds__(kBlock)
 merge_reset_kernel(const MgState s, const int64_t n, const uint8_t *__restrict__ mask, float *__restrict__ obs,
-                   const MgResetSpec rs) {
+                   const MgResetSpec rs, const uint32_t layout) {
     __shared__ __align__(16) float stage[kWarps][32 * MG_OBS_DIM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_base = ((int64_t)blockIdx.x * kWarps + warp) * 32;
@@ -530,6 +545,10 @@ merge_reset_kernel(const MgState s, const int64_t n, const uint8_t *__restrict__
         observe(r, ob);
     }
     if (!obs) return;
+    if (layout != kObsAos) {
+        if (valid) store_obs(obs, layout, e, n, ob);
+        return;
+    }
     if (warp_base + 32 <= n) {
         // the warp's 32 rows are one contiguous 1280-byte span: stage, then linear 128-bit stores
 #pragma unroll
@@ -653,6 +672,23 @@ cudaError_t launch_step(const MgState &s, const MgOut &o, const void *a1, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = MG_PDL ? 1 : 0;
     cudaError_t le = cudaSuccess;
+    const uint32_t layout = mg::obs_layout_of(flags);
+    if (layout != mg::kObsAos) {
+        // the other observation layouts are built for the common case only: uint8 actions, return accumulators kept
+        if constexpr (std::is_same<ActT, uint8_t>::value) {
+            if (!ret) return cudaErrorInvalidValue;
+#define MG_LAUNCH_L(PVP, RR, A2, L) cudaLaunchKernelEx(&cfg, mg::merge_step_kernel<EPT, uint8_t, PVP, RR, true, L>, s, o, \
+                                                       (const uint8_t *)a1, (const uint8_t *)(A2), n, rw, flags, rs, stp)
+#define MG_LAUNCH_PR(L) (a2 ? (rr ? MG_LAUNCH_L(true, true, a2, L) : MG_LAUNCH_L(true, false, a2, L))             \
+                            : (rr ? MG_LAUNCH_L(false, true, nullptr, L) : MG_LAUNCH_L(false, false, nullptr, L)))
+            le = layout == mg::kObsSoa ? MG_LAUNCH_PR(1) : MG_LAUNCH_PR(2);
+#undef MG_LAUNCH_PR
+#undef MG_LAUNCH_L
+            return le ? le : cudaGetLastError();
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
 #define MG_LAUNCH(PVP, RR, A2)                                                                        \
     le = ret ? cudaLaunchKernelEx(&cfg, mg::merge_step_kernel<EPT, ActT, PVP, RR, true>, s, o, (const ActT *)a1,  \
                                   (const ActT *)(A2), n, rw, flags, rs, stp)                            \
@@ -688,14 +724,17 @@ MG_API int mg_default_rewards(MgRewards *r) {
     return MG_OK;
 }
 
-MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask, float *obs, const MgResetSpec *reset,
-                    void *stream) {
+MG_API int mg_reset(const MgState *state, int64_t n, const uint8_t *mask, float *obs, uint32_t flags,
+                    const MgResetSpec *reset, void *stream) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
+    if ((flags & ~(MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT)) || flags == (MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT))
+        return fail(MG_ERR_BAD_FLAGS, "mg_reset flags: 0, MG_FLAG_OBS_SOA or MG_FLAG_OBS_GOAL_SLOT");
     if (int rc = check_reset(reset)) return rc;
     if (n == 0) return MG_OK;
     if (int rc = check_state(state, state && (state->ret1 || state->ret2))) return rc;
     const unsigned grid = (unsigned)((n + mg::kBlock - 1) / mg::kBlock);
-    mg::merge_reset_kernel<<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(*state, n, mask, obs, reset ? *reset : kFixedReset);
+    mg::merge_reset_kernel<<<grid, mg::kBlock, 0, (cudaStream_t)stream>>>(*state, n, mask, obs, reset ? *reset : kFixedReset,
+                                                                          mg::obs_layout_of(flags));
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_reset launch");
     return MG_OK;
 }
@@ -705,7 +744,12 @@ MG_API int mg_step(const MgState *state, int64_t n, const void *a1, const void *
                    const MgResetSpec *reset, void *stream) {
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     if (int rc = check_reset(reset)) return rc;
-    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS | MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (flags & (MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT)) {
+        if ((flags & MG_FLAG_OBS_SOA) && (flags & MG_FLAG_OBS_GOAL_SLOT)) return fail(MG_ERR_BAD_FLAGS, "MG_FLAG_OBS_SOA and MG_FLAG_OBS_GOAL_SLOT exclude each other");
+        if (act_dtype != MG_ACT_U8 || (flags & MG_FLAG_NO_RETURNS))
+            return fail(MG_ERR_BAD_FLAGS, "MG_FLAG_OBS_SOA / MG_FLAG_OBS_GOAL_SLOT need uint8 actions and the return accumulators");
+    }
     if (act_dtype < MG_ACT_U8 || act_dtype > MG_ACT_I64)
         return fail(MG_ERR_BAD_DTYPE, "act_dtype must be MG_ACT_U8, MG_ACT_I32 or MG_ACT_I64");
     if (n == 0) return MG_OK;

@@ -56,25 +56,37 @@ struct Smem {
 // aligned; a warp covers one contiguous 1280-byte span)
 // COHERENT: the fused env epilogue writes observation rows in the same launch (possibly into the buffer being read), so
 // the rows must not travel through the non-coherent (ld.global.nc) path.
+// obs_mode: bits 0-1 = observation layout (mg::kObsAos / kObsSoa / kObsGoalSlot), bit 8 = MG_MLP_FLAG_WRITE_GOAL.
 template <int IN, bool MIRROR, bool COHERENT = false>
-__device__ __forceinline__ void load_row(const float *obs, const uint8_t *__restrict__ goal,
-                                         int64_t e, int64_t n, int obs_dim, float (&x)[IN]) {
+__device__ __forceinline__ void load_row(const float *obs, const uint8_t *__restrict__ goal, int64_t e, int64_t n,
+                                         int obs_mode, float (&x)[IN]) {
     constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
-    (void)obs_dim;
+    const uint32_t layout = (uint32_t)obs_mode & 3u;
     if (e < n) {
-        if (off) x[0] = (float)goal[e];
-        if (!MIRROR) {
-            const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
+        if (layout == mg::kObsAos) {
+            if (off) x[0] = (float)goal[e];
+            if (!MIRROR) {
+                const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
-            for (int i = 0; i < MG_OBS_DIM / 2; ++i) {          // obs_dim is 10: five float2
-                const float2 v = COHERENT ? __ldcg(src + i) : __ldg(src + i);
-                x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+                for (int i = 0; i < MG_OBS_DIM / 2; ++i) {      // five float2
+                    const float2 v = COHERENT ? __ldcg(src + i) : __ldg(src + i);
+                    x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+                }
+            } else {                                            // the opponent's view: state[5:] + state[:5] (main.py:199)
+#pragma unroll
+                for (int i = 0; i < MG_OBS_DIM; ++i) {
+                    const float *q = obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM;
+                    x[off + i] = COHERENT ? __ldcg(q) : __ldg(q);
+                }
             }
-        } else {                                                // the opponent's view: state[5:] + state[:5] (main.py:199)
+        } else {
+            // [10][stride] columns, or [n][11] rows `[goal] + state` whose slot 0 an 11-input network reads as its goal
+            const int64_t stride = MG_OBS_SOA_STRIDE(n);
+            if (off) x[0] = goal ? (float)goal[e] : __ldcg(obs + e * (MG_OBS_DIM + 1));
 #pragma unroll
             for (int i = 0; i < MG_OBS_DIM; ++i) {
-                const float *q = obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM;
-                x[off + i] = COHERENT ? __ldcg(q) : __ldg(q);
+                const int k = MIRROR ? (i + MG_OBS_DIM / 2) % MG_OBS_DIM : i;
+                x[off + i] = __ldcg(layout == mg::kObsSoa ? obs + k * stride + e : obs + e * (MG_OBS_DIM + 1) + 1 + k);
             }
         }
     } else {
@@ -90,7 +102,7 @@ __device__ __forceinline__ void load_row(const float *obs, const uint8_t *__rest
 // ENV: 0 = policy only, 1 = + env step pve, 2 = + env step pvp
 template <int IN, int OUT, bool MIRROR, int ENV>
 __global__ void __launch_bounds__(TM, 1)
-mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
+mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_mode,
                const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2p,
                const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
                uint8_t *__restrict__ act, float *__restrict__ q_out, const mgpe::Args P) {
@@ -123,7 +135,7 @@ mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t
     cudaGridDependencySynchronize();
     if (ENV) cudaTriggerProgrammaticLaunchCompletion();
 #pragma unroll
-    for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
+    for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (int64_t)blockIdx.x * TM + e0 + r * (TM / LR), n, obs_mode, xr[r]);
     __syncthreads();
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -203,7 +215,7 @@ mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t
         }
         // next tile's input rows: issued now, consumed after the epilogue
 #pragma unroll
-        for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (tile + gridDim.x) * TM + e0 + r * (TM / LR), n, obs_dim, xr[r]);
+        for (int r = 0; r < LR; ++r) load_row<IN, MIRROR, ENV != 0>(obs, goal, (tile + gridDim.x) * TM + e0 + r * (TM / LR), n, obs_mode, xr[r]);
 
         // ---- layer 3 + arg-max ---------------------------------------------------------------------
         float q[4][OUT];
@@ -254,6 +266,10 @@ mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t
                 for (int e = 0; e < 4; ++e)
                     if (e0 + e < n) act[e0 + e] = a4[e];
             }
+            if (!ENV && (obs_mode & 0x100)) {                   // MG_MLP_FLAG_WRITE_GOAL: slot 0 of the `[goal] + state` rows
+                for (int e = 0; e < 4; ++e)
+                    if (e0 + e < n) const_cast<float *>(obs)[(e0 + e) * (MG_OBS_DIM + 1)] = (float)a4[e];
+            }
             if (q_out) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
@@ -277,7 +293,7 @@ mlp_act_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t
 }
 
 template <int IN, int OUT, bool MIRROR, int ENV = 0>
-cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t,
+cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_mode, const float *w1t,
                    const float *b1, const float *w2t, const float *b2, const float *w3, const float *b3,
                    uint8_t *act, float *q_out, cudaStream_t st, const mgpe::Args &P = mgpe::Args{}, bool pdl = false) {
     auto kern = mlp_act_kernel<IN, OUT, MIRROR, ENV>;
@@ -295,11 +311,32 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_dim, w1t, b1, w2t, b2, w3, b3, act, q_out, P);
+    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_mode, w1t, b1, w2t, b2, w3, b3, act, q_out, P);
     return e ? e : cudaGetLastError();
 }
 
 }  // namespace mgmlp
+
+// Shared argument check of mg_mlp_act / mg_mlp_act_tc: flags, observation layout, network input width.
+//   obs_dim 10: the network reads the ten observation values (+ the goal column when a goal array is given -> 11 inputs)
+//   obs_dim 11: only with MG_MLP_FLAG_OBS_GOAL_SLOT and no goal array — the network reads the whole `[goal] + state` row
+int mg_mlp_check_layout(uint32_t flags, int32_t obs_dim, int32_t out_dim, bool has_goal, int *in_dim, int *obs_mode) {
+    using namespace mg_abi;
+    constexpr uint32_t kAll = MG_MLP_FLAG_MIRROR | MG_MLP_FLAG_PDL | MG_MLP_FLAG_OBS_SOA | MG_MLP_FLAG_OBS_GOAL_SLOT | MG_MLP_FLAG_WRITE_GOAL;
+    if (flags & ~kAll) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    const bool soa = (flags & MG_MLP_FLAG_OBS_SOA) != 0u, slot = (flags & MG_MLP_FLAG_OBS_GOAL_SLOT) != 0u;
+    if (soa && slot) return fail(MG_ERR_BAD_FLAGS, "MG_MLP_FLAG_OBS_SOA and MG_MLP_FLAG_OBS_GOAL_SLOT exclude each other");
+    if ((flags & MG_MLP_FLAG_WRITE_GOAL) && !slot) return fail(MG_ERR_BAD_FLAGS, "MG_MLP_FLAG_WRITE_GOAL needs MG_MLP_FLAG_OBS_GOAL_SLOT");
+    if (!(out_dim == 5 || out_dim == 3) || !(obs_dim == MG_OBS_DIM || (obs_dim == MG_OBS_DIM + 1 && slot && !has_goal)))
+        return fail(MG_ERR_BAD_SIZE, "the policy kernels support observations of 10 floats (+ optional goal column; or the 11-float "
+                                     "`[goal] + state` rows of MG_MLP_FLAG_OBS_GOAL_SLOT) and 5 or 3 outputs "
+                                     "(Net(10|11, 5|3): main.py:30-47, hdqn.py:38-55)");
+    *in_dim = obs_dim == MG_OBS_DIM + 1 ? MG_OBS_DIM + 1 : MG_OBS_DIM + (has_goal ? 1 : 0);
+    if ((flags & MG_MLP_FLAG_WRITE_GOAL) && *in_dim != MG_OBS_DIM)
+        return fail(MG_ERR_BAD_FLAGS, "MG_MLP_FLAG_WRITE_GOAL is for the 10-input goal network");
+    *obs_mode = (soa ? 1 : slot ? 2 : 0) | ((flags & MG_MLP_FLAG_WRITE_GOAL) ? 0x100 : 0);
+    return MG_OK;
+}
 
 extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                                  int32_t out_dim, const float *w1t, const float *b1, const float *w2p,
@@ -307,12 +344,9 @@ extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, 
                                  float *q_out_or_null, uint32_t flags, void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
-    if (flags & ~(MG_MLP_FLAG_MIRROR | MG_MLP_FLAG_PDL)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    int in_dim = 0, obs_mode = 0;
+    if (int rc = mg_mlp_check_layout(flags, obs_dim, out_dim, goal_or_null != nullptr, &in_dim, &obs_mode)) return rc;
     const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u, pdl = (flags & MG_MLP_FLAG_PDL) != 0u;
-    const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
-    if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
-        return fail(MG_ERR_BAD_SIZE, "mg_mlp_act supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs "
-                                     "(Net(10|11, 5|3): main.py:30-47, hdqn.py:38-55)");
     if (n == 0) return MG_OK;
     if (!obs || !w1t || !b1 || !w2p || !b2 || !w3 || !b3 || !actions)
         return fail(MG_ERR_NULL_POINTER, "mg_mlp_act: NULL pointer");
@@ -321,7 +355,7 @@ extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #define MG_MLP_CASE(I, O) \
-    if (in_dim == I && out_dim == O) e = mirror ? mgmlp::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl) : mgmlp::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl); else
+    if (in_dim == I && out_dim == O) e = mirror ? mgmlp::launch<I, O, true>(obs, goal_or_null, n, obs_mode, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl) : mgmlp::launch<I, O, false>(obs, goal_or_null, n, obs_mode, w1t, b1, w2p, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl); else
     MG_MLP_CASE(10, 5) MG_MLP_CASE(10, 3) MG_MLP_CASE(11, 5) MG_MLP_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_MLP_CASE
     if (e) return cuda_fail(e, "mg_mlp_act launch");
@@ -350,7 +384,12 @@ extern "C" MG_API int mg_policy_step(const MgState *state, int64_t n, const floa
                                      void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
-    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS | MG_POLICY_FLAG_EXPLORE | MG_POLICY_FLAG_PDL)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if (flags & ~(MG_FLAG_AUTO_RESET | MG_FLAG_NO_RETURNS | MG_POLICY_FLAG_EXPLORE | MG_POLICY_FLAG_PDL | MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT |
+                  MG_POLICY_FLAG_GOAL_IN_SLOT))
+        return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    if ((flags & MG_POLICY_FLAG_GOAL_IN_SLOT) && (!(flags & MG_FLAG_OBS_GOAL_SLOT) || goal_or_null))
+        return fail(MG_ERR_BAD_FLAGS, "MG_POLICY_FLAG_GOAL_IN_SLOT needs MG_FLAG_OBS_GOAL_SLOT and no goal array");
+    if ((flags & MG_FLAG_OBS_SOA) && (flags & MG_FLAG_OBS_GOAL_SLOT)) return fail(MG_ERR_BAD_FLAGS, "MG_FLAG_OBS_SOA and MG_FLAG_OBS_GOAL_SLOT exclude each other");
     const bool pdl = (flags & MG_POLICY_FLAG_PDL) != 0u;
     if (backend != MG_POLICY_BACKEND_FP32 && backend != MG_POLICY_BACKEND_TF32X3)
         return fail(MG_ERR_BAD_FLAGS, "backend must be MG_POLICY_BACKEND_FP32 or MG_POLICY_BACKEND_TF32X3");
@@ -374,18 +413,23 @@ extern "C" MG_API int mg_policy_step(const MgState *state, int64_t n, const floa
     if (rewards) P.rw = *rewards; else mg_default_rewards(&P.rw);
     P.rs = reset_or_null ? *reset_or_null : MgResetSpec{MG_RESET_FIXED, 0u, 0ull, 0ull};
     P.flags = flags;
+    P.n = n;
     if (explore_or_null) { P.explore_seed = explore_or_null->seed; P.explore_step = explore_or_null->step; P.explore_keep = explore_or_null->keep_u32; }
-    const int in_dim = MG_OBS_DIM + (goal_or_null ? 1 : 0);
+    // network input: 10 observation values, + 1 when a goal array is given or MG_POLICY_FLAG_GOAL_IN_SLOT asks for the
+    // whole `[goal] + state` row of the MG_FLAG_OBS_GOAL_SLOT layout
+    const bool row11 = (flags & MG_POLICY_FLAG_GOAL_IN_SLOT) != 0u;
+    const int in_dim = MG_OBS_DIM + ((goal_or_null || row11) ? 1 : 0);
+    const int obs_mode = (int)mg::obs_layout_of(flags);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (backend == MG_POLICY_BACKEND_TF32X3)
         e = mg_policy_step_tc_launch(in_dim, obs_in, goal_or_null, n, w1t, b1, w2, b2, w3, b3, q_out_or_null, st, P);
     else if (in_dim == 10)
-        e = a2_or_null ? mgmlp::launch<10, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl)
-                       : mgmlp::launch<10, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl);
+        e = a2_or_null ? mgmlp::launch<10, 5, false, 2>(obs_in, goal_or_null, n, obs_mode, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl)
+                       : mgmlp::launch<10, 5, false, 1>(obs_in, goal_or_null, n, obs_mode, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl);
     else
-        e = a2_or_null ? mgmlp::launch<11, 5, false, 2>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl)
-                       : mgmlp::launch<11, 5, false, 1>(obs_in, goal_or_null, n, MG_OBS_DIM, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl);
+        e = a2_or_null ? mgmlp::launch<11, 5, false, 2>(obs_in, goal_or_null, n, obs_mode, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl)
+                       : mgmlp::launch<11, 5, false, 1>(obs_in, goal_or_null, n, obs_mode, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl);
     if (e) return cuda_fail(e, "mg_policy_step launch");
     return MG_OK;
 }

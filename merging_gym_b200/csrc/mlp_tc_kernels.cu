@@ -133,25 +133,37 @@ __device__ __forceinline__ uint32_t mbar_test(unsigned long long *b, uint32_t pa
 
 // COHERENT: the fused env epilogue writes observation rows in the same launch (possibly into the buffer being read), so
 // the rows must not travel through the non-coherent (ld.global.nc) path.
+// obs_mode: bits 0-1 = observation layout (mg::kObsAos / kObsSoa / kObsGoalSlot), bit 8 = MG_MLP_FLAG_WRITE_GOAL.
 template <int IN, bool MIRROR, bool COHERENT = false>
-__device__ __forceinline__ void load_row(const float *obs, const uint8_t *__restrict__ goal, int64_t e,
-                                         int64_t n, int obs_dim, float (&x)[IN]) {
+__device__ __forceinline__ void load_row(const float *obs, const uint8_t *__restrict__ goal, int64_t e, int64_t n,
+                                         int obs_mode, float (&x)[IN]) {
     constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
-    (void)obs_dim;
+    const uint32_t layout = (uint32_t)obs_mode & 3u;
     if (e < n) {
-        if (off) x[0] = (float)goal[e];
-        if (!MIRROR) {
-            const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
+        if (layout == mg::kObsAos) {
+            if (off) x[0] = (float)goal[e];
+            if (!MIRROR) {
+                const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
 #pragma unroll
-            for (int i = 0; i < MG_OBS_DIM / 2; ++i) {          // obs_dim is 10: five float2
-                const float2 v = COHERENT ? __ldcg(src + i) : __ldg(src + i);
-                x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+                for (int i = 0; i < MG_OBS_DIM / 2; ++i) {      // five float2
+                    const float2 v = COHERENT ? __ldcg(src + i) : __ldg(src + i);
+                    x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
+                }
+            } else {                                            // the opponent's view: state[5:] + state[:5] (main.py:199)
+#pragma unroll
+                for (int i = 0; i < MG_OBS_DIM; ++i) {
+                    const float *q = obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM;
+                    x[off + i] = COHERENT ? __ldcg(q) : __ldg(q);
+                }
             }
-        } else {                                                // the opponent's view: state[5:] + state[:5] (main.py:199)
+        } else {
+            // [10][stride] columns, or [n][11] rows `[goal] + state` whose slot 0 an 11-input network reads as its goal
+            const int64_t stride = MG_OBS_SOA_STRIDE(n);
+            if (off) x[0] = goal ? (float)goal[e] : __ldcg(obs + e * (MG_OBS_DIM + 1));
 #pragma unroll
             for (int i = 0; i < MG_OBS_DIM; ++i) {
-                const float *q = obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM;
-                x[off + i] = COHERENT ? __ldcg(q) : __ldg(q);
+                const int k = MIRROR ? (i + MG_OBS_DIM / 2) % MG_OBS_DIM : i;
+                x[off + i] = __ldcg(layout == mg::kObsSoa ? obs + k * stride + e : obs + e * (MG_OBS_DIM + 1) + 1 + k);
             }
         }
     } else {
@@ -166,7 +178,7 @@ __device__ __forceinline__ void load_row(const float *obs, const uint8_t *__rest
 // ENV: 0 = policy only, 1 = + env step pve, 2 = + env step pvp
 template <int IN, int OUT, bool MIRROR, int ENV>
 __global__ void __launch_bounds__(NUM_THREADS + (ENV ? 32 * ENV_WARPS : 0), 1)
-mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_dim,
+mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_mode,
                   const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2_tc,
                   const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
                   uint8_t *__restrict__ act, float *__restrict__ q_out, const mgpe::Args P) {
@@ -249,7 +261,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
         {
             const int64_t e0 = (int64_t)blockIdx.x * TM + lane;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR, ENV != 0>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR, ENV != 0>(obs, goal, e0 + 32 * j, n, obs_mode, x[j]);
         }
         for (uint32_t g = (uint32_t)warp; g < total; g += PRODUCER_WARPS) {
             const uint32_t tl = g / KSTEPS, ks = g - tl * KSTEPS;
@@ -282,7 +294,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
             if ((g + PRODUCER_WARPS) / KSTEPS != tl) {
                 const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)(tl + 1) * gridDim.x) * TM + lane;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR, ENV != 0>(obs, goal, e0 + 32 * j, n, obs_dim, x[j]);
+                for (int j = 0; j < 4; ++j) load_row<IN, MIRROR, ENV != 0>(obs, goal, e0 + 32 * j, n, obs_mode, x[j]);
             }
             // Ring slot s = g % 4 is filled alternately by warps s and s + 4.  A parity wait is only meaningful when
             // the waiter is at most one phase behind the barrier, so every producer warp has its OWN pair of
@@ -461,6 +473,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
                 if (mine[o] > bv) { bv = mine[o]; best = o; }       // first maximum, like torch.max
             if (e < n) {
                 if (!ENV) act[e] = (uint8_t)best;
+                if (!ENV && (obs_mode & 0x100)) const_cast<float *>(obs)[e * (MG_OBS_DIM + 1)] = (float)best;   // MG_MLP_FLAG_WRITE_GOAL
                 if (q_out) {
 #pragma unroll
                     for (int o = 0; o < OUT; ++o) q_out[e * OUT + o] = mine[o];
@@ -481,7 +494,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
 }
 
 template <int IN, int OUT, bool MIRROR, int ENV = 0>
-cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim, const float *w1t, const float *b1,
+cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_mode, const float *w1t, const float *b1,
                    const float *w2_tc, const float *b2, const float *w3, const float *b3, uint8_t *act, float *q_out,
                    cudaStream_t st, const mgpe::Args &P = mgpe::Args{}, bool pdl = false) {
     auto kern = mlp_act_tc_kernel<IN, OUT, MIRROR, ENV>;
@@ -499,19 +512,22 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_dim
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, act, q_out, P);
+    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_mode, w1t, b1, w2_tc, b2, w3, b3, act, q_out, P);
     return e ? e : cudaGetLastError();
 }
 
 }  // namespace mgtc
+
+int mg_mlp_check_layout(uint32_t flags, int32_t obs_dim, int32_t out_dim, bool has_goal, int *in_dim, int *obs_mode);
 
 // the fused policy + env step on the tensor-core backend (called by mg_policy_step in mlp_kernels.cu)
 cudaError_t mg_policy_step_tc_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const float *w1t,
                                      const float *b1, const float *w2_tc, const float *b2, const float *w3, const float *b3,
                                      float *q_out, cudaStream_t st, const mgpe::Args &P) {
     const bool pvp = P.a2 != nullptr, pdl = (P.flags & MG_POLICY_FLAG_PDL) != 0u;
-#define MG_TC_ENV(I) (pvp ? mgtc::launch<I, 5, false, 2>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P, pdl) \
-                          : mgtc::launch<I, 5, false, 1>(obs, goal, n, MG_OBS_DIM, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P, pdl))
+    const int obs_mode = (int)mg::obs_layout_of(P.flags);
+#define MG_TC_ENV(I) (pvp ? mgtc::launch<I, 5, false, 2>(obs, goal, n, obs_mode, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P, pdl) \
+                          : mgtc::launch<I, 5, false, 1>(obs, goal, n, obs_mode, w1t, b1, w2_tc, b2, w3, b3, nullptr, q_out, st, P, pdl))
     if (in_dim == 10) return MG_TC_ENV(10);
     if (in_dim == 11) return MG_TC_ENV(11);
 #undef MG_TC_ENV
@@ -524,11 +540,9 @@ extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_nul
                                     float *q_out_or_null, uint32_t flags, void *stream) {
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
-    if (flags & ~(MG_MLP_FLAG_MIRROR | MG_MLP_FLAG_PDL)) return fail(MG_ERR_BAD_FLAGS, "unknown flag bits");
+    int in_dim = 0, obs_mode = 0;
+    if (int rc = mg_mlp_check_layout(flags, obs_dim, out_dim, goal_or_null != nullptr, &in_dim, &obs_mode)) return rc;
     const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u, pdl = (flags & MG_MLP_FLAG_PDL) != 0u;
-    const int in_dim = obs_dim + (goal_or_null ? 1 : 0);
-    if (obs_dim != MG_OBS_DIM || !(out_dim == 5 || out_dim == 3))
-        return fail(MG_ERR_BAD_SIZE, "mg_mlp_act_tc supports obs rows of 10 floats (+ optional goal) and 5 or 3 outputs");
     if (n == 0) return MG_OK;
     if (!obs || !w1t || !b1 || !w2_tc || !b2 || !w3 || !b3 || !actions)
         return fail(MG_ERR_NULL_POINTER, "mg_mlp_act_tc: NULL pointer");
@@ -537,7 +551,7 @@ extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_nul
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #define MG_TC_CASE(I, O) \
-    if (in_dim == I && out_dim == O) e = mirror ? mgtc::launch<I, O, true>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl) : mgtc::launch<I, O, false>(obs, goal_or_null, n, obs_dim, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl); else
+    if (in_dim == I && out_dim == O) e = mirror ? mgtc::launch<I, O, true>(obs, goal_or_null, n, obs_mode, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl) : mgtc::launch<I, O, false>(obs, goal_or_null, n, obs_mode, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl); else
     MG_TC_CASE(10, 5) MG_TC_CASE(10, 3) MG_TC_CASE(11, 5) MG_TC_CASE(11, 3) e = cudaErrorInvalidValue;
 #undef MG_TC_CASE
     if (e) return cuda_fail(e, "mg_mlp_act_tc launch");

@@ -26,7 +26,8 @@ struct Args {
     MgResetSpec rs;
     uint64_t explore_seed, explore_step;
     uint32_t explore_keep;           // keep the greedy action iff Philox u32 < explore_keep
-    uint32_t flags;                  // MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE
+    uint32_t flags;                  // MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE | MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT
+    int64_t n;                       // number of envs (the SoA column stride derives from it)
 };
 
 // The scripts' exploration rule (main.py:103-110, hdqn.py:84-92,168-176): `if np.random.randn() <= EPISILO:` the
@@ -96,9 +97,7 @@ __device__ __forceinline__ void step_loaded(const Args &A, int64_t e, Loaded &x,
     A.s.pos1[e] = env[0].p1; A.s.vel1[e] = env[0].v1; A.s.pos2[e] = env[0].p2; A.s.vel2[e] = env[0].v2;
     if (ret) { A.s.ret1[e] = env[0].R1; A.s.ret2[e] = env[0].R2; }
     A.s.meta[e] = env[0].meta;
-    float2 *row = reinterpret_cast<float2 *>(A.o.obs + e * MG_OBS_DIM);      // 40-byte rows: 8-byte aligned
-#pragma unroll
-    for (int k = 0; k < MG_OBS_DIM / 2; ++k) row[k] = make_float2(r.obs[2 * k], r.obs[2 * k + 1]);
+    store_obs(A.o.obs, obs_layout_of(A.flags), e, A.n, r.obs);
     *reinterpret_cast<float2 *>(A.o.rew + 2 * e) = make_float2(r.r1, r.r2);
     if (A.o.done) A.o.done[e] = r.done ? 1 : 0;
     A.o.info[e] = (uint8_t)r.info;

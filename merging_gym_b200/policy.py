@@ -110,13 +110,20 @@ class MLPPolicy:
         return torch.addmm(self.b3, h, self.w3.t())
 
     def act(self, obs: torch.Tensor, goal: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-            q_out: Optional[torch.Tensor] = None, mirror: bool = False, pdl: Optional[bool] = None) -> torch.Tensor:
+            q_out: Optional[torch.Tensor] = None, mirror: bool = False, pdl: Optional[bool] = None,
+            obs_layout: str = "aos", n: Optional[int] = None, write_goal: bool = False) -> torch.Tensor:
         """Greedy actions uint8[N] = argmax_a Q(obs)[a] (first maximum wins, as torch.max does).
         `mirror=True` evaluates the network on the opponent's view `state[5:] + state[:5]` (main.py:199) of every
         row; the fused kernels swap the halves while they read the row.
         `pdl` (default `self.pdl`): programmatic dependent launch — the kernel stages its weights while the previous
         kernel of the stream is still draining (`MG_MLP_FLAG_PDL`).  Only valid when that kernel does not write this
-        policy's weights; in a rollout loop it is the env step, so `GraphedPolicyRollout` and `bench_policy` turn it on."""
+        policy's weights; in a rollout loop it is the env step, so `GraphedPolicyRollout` and `bench_policy` turn it on.
+        `obs_layout` ("aos" [N,10] / "soa" [10,S] with `n` given / "goal_slot" [N,11]): the layout of `obs`
+        (`MergeVecEnv(obs_layout=...)`).  On "goal_slot" rows a 10-input network reads slots 1..10 and, with
+        `write_goal=True`, also stores its arg-max into slot 0 (`goal = choose_goal(state)` feeding `[goal] + state`,
+        hdqn.py:283,291); an 11-input network given no `goal` reads the whole row."""
+        if obs_layout != "aos":
+            return self._act_layout(obs, goal, out, q_out, mirror, pdl, obs_layout, n, write_goal)
         n = obs.shape[0]
         if mirror and self.backend == "torch":
             obs = torch.cat([obs[:, 5:], obs[:, :5]], dim=1)
@@ -152,6 +159,37 @@ class MLPPolicy:
         return out
 
     __call__ = act
+
+    def _act_layout(self, obs, goal, out, q_out, mirror, pdl, obs_layout, n, write_goal):
+        if self.backend == "torch":
+            raise ValueError("backend 'torch' reads the default [N,10] rows only")
+        if obs_layout not in nat.OBS_LAYOUTS:
+            raise ValueError(f"obs_layout must be one of {nat.OBS_LAYOUTS}")
+        if not (obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous()):
+            raise ValueError("obs must be a contiguous float32 CUDA tensor")
+        if obs_layout == "soa":
+            if n is None or tuple(obs.shape) != (nat.OBS_DIM, nat.soa_stride(n)):
+                raise ValueError("obs_layout='soa': pass n and obs of shape [10, (n + 15) & ~15]")
+        else:
+            n = obs.shape[0]
+            if obs.shape[1] != nat.OBS_DIM + 1:
+                raise ValueError("obs_layout='goal_slot': obs must be [N, 11]")
+        row11 = obs_layout == "goal_slot" and goal is None and self.in_dim == nat.OBS_DIM + 1
+        if self.in_dim != nat.OBS_DIM + (0 if goal is None else 1) and not row11:
+            raise ValueError("obs/goal widths do not match the network input")
+        if goal is not None and not (goal.dtype == torch.uint8 and goal.is_contiguous()):
+            raise ValueError("goal must be a contiguous uint8 tensor")
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        flags = (nat.MLP_FLAG_MIRROR if mirror else 0) | (nat.MLP_FLAG_PDL if (self.pdl if pdl is None else pdl) else 0) | \
+            nat.MLP_LAYOUT_FLAG[obs_layout] | (nat.MLP_FLAG_WRITE_GOAL if write_goal else 0)
+        fn = nat.load().mg_mlp_act_tc if self.backend == "tf32x3" else nat.load().mg_mlp_act
+        w2 = self.w2_tc if self.backend == "tf32x3" else self.w2_p
+        with torch.cuda.device(self.device):
+            nat.check(fn(_ptr(obs), _ptr(goal), n, nat.OBS_DIM + (1 if row11 else 0), self.out_dim, _ptr(self.w1_t), _ptr(self.b1),
+                         _ptr(w2), _ptr(self.b2), _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), flags,
+                         C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "mg_mlp_act (layout)")
+        return out
 
 
 class Exploration:
@@ -224,11 +262,17 @@ class HDQNPolicy:
         self.ctrl = MLPPolicy(11, 5, device, ctrl_state, seed + 1, backend)
         self.goal: Optional[torch.Tensor] = None
 
-    def act(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if self.goal is None or self.goal.shape[0] != obs.shape[0]:
-            self.goal = torch.empty(obs.shape[0], dtype=torch.uint8, device=obs.device)
-        self.meta.act(obs, out=self.goal)                       # hdqn.py:283,303  choose_goal
-        return self.ctrl.act(obs, goal=self.goal, out=out)      # hdqn.py:291-292  [goal] + state
+    def act(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None, obs_layout: str = "aos",
+            n: Optional[int] = None) -> torch.Tensor:
+        n = obs.shape[0] if obs_layout != "soa" else n
+        if self.goal is None or self.goal.shape[0] != n:
+            self.goal = torch.empty(n, dtype=torch.uint8, device=obs.device)
+        if obs_layout == "goal_slot":
+            # `[goal] + state` rows: the goal network drops its choice into slot 0, the controller reads the row as it is
+            self.meta.act(obs, out=self.goal, obs_layout=obs_layout, write_goal=True)
+            return self.ctrl.act(obs, out=out, obs_layout=obs_layout)
+        self.meta.act(obs, out=self.goal, obs_layout=obs_layout, n=n)          # hdqn.py:283,303  choose_goal
+        return self.ctrl.act(obs, goal=self.goal, out=out, obs_layout=obs_layout, n=n)   # hdqn.py:291-292  [goal] + state
 
     __call__ = act
 
@@ -237,10 +281,13 @@ class HDQNPolicy:
         """One iteration of the h-DQN loop (hdqn.py:288-303) in two launches: `choose_goal(state)` (meta forward +
         arg-max [+ exploration, salt 1]) and `mg_policy_step` with the controller on `[goal] + state` — forward,
         arg-max, exploration and `env.step` fused.  Returns the step tuple; `self.goal` holds the goals acted on."""
-        obs = env.obs_buf[env._slot]
-        if self.goal is None or self.goal.shape[0] != obs.shape[0]:
-            self.goal = torch.empty(obs.shape[0], dtype=torch.uint8, device=obs.device)
-        self.meta.act(obs, out=self.goal)
+        obs, n = env.obs_buf[env._slot], env.num_envs
+        if self.goal is None or self.goal.shape[0] != n:
+            self.goal = torch.empty(n, dtype=torch.uint8, device=obs.device)
+        if env.obs_layout == "goal_slot" and explore is None:
+            self.meta.act(obs, out=self.goal, obs_layout="goal_slot", write_goal=True)
+            return env.policy_step(self.ctrl, a2=a2, actions_out=actions_out)          # the controller reads slot 0
+        self.meta.act(obs, out=self.goal, obs_layout=env.obs_layout, n=n)
         if explore is not None:
             explore.apply(self.goal, self.meta.out_dim, env, salt=1)
         return env.policy_step(self.ctrl, goal=self.goal, a2=a2, explore=explore, actions_out=actions_out)

@@ -54,6 +54,8 @@ class TransitionRecorder:
                  mask: str = "winner_not_1", track_env_ids: bool = False):
         if format not in _FORMATS or mask not in _MASKS or player not in (1, 2):
             raise ValueError("format in {'replay','log','hdqn'}, mask in {'winner_not_1','all','explicit'}, player in {1,2}")
+        if getattr(env, "obs_layout", "aos") != "aos":
+            raise ValueError("the recorders read the default [N,10] observation rows: create the env with obs_layout='aos'")
         if format != "log" and env.auto_reset and env.terminal_obs is None:
             raise ValueError("replay rows need the terminal observation: create the env with episode_info=True")
         self.env, self.capacity = env, int(capacity)

@@ -113,6 +113,12 @@ class MergeVecEnv:
                   are then unavailable.
     host_slots    pinned host buffer sets of the host-buffer path (`step_host_async` keeps up to this
                   many steps in flight).
+    obs_layout    "aos" (default): `obs f32[N,10]`, the gym-shaped rows.  "soa": `obs f32[10,S]`, S = N rounded up to 16 —
+                  one column per feature, what a fused policy consumer reads best.  "goal_slot": `obs f32[N,11]`, rows
+                  `[goal] + state` (hdqn.py:291) whose slot 0 belongs to the goal policy (`HDQNPolicy` writes its goal
+                  there and its controller reads the row as it is; the env never touches slot 0).  `observation()` gives
+                  an [N,10] view of any of them.  Supported by reset / step / policy_step and the policy kernels;
+                  `rollout(obs=...)`, `step_host*` and the recorders need the default rows.
     lanes         L > 1 splits the envs into L contiguous sub-shards ("lanes", whole 256-env blocks), each
                   stepped by its own launch on its own CUDA stream: `step_lane_async(l, ...)` /
                   `step_lane_wait(l)`.  A lane depends only on its own previous step, so the launch of one
@@ -125,7 +131,7 @@ class MergeVecEnv:
                  seed: int = ACTION_SEED_DEFAULT, env_id_base: int = 0, out_slots: int = 1,
                  episode_info: bool = True, track_stats: bool = True, rewards: Optional[dict] = None,
                  validate_actions: bool = False, reset_mode: str = "fixed", reset_seed: Optional[int] = None,
-                 track_returns: bool = True, host_slots: int = 2, lanes: int = 1):
+                 track_returns: bool = True, host_slots: int = 2, lanes: int = 1, obs_layout: str = "aos"):
         if mode not in ("pvp", "pve"):
             raise ValueError("mode must be 'pvp' or 'pve'")
         if num_envs < 0 or out_slots < 1:
@@ -136,6 +142,11 @@ class MergeVecEnv:
             raise ValueError("host_slots must be >= 1")
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
+        if obs_layout not in nat.OBS_LAYOUTS:
+            raise ValueError(f"obs_layout must be one of {nat.OBS_LAYOUTS}")
+        if obs_layout != "aos" and (lanes != 1 or not track_returns):
+            raise ValueError("obs_layout 'soa' / 'goal_slot' needs lanes=1 and track_returns=True")
+        self.obs_layout = obs_layout
         self._lib = nat.load()                       # raises if the CUDA library is not built
         if not torch.cuda.is_available():
             raise nat.NativeError("merging_gym_b200 needs a CUDA device (no CPU fallback exists)")
@@ -183,6 +194,10 @@ class MergeVecEnv:
         # host-buffer path can fetch a whole slot with ONE device-to-host copy
         self._out_block = torch.zeros(K * n_pad * 50, dtype=torch.uint8, device=dev)
         self.obs_buf, self.rew_buf, self.done_buf, self.info_buf = _slot_views(self._out_block, K, n, n_pad)
+        if obs_layout == "soa":                      # [10, S] per slot; S * 4 bytes keeps every column 64-byte aligned
+            self.obs_buf = torch.zeros(K, nat.OBS_DIM, nat.soa_stride(n), dtype=torch.float32, device=dev)
+        elif obs_layout == "goal_slot":              # [N, 11] rows `[goal] + state`
+            self.obs_buf = torch.zeros(K, n_pad, nat.OBS_DIM + 1, dtype=torch.float32, device=dev)[:, :n]   # slots 16-byte aligned
         self._extras = {}
         if episode_info:
             self.terminal_obs = torch.zeros(n, nat.OBS_DIM, dtype=torch.float32, device=dev)
@@ -246,6 +261,25 @@ class MergeVecEnv:
     def _flags(self):
         return (nat.FLAG_AUTO_RESET if self.auto_reset else 0) | (0 if self.track_returns else nat.FLAG_NO_RETURNS)
 
+    def _step_flags(self):
+        """`_flags()` + the observation layout (mg_step / mg_policy_step write their observations in it)."""
+        return self._flags() | nat.OBS_LAYOUT_FLAG[self.obs_layout]
+
+    def _need_rows(self, what: str) -> None:
+        if self.obs_layout != "aos":
+            raise ValueError(f"{what} works on the default [N,10] observation rows (obs_layout='aos'), "
+                             f"this env has obs_layout={self.obs_layout!r}")
+
+    def observation(self, slot: Optional[int] = None) -> torch.Tensor:
+        """The observations of output slot `slot` (default: the current one) as an [N,10] tensor whatever the layout —
+        the buffer itself for "aos", a strided view for "soa" / "goal_slot" (`.contiguous()` copies)."""
+        o = self.obs_buf[self._slot if slot is None else slot]
+        if self.obs_layout == "soa":
+            return o[:, :self.num_envs].t()
+        if self.obs_layout == "goal_slot":
+            return o[:, 1:]
+        return o
+
     def lane_stream(self, lane: int):
         """The CUDA stream lane `lane`'s launches run on (the current stream for a single-lane env)."""
         return self._lane_streams[lane] if self.lanes > 1 else torch.cuda.current_stream(self.device)
@@ -291,7 +325,7 @@ class MergeVecEnv:
         self._join_lanes()
         with torch.cuda.device(self.device), nvtx_range("mg.reset"):
             nat.check(self._lib.mg_reset(C.byref(self._state), self.num_envs, _ptr(m), _ptr(obs),
-                                         C.byref(self._rs), self._stream()), "mg_reset")
+                                         nat.OBS_LAYOUT_FLAG[self.obs_layout], C.byref(self._rs), self._stream()), "mg_reset")
         return obs
 
     # ------------------------------------------------------------------ lanes
@@ -406,7 +440,7 @@ class MergeVecEnv:
         with torch.cuda.device(self.device), nvtx_range("mg.step"):
             nat.check(self._lib.mg_step(C.byref(self._state), self.num_envs, _ptr(a1), _ptr(a2),
                                         self._ACT_DTYPE[a1.dtype], C.byref(self._rw),
-                                        C.byref(self._outs[k]), _ptr(self.stats_buf), self._flags(),
+                                        C.byref(self._outs[k]), _ptr(self.stats_buf), self._step_flags(),
                                         C.byref(self._rs), self._stream()), "mg_step")
         self._pending = k
 
@@ -451,7 +485,8 @@ class MergeVecEnv:
         from .policy import POLICY_BACKENDS
         if policy.out_dim != nat.NUM_ACTIONS or policy.backend not in POLICY_BACKENDS:
             raise ValueError("policy_step needs an MLPPolicy with 5 outputs and backend 'fused' or 'tf32x3'")
-        if policy.in_dim != nat.OBS_DIM + (0 if goal is None else 1):
+        goal_in_slot = goal is None and self.obs_layout == "goal_slot" and policy.in_dim == nat.OBS_DIM + 1
+        if policy.in_dim != nat.OBS_DIM + (0 if goal is None else 1) and not goal_in_slot:
             raise ValueError("policy input width does not match obs (+ goal)")
         n = self.num_envs
 
@@ -470,7 +505,9 @@ class MergeVecEnv:
         obs_in = self.obs_buf[self._slot]
         self._slot = (self._slot + 1) % self.out_slots
         k = self._slot
-        flags = self._flags()
+        flags = self._step_flags()
+        if goal is None and policy.in_dim == nat.OBS_DIM + 1:
+            flags |= nat.POLICY_FLAG_GOAL_IN_SLOT        # the controller reads `[goal] + state` rows as they are
         ex = None
         if explore is not None:
             ex = explore.spec()
@@ -568,6 +605,8 @@ class MergeVecEnv:
         policy should act on next; pass False when only the time-major outputs are used.
         """
         n, k = self.num_envs, int(k_steps)
+        if obs is not None:
+            self._need_rows("rollout(obs=...)")
         if step0 is None:
             step0 = self.step_count
             self.step_count += k
@@ -601,7 +640,8 @@ class MergeVecEnv:
         self._join_lanes()
         with torch.cuda.device(self.device):
             nat.check(self._lib.mg_reset(C.byref(self._state), self.num_envs, _ptr(self._zero_mask), _ptr(obs),
-                                         C.byref(self._rs), self._stream()), "mg_reset (observe)")
+                                         nat.OBS_LAYOUT_FLAG[self.obs_layout], C.byref(self._rs), self._stream()),
+                      "mg_reset (observe)")
         return obs
 
     # ------------------------------------------------------------------ host-buffer path
@@ -692,6 +732,7 @@ class MergeVecEnv:
         The reference's contract per call is `return obs, rewards, done, info` (merging_env.py:195): a caller that
         only logs rewards / dones (its policy reading the device-resident observation) moves 10 B per env instead of 50.
         """
+        self._need_rows("step_host_async")
         slots = self._host_slots()
         self._join_lanes()
         if len(self._hfly) >= self.host_slots:
@@ -746,6 +787,7 @@ class MergeVecEnv:
         Returns (obs, rewards, done, info_flags) as NumPy views of the pinned buffers (overwritten
         by the next call).
         """
+        self._need_rows("step_host")
         if self._hfly:
             raise RuntimeError("step_host() while step_host_async() calls are in flight: call step_host_wait() first")
         if fields is not None:

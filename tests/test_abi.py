@@ -99,11 +99,11 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, C.byref(bad_rs), None) == -4
     st = nat.MgState(*([0x1008] * 7))                                # not 16-byte aligned
     assert lib.mg_step(C.byref(st), 8, None, None, 0, C.byref(rw), C.byref(out), None, 0, None, None) == -3
-    assert lib.mg_reset(None, 8, None, None, None, None) == -1
+    assert lib.mg_reset(None, 8, None, None, 0, None, None) == -1
     assert lib.mg_get_constants(None) == -1
     # n == 0 is a no-op that needs no device
     assert lib.mg_step(C.byref(nat.MgState()), 0, None, None, 0, None, C.byref(out), None, 1, None, None) == 0
-    assert lib.mg_reset(C.byref(nat.MgState()), 0, None, None, None, None) == 0
+    assert lib.mg_reset(C.byref(nat.MgState()), 0, None, None, 0, None, None) == 0
     assert lib.mg_rollout(C.byref(nat.MgState()), 0, 1, 0, 0, 0, 4, None, C.byref(out), None, None, 1, None, None) == 0
     assert lib.mg_sample_actions(None, None, 0, 0, 0, 0, None) == 0
     assert lib.mg_mlp_act(None, None, 0, 10, 5, None, None, None, None, None, None, None, None, 0, None) == 0

@@ -60,7 +60,7 @@ def test_no_kernel_writes_out_of_bounds(n, random_reset):
     rs = nat.MgResetSpec(nat.RESET_RANDOM if random_reset else nat.RESET_FIXED, 0, 7, 1 << 40)
     rw = nat.default_rewards()
     s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    nat.check(lib.mg_reset(C.byref(st), n, None, p(obs), C.byref(rs), s), "reset")
+    nat.check(lib.mg_reset(C.byref(st), n, None, p(obs), 0, C.byref(rs), s), "reset")
     for t in range(60):
         nat.check(lib.mg_sample_actions(p(a1), p(a2), n, 5, 0, t, s), "sample")
         nat.check(lib.mg_step(C.byref(st), n, p(a1), p(a2), nat.ACT_U8, C.byref(rw), C.byref(out), p(stats), 1,
@@ -72,7 +72,7 @@ def test_no_kernel_writes_out_of_bounds(n, random_reset):
     for pvp in (1, 0):
         nat.check(lib.mg_rollout(C.byref(st), n, pvp, 5, 0, 100, K, C.byref(rw), C.byref(out), p(acts), p(stats), 1,
                                  C.byref(rs), s), "rollout")
-    nat.check(lib.mg_reset(C.byref(st), n, p(a1), p(obs), C.byref(rs), s), "masked reset")
+    nat.check(lib.mg_reset(C.byref(st), n, p(a1), p(obs), 0, C.byref(rs), s), "masked reset")
     nat.check(lib.mg_record_transitions(p(obs), p(obs), p(term), p(a1), p(a2), p(rew), p(done), p(info), None, None, n, 1, 0, 1,
                                         p(ring), 50, p(ids), p(counter), p(scratch), s), "record")
     nat.check(lib.mg_record_transitions(p(obs), p(obs), None, p(a1), None, p(rew), p(done), p(info), None, None, n, 0, 1, 2,
