@@ -711,6 +711,10 @@ def run_b200(args):
         return 0
 
     LPS = henvs[0].lanes
+    tr = load_traffic() or {}
+    traffic_per_step = None
+    if tr.get("dram_bytes_per_launch") and tr.get("envs_per_launch"):     # ncu bytes of one launch, scaled to one 2^20-env step
+        traffic_per_step = tr["dram_bytes_per_launch"] * (n / tr["envs_per_launch"])
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _, _ = cpu_baseline_object(args.cpu_seconds, ref_steps=args.ref_python_steps)
@@ -736,7 +740,7 @@ def run_b200(args):
                                            f"under the step launches ({n_reductions} reductions; banked: no statistics kernel "
                                            "on the timed streams)"},
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": per_gpu_gbs / peak, "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
+                         "frac": per_gpu_gbs / peak, "traffic": traffic_per_step,
                          "kernel": "mg::merge_step_kernel<2, uint8_t, true, false, true>",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": peak_src,
                          "per": ("GPU; achieved = 156 B x envs stepped in the timed region / its duration (CUDA events); with "
