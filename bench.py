@@ -442,6 +442,29 @@ def run_b200(args):
         return {"value": total_envs * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k, "steps": k,
                 "algorithmic_gbs_per_gpu": gbs, "frac_of_peak": gbs / peak}
 
+    extra_errors = {}
+
+    class guard:
+        """`with guard("name"):` around an extra measurement: a failure must never cost the line its contract keys; it
+        is reported under `extra_errors` and the extra stays null."""
+
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, et, ev, tb):
+            if et is None or not issubclass(et, Exception):
+                return False
+            extra_errors[self.name] = repr(ev)
+            print(f"# bench.py: extra measurement {self.name!r} failed: {ev!r}", file=sys.stderr)
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa
+                pass
+            return True
+
     ms, G, eager, clocks = timed_region(henvs, K, W, True, lanes=laned_headline)
     host_issue_ms = last_host_ms[0]
     value = total_envs * K / (ms * 1e-3)
@@ -449,113 +472,121 @@ def run_b200(args):
     n_reductions = reducer.submissions if reducer else 0
     # the other launch scheme over the same K steps, reported beside the headline
     other = None
-    if lenvs is not None:
-        ms_o, G_o, _, _ = timed_region(envs if laned_headline else lenvs, K, W, False, lanes=not laned_headline)
-        other = dict(rate(ms_o, K), launch=f"CUDA graph of {G_o} steps" if G_o else "eager")
+    with guard("serialized_at_headline_steps"):
+        if lenvs is not None:
+            ms_o, G_o, _, _ = timed_region(envs if laned_headline else lenvs, K, W, False, lanes=not laned_headline)
+            other = dict(rate(ms_o, K), launch=f"CUDA graph of {G_o} steps" if G_o else "eager")
 
     # ---- sustained: the same region at 2000 steps (graph of 200) whatever --steps says ------------------------
     sustained = None
-    if args.sustained_steps > 0:
-        if K >= args.sustained_steps:
-            sustained = dict(rate(ms, K), note="the headline region itself")
-        else:
-            ms_s, G_s, _, _ = timed_region(henvs, args.sustained_steps, W, False, lanes=laned_headline)
-            sustained = dict(rate(ms_s, args.sustained_steps),
-                             note=f"same shards and launches as `value`, {args.sustained_steps} steps as a CUDA graph of {G_s} "
-                                  "replayed; shows what the short driver-run region (--steps) cannot amortise")
+    with guard("sustained"):
+        if args.sustained_steps > 0:
+            if K >= args.sustained_steps:
+                sustained = dict(rate(ms, K), note="the headline region itself")
+            else:
+                ms_s, G_s, _, _ = timed_region(henvs, args.sustained_steps, W, False, lanes=laned_headline)
+                sustained = dict(rate(ms_s, args.sustained_steps),
+                                 note=f"same shards and launches as `value`, {args.sustained_steps} steps as a CUDA graph of {G_s} "
+                                      "replayed; shows what the short driver-run region (--steps) cannot amortise")
     # same kernel, ONE shard stepped in place: its 54.5 MB state is partly L2-resident between steps
-    ms_warm, _, _, _ = timed_region(envs[:1], max(K, 200), W, False)
-    Kw = max(K, 200)
+    ms_warm, Kw = None, max(K, 200)
+    with guard("l2_warm"):
+        ms_warm, _, _, _ = timed_region(envs[:1], Kw, W, False)
 
     # ---- extra: the same shards on two CUDA streams, so the ramp-up of one shard's launch overlaps the
     #      drain of another's (a forked CUDA graph); whole-GPU throughput, not a per-launch figure -----------
     overlapped = None
     Ko = max(K, 400)
-    if args.overlap_streams > 1 and R % args.overlap_streams == 0:
-        ms_ov, _, _, _ = timed_region(envs, Ko, W, False, n_streams=args.overlap_streams)
-        overlapped = dict(rate(ms_ov, Ko), streams=args.overlap_streams,
-                          note=f"the same {R} shards, shard r on stream r % {args.overlap_streams}: launches of "
-                               "independent shards overlap, which hides the per-launch ramp-up/drain that separates "
-                               "the serialised 2^20-env launch from the copy peak; launches are concurrent, so this "
-                               "is aggregate throughput and is not used for value/roofline")
+    with guard("overlapped_streams"):
+        if args.overlap_streams > 1 and R % args.overlap_streams == 0:
+            ms_ov, _, _, _ = timed_region(envs, Ko, W, False, n_streams=args.overlap_streams)
+            overlapped = dict(rate(ms_ov, Ko), streams=args.overlap_streams,
+                              note=f"the same {R} shards, shard r on stream r % {args.overlap_streams}: launches of "
+                                   "independent shards overlap, which hides the per-launch ramp-up/drain that separates "
+                                   "the serialised 2^20-env launch from the copy peak; launches are concurrent, so this "
+                                   "is aggregate throughput and is not used for value/roofline")
 
     # ---- extra: the other launch scheme at the longer step count -------------------------------------------------
     laned = serialized = None
-    if lenvs is not None:
-        ms_l, _, _, _ = timed_region(envs if laned_headline else lenvs, Ko, W, False, lanes=not laned_headline)
-        o = dict(rate(ms_l, Ko), at_headline_steps=other)
-        if laned_headline:
-            serialized = dict(o, note="one mg_step launch per 2^20-env step, all on ONE stream (round 1's headline): each launch "
-                                      "pays its own ramp-up and drain")
-        else:
-            laned = dict(o, lanes=args.lanes, launches_per_step=args.lanes,
-                         note=f"MergeVecEnv(lanes={args.lanes}): each step issued as {args.lanes} launches on the lanes' streams")
+    with guard("other_scheme"):
+        if lenvs is not None:
+            ms_l, _, _, _ = timed_region(envs if laned_headline else lenvs, Ko, W, False, lanes=not laned_headline)
+            o = dict(rate(ms_l, Ko), at_headline_steps=other)
+            if laned_headline:
+                serialized = dict(o, note="one mg_step launch per 2^20-env step, all on ONE stream (round 1's headline): each launch "
+                                          "pays its own ramp-up and drain")
+            else:
+                laned = dict(o, lanes=args.lanes, launches_per_step=args.lanes,
+                             note=f"MergeVecEnv(lanes={args.lanes}): each step issued as {args.lanes} launches on the lanes' streams")
     # ---- extra: track_returns=False (no float64 return accumulators): 124 B/env-step ------------------------------
     lean = None
-    if args.lean:
-        nenvs = [mg.MergeVecEnv(n, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=(rank * R + r) * n,
-                                out_slots=S, episode_info=False, track_stats=True, track_returns=False) for r in range(R)]
-        for e in nenvs:
-            e.rollout(args.mix_steps, step0=1000)
-        ms_n, _, _, _ = timed_region(nenvs, Ko, W, False)
-        lean = dict(rate(ms_n, Ko, BYTES_PER_ENV_STEP_LEAN), bytes_per_env_step=BYTES_PER_ENV_STEP_LEAN,
-                    note="MergeVecEnv(track_returns=False): r1_accumulate / r2_accumulate (merging_env.py:191-192) are not "
-                         "kept, 124 instead of 156 B of HBM traffic per env-step; frac_of_peak uses 124 B")
-        del nenvs
+    with guard("lean_no_returns"):
+        if args.lean:
+            nenvs = [mg.MergeVecEnv(n, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=(rank * R + r) * n,
+                                    out_slots=S, episode_info=False, track_stats=True, track_returns=False) for r in range(R)]
+            for e in nenvs:
+                e.rollout(args.mix_steps, step0=1000)
+            ms_n, _, _, _ = timed_region(nenvs, Ko, W, False)
+            lean = dict(rate(ms_n, Ko, BYTES_PER_ENV_STEP_LEAN), bytes_per_env_step=BYTES_PER_ENV_STEP_LEAN,
+                        note="MergeVecEnv(track_returns=False): r1_accumulate / r2_accumulate (merging_env.py:191-192) are not "
+                             "kept, 124 instead of 156 B of HBM traffic per env-step; frac_of_peak uses 124 B")
+            del nenvs
 
     # ---- cross-check of the L2 methodology: ONE shard stepped in place with L2 flushed (a 512 MB
     #      buffer overwritten) before every timed launch, each launch bracketed by its own events ------
     flushed = None
-    if args.flush_steps > 0:
-        fl = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-        fr = torch.zeros(64 << 20, dtype=torch.int64, device=dev)          # 512 MB, only ever read
-        sink = torch.zeros((), dtype=torch.int64, device=dev)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-               for _ in range(args.flush_steps)]
-        for i, (a, b) in enumerate(evs):
-            fl.fill_(i & 0xFF)                            # evicts the shard's state and outputs from L2 ...
-            sink += fr.sum()                              # ... and a read pass leaves L2 full of CLEAN lines, so
-            a.record()                                    # the timed launch does not pay for the flush's write-back
-            env.step_async(acts1[i % A], acts2[i % A])
-            b.record()
-        torch.cuda.synchronize()
-        fms = sorted(a.elapsed_time(b) for a, b in evs)
-        fmed = fms[len(fms) // 2]
-        flushed = {"ms_per_step_median": fmed, "ms_per_step_min": fms[0], "steps": len(fms),
-                   "value": n / (fmed * 1e-3), "unit": UNIT + " per GPU",
-                   "frac_of_peak": n * BYTES_PER_ENV_STEP / (fmed * 1e-3) / 1e9 / peak,
-                   "note": "single shard in place; before every launch 512 MB are written and then 512 MB read to "
-                           "flush the 126 MB L2 (leaving clean lines); one event pair per eager launch, so the "
-                           "figure includes launch/event overhead and has no PDL or graph overlap"}
-        del fl, fr
+    with guard("l2_flushed"):
+        if args.flush_steps > 0:
+            fl = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+            fr = torch.zeros(64 << 20, dtype=torch.int64, device=dev)          # 512 MB, only ever read
+            sink = torch.zeros((), dtype=torch.int64, device=dev)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(args.flush_steps)]
+            for i, (a, b) in enumerate(evs):
+                fl.fill_(i & 0xFF)                            # evicts the shard's state and outputs from L2 ...
+                sink += fr.sum()                              # ... and a read pass leaves L2 full of CLEAN lines, so
+                a.record()                                    # the timed launch does not pay for the flush's write-back
+                env.step_async(acts1[i % A], acts2[i % A])
+                b.record()
+            torch.cuda.synchronize()
+            fms = sorted(a.elapsed_time(b) for a, b in evs)
+            fmed = fms[len(fms) // 2]
+            flushed = {"ms_per_step_median": fmed, "ms_per_step_min": fms[0], "steps": len(fms),
+                       "value": n / (fmed * 1e-3), "unit": UNIT + " per GPU",
+                       "frac_of_peak": n * BYTES_PER_ENV_STEP / (fmed * 1e-3) / 1e9 / peak,
+                       "note": "single shard in place; before every launch 512 MB are written and then 512 MB read to "
+                               "flush the 126 MB L2 (leaving clean lines); one event pair per eager launch, so the "
+                               "figure includes launch/event overhead and has no PDL or graph overlap"}
+            del fl, fr
 
     # ---- extra: K fused steps per launch with in-kernel Philox actions (mg_rollout), all outputs on ----
     RK = args.rollout_k
     rollout = None
-    if RK > 0:
-        ro = torch.empty(RK, n, 10, device=dev); rr = torch.empty(RK, n, 2, device=dev)
-        rd = torch.empty(RK, n, dtype=torch.uint8, device=dev); ri = torch.empty(RK, n, dtype=torch.uint8, device=dev)
-        for _ in range(2):
-            env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri, refresh_obs=False)
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        r0.record()
-        for _ in range(8):
-            env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri, refresh_obs=False)
-        r1.record()
-        torch.cuda.synchronize()
-        rms = r0.elapsed_time(r1) / (8 * RK)
-        t = torch.tensor([rms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rms = float(t.item())
-        rb = 50 + 104.0 / RK
-        rollout = {"value": total_envs / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms, "k_steps_per_launch": RK,
-                   "bytes_per_env_step": rb, "achieved_gbs_per_gpu": n * rb / (rms * 1e-3) / 1e9,
-                   "note": "mg_rollout: state stays in registers for K steps, actions from in-kernel Philox, "
-                           "obs/rew/done/info written time-major every step (the last row is the current observation); "
-                           "instruction-issue bound, not HBM bound"}
-        del ro, rr, rd, ri
+    with guard("rollout_fused"):
+        if RK > 0:
+            ro = torch.empty(RK, n, 10, device=dev); rr = torch.empty(RK, n, 2, device=dev)
+            rd = torch.empty(RK, n, dtype=torch.uint8, device=dev); ri = torch.empty(RK, n, dtype=torch.uint8, device=dev)
+            for _ in range(2):
+                env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri, refresh_obs=False)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            r0.record()
+            for _ in range(8):
+                env.rollout(RK, obs=ro, rew=rr, done=rd, info=ri, refresh_obs=False)
+            r1.record()
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1) / (8 * RK)
+            t = torch.tensor([rms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rms = float(t.item())
+            rb = 50 + 104.0 / RK
+            rollout = {"value": total_envs / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms, "k_steps_per_launch": RK,
+                       "bytes_per_env_step": rb, "achieved_gbs_per_gpu": n * rb / (rms * 1e-3) / 1e9,
+                       "note": "mg_rollout: state stays in registers for K steps, actions from in-kernel Philox, "
+                               "obs/rew/done/info written time-major every step (the last row is the current observation); "
+                               "instruction-issue bound, not HBM bound"}
+            del ro, rr, rd, ri
 
     # ---- end-to-end through the host-buffer API ------------------------------------------------------------------
     E = max(3, min(K, args.e2e_steps))
@@ -632,77 +663,79 @@ def run_b200(args):
 
     # ---- BASELINE configs[3]: 2^23 envs over all ranks, statistics all-reduced every 64 steps -------------------
     strong = None
-    if args.strong_envs > 0:
-        base, cnt = shard_range(args.strong_envs, rank, world)
-        senv = mg.MergeVecEnv(cnt, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=base, out_slots=2,
-                              episode_info=False, track_stats=True)
-        SA = 4
-        sa1 = torch.empty(SA, cnt, dtype=torch.uint8, device=dev); sa2 = torch.empty(SA, cnt, dtype=torch.uint8, device=dev)
-        for i in range(SA):
-            a1, a2 = senv.sample_actions(i)
-            sa1[i].copy_(a1); sa2[i].copy_(a2)
-        sred = mg.AsyncStatsReducer(senv, banked=True)
-        ctr = [0]
+    with guard("strong_8m"):
+        if args.strong_envs > 0:
+            base, cnt = shard_range(args.strong_envs, rank, world)
+            senv = mg.MergeVecEnv(cnt, mode="pvp", device=dev, auto_reset=True, seed=0x5EED, env_id_base=base, out_slots=2,
+                                  episode_info=False, track_stats=True)
+            SA = 4
+            sa1 = torch.empty(SA, cnt, dtype=torch.uint8, device=dev); sa2 = torch.empty(SA, cnt, dtype=torch.uint8, device=dev)
+            for i in range(SA):
+                a1, a2 = senv.sample_actions(i)
+                sa1[i].copy_(a1); sa2[i].copy_(a2)
+            sred = mg.AsyncStatsReducer(senv, banked=True)
+            ctr = [0]
 
-        def s_issue():
+            def s_issue():
+                senv._slot = 0
+                for i in range(STRONG_REDUCE_EVERY):
+                    senv.step_async(sa1[i % SA], sa2[i % SA])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(4):
+                    senv.step_async(sa1[i % SA], sa2[i % SA])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            sgraphs = sred.capture_per_bank(s_issue)
+            senv.reset()                                          # the digest run starts from reset, statistics zeroed
+            senv.stats(reset=True)
             senv._slot = 0
-            for i in range(STRONG_REDUCE_EVERY):
-                senv.step_async(sa1[i % SA], sa2[i % SA])
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for i in range(4):
-                senv.step_async(sa1[i % SA], sa2[i % SA])
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        sgraphs = sred.capture_per_bank(s_issue)
-        senv.reset()                                          # the digest run starts from reset, statistics zeroed
-        senv.stats(reset=True)
-        senv._slot = 0
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(STRONG_STEPS // STRONG_REDUCE_EVERY):
-            sred.replay(sgraphs)
-            sred.submit()
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sms = float(t.item())
-        totals = [int(v) for v in sred.latest().cpu().tolist()]
-        strong = {"value": args.strong_envs * STRONG_STEPS / (sms * 1e-3), "unit": UNIT, "scaling": "strong",
-                  "total_envs": args.strong_envs, "envs_per_gpu": cnt, "steps": STRONG_STEPS, "ms_per_step": sms / STRONG_STEPS,
-                  "reductions": sred.submissions, "reduce_every": STRONG_REDUCE_EVERY,
-                  "algorithmic_gbs_per_gpu": cnt * STRONG_STEPS * BYTES_PER_ENV_STEP / (sms * 1e-3) / 1e9,
-                  "stats_totals": totals,
-                  "stats_digest": hashlib.sha256(json.dumps(totals).encode()).hexdigest()[:16],
-                  "note": f"BASELINE configs[3]: {args.strong_envs} envs in total sharded contiguously over the ranks, "
-                          f"{STRONG_STEPS} steps from reset as CUDA graphs of {STRONG_REDUCE_EVERY} mg_step launches, the int64 "
-                          "statistics all-reduced (NCCL, side stream, banked: no statistics kernel on the launching stream) "
-                          "after every graph; stats_digest = sha256 of the reduced totals after the last step — it must be "
-                          "the same at every world size (actions are Philox over GLOBAL env ids)"}
-        del senv, sa1, sa2
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(STRONG_STEPS // STRONG_REDUCE_EVERY):
+                sred.replay(sgraphs)
+                sred.submit()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sms = float(t.item())
+            totals = [int(v) for v in sred.latest().cpu().tolist()]
+            strong = {"value": args.strong_envs * STRONG_STEPS / (sms * 1e-3), "unit": UNIT, "scaling": "strong",
+                      "total_envs": args.strong_envs, "envs_per_gpu": cnt, "steps": STRONG_STEPS, "ms_per_step": sms / STRONG_STEPS,
+                      "reductions": sred.submissions, "reduce_every": STRONG_REDUCE_EVERY,
+                      "algorithmic_gbs_per_gpu": cnt * STRONG_STEPS * BYTES_PER_ENV_STEP / (sms * 1e-3) / 1e9,
+                      "stats_totals": totals,
+                      "stats_digest": hashlib.sha256(json.dumps(totals).encode()).hexdigest()[:16],
+                      "note": f"BASELINE configs[3]: {args.strong_envs} envs in total sharded contiguously over the ranks, "
+                              f"{STRONG_STEPS} steps from reset as CUDA graphs of {STRONG_REDUCE_EVERY} mg_step launches, the int64 "
+                              "statistics all-reduced (NCCL, side stream, banked: no statistics kernel on the launching stream) "
+                              "after every graph; stats_digest = sha256 of the reduced totals after the last step — it must be "
+                              "the same at every world size (actions are Philox over GLOBAL env ids)"}
+            del senv, sa1, sa2
 
     # ---- BASELINE configs[4]: DQN policy forward in the loop, 2^18 envs per GPU --------------------------------------
     policy = None
-    if args.policy_envs > 0 and rank == 0:
-        import bench_policy
-        policy = {"note": "BASELINE configs[4]: pve, policy forward + arg-max -> mg_step on the device, random starts; "
-                          "graph-timed (bench_policy.measure); rank 0 only"}
-        for be in ("fused", "tf32x3"):
-            try:
-                policy[be] = bench_policy.measure(args.policy_envs, "dqn", be, device=dev)
+    with guard("policy_in_loop"):
+        if args.policy_envs > 0 and rank == 0:
+            import bench_policy
+            policy = {"note": "BASELINE configs[4]: pve, policy forward + arg-max -> mg_step on the device, random starts; "
+                              "graph-timed (bench_policy.measure); rank 0 only"}
+            for be in ("fused", "tf32x3"):
+                try:
+                    policy[be] = bench_policy.measure(args.policy_envs, "dqn", be, device=dev)
+                except Exception as e:  # noqa
+                    policy[be] = {"error": repr(e)}
+            try:        # the launch-bound end of the same loop: 4096 envs, where one launch per step (mg_policy_step) pays
+                small = bench_policy.measure(4096, "dqn", "tf32x3", device=dev, k=32, replays=8)
+                policy["tf32x3_4096_envs"] = {k_: small[k_] for k_ in ("value", "ms_per_step", "fused_step", "envs")}
             except Exception as e:  # noqa
-                policy[be] = {"error": repr(e)}
-        try:        # the launch-bound end of the same loop: 4096 envs, where one launch per step (mg_policy_step) pays
-            small = bench_policy.measure(4096, "dqn", "tf32x3", device=dev, k=32, replays=8)
-            policy["tf32x3_4096_envs"] = {k_: small[k_] for k_ in ("value", "ms_per_step", "fused_step", "envs")}
-        except Exception as e:  # noqa
-            policy["tf32x3_4096_envs"] = {"error": repr(e)}
+                policy["tf32x3_4096_envs"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -750,10 +783,10 @@ def run_b200(args):
                                  "GPU; achieved = 156 B x envs_per_gpu / (timed ms / steps)")},
             "serialized": serialized,
             "sustained": sustained,
-            "l2_warm": dict(rate(ms_warm, Kw),
-                            note="one 2^20-env shard stepped in place (the literal 1M-envs/GPU deployment): its "
-                                 "54.5 MB state is partly L2-resident between steps, so it runs faster than the "
-                                 "HBM roofline allows; not used for value/roofline"),
+            "l2_warm": None if ms_warm is None else dict(
+                rate(ms_warm, Kw), note="one 2^20-env shard stepped in place (the literal 1M-envs/GPU deployment): its "
+                                        "54.5 MB state is partly L2-resident between steps, so it runs faster than the "
+                                        "HBM roofline allows; not used for value/roofline"),
             "l2_flushed": flushed,
             "overlapped_streams": overlapped,
             "laned": laned,
@@ -761,6 +794,7 @@ def run_b200(args):
             "rollout_fused": rollout,
             "policy_in_loop": policy,
             "strong_8m": strong,
+            "extra_errors": extra_errors or None,
             "e2e": e2e, "gpu_launches": K * LPS, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "collision_rate", "merge_success_rate",
                                                     "mean_length", "mean_return1", "mean_return2")}}

@@ -50,10 +50,13 @@ class GraphedPolicyRollout:
         if (policy2 is not None) != (env.mode == "pvp"):
             raise ValueError("policy2 is required for, and only for, a pvp env")
         self.env, self.k_steps = env, int(k_steps)
-        for p in (policy1, policy2):        # inside this loop the kernel before a policy kernel is the env step (or the
-            for q in (p, getattr(p, "meta", None), getattr(p, "ctrl", None)):   # recorder): the weights are not written
-                if hasattr(q, "pdl"):
-                    q.pdl = True
+        # Inside this loop the kernel in front of a policy kernel is the env step (or the recorder), never one that writes
+        # the weights, so the policy kernels are captured with programmatic dependent launch; the policies' own `pdl`
+        # setting is put back after the capture (eager calls behind e.g. load_state_dict() must not use it).
+        nets = [q for p in (policy1, policy2) for q in (p, getattr(p, "meta", None), getattr(p, "ctrl", None)) if hasattr(q, "pdl")]
+        saved_pdl = [q.pdl for q in nets]
+        for q in nets:
+            q.pdl = True
         self._p1, self._p2, self._after = policy1, policy2, after_step
         n, dev = env.num_envs, env.device
         self._a1 = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -73,6 +76,8 @@ class GraphedPolicyRollout:
         with torch.cuda.graph(self.graph):
             for _ in range(self.k_steps):
                 self.last = self._one_step()
+        for q, v in zip(nets, saved_pdl):
+            q.pdl = v
 
     def _one_step(self):
         env = self.env

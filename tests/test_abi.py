@@ -131,3 +131,51 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(nat, "_lib", None)
     with pytest.raises(nat.NativeError, match="no CPU or PyTorch fallback"):
         nat.load()
+
+
+def test_python_constants_match_the_header():
+    """Every flag / enum value the ctypes binding hard-codes equals the header's #define (the header is the contract)."""
+    src = open(HEADER).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(MG_\w+)\s+(0x[0-9a-fA-F]+|\d+)u?\b", src)}
+    pairs = {"MG_ABI_VERSION": nat.MG_ABI_VERSION, "MG_OBS_DIM": nat.OBS_DIM, "MG_NUM_ACTIONS": nat.NUM_ACTIONS,
+             "MG_FLAG_AUTO_RESET": nat.FLAG_AUTO_RESET, "MG_FLAG_NO_RETURNS": nat.FLAG_NO_RETURNS,
+             "MG_FLAG_OBS_SOA": nat.FLAG_OBS_SOA, "MG_FLAG_OBS_GOAL_SLOT": nat.FLAG_OBS_GOAL_SLOT,
+             "MG_POLICY_FLAG_EXPLORE": nat.POLICY_FLAG_EXPLORE, "MG_POLICY_FLAG_PDL": nat.POLICY_FLAG_PDL,
+             "MG_POLICY_FLAG_GOAL_IN_SLOT": nat.POLICY_FLAG_GOAL_IN_SLOT,
+             "MG_POLICY_BACKEND_FP32": nat.POLICY_BACKEND_FP32, "MG_POLICY_BACKEND_TF32X3": nat.POLICY_BACKEND_TF32X3,
+             "MG_MLP_FLAG_MIRROR": nat.MLP_FLAG_MIRROR, "MG_MLP_FLAG_PDL": nat.MLP_FLAG_PDL,
+             "MG_MLP_FLAG_OBS_SOA": nat.MLP_FLAG_OBS_SOA, "MG_MLP_FLAG_OBS_GOAL_SLOT": nat.MLP_FLAG_OBS_GOAL_SLOT,
+             "MG_MLP_FLAG_WRITE_GOAL": nat.MLP_FLAG_WRITE_GOAL,
+             "MG_FIELD_OBS": nat.FIELD_OBS, "MG_FIELD_REW": nat.FIELD_REW, "MG_FIELD_DONE": nat.FIELD_DONE,
+             "MG_FIELD_INFO": nat.FIELD_INFO, "MG_FIELD_ALL": nat.FIELD_ALL,
+             "MG_INFO_COLLISION": nat.INFO_COLLISION, "MG_INFO_WINNER_SHIFT": nat.INFO_WINNER_SHIFT,
+             "MG_INFO_WINNER_MASK": nat.INFO_WINNER_MASK, "MG_INFO_TIMEOUT": nat.INFO_TIMEOUT, "MG_INFO_DONE": nat.INFO_DONE,
+             "MG_INFO_BAD_ACTION": nat.INFO_BAD_ACTION, "MG_META_STEPS_MASK": nat.META_STEPS_MASK,
+             "MG_META_WINNER_SHIFT": nat.META_WINNER_SHIFT, "MG_META_DONE": nat.META_DONE,
+             "MG_META_RESETS_SHIFT": nat.META_RESETS_SHIFT, "MG_RESET_FIXED": nat.RESET_FIXED, "MG_RESET_RANDOM": nat.RESET_RANDOM,
+             "MG_STATS_ROWS": nat.STATS_ROWS, "MG_STATS_COLS": nat.STATS_COLS}
+    for name, value in pairs.items():
+        assert name in defs, f"{name} is not #defined in the header"
+        assert defs[name] == value, f"{name}: header {defs[name]} != binding {value}"
+    assert nat.soa_stride(1) == 16 and nat.soa_stride(16) == 16 and nat.soa_stride(4099) == 4112
+    assert C.sizeof(nat.MgExplore) == 24 and C.sizeof(nat.MgHostSlot) == 4 * 8 + 2 * 56 + 3 * 8
+
+
+def test_policy_step_and_layout_argument_errors_without_a_gpu(lib):
+    """Argument validation happens before any CUDA call."""
+    st, out, rw = nat.MgState(), nat.MgOut(), nat.default_rewards()
+    vp = C.c_void_p
+    z = [None] * 6
+    assert lib.mg_policy_step(C.byref(st), -1, None, None, 0, *z, None, C.byref(rw), C.byref(out), None, 0, None, None, None, None, None) == -2
+    assert lib.mg_policy_step(C.byref(st), 8, None, None, 7, *z, None, C.byref(rw), C.byref(out), None, 0, None, None, None, None, None) == -4
+    assert lib.mg_policy_step(C.byref(st), 8, None, None, 0, *z, None, C.byref(rw), C.byref(out), None, nat.POLICY_FLAG_EXPLORE,
+                              None, None, None, None, None) == -1          # MG_POLICY_FLAG_EXPLORE without an MgExplore
+    assert lib.mg_policy_step(C.byref(st), 8, None, None, 0, *z, None, C.byref(rw), C.byref(out), None,
+                              nat.FLAG_OBS_SOA | nat.FLAG_OBS_GOAL_SLOT, None, None, None, None, None) == -4
+    assert lib.mg_policy_step(C.byref(st), 0, None, None, 0, *z, None, C.byref(rw), C.byref(out), None, 0, None, None, None, None, None) == 0
+    assert lib.mg_reset(C.byref(st), 8, None, None, nat.FLAG_AUTO_RESET, None, None) == -4       # not a layout flag
+    assert lib.mg_mlp_act(vp(16), None, 8, 10, 5, *[vp(16)] * 6, vp(16), None, nat.MLP_FLAG_WRITE_GOAL, None) == -4   # needs the goal-slot layout
+    assert lib.mg_mlp_act(vp(16), None, 8, 11, 5, *[vp(16)] * 6, vp(16), None, 0, None) == -2                         # 11-float rows need the layout flag
+    assert lib.mg_explore(None, 8, 5, None, None, 0, 0, None) == -1 and lib.mg_explore(None, 0, 5, None, None, 0, 0, None) == 0
+    assert lib.mg_option_update(None, None, None, None, None, 8, None, None, None, None, None) == -1
+    assert b"NULL" in lib.mg_last_error()

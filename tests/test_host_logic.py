@@ -1,3 +1,4 @@
+import os
 """Host-side logic that needs no GPU: spaces, sharding arithmetic, statistics decoding, lazy info,
 and that the product refuses to run without CUDA (no CPU fallback)."""
 import numpy as np
@@ -78,3 +79,27 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "merge_oracle" not in src or f.endswith((".cuh", ".cu")), f
+
+
+def test_exploration_rule_constants():
+    """`np.random.randn() <= 0.7` (main.py:103) holds with probability Phi(0.7); the device compares a u32 with floor(p * 2^32)."""
+    import math
+    from merging_gym_b200.policy import EPISILO, Exploration
+    ex = Exploration()
+    assert ex.threshold == EPISILO == 0.7
+    assert abs(ex.keep_prob - 0.5 * (1 + math.erf(0.7 / math.sqrt(2)))) < 1e-15 and abs(ex.keep_prob - 0.7580363) < 1e-7
+    assert ex.keep_u32 == int(ex.keep_prob * 2 ** 32)
+    assert Exploration(threshold=10.0).keep_u32 == 0xFFFFFFFF and Exploration(threshold=-10.0).keep_u32 == 0
+    sp = Exploration(seed=5, step=9).spec()
+    assert (sp.seed, sp.step, sp.keep_u32) == (5, 9, ex.keep_u32)
+
+
+def test_nvtx_ranges_are_off_by_default():
+    import contextlib
+    from merging_gym_b200 import tracing
+    assert not tracing.enabled() or os.environ.get("MG_NVTX", "0") not in ("", "0")
+    if not tracing.enabled():
+        assert isinstance(tracing.nvtx_range("x"), contextlib.nullcontext)
+    tracing.enable(True)
+    assert tracing.enabled() and tracing.nvtx_range("x").name == "x"
+    tracing.enable(False)
