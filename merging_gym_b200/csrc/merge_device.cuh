@@ -202,7 +202,15 @@ __device__ __forceinline__ void reset_obs_fixed(float *obs) {
 // Returned by value (pos1, vel1, pos2, vel2): a reference parameter of a non-inlined function would force the caller's
 // env registers into local memory.
 struct StartState { double p1, v1, p2, v2; };
-static __device__ __noinline__ StartState random_start_state(uint64_t seed, uint64_t env_id, uint32_t count) {
+#ifndef MG_RANDOM_START_INLINE
+#define MG_RANDOM_START_INLINE 0
+#endif
+#if MG_RANDOM_START_INLINE
+__device__ __forceinline__
+#else
+static __device__ __noinline__
+#endif
+StartState random_start_state(uint64_t seed, uint64_t env_id, uint32_t count) {
     uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = count, c3 = 0u;
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x52535445u);
     const double k32 = 1.0 / 4294967296.0;

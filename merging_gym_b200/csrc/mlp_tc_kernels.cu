@@ -28,6 +28,8 @@
 // timeline is measured by profiles/exp_tc_trace.cu (-DMG_TC_TRACE=1).
 // Every mbarrier wait is bounded and traps instead of hanging.
 #include "abi_common.h"
+// ptxas 12.9 crashes on setmaxnreg in a kernel that also CALLS a function: the random-start draw is inlined in this file
+#define MG_RANDOM_START_INLINE 1
 #include "policy_env.cuh"
 
 // 1 = a single MMA-issuing warp with its K loop fully unrolled: accumulation order in TMEM is the K-step order, the
@@ -66,8 +68,24 @@ constexpr int TMEM_COLS = 512;                // 2 accumulator buffers x 256 col
 constexpr int PRODUCER_WARPS = 8;             // thread = 4 envs x one K-step
 constexpr int MMA_WARPS = MG_TC_MMA_WARPS;     // warps 12.. issue the MMAs, K-steps interleaved
 constexpr int NUM_THREADS = 384 + 32 * MMA_WARPS;   // 8 producer warps + 4 epilogue warps + the MMA warps
-constexpr int ENV_WARP0 = 12 + MMA_WARPS;           // mg_policy_step only: ENV_WARPS more warps that own the env step
-constexpr int ENV_WARPS = 2;                        // 480 threads: ptxas still budgets 128 registers (512-thread granule)
+// mg_policy_step only: ENV_WARPS more warps own the env step.  MG_TC_ENV_WARPS = 3: 16 warps = 512 threads,
+// every warp keeps the 128 registers of the policy-only kernel.  MG_TC_ENV_WARPS = 7 (default): 20 warps = 5 warpgroups, every
+// warp is launched with 96 registers (65 536 / 640 rounded down to a multiple of 8) and each role starts by
+// re-partitioning the CTA's register pool with setmaxnreg: producers (warps 0-7) 112, epilogue (8-11) 104, the
+// warpgroup of the MMA warp and env warps 13-15 88, env warps 16-19 64 — 28 672 + 13 312 + 11 264 + 8 192 = 61 440 =
+// 640 x 96: the pool is what the CTA was launched with, NOT the SM's 65 536 (a partition that sums to more deadlocks
+// in setmaxnreg.inc).  Measured at 2^18 envs: 3 warps 86.4 us, 7 warps 82.7 us (the env warps then idle 73 % of the time;
+// profiles/r02_policy_step_tc_regions.md).
+#ifndef MG_TC_ENV_WARPS
+#define MG_TC_ENV_WARPS 7
+#endif
+constexpr int ENV_WARP0 = 12 + MMA_WARPS;
+constexpr int ENV_WARPS = MG_TC_ENV_WARPS;
+constexpr bool ENV_SETMAXNREG = ENV_WARPS > 3;      // more than 16 warps: the register file has to be re-partitioned
+constexpr int ENV_BUFS = 4;                         // action tiles in flight between the epilogue and the env warps
+constexpr int NUM_THREADS_ENV = 32 * (ENV_WARP0 + ENV_WARPS);
+static_assert(MMA_WARPS == 1 && (ENV_WARPS == 3 || ENV_WARPS == 7), "register budgets are laid out for 16 or 20 warps");
+static_assert(256 * 112 + 128 * 104 + 128 * 88 + 128 * 64 <= 640 * 96, "setmaxnreg partition exceeds the CTA pool");
 constexpr int MAX_OUT = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -82,7 +100,7 @@ struct Smem {
     unsigned long long full[PRODUCER_WARPS], empty[PRODUCER_WARPS], tmem_full[2], tmem_empty[2];
     unsigned long long w2_ready;              // completes when the bulk copies of b_cat have landed
     uint32_t tmem_base;
-    mgpe::Handoff<TM, ENV_WARPS> env;                    // ENV: the tile's actions, epilogue warps -> env warp
+    mgpe::Handoff<TM, ENV_BUFS> env;                     // ENV: the tile's actions, epilogue warps -> env warp
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -177,7 +195,7 @@ __device__ __forceinline__ void load_row(const float *obs, const uint8_t *__rest
 // themselves doubled the tile period: the epilogue warps have no slack, profiles/r02_policy_step_*.)
 // ENV: 0 = policy only, 1 = + env step pve, 2 = + env step pvp
 template <int IN, int OUT, bool MIRROR, int ENV>
-__global__ void __launch_bounds__(NUM_THREADS + (ENV ? 32 * ENV_WARPS : 0), 1)
+__global__ void __launch_bounds__(ENV ? NUM_THREADS_ENV : NUM_THREADS, 1)
 mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_mode,
                   const float *__restrict__ w1t, const float *__restrict__ b1, const float *__restrict__ w2_tc,
                   const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
@@ -197,7 +215,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
         for (int s = 0; s < PRODUCER_WARPS; ++s) { mbar_init(&S.full[s], 32); mbar_init(&S.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], MMA_WARPS); mbar_init(&S.tmem_empty[b], TM); }
         mbar_init(&S.w2_ready, 1);
-        if (ENV) mgpe::handoff_init(S.env, TM, ENV_WARPS);
+        if (ENV) mgpe::handoff_init(S.env, TM, TM / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         constexpr uint32_t kChunk = B_BYTES / 5;      // 35 840 B, a multiple of 16
         static_assert(kChunk * 5 == B_BYTES && kChunk % 16 == 0, "W2 is copied in five equal 16-byte-aligned pieces");
@@ -245,6 +263,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
                                                                // (an early trigger in front of mg_step made that step slower)
 
     if (warp < PRODUCER_WARPS) {
+        if (ENV && ENV_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // =================================== PRODUCERS: layer 1 ===================================
         // The CTA's K-steps are numbered g = 25 * (local tile) + ks; warp w produces g = w, w + 8, ... into ring
         // slot g % 4.  Its layer-1 arithmetic for K-step g runs while the MMAs of g-8 .. g-1 are in flight; only the
@@ -325,10 +344,21 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
             MG_TRACE(g_trace_prod, g, 4);
         }
     } else if (ENV && warp >= ENV_WARP0) {
+        if (ENV_SETMAXNREG) {
+            if (warp < 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");  // same warpgroup as the MMA warp
+            else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        }
         // =================================== ENV WARPS: MergeEnv.step of the tiles the epilogue has finished ==========
-        mgpe::env_warp_loop<TM, ENV_WARPS, ENV_WARPS, ENV == 2>(P, S.env, warp - ENV_WARP0, blockIdx.x, gridDim.x, n_tiles, n, lane,
-                                                     (int)(blockIdx.x % MG_STATS_ROWS));
+        // warp 16 shares its scheduler (warp % 4) with the MMA-issuing warp 12: it stays idle (MG_TC_ENV_SKIP16)
+#ifndef MG_TC_ENV_SKIP16
+#define MG_TC_ENV_SKIP16 0
+#endif
+        if (!(MG_TC_ENV_SKIP16 && warp == 16))
+            mgpe::env_warp_loop<TM, ENV_BUFS, ENV_WARPS - MG_TC_ENV_SKIP16, ENV == 2>(
+                P, S.env, warp - ENV_WARP0 - ((MG_TC_ENV_SKIP16 && warp > 16) ? 1 : 0), blockIdx.x, gridDim.x, n_tiles, n, lane,
+                (int)(blockIdx.x % MG_STATS_ROWS));
     } else if (warp >= 12) {
+        if (ENV && ENV_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         // =================================== MMA ISSUERS =========================================
         // The issuing warp runs its loop whole-warp and issues by PREDICATION from one elected lane (inside an
         // `if (lane == 0)` region the compiler rebuilt every descriptor through R2UR and wrapped each tcgen05
@@ -385,6 +415,7 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
             }
         }
     } else {
+        if (ENV && ENV_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // =================================== EPILOGUE: layer 3 + arg-max ===========================
         // tcgen05.ld.16x256b.x2: lanes 16h .. 16h+15 of this warp's TMEM quarter, 16 columns; thread (t1 = lane / 4,
         // t0 = lane % 4) receives rows t1 and t1 + 8 at columns 8b + 2 t0 + {0, 1} of both 8-column blocks b:
@@ -507,7 +538,7 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_mod
     const int64_t tiles = (n + TM - 1) / TM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS + (ENV ? 32 * ENV_WARPS : 0)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ENV ? NUM_THREADS_ENV : NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

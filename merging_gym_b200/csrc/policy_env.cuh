@@ -148,32 +148,35 @@ __device__ __forceinline__ uint8_t *handoff_acquire(Handoff<TM, NB> &H, uint32_t
 template <int TM, int NB>
 __device__ __forceinline__ void handoff_publish(Handoff<TM, NB> &H, uint32_t tl) { hs_arrive(&H.full[tl % NB]); }
 
-// env warp w of NW: rounds w, w + NW, ... (32 envs each) of EVERY tile of this CTA (global tile = first_tile + tl *
-// tile_stride, TM envs): the warps share a tile so that what is left to do after the policy warps' last tile — the only
-// part of the env work that is not hidden — is 1/NW of a tile per warp.  empty[] therefore counts NW arrivals.
+// env warp w of NW: the CTA's env work is a sequence of ROUNDS of 32 envs — round q = (tile number tl = q / R, round r
+// = q % R of that tile, R = TM / 32) — and warp w takes q = w, w + NW, ...: whatever NW is, the rounds are spread evenly
+// and a warp has NW / R tile periods for each of its rounds.  A tile's buffer goes back to the policy warps when its R
+// rounds have arrived on empty[] (count R).  The state of a round does not depend on the actions: it is requested
+// before the warp waits for them.
 template <int TM, int NB, int NW, bool PVP>
 __device__ __forceinline__ void env_warp_loop(const Args &A, Handoff<TM, NB> &H, int w, int64_t first_tile, int64_t tile_stride,
                                               int64_t n_tiles, int64_t n, int lane, int stats_row) {
     static_assert(TM % 32 == 0, "a tile is a whole number of warp rounds");
-    constexpr int ROUNDS = TM / 32;
-    uint32_t tl = 0;
-    for (int64_t tile = first_tile; tile < n_tiles; tile += tile_stride, ++tl) {
-        const uint32_t buf = tl % NB;
-        const int64_t e0 = tile * TM + lane;
-        Loaded cur, nxt;
-        load_env<PVP>(A, e0 + 32 * w, n, nxt);            // the state does not depend on the actions: ask for it first
+    constexpr uint32_t R = TM / 32;
+    const int64_t my_tiles = first_tile < n_tiles ? (n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
+    const uint32_t total = (uint32_t)my_tiles * R;
+    mg::StatAcc st;
+    for (uint32_t q = (uint32_t)w; q < total; q += NW) {
+        const uint32_t tl = q / R, r = q % R, buf = tl % NB;
+        const int64_t e = (first_tile + (int64_t)tl * tile_stride) * TM + 32 * r + lane;
+        Loaded x;
+        load_env<PVP>(A, e, n, x);
         hs_wait(&H.full[buf], (tl / NB) & 1u);
-        mg::StatAcc st;
-#pragma unroll 1
-        for (int r = w; r < ROUNDS; r += NW) {
-            cur = nxt;
-            if (r + NW < ROUNDS) load_env<PVP>(A, e0 + 32 * (r + NW), n, nxt);
-            step_loaded<PVP>(A, e0 + 32 * r, cur, (int)H.tile[buf][32 * r + lane], st);
-        }
-        if (A.stats) mg::flush_stats(st, A.stats + (size_t)stats_row * MG_STATS_COLS, 0xFFFFFFFFu, lane);
+        const int greedy = (int)H.tile[buf][32 * r + lane];
         __syncwarp();
-        if (lane == 0) hs_arrive(&H.empty[buf]);
+        if (lane == 0) hs_arrive(&H.empty[buf]);         // the action is in a register: the slot may be reused
+#ifndef MG_TC_ENV_NOWORK                                 // timing experiment only: hand-over without the env step
+        step_loaded<PVP>(A, e, x, greedy, st);
+#else
+        (void)greedy;
+#endif
     }
+    if (A.stats) mg::flush_stats(st, A.stats + (size_t)stats_row * MG_STATS_COLS, 0xFFFFFFFFu, lane);
 }
 
 }  // namespace mgpe
