@@ -380,8 +380,11 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
             const uint32_t d = tmem_base + buf * 256u;
             const uint32_t tm_full = smem_u32(&S.tmem_full[buf]);
             uint32_t have = 0;                              // the barrier about to be waited for was already seen complete
-#pragma unroll                                      // fully unrolled: 74.7 -> 69.6 us with one issuing warp
-            for (int ks = j; ks < KSTEPS; ks += MMA_WARPS) {
+            // One K-step; the loop around it is fully unrolled in the policy-only kernel (74.7 -> 69.6 us in round 1: the
+            // descriptor arithmetic of the next K-steps overlaps the waits) and unrolled 5x in the fused kernel, where
+            // 1 450 straight-line instructions per tile cost more in instruction-cache misses — the env warps' code shares
+            // the cache — than the overlap buys (84.7 -> 79.6 us at 2^18 envs; the policy-only kernel loses 0.5 us with it).
+            auto kstep = [&](const int ks) {
                 const uint32_t it = tl * KSTEPS + (uint32_t)ks;
                 const uint32_t s = it % STAGES, pw = it % PRODUCER_WARPS;
                 // everything the elected lane needs is computed BEFORE the wait, in ordinary registers
@@ -412,6 +415,13 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
                        "r"(last), "r"(done_bar), "r"(tm_full)
                     : "memory");
                 MG_TRACE(g_trace_mma, it, 2);
+            };
+            if (ENV) {
+#pragma unroll 5
+                for (int ks = j; ks < KSTEPS; ks += MMA_WARPS) kstep(ks);
+            } else {
+#pragma unroll
+                for (int ks = j; ks < KSTEPS; ks += MMA_WARPS) kstep(ks);
             }
         }
     } else {
