@@ -349,14 +349,9 @@ mlp_act_tc_kernel(const float *obs, const uint8_t *__restrict__ goal, const int6
             else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         }
         // =================================== ENV WARPS: MergeEnv.step of the tiles the epilogue has finished ==========
-        // warp 16 shares its scheduler (warp % 4) with the MMA-issuing warp 12: it stays idle (MG_TC_ENV_SKIP16)
-#ifndef MG_TC_ENV_SKIP16
-#define MG_TC_ENV_SKIP16 0
-#endif
-        if (!(MG_TC_ENV_SKIP16 && warp == 16))
-            mgpe::env_warp_loop<TM, ENV_BUFS, ENV_WARPS - MG_TC_ENV_SKIP16, ENV == 2>(
-                P, S.env, warp - ENV_WARP0 - ((MG_TC_ENV_SKIP16 && warp > 16) ? 1 : 0), blockIdx.x, gridDim.x, n_tiles, n, lane,
-                (int)(blockIdx.x % MG_STATS_ROWS));
+        // (keeping env warp 16 off the MMA-issuing warp's scheduler — warp % 4 — changed nothing: 90.9 vs 92.0 us)
+        mgpe::env_warp_loop<TM, ENV_BUFS, ENV_WARPS, ENV == 2>(P, S.env, warp - ENV_WARP0, blockIdx.x, gridDim.x, n_tiles, n, lane,
+                                                               (int)(blockIdx.x % MG_STATS_ROWS));
     } else if (warp >= 12) {
         if (ENV && ENV_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         // =================================== MMA ISSUERS =========================================

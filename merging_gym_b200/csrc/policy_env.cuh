@@ -108,9 +108,10 @@ __device__ __forceinline__ void step_loaded(const Args &A, int64_t e, Loaded &x,
 // The tensor-core policy kernel is bound by its matrix pipeline and its epilogue warps have no slack (ncu,
 // profiles/r02_policy_step_tc_*): an env step run BY the epilogue threads lengthened the tile period from 9 200 to
 // 18 400 cycles.  Extra warps therefore own the env: the arg-max threads drop tile tl's actions into tile[tl % NB]
-// and arrive on full[tl % NB]; the env warps step the tile's envs — one env per lane, rounds of the same small loop
-// body, the next round's state requested before the current one is computed — while the policy warps are already
-// on the following tiles, and hand the buffer back through empty[].  mbarrier arrive / try_wait carry release /
+// and arrive on full[tl % NB]; the env warps step the tile's envs — one env per lane, 32-env rounds of the same small
+// loop body dealt round-robin over the warps — while the policy warps are already
+// on the following tiles (a round's state is requested before the warp waits for its actions), and hand the buffer
+// back through empty[] as soon as the actions are in registers.  mbarrier arrive / try_wait carry release /
 // acquire semantics at CTA scope.
 template <int TM, int NB>
 struct Handoff {
@@ -170,8 +171,8 @@ __device__ __forceinline__ void env_warp_loop(const Args &A, Handoff<TM, NB> &H,
         const int greedy = (int)H.tile[buf][32 * r + lane];
         __syncwarp();
         if (lane == 0) hs_arrive(&H.empty[buf]);         // the action is in a register: the slot may be reused
-#ifndef MG_TC_ENV_NOWORK                                 // timing experiment only: hand-over without the env step
-        step_loaded<PVP>(A, e, x, greedy, st);
+#ifndef MG_TC_ENV_NOWORK                                 // -DMG_TC_ENV_NOWORK: timing experiment only (hand-over without the env
+        step_loaded<PVP>(A, e, x, greedy, st);           // step; profiles/r02_policy_step_tc_regions.md)
 #else
         (void)greedy;
 #endif
