@@ -5,21 +5,24 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-A "step" is ONE `mg_step` launch advancing every env of the rank's shard by one dT with external
-uint8 actions (pvp, auto-reset): BASELINE.json configs[2], 2^20 envs per launch per GPU.
+A "step" advances every env of the rank's 2^20-env shard by one dT with external uint8 actions (pvp, auto-reset):
+BASELINE.json configs[2].  The shard is a `MergeVecEnv(lanes=2)` — a step is two `mg_step` launches of 2^19 envs on the
+lanes' two CUDA streams, each ordered only behind its own lane's previous step (`--headline serialized`: one launch per
+step on one stream; whichever is not the headline is reported beside it as `serialized` / `laned`).
 Actions are pre-generated on the device (Philox, global env ids), so inputs are HBM-resident.
-L2 rule: one shard's inputs (56.6 MB) would fit the 126 MB L2, so the timed region steps
-`--shards` (4) independent 2^20-env shards round-robin — inputs larger than L2, no flush — and
-every launch reads its state from HBM.  Timed with CUDA events on the launching (current torch)
-stream, barrier + synchronize on both sides, max over ranks.
+L2 rule: one shard's inputs (56.6 MB) would fit the 126 MB L2, so the timed region steps `--shards` (4) independent
+2^20-env shards round-robin — inputs larger than L2, no flush — and every launch reads its state from HBM.  Timed with
+CUDA events on the launching (current torch) stream behind a spin-kernel gate (so that the host has queued the region
+before the device starts it), barrier + synchronize on both sides, max over ranks.
 
 The JSON line (rank 0) carries, besides the contract keys:
   roofline       HBM, algorithmic bytes = 156 B/env-step
   e2e            the same step through the host-buffer API (`MergeVecEnv.step_host_async/_wait`): actions in pinned
                  host memory, obs/rew/done/info copied back every step; + the synchronous call, the reduced-field
                  variant and the box's measured device->host copy ceiling
-  sustained      the same measurement at 2000 steps whatever --steps says
-  l2_warm, l2_flushed, overlapped_streams, laned, lean_no_returns, rollout_fused      extra device-side figures
+  sustained      the same measurement at 2000 steps whatever --steps says (clocks are sampled over it as well)
+  serialized, l2_warm, l2_flushed, overlapped_streams, lean_no_returns, rollout_fused      extra device-side figures
+  extra_errors   an extra that failed (null when none did): extras never cost the line its contract keys
   policy_in_loop BASELINE configs[4] (2^18 envs, DQN forward in the loop)
   strong_8m      BASELINE configs[3] (2^23 envs over all ranks, NCCL statistics reduction every 64 steps) with a
                  digest of the reduced statistics that must be equal for every world size
@@ -329,7 +332,7 @@ def run_b200(args):
     gate_hz = 1e3 * float(getattr(torch.cuda.get_device_properties(dev), "clock_rate", 1.9e6))   # kHz -> Hz
     last_host_ms = [0.0]
 
-    def timed_region(shards, K, W, sample_clocks, n_streams=1, graph_steps=None, lanes=False):
+    def timed_region(shards, K, W, sample_clocks, n_streams=1, graph_steps=None, lanes=False, with_reducer=True):
         """W warm-up + K timed step launches round-robin over `shards`; returns (ms, G, eager, clocks).
         n_streams > 1: shard r is stepped on stream r % n_streams (forked from / joined to the current
         stream around every batch), so launches of independent shards may overlap.
@@ -376,7 +379,7 @@ def run_b200(args):
         cyc = cyc * A // math.gcd(cyc, A)                 # slot ring, shard ring and action ring line up
         if not args.no_graph and K >= cyc:
             G = (min(K, max(gsteps, cyc)) // cyc) * cyc
-        use_reducer = reducer is not None and sample_clocks and shards[0] is reducer.env
+        use_reducer = reducer is not None and sample_clocks and with_reducer and shards[0] is reducer.env
         if G > 0:
             rewind()
             side = torch.cuda.Stream()
@@ -484,7 +487,12 @@ def run_b200(args):
             if K >= args.sustained_steps:
                 sustained = dict(rate(ms, K), note="the headline region itself")
             else:
-                ms_s, G_s, _, _ = timed_region(henvs, args.sustained_steps, W, False, lanes=laned_headline)
+                # the driver's --steps region lasts half a millisecond, too short for NVML to see: the clocks are sampled
+                # over this longer region as well (`clocks.sustained`)
+                ms_s, G_s, _, clocks_s = timed_region(henvs, args.sustained_steps, W, True, lanes=laned_headline, with_reducer=False)
+                if clocks is not None and clocks_s is not None:
+                    clocks["sustained"] = clocks_s
+                    clocks["reasons"] = sorted(set(clocks["reasons"]) | set(clocks_s["reasons"]))
                 sustained = dict(rate(ms_s, args.sustained_steps),
                                  note=f"same shards and launches as `value`, {args.sustained_steps} steps as a CUDA graph of {G_s} "
                                       "replayed; shows what the short driver-run region (--steps) cannot amortise")
