@@ -37,7 +37,7 @@ extern "C" {
 #define MG_API __attribute__((visibility("default")))
 #endif
 
-#define MG_ABI_VERSION 6
+#define MG_ABI_VERSION 7
 #define MG_OBS_DIM 10      /* merging_env.py:75,118-132 */
 #define MG_NUM_ACTIONS 5   /* merging_env.py:101-102   */
 
@@ -350,7 +350,10 @@ MG_API int mg_explore(uint8_t *choices, int64_t n, int32_t num_choices, const Mg
  *                        r_int = 1 if g' == goal_status(s) else 0 (hdqn.py:223-236,314); the reference stores it
  *                        every step (mask_mode 0)
  * counter: device uint64, total rows ever appended (caller zero-initialises).
- * scratch: device uint32[(n+31)/32 + 4].  env_ids_or_null: int32[capacity], env of each row. */
+ * scratch: device uint32[mg_record_scratch_words(n)] (= (n+31)/32 + 4), 8-byte aligned; the library's work area for the
+ *          block counts / offsets of the call (count -> scan -> write, three launches; the write pass is a programmatic
+ *          dependent of the scan).  env_ids_or_null: int32[capacity], env of each row. */
+MG_API int64_t mg_record_scratch_words(int64_t n);
 MG_API int mg_record_transitions(const float *obs_prev, const float *obs_next,
                                  const float *term_obs_or_null, const uint8_t *a1,
                                  const uint8_t *a2_or_null, const float *rew, const uint8_t *done,

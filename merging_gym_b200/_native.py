@@ -10,7 +10,7 @@ import os
 
 from ._paths import LIB_PATH
 
-MG_ABI_VERSION = 6
+MG_ABI_VERSION = 7
 OBS_DIM = 10
 NUM_ACTIONS = 5
 STATS_ROWS = 1024
@@ -141,6 +141,8 @@ def load():
     lib.mg_option_update.restype = C.c_int
     lib.mg_record_transitions.argtypes = [vp] * 10 + [i64, i32, i32, i32, vp, i64, vp, vp, vp, vp]
     lib.mg_record_transitions.restype = C.c_int
+    lib.mg_record_scratch_words.argtypes = [i64]
+    lib.mg_record_scratch_words.restype = i64
     for f in (lib.mg_get_constants, lib.mg_default_rewards, lib.mg_reset, lib.mg_step,
               lib.mg_sample_actions, lib.mg_rollout, lib.mg_step_host, lib.mg_step_host_async,
               lib.mg_step_host_wait):

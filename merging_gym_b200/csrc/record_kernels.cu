@@ -8,10 +8,16 @@
 //
 // Deterministic three-pass compaction (no atomics, so the ring content is reproducible and equals a
 // sequential loop over env ids):
-//   count  : ballot + popc per warp, summed per 256-env block          -> block_counts
+//   count  : every thread takes 16 consecutive info bytes (one 128-bit load), half-warps sum them into the counts of
+//            the 256-env blocks                                            -> block_counts
 //   scan   : one CTA, exclusive scan of block_counts (n / 256 entries), advances the ring counter
 //   write  : a block re-derives its warps' ranks from the ballots; every selected env writes its row at
 //            (counter + offset) % capacity
+// The write pass is launched as a programmatic dependent of the scan: its blocks request their observation rows and take
+// their ballots while the single scan CTA is still running, and only then wait for the offsets (47 -> 4x us per 2^20 rows
+// inside a CUDA graph).  A one-launch variant (tiles by ticket, decoupled look-back over per-tile words) was measured and
+// dropped: 57 us against 47 (profiles/r02_record_onepass_experiment.patch, r02_record_onepass_vs_three_pass.jsonl) — the
+// ticket, publication and look-back round trips put ~5 us of latency in front of every block's first store.
 #include "abi_common.h"
 
 namespace mgrec {
@@ -27,20 +33,43 @@ __device__ __forceinline__ bool selected(const uint8_t *info, int64_t e, int mas
     return ((info[e] & MG_INFO_WINNER_MASK) >> MG_INFO_WINNER_SHIFT) != 1u;
 }
 
+// One thread = 16 consecutive envs (their info bytes are one 16-byte load), 16 threads = one 256-env block of the write
+// pass: a half-warp shuffle sum gives that block's count.  The ragged tail (and a misaligned info pointer) goes byte by byte.
+constexpr int kCountPerThread = 16;
 __global__ void __launch_bounds__(kBlock)
 count_kernel(const uint8_t *__restrict__ info, int64_t n, int mask_mode, uint32_t *__restrict__ block_counts) {
-    __shared__ uint32_t s_cnt[kBlock / 32];
-    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const bool sel = e < n && selected(info, e, mask_mode);
-    const unsigned b = __ballot_sync(0xFFFFFFFFu, sel);
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(b);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t e0 = t * kCountPerThread;
+    uint32_t c = 0;
+    if (e0 < n) {
+        if (mask_mode == 0) {
+            c = (uint32_t)min((int64_t)kCountPerThread, n - e0);
+        } else if (e0 + kCountPerThread <= n && (reinterpret_cast<uintptr_t>(info) & 15u) == 0) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(info + e0));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; ++w) tot += s_cnt[w];
-        block_counts[blockIdx.x] = tot;
+            for (int k = 0; k < 4; ++k) {
+                if (mask_mode == 2) {
+                    // bytes != 0: fold each byte's bits into its bit 0
+                    uint32_t x = w[k];
+                    x |= x >> 4; x |= x >> 2; x |= x >> 1;
+                    c += __popc(x & 0x01010101u);
+                } else {
+                    // winner field != 1 in every byte: XOR with the pattern "1", then any bit left in the field
+                    constexpr uint32_t m = MG_INFO_WINNER_MASK * 0x01010101u;
+                    constexpr uint32_t one = (1u << MG_INFO_WINNER_SHIFT) * 0x01010101u;
+                    uint32_t x = ((w[k] & m) ^ one) >> MG_INFO_WINNER_SHIFT;      // field value ^ 1, per byte, at bit 0 ..
+                    x |= x >> 4; x |= x >> 2; x |= x >> 1;
+                    c += __popc(x & 0x01010101u);
+                }
+            }
+        } else {
+            for (int64_t e = e0; e < min(n, e0 + kCountPerThread); ++e) c += selected(info, e, mask_mode) ? 1u : 0u;
+        }
     }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);      // 16 threads = 256 envs
+    if ((threadIdx.x & 15) == 0 && e0 < n) block_counts[t / 16] = c;
 }
 
 // Single CTA: in-place exclusive scan of block_counts[0..m), total added to *counter (int64 rows
@@ -51,6 +80,9 @@ scan_kernel(uint32_t *__restrict__ warp_counts, int64_t m, unsigned long long *_
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_s;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    // the write pass may become resident now (on the other SMs): it loads its rows and waits for this grid's completion
+    // before it reads the offsets
+    cudaTriggerProgrammaticLaunchCompletion();
     if (t == 0) carry_s = 0;
     __syncthreads();
     for (int64_t i0 = 0; i0 < m; i0 += 4096) {             // 4 entries per thread and pass
@@ -102,67 +134,102 @@ scan_kernel(uint32_t *__restrict__ warp_counts, int64_t m, unsigned long long *_
 // One warp handles 32 consecutive envs: their observation rows are one contiguous 1280-byte span, loaded
 // with coalesced 128-bit loads into shared memory; the selected lanes assemble their rows in shared memory
 // at consecutive ranks; the warp then writes that contiguous piece of the ring with coalesced stores.
+template <int FORMAT> struct RowFmt {
+    static constexpr int WIDTH = FORMAT == 0 ? 2 * kObs + 2 : FORMAT == 1 ? kObs + 4 : 2 * kObs + 4;
+};
+constexpr int kWarps = kBlock / 32;
+
 template <int FORMAT>
-__global__ void __launch_bounds__(kBlock)
-write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_next,
-             const float *__restrict__ term_obs, const uint8_t *__restrict__ a1, const uint8_t *__restrict__ a2,
-             const float *__restrict__ rew, const uint8_t *__restrict__ done, const uint8_t *__restrict__ info,
-             const uint8_t *__restrict__ goal_prev, const uint8_t *__restrict__ goal_next,
-             int64_t n, int mask_mode, int player, const uint32_t *__restrict__ block_offsets,
-             const unsigned long long *__restrict__ base, const unsigned long long *__restrict__ counter,
-             float *__restrict__ ring, int64_t capacity, int32_t *__restrict__ env_ids) {
-    constexpr int WIDTH = FORMAT == 0 ? 2 * kObs + 2 : FORMAT == 1 ? kObs + 4 : 2 * kObs + 4;
-    constexpr int kWarps = kBlock / 32;
-    __shared__ __align__(16) float s_prev[kWarps][32 * kObs];
-    __shared__ __align__(16) float s_next[kWarps][FORMAT != 1 ? 32 * kObs : 4];
-    __shared__ __align__(16) float s_out[kWarps][32 * WIDTH];
-    __shared__ uint32_t s_cnt[kWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t w0 = ((int64_t)blockIdx.x * kBlock + warp * 32);          // first env of this warp
+struct RowSmem {
+    float prev[kWarps][32 * kObs];
+    float next[kWarps][FORMAT != 1 ? 32 * kObs : 4];
+    float out[kWarps][32 * RowFmt<FORMAT>::WIDTH];
+};
+
+struct RowArgs {
+    const float *obs_prev, *obs_next, *term_obs;
+    const uint8_t *a1, *a2;
+    const float *rew;
+    const uint8_t *done, *info, *goal_prev, *goal_next;
+    int64_t n;
+    int mask_mode, player;
+    float *ring;
+    int64_t capacity;
+    int32_t *env_ids;
+};
+
+// Part 0: a full warp's 32 observation rows (s, and s' for the replay formats) are 80 float4 each: every lane requests
+// its 2-3 pieces of both arrays before anything waits on them, so that a warp has up to six 128-bit loads in flight
+// (the first version looped load -> shared store and kept one: 57 us per 2^20 rows).
+struct RowRegs { float4 p[3], q[3]; };
+template <int FORMAT>
+__device__ __forceinline__ void request_rows(const RowArgs &A, int lane, int64_t w0, RowRegs &R) {
+    const float4 *gp = reinterpret_cast<const float4 *>(A.obs_prev + w0 * kObs);
+    R.p[0] = __ldg(gp + lane); R.p[1] = __ldg(gp + lane + 32);
+    if (lane < 16) R.p[2] = __ldg(gp + lane + 64);
+    if (FORMAT != 1) {
+        const float4 *gn = reinterpret_cast<const float4 *>(A.obs_next + w0 * kObs);
+        R.q[0] = __ldg(gn + lane); R.q[1] = __ldg(gn + lane + 32);
+        if (lane < 16) R.q[2] = __ldg(gn + lane + 64);
+    }
+}
+
+// Part 1: the warp's observation rows into shared memory (coalesced 128-bit accesses; w0 * 40 bytes is 16-byte
+// aligned because w0 % 32 == 0), then every selected lane assembles its row at its rank inside the warp.  `full` = the
+// warp has all 32 envs and R holds their rows (request_rows); the last, ragged warp loads them here.
+template <int FORMAT>
+__device__ __forceinline__ void assemble_rows(const RowArgs &A, RowSmem<FORMAT> &sm, int warp, int lane, int64_t w0,
+                                              bool sel, unsigned b, bool full, const RowRegs &R) {
+    constexpr int WIDTH = RowFmt<FORMAT>::WIDTH;
     const int64_t e = w0 + lane;
-    const bool sel = e < n && selected(info, e, mask_mode);
-    const unsigned b = __ballot_sync(0xFFFFFFFFu, sel);
-    const int cnt = __popc(b);
-    if (lane == 0) s_cnt[warp] = (uint32_t)cnt;
-    __syncthreads();                                                         // the only block-wide step
-    if (w0 >= n) return;
-    uint32_t before = 0;                                                     // selected envs of the lower warps of this block
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) before += w < warp ? s_cnt[w] : 0u;
-    const int rows = (int)min((int64_t)32, n - w0);
-    // ---- coalesced loads of the warp's observation rows (w0 * 40 bytes is 16-byte aligned: w0 % 32 == 0) ----
-    {
-        const float4 *gp = reinterpret_cast<const float4 *>(obs_prev + w0 * kObs);
-        float4 *sp = reinterpret_cast<float4 *>(s_prev[warp]);
-        for (int i = lane; i < rows * kObs / 4; i += 32) sp[i] = __ldg(gp + i);
-        for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) s_prev[warp][i] = obs_prev[w0 * kObs + i];
+    // the selected lanes' own scalars: requested before the staging below waits on the row loads
+    float act1 = 0.f, act2 = 0.f, g = 0.f, gn = 0.f;
+    float2 rw = make_float2(0.f, 0.f);
+    bool use_term = false;
+    if (sel) {
+        act1 = (float)A.a1[e];
+        act2 = A.a2 ? (float)A.a2[e] : 0.f;
+        if (FORMAT != 2) rw = __ldg(reinterpret_cast<const float2 *>(A.rew) + e);
+        // s' is the observation of the stepped state: under auto-reset obs_next holds the RESET
+        // observation for finished envs, the terminal one is in term_obs
+        use_term = FORMAT != 1 && A.term_obs && A.done[e];
+        if (FORMAT == 2) { g = (float)A.goal_prev[e]; gn = (float)A.goal_next[e]; }
+    }
+    if (full) {
+        float4 *sp = reinterpret_cast<float4 *>(sm.prev[warp]);
+        sp[lane] = R.p[0]; sp[lane + 32] = R.p[1];
+        if (lane < 16) sp[lane + 64] = R.p[2];
         if (FORMAT != 1) {
-            const float4 *gn = reinterpret_cast<const float4 *>(obs_next + w0 * kObs);
-            float4 *sn = reinterpret_cast<float4 *>(s_next[warp]);
-            for (int i = lane; i < rows * kObs / 4; i += 32) sn[i] = __ldg(gn + i);
-            for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) s_next[warp][i] = obs_next[w0 * kObs + i];
+            float4 *sn = reinterpret_cast<float4 *>(sm.next[warp]);
+            sn[lane] = R.q[0]; sn[lane + 32] = R.q[1];
+            if (lane < 16) sn[lane + 64] = R.q[2];
+        }
+    } else {
+        const int rows = (int)(A.n - w0);
+        const float4 *gp = reinterpret_cast<const float4 *>(A.obs_prev + w0 * kObs);
+        float4 *sp = reinterpret_cast<float4 *>(sm.prev[warp]);
+        for (int i = lane; i < rows * kObs / 4; i += 32) sp[i] = __ldg(gp + i);
+        for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) sm.prev[warp][i] = A.obs_prev[w0 * kObs + i];
+        if (FORMAT != 1) {
+            const float4 *gq = reinterpret_cast<const float4 *>(A.obs_next + w0 * kObs);
+            float4 *sn = reinterpret_cast<float4 *>(sm.next[warp]);
+            for (int i = lane; i < rows * kObs / 4; i += 32) sn[i] = __ldg(gq + i);
+            for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) sm.next[warp][i] = A.obs_next[w0 * kObs + i];
         }
     }
     __syncwarp();
-    const uint64_t rank0 = (uint64_t)block_offsets[blockIdx.x] + before;
-    const uint64_t total = *counter - *base;
     if (sel) {
         const int r = __popc(b & ((1u << lane) - 1u));
-        float *row = s_out[warp] + r * WIDTH;
-        const float *sp = s_prev[warp] + lane * kObs;
-        const float act1 = (float)a1[e], act2 = a2 ? (float)a2[e] : 0.f;
-        // s' is the observation of the stepped state: under auto-reset obs_next holds the RESET
-        // observation for finished envs, the terminal one is in term_obs
-        const bool use_term = FORMAT != 1 && term_obs && done[e];
-        const float *sn = use_term ? term_obs + e * kObs : s_next[warp] + lane * kObs;
+        float *row = sm.out[warp] + r * WIDTH;
+        const float *sp = sm.prev[warp] + lane * kObs;
+        const float *sn = use_term ? A.term_obs + e * kObs : sm.next[warp] + lane * kObs;
         if (FORMAT == 2) {
-            const float g = (float)goal_prev[e], gn = (float)goal_next[e];
             const float dx1 = sp[0], v2 = sp[9];                                  // goal_status, hdqn.py:223-236
             const float status = dx1 < -0.5f * v2 ? 0.f : dx1 < 0.5f * v2 ? 1.f : 2.f;
             row[0] = g;
 #pragma unroll
             for (int k = 0; k < kObs; ++k) row[1 + k] = sp[k];
-            row[kObs + 1] = player == 2 ? act2 : act1;
+            row[kObs + 1] = A.player == 2 ? act2 : act1;
             row[kObs + 2] = gn == status ? 1.f : 0.f;
             row[kObs + 3] = gn;
 #pragma unroll
@@ -171,39 +238,90 @@ write_kernel(const float *__restrict__ obs_prev, const float *__restrict__ obs_n
 #pragma unroll
             for (int k = 0; k < kObs; ++k) row[k] = sp[k];
             if (FORMAT == 0) {
-                row[kObs] = player == 2 ? act2 : act1;
-                row[kObs + 1] = rew[2 * e + (player == 2 ? 1 : 0)];
+                row[kObs] = A.player == 2 ? act2 : act1;
+                row[kObs + 1] = A.player == 2 ? rw.y : rw.x;
 #pragma unroll
                 for (int k = 0; k < kObs; ++k) row[kObs + 2 + k] = sn[k];
             } else {
                 row[kObs] = act1; row[kObs + 1] = act2;
-                row[kObs + 2] = rew[2 * e]; row[kObs + 3] = rew[2 * e + 1];
+                row[kObs + 2] = rw.x; row[kObs + 3] = rw.y;
             }
         }
-        // rows a sequential writer would overwrite later in this same call are skipped below via `skip`
-        if (env_ids && !(rank0 + r + (uint64_t)capacity < total))
-            env_ids[(int64_t)((*base + rank0 + r) % (unsigned long long)capacity)] = (int32_t)e;
     }
     __syncwarp();
-    // ---- coalesced write of the warp's cnt rows: ring positions (base + rank0 + r) % capacity ----------
-    const unsigned long long cap = (unsigned long long)capacity;
-    const unsigned long long slot0 = (*base + rank0) % cap;
+}
+
+// Part 2: coalesced write of the warp's cnt rows to ring positions (base + rank0 + r) % capacity.  `total` = rows the
+// whole call appends: rows a sequential writer would overwrite later in this same call are skipped.
+template <int FORMAT>
+__device__ __forceinline__ void store_rows(const RowArgs &A, RowSmem<FORMAT> &sm, int warp, int lane, int64_t w0, bool sel,
+                                           unsigned b, unsigned long long base, uint64_t rank0, uint64_t total) {
+    constexpr int WIDTH = RowFmt<FORMAT>::WIDTH;
+    const int cnt = __popc(b);
+    const unsigned long long cap = (unsigned long long)A.capacity;
+    const unsigned long long slot0 = (base + rank0) % cap;
+    if (sel && A.env_ids) {
+        const int r = __popc(b & ((1u << lane) - 1u));
+        if (!(rank0 + r + cap < total)) A.env_ids[(int64_t)((slot0 + (unsigned long long)r) % cap)] = (int32_t)(w0 + lane);
+    }
     if (total <= cap && slot0 + (unsigned long long)cnt <= cap) {
-        // common case: one contiguous span, 8-byte aligned (row width 88 or 56 bytes) -> 64-bit stores
-        const float2 *src = reinterpret_cast<const float2 *>(s_out[warp]);
-        float2 *dst = reinterpret_cast<float2 *>(ring + slot0 * WIDTH);
+        // common case: one contiguous span, 8-byte aligned (row width 88, 56 or 96 bytes) -> 64-bit stores
+        const float2 *src = reinterpret_cast<const float2 *>(sm.out[warp]);
+        float2 *dst = reinterpret_cast<float2 *>(A.ring + slot0 * WIDTH);
         for (int i = lane; i < cnt * WIDTH / 2; i += 32) dst[i] = src[i];
     } else {
         for (int i = lane; i < cnt * WIDTH; i += 32) {
             const int r = i / WIDTH, c = i - r * WIDTH;
-            if (rank0 + r + (uint64_t)capacity < total) continue;          // overwritten later in this call
+            if (rank0 + r + cap < total) continue;                         // overwritten later in this call
             const unsigned long long slot = (slot0 + (unsigned long long)r) % cap;
-            ring[slot * WIDTH + c] = s_out[warp][i];
+            A.ring[slot * WIDTH + c] = sm.out[warp][i];
         }
     }
 }
 
+// format 0 (replay, main.py:115-119): [s(10), a_p, r_p, s'(10)]              22 floats, player p
+// format 1 (log, human_player.py:111) : [s(10), a1, a2, r1, r2]               14 floats
+// format 2 (h-DQN controller, hdqn.py:180-184,291-316): [g, s(10), a, r_int, g', s'(10)]   24 floats, with
+//          r_int = 1 if g' == goal_status(s) else 0 (hdqn.py:314; goal_status :223-236 on the state the action was
+//          chosen from, g' the goal re-chosen from the next state)
+// One warp handles 32 consecutive envs: their observation rows are one contiguous 1280-byte span, loaded
+// with coalesced 128-bit loads into shared memory; the selected lanes assemble their rows in shared memory
+// at consecutive ranks; the warp then writes that contiguous piece of the ring with coalesced stores.
+template <int FORMAT>
+__global__ void __launch_bounds__(kBlock)
+write_kernel(const RowArgs A, const uint32_t *block_offsets, const unsigned long long *base, const unsigned long long *counter) {
+    __shared__ __align__(16) RowSmem<FORMAT> sm;
+    __shared__ uint32_t s_cnt[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w0 = ((int64_t)blockIdx.x * kBlock + warp * 32);          // first env of this warp
+    const int64_t e = w0 + lane;
+    const bool full = w0 + 32 <= A.n;
+    RowRegs R;
+    if (full) request_rows<FORMAT>(A, lane, w0, R);
+    const bool sel = e < A.n && selected(A.info, e, A.mask_mode);
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, sel);
+    if (lane == 0) s_cnt[warp] = (uint32_t)__popc(b);
+    __syncthreads();                                                         // the only block-wide step
+    if (w0 >= A.n) return;
+    uint32_t before = 0;                                                     // selected envs of the lower warps of this block
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) before += w < warp ? s_cnt[w] : 0u;
+    assemble_rows<FORMAT>(A, sm, warp, lane, w0, sel, b, full, R);
+    // Everything above read only what was complete before this call's count pass; the offsets, the pre-increment counter
+    // and the new counter come from the scan, whose single CTA may still be running (programmatic dependent launch).
+    // They are read with plain coherent loads through unqualified pointers: a `const __restrict__` load is invariant to
+    // the compiler and was hoisted above the wait (stale offsets once the scan took several passes).
+    cudaGridDependencySynchronize();
+    const unsigned long long base_v = __ldcg(base), total_v = __ldcg(counter) - base_v;
+    store_rows<FORMAT>(A, sm, warp, lane, w0, sel, b, base_v, (uint64_t)__ldcg(block_offsets + blockIdx.x) + before, total_v);
+}
+
 }  // namespace mgrec
+
+extern "C" MG_API int64_t mg_record_scratch_words(int64_t n) {
+    if (n < 0) return 0;
+    return (n + 31) / 32 + 4;
+}
 
 extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *obs_next,
                                             const float *term_obs_or_null, const uint8_t *a1,
@@ -227,21 +345,31 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((n + mgrec::kBlock - 1) / mgrec::kBlock);
     const int64_t m = (n + 31) / 32;
-    // scratch: uint32[m + 2] (the documented size) — the first `grid` entries hold the block counts / offsets, the
+    // scratch: uint32[mg_record_scratch_words(n)] — the first `grid` entries hold the block counts / offsets, the
     // 64-bit pre-increment counter sits behind entry m (8-byte aligned)
-    uint32_t *warp_counts = scratch;
+    uint32_t *block_counts = scratch;
     auto *base = reinterpret_cast<unsigned long long *>(scratch + ((m + 1) & ~(int64_t)1));
-    mgrec::count_kernel<<<grid, mgrec::kBlock, 0, st>>>(info, n, mask_mode, warp_counts);
-    mgrec::scan_kernel<<<1, 1024, 0, st>>>(warp_counts, (int64_t)grid, reinterpret_cast<unsigned long long *>(counter), base);
-#define MG_REC_LAUNCH(F)                                                                                            \
-    mgrec::write_kernel<F><<<grid, mgrec::kBlock, 0, st>>>(obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew, done, \
-                                                           info, goal_prev_or_null, goal_next_or_null, n, mask_mode, player, \
-                                                           warp_counts, base, reinterpret_cast<unsigned long long *>(counter), \
-                                                           ring, capacity, env_ids_or_null)
-    if (format == 0) MG_REC_LAUNCH(0);
-    else if (format == 1) MG_REC_LAUNCH(1);
-    else MG_REC_LAUNCH(2);
-#undef MG_REC_LAUNCH
+    auto *ctr = reinterpret_cast<unsigned long long *>(counter);
+    const mgrec::RowArgs A{obs_prev, obs_next, term_obs_or_null, a1, a2_or_null, rew, done, info, goal_prev_or_null,
+                           goal_next_or_null, n, mask_mode, player, ring, capacity, env_ids_or_null};
+    const unsigned count_grid = (unsigned)((n + (int64_t)mgrec::kBlock * mgrec::kCountPerThread - 1) /
+                                           ((int64_t)mgrec::kBlock * mgrec::kCountPerThread));
+    mgrec::count_kernel<<<count_grid, mgrec::kBlock, 0, st>>>(info, n, mask_mode, block_counts);
+    mgrec::scan_kernel<<<1, 1024, 0, st>>>(block_counts, (int64_t)grid, ctr, base);
+    // the write pass starts under the scan (programmatic dependent launch): see write_kernel
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(mgrec::kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const uint32_t *offs = block_counts;
+    const unsigned long long *cbase = base, *cctr = ctr;
+    cudaError_t le;
+    if (format == 0) le = cudaLaunchKernelEx(&cfg, mgrec::write_kernel<0>, A, offs, cbase, cctr);
+    else if (format == 1) le = cudaLaunchKernelEx(&cfg, mgrec::write_kernel<1>, A, offs, cbase, cctr);
+    else le = cudaLaunchKernelEx(&cfg, mgrec::write_kernel<2>, A, offs, cbase, cctr);
+    if (le) return cuda_fail(le, "mg_record_transitions launch");
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_record_transitions launch");
     return MG_OK;
 }

@@ -65,8 +65,8 @@ class TransitionRecorder:
         self.ring = torch.zeros(self.capacity, self.width, dtype=torch.float32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)        # memory_counter, main.py:91
         self.env_ids = torch.full((self.capacity,), -1, dtype=torch.int32, device=dev) if track_env_ids else None
-        self._scratch = torch.zeros((env.num_envs + 31) // 32 + 4, dtype=torch.int32, device=dev)
         self._lib = nat.load()
+        self._scratch = torch.zeros(int(self._lib.mg_record_scratch_words(env.num_envs)), dtype=torch.int32, device=dev)
         self._same_obs_ok = False       # OptionRecorder stores [s_end, goal, sum_r, s_end]: s == s' on purpose
 
     def record(self, obs_prev: torch.Tensor, a1: torch.Tensor, a2: Optional[torch.Tensor], step_out,

@@ -31,7 +31,7 @@ def test_header_declares_expected_entry_points():
     assert declared_symbols() == sorted([
         "mg_version", "mg_last_error", "mg_get_constants", "mg_default_rewards", "mg_reset",
         "mg_step", "mg_sample_actions", "mg_rollout", "mg_step_host", "mg_step_host_async", "mg_step_host_wait",
-        "mg_mlp_act", "mg_mlp_act_tc", "mg_record_transitions", "mg_policy_step", "mg_explore", "mg_option_update"])
+        "mg_mlp_act", "mg_mlp_act_tc", "mg_record_transitions", "mg_record_scratch_words", "mg_policy_step", "mg_explore", "mg_option_update"])
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -40,6 +40,15 @@ def test_library_exports_every_declared_symbol(lib):
     out = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH], text=True)
     exported = set(re.findall(r"\bT (mg_\w+)", out))
     assert exported == set(declared_symbols())       # nothing else leaks (visibility=hidden)
+
+
+def test_record_scratch_words(lib):
+    # [0, n/256) block counts, then the 64-bit pre-increment counter behind entry (n+31)/32 (8-byte aligned)
+    for n in (0, 1, 31, 32, 33, 255, 256, 257, 4096, (1 << 20) + 1):
+        m = (n + 31) // 32
+        words = lib.mg_record_scratch_words(n)
+        assert words == m + 4 and ((m + 1) & ~1) + 2 <= words and (n + 255) // 256 <= m
+    assert lib.mg_record_scratch_words(-5) == 0
 
 
 def test_library_is_sm100a_native():

@@ -49,7 +49,7 @@ def test_no_kernel_writes_out_of_bounds(n, random_reset):
     a64 = ar.take(8 * n, 0)
     stats = ar.take(8 * nat.STATS_ROWS * nat.STATS_COLS, 0)
     ring = ar.take(4 * 22 * 50, 0); counter = ar.take(8, 0); ids = ar.take(4 * 50, 0)
-    scratch = ar.take(4 * ((n + 31) // 32 + 4), 0)
+    scratch = ar.take(4 * int(lib.mg_record_scratch_words(n)), 0)
     act_out = ar.take(n); q_out = ar.take(4 * 5 * n)
     w1t = ar.take(4 * 10 * 200, 0); b1 = ar.take(4 * 200, 0); w2t = ar.take(4 * 200 * 4 * 28, 0)
     b2 = ar.take(4 * 100, 0); w3 = ar.take(4 * 5 * 100, 0); b3 = ar.take(4 * 5, 0)

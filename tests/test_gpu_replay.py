@@ -79,6 +79,60 @@ def test_transition_ring_large_n_multi_pass_scan(mg):
     assert torch.equal(rec.ring[:ids.numel()], rows)
 
 
+@pytest.mark.parametrize("n,extra,density", [(100_003, 37, 0.5), (1 << 18, 0, 0.03), (300, 1, 0.9), (70_000, 5000, 1.0),
+                                             (4099, -1000, 0.7)])
+def test_writer_wraps_and_replays_in_a_graph(mg, n, extra, density):
+    """The ring wraps at a different row of every call (capacity = n + extra), the explicit mask changes from call to
+    call (the count pass reads it 16 bytes per thread), and the last calls are replays of one captured CUDA graph (count,
+    scan and the programmatically dependent write pass): every call must leave exactly what a sequential
+    `store_transition` loop over env ids leaves."""
+    cap = n + extra
+    env = mg.MergeVecEnv(n, out_slots=2, seed=3, episode_info=True)
+    env.rollout(100)
+    rec = mg.TransitionRecorder(env, cap, mask="explicit", track_env_ids=True)
+    obs_prev = env.obs_buf[env._slot].clone()
+    a1, a2 = env.sample_actions()
+    out = env.step(a1, a2)
+    obs, rew, done, info = out
+    nxt = torch.where(done.bool().unsqueeze(1), info["terminal_observation"], obs)
+    all_rows = torch.cat([obs_prev, a1.float().unsqueeze(1), rew[:, 0:1], nxt], 1)
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    select = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    want_ring = torch.zeros(cap, 22, device="cuda"); want_ids = torch.full((cap,), -1, dtype=torch.int32, device="cuda")
+    counter = 0
+
+    def expect():
+        nonlocal counter
+        keep = torch.nonzero(select).squeeze(1)
+        slots = (counter + torch.arange(keep.numel(), device="cuda")) % cap
+        want_ring[slots] = all_rows[keep]; want_ids[slots] = keep.int()
+        counter += keep.numel()
+
+    def new_mask():
+        select.copy_((torch.rand(n, device="cuda", generator=gen) < density).to(torch.uint8))
+
+    for call in range(7):
+        new_mask()
+        rec.record(obs_prev, a1, a2, out, select=select)
+        expect()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        rec.record(obs_prev, a1, a2, out, select=select); expect()          # warm-up on the capture stream
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            rec.record(obs_prev, a1, a2, out, select=select)
+            rec.record(obs_prev, a1, a2, out, select=select)
+    torch.cuda.current_stream().wait_stream(side)
+    for replay in range(4):
+        new_mask()
+        g.replay(); expect(); expect()
+    torch.cuda.synchronize()
+    assert int(rec.counter.item()) == counter and (counter > cap or density < 0.1)
+    assert torch.equal(rec.env_ids, want_ids)
+    assert torch.equal(rec.ring, want_ring)
+
+
 def test_recorder_all_mask_and_sticky_done(mg):
     n = 200
     env = mg.MergeVecEnv(n, out_slots=2, auto_reset=False, episode_info=False)
