@@ -2,7 +2,7 @@
 """bench_policy.py — BASELINE.json configs[4]: pve rollout with the DQN / h-DQN policy forward in the loop,
 2^18 envs per GPU, observations and actions handed over on the device (no host round-trip).
 
-    python bench_policy.py [--envs 262144] [--steps 400] [--policy dqn|hdqn] [--backend fused|tf32x3|torch]
+    python bench_policy.py [--envs 262144] [--steps 400] [--policy dqn|hdqn] [--backend fused|tf32x3|f16x3|torch]
 
 One step = fused Q-network forward + arg-max (`mg_mlp_act` / `mg_mlp_act_tc`) -> `mg_step` (pve, auto-reset, RANDOM
 starts so that the envs de-synchronise: with the fixed start and a greedy policy all envs would run in lockstep).
@@ -92,7 +92,7 @@ def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="c
     st = env.stats()
     ms_pol = graph_ms(policy_only, k, replays)
     fused = None
-    if backend in ("fused", "tf32x3"):
+    if backend in ("fused", "tf32x3"):             # f16x3 has no fused variant: act() + step() only
         for _ in range(3):
             one_step_fused()
         ms_f = graph_ms(one_step_fused, k, replays)
@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 18)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--policy", default="dqn", choices=["dqn", "hdqn"])
-    ap.add_argument("--backend", default="fused", choices=["fused", "tf32x3", "torch"])
+    ap.add_argument("--backend", default="fused", choices=["fused", "tf32x3", "f16x3", "torch"])
     ap.add_argument("--reset-mode", default="random", choices=["fixed", "random"])
     ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the policy kernels (0/1)")
     args = ap.parse_args()

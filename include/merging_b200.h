@@ -282,7 +282,19 @@ MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, 
  * fp32 FFMA evaluation, hence a separate, opt-in entry point.  Same arguments except w2_tc: float
  * [25][28][2][8][4] = fc2.weight (zero-padded to 112 rows) split into its tf32 hi part (top 19 bits; row
  * groups 0-13) and the remainder lo = w - hi (row groups 14-27), stacked as one 224-row UMMA B operand in
- * the canonical K-major core-matrix layout [K-step][8-row group][K half][row][4 k]. */
+ * the canonical K-major core-matrix layout [K-step][8-row group][K half][row][4 k].
+ * With MG_MLP_FLAG_F16X3 BOTH hidden layers run on the tensor cores as three-product sums of fp16 operands
+ * (kind::f16; csrc/mlp_tc16_kernels.cu): w1t and b1 are ignored (may be NULL) and w2_tc points to one packed blob,
+ * 16-byte aligned:
+ *   bytes [0,64)        float c1, c2 (+ padding): a1 = relu(acc1 * c1) = h1 / 8, h2 = relu(acc2 * c2 + b2)
+ *   bytes [64,13376)    __half [52][2][8][8]: layer-1 operand, N = 208 hidden units (200 + zero pad) x K = 16 (inputs in
+ *                       K slots 0..in-1, fc1.bias in slot 15, the rest 0), times 2^s1; row groups 0-25 hi = fp16(v),
+ *                       26-51 lo = fp16(v - hi); canonical K-major core-matrix layout [8-row group][K half][row][8 k]
+ *   bytes [13376,106560) __half [13][28][2][8][8]: layer-2 operand, fc2.weight zero-padded to 112 rows x 208 columns, times
+ *                       2^s2; per K-step of 16: row groups 0-13 hi, 14-27 lo
+ *   with c1 = 2^-s1 / 8 and c2 = 8 * 2^-s2; s1, s2 chosen so that the largest scaled entry lies in [256, 512).
+ * Same ~22 significant bits per product as 3xTF32; hidden-layer-1 activations saturate at 5.2e5 (fp16 range). */
+#define MG_MLP_FLAG_F16X3 0x20u
 MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                          int32_t out_dim, const float *w1t, const float *b1, const float *w2_tc,
                          const float *b2, const float *w3, const float *b3, uint8_t *actions,

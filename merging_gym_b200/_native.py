@@ -24,6 +24,7 @@ POLICY_FLAG_PDL = 0x200
 POLICY_FLAG_GOAL_IN_SLOT = 0x400
 MLP_FLAG_MIRROR, MLP_FLAG_PDL = 0x1, 0x2
 MLP_FLAG_OBS_SOA, MLP_FLAG_OBS_GOAL_SLOT, MLP_FLAG_WRITE_GOAL = 0x4, 0x8, 0x10
+MLP_FLAG_F16X3 = 0x20
 FLAG_OBS_SOA, FLAG_OBS_GOAL_SLOT = 0x10, 0x20
 OBS_LAYOUTS = ("aos", "soa", "goal_slot")
 OBS_LAYOUT_FLAG = {"aos": 0, "soa": FLAG_OBS_SOA, "goal_slot": FLAG_OBS_GOAL_SLOT}

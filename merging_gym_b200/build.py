@@ -15,8 +15,10 @@ import sys
 from ._paths import CSRC, INCLUDE_DIR, LIB_DIR, LIB_PATH
 
 SOURCES = [os.path.join(CSRC, "merge_kernels.cu"), os.path.join(CSRC, "mlp_kernels.cu"), os.path.join(CSRC, "mlp_tc_kernels.cu"),
+           os.path.join(CSRC, "mlp_tc16_kernels.cu"),
            os.path.join(CSRC, "record_kernels.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "merge_device.cuh"), os.path.join(CSRC, "policy_env.cuh"), os.path.join(CSRC, "abi_common.h"),
+DEPS = SOURCES + [os.path.join(CSRC, "merge_device.cuh"), os.path.join(CSRC, "policy_env.cuh"), os.path.join(CSRC, "tc_common.cuh"),
+                  os.path.join(CSRC, "abi_common.h"),
                   os.path.join(INCLUDE_DIR, "merging_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]

@@ -31,6 +31,7 @@
 // ptxas 12.9 crashes on setmaxnreg in a kernel that also CALLS a function: the random-start draw is inlined in this file
 #define MG_RANDOM_START_INLINE 1
 #include "policy_env.cuh"
+#include "tc_common.cuh"
 
 // 1 = a single MMA-issuing warp with its K loop fully unrolled: accumulation order in TMEM is the K-step order, the
 //     kernel is bitwise reproducible (69.6 us per 2^18 envs);
@@ -56,7 +57,6 @@ __device__ long long g_trace_epi[16][3];        // wait start, wait end, done (w
 #endif
 
 constexpr int H1 = 200, H2 = 100;
-constexpr int TM = 128;                       // envs per tile = UMMA M
 constexpr int UN = 112;                       // UMMA N (multiple of 16 for M = 128)
 constexpr int KSTEPS = H1 / 8;                // 25 K-steps of 8 (tf32: 32 bytes of K per MMA)
 constexpr int STAGES = 4;                     // ring slots; one slot = one K-step (8 hidden units) of all 128 envs
@@ -87,7 +87,6 @@ constexpr int NUM_THREADS_ENV = 32 * (ENV_WARP0 + ENV_WARPS);
 static_assert(MMA_WARPS == 1 && (ENV_WARPS == 3 || ENV_WARPS == 7), "register budgets are laid out for 16 or 20 warps");
 static_assert(256 * 112 + 128 * 104 + 128 * 88 + 128 * 64 <= 640 * 96, "setmaxnreg partition exceeds the CTA pool");
 constexpr int MAX_OUT = 8;
-constexpr uint32_t kSpinLimit = 1u << 26;
 
 template <int IN, int OUT>
 struct Smem {
@@ -103,93 +102,15 @@ struct Smem {
     mgpe::Handoff<TM, ENV_BUFS> env;                     // ENV: the tile's actions, epilogue warps -> env warp
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// tcgen05 shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes stored as
-// 128 contiguous bytes; LBO = byte distance between the two core matrices of a K-step (128), SBO = byte
-// distance between 8-row groups (256).  Verified numerically in profiles/exp_tcgen05.cu.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
-           ((uint64_t)1 << 46);
-}
-constexpr uint64_t kDescHi = ((uint64_t)(256u >> 4) << 32) | ((uint64_t)1 << 46);   // SBO and version: the constant high word
 // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24); }
 constexpr uint32_t kIdesc112 = idesc_n(UN), kIdesc224 = idesc_n(2 * UN);
 
-__device__ __forceinline__ void mbar_init(unsigned long long *b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t it = 0; it < kSpinLimit && !done; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(smem_u32(b)), "r"(parity)
-            : "memory");
-    }
-    if (!done) __trap();                      // never hang the GPU on a protocol bug
-}
 // zero 16 columns of the calling warp's 32 TMEM lanes
 __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
     const uint32_t z = 0u;
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
 }
-__device__ __forceinline__ uint32_t mbar_test(unsigned long long *b, uint32_t parity) {   // one non-blocking poll
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done)
-        : "r"(smem_u32(b)), "r"(parity)
-        : "memory");
-    return done;
-}
-
-// COHERENT: the fused env epilogue writes observation rows in the same launch (possibly into the buffer being read), so
-// the rows must not travel through the non-coherent (ld.global.nc) path.
-// obs_mode: bits 0-1 = observation layout (mg::kObsAos / kObsSoa / kObsGoalSlot), bit 8 = MG_MLP_FLAG_WRITE_GOAL.
-template <int IN, bool MIRROR, bool COHERENT = false>
-__device__ __forceinline__ void load_row(const float *obs, const uint8_t *__restrict__ goal, int64_t e, int64_t n,
-                                         int obs_mode, float (&x)[IN]) {
-    constexpr int off = IN - MG_OBS_DIM;   // 1 when a goal column is prepended (hdqn.py:291); compile-time so x[] stays in registers
-    const uint32_t layout = (uint32_t)obs_mode & 3u;
-    if (e < n) {
-        if (layout == mg::kObsAos) {
-            if (off) x[0] = (float)goal[e];
-            if (!MIRROR) {
-                const float2 *src = reinterpret_cast<const float2 *>(obs + e * MG_OBS_DIM);
-#pragma unroll
-                for (int i = 0; i < MG_OBS_DIM / 2; ++i) {      // five float2
-                    const float2 v = COHERENT ? __ldcg(src + i) : __ldg(src + i);
-                    x[off + 2 * i] = v.x; x[off + 2 * i + 1] = v.y;
-                }
-            } else {                                            // the opponent's view: state[5:] + state[:5] (main.py:199)
-#pragma unroll
-                for (int i = 0; i < MG_OBS_DIM; ++i) {
-                    const float *q = obs + e * MG_OBS_DIM + (i + MG_OBS_DIM / 2) % MG_OBS_DIM;
-                    x[off + i] = COHERENT ? __ldcg(q) : __ldg(q);
-                }
-            }
-        } else {
-            // [10][stride] columns, or [n][11] rows `[goal] + state` whose slot 0 an 11-input network reads as its goal
-            const int64_t stride = MG_OBS_SOA_STRIDE(n);
-            if (off) x[0] = goal ? (float)goal[e] : __ldcg(obs + e * (MG_OBS_DIM + 1));
-#pragma unroll
-            for (int i = 0; i < MG_OBS_DIM; ++i) {
-                const int k = MIRROR ? (i + MG_OBS_DIM / 2) % MG_OBS_DIM : i;
-                x[off + i] = __ldcg(layout == mg::kObsSoa ? obs + k * stride + e : obs + e * (MG_OBS_DIM + 1) + 1 + k);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < IN; ++i) x[i] = 0.f;
-    }
-}
-
 // ENV: `mg_policy_step` — the epilogue threads drop the tile's actions into shared memory and one extra warp steps the
 // tile's envs (policy_env.cuh) while the other warps are on the next tile.  (Stepping the env in the epilogue threads
 // themselves doubled the tile period: the epilogue warps have no slack, profiles/r02_policy_step_*.)
@@ -555,6 +476,10 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_mod
 }  // namespace mgtc
 
 int mg_mlp_check_layout(uint32_t flags, int32_t obs_dim, int32_t out_dim, bool has_goal, int *in_dim, int *obs_mode);
+// mlp_tc16_kernels.cu: MG_MLP_FLAG_F16X3
+cudaError_t mg_mlp_act_tc16_launch(int in_dim, int out_dim, bool mirror, const float *obs, const uint8_t *goal, int64_t n,
+                                   int obs_mode, const void *blob, const float *b2, const float *w3, const float *b3,
+                                   uint8_t *act, float *q_out, cudaStream_t st, bool pdl);
 
 // the fused policy + env step on the tensor-core backend (called by mg_policy_step in mlp_kernels.cu)
 cudaError_t mg_policy_step_tc_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const float *w1t,
@@ -577,15 +502,21 @@ extern "C" MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_nul
     using namespace mg_abi;
     if (n < 0) return fail(MG_ERR_BAD_SIZE, "n < 0");
     int in_dim = 0, obs_mode = 0;
-    if (int rc = mg_mlp_check_layout(flags, obs_dim, out_dim, goal_or_null != nullptr, &in_dim, &obs_mode)) return rc;
+    const bool f16 = (flags & MG_MLP_FLAG_F16X3) != 0u;           // w2_tc is then the packed fp16 operand blob (see the header)
+    if (int rc = mg_mlp_check_layout(flags & ~MG_MLP_FLAG_F16X3, obs_dim, out_dim, goal_or_null != nullptr, &in_dim, &obs_mode)) return rc;
     const bool mirror = (flags & MG_MLP_FLAG_MIRROR) != 0u, pdl = (flags & MG_MLP_FLAG_PDL) != 0u;
     if (n == 0) return MG_OK;
-    if (!obs || !w1t || !b1 || !w2_tc || !b2 || !w3 || !b3 || !actions)
+    if (!obs || (!f16 && (!w1t || !b1)) || !w2_tc || !b2 || !w3 || !b3 || !actions)
         return fail(MG_ERR_NULL_POINTER, "mg_mlp_act_tc: NULL pointer");
-    if (!aligned16(obs) || !aligned16(w1t) || !aligned16(w2_tc))
+    if (!aligned16(obs) || (!f16 && !aligned16(w1t)) || !aligned16(w2_tc))
         return fail(MG_ERR_ALIGNMENT, "obs and weight arrays must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    if (f16) {
+        e = mg_mlp_act_tc16_launch(in_dim, out_dim, mirror, obs, goal_or_null, n, obs_mode, w2_tc, b2, w3, b3, actions, q_out_or_null, st, pdl);
+        if (e) return cuda_fail(e, "mg_mlp_act_tc (f16x3) launch");
+        return MG_OK;
+    }
 #define MG_TC_CASE(I, O) \
     if (in_dim == I && out_dim == O) e = mirror ? mgtc::launch<I, O, true>(obs, goal_or_null, n, obs_mode, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl) : mgtc::launch<I, O, false>(obs, goal_or_null, n, obs_mode, w1t, b1, w2_tc, b2, w3, b3, actions, q_out_or_null, st, mgpe::Args{}, pdl); else
     MG_TC_CASE(10, 5) MG_TC_CASE(10, 3) MG_TC_CASE(11, 5) MG_TC_CASE(11, 3) e = cudaErrorInvalidValue;

@@ -14,7 +14,7 @@
 //   write  : a block re-derives its warps' ranks from the ballots; every selected env writes its row at
 //            (counter + offset) % capacity
 // The write pass is launched as a programmatic dependent of the scan: its blocks request their observation rows and take
-// their ballots while the single scan CTA is still running, and only then wait for the offsets (47 -> 4x us per 2^20 rows
+// their ballots while the single scan CTA is still running, and only then wait for the offsets (47 -> 44 us per 2^20 rows
 // inside a CUDA graph).  A one-launch variant (tiles by ticket, decoupled look-back over per-tile words) was measured and
 // dropped: 57 us against 47 (profiles/r02_record_onepass_experiment.patch, r02_record_onepass_vs_three_pass.jsonl) — the
 // ticket, publication and look-back round trips put ~5 us of latency in front of every block's first store.

@@ -12,7 +12,10 @@ Reference pieces mirrored here
 `backend="fused"` (default) runs the hand-written CUDA kernel `mg_mlp_act` (one launch: three layers,
 bias, ReLU, arg-max, exactly the reference's fp32 arithmetic on FFMA2); `backend="tf32x3"` runs
 `mg_mlp_act_tc`, the same operator with the 200x100 layer on the tcgen05 tensor cores as an
-error-compensated 3xTF32 product (fp32-level accuracy, not bit-identical); `backend="torch"` is the
+error-compensated 3xTF32 product (fp32-level accuracy, not bit-identical); `backend="f16x3"`
+(`MG_MLP_FLAG_F16X3`, csrc/mlp_tc16_kernels.cu) puts BOTH hidden layers on the tensor cores as three-product sums of
+fp16 hi / lo operands (the same ~22 significant bits per product; activations limited to fp16's range after scaling —
+the fastest policy kernel; not available fused with the env step); `backend="torch"` is the
 plain PyTorch fp32 reference of the same op (cuBLAS), kept for the numerics tests.
 """
 from __future__ import annotations
@@ -27,7 +30,8 @@ from . import _native as nat
 
 EPISILO = 0.7          # scripts/main.py:16, hdqn.py:20
 HIDDEN1, HIDDEN2 = 200, 100
-POLICY_BACKENDS = {"fused": nat.POLICY_BACKEND_FP32, "tf32x3": nat.POLICY_BACKEND_TF32X3}
+POLICY_BACKENDS = {"fused": nat.POLICY_BACKEND_FP32, "tf32x3": nat.POLICY_BACKEND_TF32X3}    # mg_policy_step (fused with the env step)
+TC_BACKENDS = ("tf32x3", "f16x3")
 
 
 def _ptr(t):
@@ -39,8 +43,8 @@ class MLPPolicy:
 
     def __init__(self, in_dim: int = 10, out_dim: int = 5, device="cuda", state_dict: Optional[dict] = None,
                  seed: Optional[int] = None, backend: str = "fused"):
-        if backend not in ("fused", "tf32x3", "torch"):
-            raise ValueError("backend must be 'fused', 'tf32x3' or 'torch'")
+        if backend not in ("fused", "tf32x3", "f16x3", "torch"):
+            raise ValueError("backend must be 'fused', 'tf32x3', 'f16x3' or 'torch'")
         self.in_dim, self.out_dim, self.backend = int(in_dim), int(out_dim), backend
         self.device = torch.device(device)
         self.pdl = False                     # see act(): set True when no kernel that writes the weights precedes act()
@@ -83,6 +87,34 @@ class MLPPolicy:
 
         cat = torch.cat([hi, lo], dim=0)                      # 224 rows: hi 0-111, lo 112-223 (one stacked B operand)
         self.w2_tc = cat.view(28, 8, 25, 2, 4).permute(2, 0, 3, 1, 4).contiguous().view(-1)
+        # f16x3 (csrc/mlp_tc16_kernels.cu): both hidden layers as fp16 hi / lo operands in ONE blob (include/merging_b200.h):
+        # [c1, c2 | layer 1: N = 208 x K = 16 with fc1.bias in K slot 15 | layer 2: 13 K-steps of N = 112 x K = 16], each
+        # operand times a power of two that puts its largest entry in [256, 512), hi = fp16(v), lo = fp16(v - hi)
+        def scale_exp(t):
+            m = float(t.abs().max())
+            return 0 if m == 0.0 else 8 - int(np.floor(np.log2(m)))
+        w1op = torch.zeros(208, 16, dtype=torch.float32, device=self.device)
+        w1op[:HIDDEN1, :self.in_dim] = self.w1
+        w1op[:HIDDEN1, 15] = self.b1
+        s1, s2 = scale_exp(w1op), scale_exp(self.w2)
+        w1op = torch.ldexp(w1op, torch.tensor(s1, device=self.device))
+        hi1 = w1op.to(torch.float16)
+        lo1 = (w1op - hi1.float()).to(torch.float16)
+        op1 = torch.cat([hi1, lo1], dim=0).view(52, 8, 2, 8).permute(0, 2, 1, 3).contiguous()      # [row group][K half][row][k]
+        w2op = torch.zeros(112, 208, dtype=torch.float32, device=self.device)
+        w2op[:HIDDEN2, :HIDDEN1] = torch.ldexp(self.w2, torch.tensor(s2, device=self.device))
+        hi2 = w2op.to(torch.float16)
+        lo2 = (w2op - hi2.float()).to(torch.float16)
+        op2 = torch.cat([hi2, lo2], dim=0).view(28, 8, 13, 2, 8).permute(2, 0, 3, 1, 4).contiguous()  # [K-step][row group][K half][row][k]
+        hdr = torch.zeros(16, dtype=torch.float32, device=self.device)
+        hdr[0], hdr[1] = 2.0 ** (-s1 - 3), 2.0 ** (3 - s2)
+        self.w2_f16 = torch.cat([hdr.view(torch.uint8), op1.view(torch.uint8).view(-1), op2.view(torch.uint8).view(-1)])
+        assert self.w2_f16.numel() == 64 + 13312 + 93184
+
+    @property
+    def w2_native(self) -> torch.Tensor:
+        """fc2.weight in the layout the backend's kernel reads."""
+        return {"tf32x3": self.w2_tc, "f16x3": self.w2_f16}.get(self.backend, self.w2_p)
 
     def state_dict(self) -> dict:
         return {"fc1.weight": self.w1, "fc1.bias": self.b1, "fc2.weight": self.w2, "fc2.bias": self.b2,
@@ -146,9 +178,10 @@ class MLPPolicy:
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         flags = (nat.MLP_FLAG_MIRROR if mirror else 0) | (nat.MLP_FLAG_PDL if (self.pdl if pdl is None else pdl) else 0)
         with torch.cuda.device(self.device):
-            if self.backend == "tf32x3":
+            if self.backend in TC_BACKENDS:
+                flags |= nat.MLP_FLAG_F16X3 if self.backend == "f16x3" else 0
                 nat.check(lib.mg_mlp_act_tc(_ptr(obs), _ptr(goal), n, obs_dim, self.out_dim,
-                                            _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_tc), _ptr(self.b2),
+                                            _ptr(self.w1_t), _ptr(self.b1), _ptr(self.w2_native), _ptr(self.b2),
                                             _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), flags, stream),
                           "mg_mlp_act_tc")
             else:
@@ -183,8 +216,9 @@ class MLPPolicy:
             out = torch.empty(n, dtype=torch.uint8, device=self.device)
         flags = (nat.MLP_FLAG_MIRROR if mirror else 0) | (nat.MLP_FLAG_PDL if (self.pdl if pdl is None else pdl) else 0) | \
             nat.MLP_LAYOUT_FLAG[obs_layout] | (nat.MLP_FLAG_WRITE_GOAL if write_goal else 0)
-        fn = nat.load().mg_mlp_act_tc if self.backend == "tf32x3" else nat.load().mg_mlp_act
-        w2 = self.w2_tc if self.backend == "tf32x3" else self.w2_p
+        fn = nat.load().mg_mlp_act_tc if self.backend in TC_BACKENDS else nat.load().mg_mlp_act
+        flags |= nat.MLP_FLAG_F16X3 if self.backend == "f16x3" else 0
+        w2 = self.w2_native
         with torch.cuda.device(self.device):
             nat.check(fn(_ptr(obs), _ptr(goal), n, nat.OBS_DIM + (1 if row11 else 0), self.out_dim, _ptr(self.w1_t), _ptr(self.b1),
                          _ptr(w2), _ptr(self.b2), _ptr(self.w3), _ptr(self.b3), _ptr(out), _ptr(q_out), flags,

@@ -484,7 +484,7 @@ class MergeVecEnv:
         """
         from .policy import POLICY_BACKENDS
         if policy.out_dim != nat.NUM_ACTIONS or policy.backend not in POLICY_BACKENDS:
-            raise ValueError("policy_step needs an MLPPolicy with 5 outputs and backend 'fused' or 'tf32x3'")
+            raise ValueError("policy_step needs an MLPPolicy with 5 outputs and backend 'fused' or 'tf32x3' (use act() + step() with 'f16x3')")
         goal_in_slot = goal is None and self.obs_layout == "goal_slot" and policy.in_dim == nat.OBS_DIM + 1
         if policy.in_dim != nat.OBS_DIM + (0 if goal is None else 1) and not goal_in_slot:
             raise ValueError("policy input width does not match obs (+ goal)")
@@ -514,7 +514,7 @@ class MergeVecEnv:
             flags |= nat.POLICY_FLAG_EXPLORE
         if policy.pdl:
             flags |= nat.POLICY_FLAG_PDL
-        w2 = policy.w2_tc if policy.backend == "tf32x3" else policy.w2_p
+        w2 = policy.w2_native
         with torch.cuda.device(self.device), nvtx_range("mg.policy_step"):
             nat.check(self._lib.mg_policy_step(C.byref(self._state), n, _ptr(obs_in), _ptr(goal), POLICY_BACKENDS[policy.backend],
                                                _ptr(policy.w1_t), _ptr(policy.b1), _ptr(w2), _ptr(policy.b2), _ptr(policy.w3),
