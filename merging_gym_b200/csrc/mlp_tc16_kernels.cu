@@ -48,7 +48,10 @@ constexpr int H1 = 200, H1P = 208, H2 = 100;
 constexpr int UN = 112;                       // layer-2 UMMA N (100 neurons + zero pad; multiple of 16 for M = 128)
 constexpr int H2P = 104;                      // layer-3 weights padded to whole 8-column blocks
 constexpr int KSTEPS = H1P / 16;              // 13 layer-2 K-steps of 16 hidden units
-constexpr int STAGES = 8;                     // A-operand ring slots, one K-step each
+#ifndef MG_TC16_STAGES
+#define MG_TC16_STAGES 8
+#endif
+constexpr int STAGES = MG_TC16_STAGES;        // A-operand ring slots, one K-step each
 constexpr int A_STEP = (TM / 8) * 256;        // 4096 B: 16 row groups x 2 K halves x (8 rows x 16 B)
 constexpr int W2_STEP = (2 * UN / 8) * 256;   // 7168 B: one K-step of [W2_hi (14 row groups) ; W2_lo (14 row groups)]
 constexpr int W2_BYTES = KSTEPS * W2_STEP;    // 93 184 B
@@ -57,9 +60,35 @@ constexpr int HDR_BYTES = 64;                 // float c1, c2 and padding in fro
 constexpr int W_BYTES = W1_BYTES + W2_BYTES;  // 106 496 B, copied as 8 pieces of W1_BYTES
 static_assert(W2_BYTES == 7 * W1_BYTES, "the weight blob is copied in eight equal pieces");
 constexpr int L2_COL0 = 0, L2_COL1 = 128, L1_COL = 256, TMEM_COLS = 512;
-constexpr int CONV_WARPS = 8, EPI_WARP0 = 8, MMA_WARP = 12, X_WARP = 13;
-constexpr int NUM_THREADS = 32 * 14;
-constexpr int L1_ISSUE_AT = 4;                // layer 1 of tile t+1 is issued after a layer-2 K-step >= 4 of tile t
+#ifndef MG_TC16_CONV_GROUPS
+#define MG_TC16_CONV_GROUPS 2
+#endif
+constexpr int CONV_GROUPS = MG_TC16_CONV_GROUPS;                 // converter warps per TMEM lane quarter: K-steps interleaved over them
+constexpr int CONV_WARPS = 4 * CONV_GROUPS, EPI_WARP0 = CONV_WARPS, MMA_WARP = CONV_WARPS + 4, X_WARP = CONV_WARPS + 5;
+constexpr int NUM_THREADS = 32 * (CONV_WARPS + 6);
+#ifndef MG_TC16_TRACE
+#define MG_TC16_TRACE 0                       // 1: CTA 0 records clock64() at the hand-over points (profiles/exp_tc16_trace.cu)
+#endif
+#if MG_TC16_TRACE
+constexpr int TRACE_G = 13 * 10;              // K-steps traced (10 tiles of CTA 0)
+__device__ long long g_trace_conv[TRACE_G][6];   // top, l1 ready, ld done, converted, slot free, arrived (lane-quarter 0 warps)
+__device__ long long g_trace_mma[TRACE_G][4];    // top, full seen, issued, after l1 poll
+__device__ long long g_trace_epi[16][3];         // wait start, wait end, done (quarter 0)
+__device__ long long g_trace_l1[32][2];          // layer1(tile, half): start, issued
+#define MG_TRACE16(arr, idx, k) do { if (blockIdx.x == 0 && lane == 0 && (idx) < (uint32_t)(sizeof(arr) / sizeof(arr[0]))) arr[idx][k] = clock64(); } while (0)
+#else
+#define MG_TRACE16(arr, idx, k) do { } while (0)
+#endif
+// Layer 1 is computed, consumed and released in two halves: hidden units [0,112) = K-steps 0-6 and [112,208) = K-steps 7-12.
+// The first half of the NEXT tile is issued while the converters are still in the second half of this one, so they never
+// wait at a tile boundary (with one 208-column accumulator they idled ~1500 cycles per tile: it could only be issued once
+// they had read its last columns, and then ran behind the queued layer-2 MMAs).
+#ifndef MG_TC16_KS_HALF
+#define MG_TC16_KS_HALF 7                     // 13 = one 208-column accumulator (experiment switch)
+#endif
+constexpr int KS_HALF = MG_TC16_KS_HALF, L1_NA = 16 * KS_HALF, L1_NB = H1P - L1_NA;          // N = 112 and 96
+constexpr int L1_POLL_FROM = L1_NB ? KS_HALF : 10;
+static_assert(L1_NA % 16 == 0 && L1_NB % 16 == 0 && (L1_NB == 0 || CONV_GROUPS <= KSTEPS - KS_HALF), "every converter warp has a K-step in both halves");
 constexpr int MAX_OUT = 8;
 
 template <int OUT>
@@ -73,19 +102,28 @@ struct Smem {
     float w3[OUT][H2P];
     float b2[H2 + 12], b3[MAX_OUT];
     float c1, c2;
-    unsigned long long full[STAGES], empty[STAGES], x_full[2], x_empty[2], l1_full, l1_empty, tmem_full[2], tmem_empty[2], w_ready;
+    unsigned long long full[STAGES], empty[STAGES], x_full[2], x_empty[2], l1_full[2], l1_empty[2], tmem_full[2], tmem_empty[2], w_ready;
     uint32_t tmem_base;
 };
 
 // kind::f16 with fp16 operands (format fields 0), D = f32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t idesc_n(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24); }
-constexpr uint32_t kIdesc112 = idesc_n(UN), kIdesc208 = idesc_n(H1P);
+constexpr uint32_t kIdesc112 = idesc_n(UN), kIdescA = idesc_n(L1_NA), kIdescB = idesc_n(L1_NB ? L1_NB : 16);
 
 // hi = fp16(v) (round to nearest, saturating), lo = fp16(v - hi) for two values; v >= 0 is the caller's business
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t &hi, uint32_t &lo) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
     const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - back.y), "f"(v0 - back.x));
+}
+
+// The same for relu(v): hi rounds toward zero, so v - hi >= 0 wherever v > 0 and is v itself (< 0) wherever the ReLU'd hi
+// is 0 — a second ReLU inside the lo conversion finishes the job.  Three instructions per value; lo can be a whole fp16
+// ulp of hi (round to nearest: half), i.e. one bit less than split2, the bit 3xTF32's truncation gives up as well.
+__device__ __forceinline__ void split2_relu(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+    const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - back.y), "f"(v0 - back.x));
 }
 
 template <int IN, int OUT, bool MIRROR>
@@ -106,7 +144,8 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
             mbar_init(&S.x_full[b], 32); mbar_init(&S.x_empty[b], 1);
             mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 128);
         }
-        mbar_init(&S.l1_full, 1); mbar_init(&S.l1_empty, 32 * CONV_WARPS); mbar_init(&S.w_ready, 1);
+        for (int h = 0; h < 2; ++h) { mbar_init(&S.l1_full[h], 1); mbar_init(&S.l1_empty[h], 32 * CONV_WARPS); }
+        mbar_init(&S.w_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.w_ready)), "r"((uint32_t)W_BYTES) : "memory");
         for (uint32_t c = 0; c < 8; ++c)
@@ -136,42 +175,49 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
 
     if (warp < CONV_WARPS) {
         // =================================== CONVERTERS: layer-1 accumulator -> layer-2 A operand ===================
-        const int q = warp & 3, grp = warp >> 2;
+        const int q = warp & 3, grp = warp >> 2;                        // TMEM lane quarter, K-step residue
         const uint32_t total = my_tiles * KSTEPS;
         const float c1 = S.c1;
         const int m = q * 32 + lane;                                    // the env row this thread converts
         const uint32_t off = (uint32_t)((m >> 3) * 256 + (m & 7) * 16);
         const uint32_t tl1 = tmem_base + (uint32_t)L1_COL + ((uint32_t)(q * 32) << 16);
         uint32_t cur = 0xFFFFFFFFu;
-        for (uint32_t it = (uint32_t)grp; it < total; it += 2) {
+        for (uint32_t it = (uint32_t)grp; it < total; it += CONV_GROUPS) {
             const uint32_t tl = it / KSTEPS, ks = it - tl * KSTEPS;
-            if (tl != cur) {                                            // layer 1 of this tile has been computed
-                mbar_wait(&S.l1_full, tl & 1u);
+            if (q == 0) MG_TRACE16(g_trace_conv, it, 0);
+            const uint32_t half = (L1_NB && ks >= (uint32_t)KS_HALF) ? 1u : 0u;
+            if (2u * tl + half != cur) {                                // this half of the tile's layer 1 has been computed
+                mbar_wait(&S.l1_full[half], tl & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                cur = tl;
+                cur = 2u * tl + half;
             }
+            if (q == 0) MG_TRACE16(g_trace_conv, it, 1);
             uint32_t v[16];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                          : "r"(tl1 + 16u * ks));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ks + 2 >= (uint32_t)KSTEPS) {                           // this warp's last K-step of the tile: its columns are free
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&S.l1_empty);
+            if (q == 0) MG_TRACE16(g_trace_conv, it, 2);
+            if (ks + CONV_GROUPS >= ((half || !L1_NB) ? (uint32_t)KSTEPS : (uint32_t)KS_HALF)) {   // this warp's last K-step of the half:
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the next tile's layer 1 may overwrite it
+                mbar_arrive(&S.l1_empty[half]);
             }
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p)
-                split2(fmaxf(__uint_as_float(v[2 * p]) * c1, 0.f), fmaxf(__uint_as_float(v[2 * p + 1]) * c1, 0.f), hi[p], lo[p]);
+                split2_relu(__uint_as_float(v[2 * p]) * c1, __uint_as_float(v[2 * p + 1]) * c1, hi[p], lo[p]);
+            if (q == 0) MG_TRACE16(g_trace_conv, it, 3);
             const uint32_t s = it % STAGES;
             mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);          // the MMAs that read this slot last have completed
+            if (q == 0) MG_TRACE16(g_trace_conv, it, 4);
             *reinterpret_cast<uint4 *>(S.a_hi[s] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);          // units 0-7
             *reinterpret_cast<uint4 *>(S.a_hi[s] + off + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);    // units 8-15
             *reinterpret_cast<uint4 *>(S.a_lo[s] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<uint4 *>(S.a_lo[s] + off + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                   // visible to the tensor core
             mbar_arrive(&S.full[s]);
+            if (q == 0) MG_TRACE16(g_trace_conv, it, 5);
         }
     } else if (warp == X_WARP) {
         // =================================== X LOADER: observation rows -> layer-1 A operand ========================
@@ -212,40 +258,56 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
         const uint32_t deschi = (uint32_t)(kDescHi >> 32);
         const uint32_t d1 = tmem_base + (uint32_t)L1_COL;
         mbar_wait(&S.w_ready, 0u);                                      // the bulk copies of the weights have landed
-        auto layer1 = [&](const uint32_t tl) {
+        // one half of a tile's layer 1: hidden units [0,112) (half 0) or [112,208) (half 1) into their own accumulator columns;
+        // half 1 is the last reader of the tile's observation operand
+        auto layer1 = [&](const uint32_t tl, const uint32_t half) {
             const uint32_t b = tl & 1u;
+            MG_TRACE16(g_trace_l1, 2u * tl + half, 0);
             mbar_wait(&S.x_full[b], (tl >> 1) & 1u);                    // the tile's observation operand is stored
-            mbar_wait(&S.l1_empty, (tl & 1u) ^ 1u);                     // the converters have read tile tl - 1's columns
+            mbar_wait(&S.l1_empty[half], (tl & 1u) ^ 1u);               // the converters have read tile tl - 1's columns
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t rows = half ? (uint32_t)(L1_NA / 8) * (256u >> 4) : 0u;        // descriptor offset of row group 14
             asm volatile(
-                "{\n\t.reg .pred E;\n\t.reg .b64 dxh, dxl, dwh, dwl;\n\t"
+                "{\n\t.reg .pred E, X;\n\t.reg .b64 dxh, dxl, dwh, dwl;\n\t"
                 "elect.sync _|E, 0xffffffff;\n\t"
+                "setp.ne.and.b32 X, %9, 0, E;\n\t"
                 "mov.b64 dxh, {%1, %5};\n\tmov.b64 dxl, {%2, %5};\n\tmov.b64 dwh, {%3, %5};\n\tmov.b64 dwl, {%4, %5};\n\t"
                 "@E tcgen05.mma.cta_group::1.kind::f16 [%0], dxh, dwh, %6, 0;\n\t"
                 "@E tcgen05.mma.cta_group::1.kind::f16 [%0], dxh, dwl, %6, 1;\n\t"
                 "@E tcgen05.mma.cta_group::1.kind::f16 [%0], dxl, dwh, %6, 1;\n\t"
                 "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
-                "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}\n"
-                :: "r"(d1), "r"(x_hi0 + b * (A_STEP >> 4)), "r"(x_lo0 + b * (A_STEP >> 4)), "r"(w1_hi), "r"(w1_lo), "r"(deschi),
-                   "r"(kIdesc208), "r"(smem_u32(&S.l1_full)), "r"(smem_u32(&S.x_empty[b]))
+                "@X tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}\n"
+                :: "r"(d1 + (half ? (uint32_t)L1_NA : 0u)), "r"(x_hi0 + b * (A_STEP >> 4)), "r"(x_lo0 + b * (A_STEP >> 4)),
+                   "r"(w1_hi + rows), "r"(w1_lo + rows), "r"(deschi), "r"(half ? kIdescB : kIdescA),
+                   "r"(smem_u32(&S.l1_full[half])), "r"(smem_u32(&S.x_empty[b])), "r"((half || !L1_NB) ? 1u : 0u)
                 : "memory");
+            MG_TRACE16(g_trace_l1, 2u * tl + half, 1);
         };
-        if (my_tiles) layer1(0u);
+        if (my_tiles) { layer1(0u, 0u); if (L1_NB) layer1(0u, 1u); }
         for (uint32_t tl = 0; tl < my_tiles; ++tl) {
             const uint32_t buf = tl & 1u;
             mbar_wait(&S.tmem_empty[buf], ((tl >> 1) & 1u) ^ 1u);       // the epilogue has read this accumulator buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + (buf ? (uint32_t)L2_COL1 : (uint32_t)L2_COL0);
             const uint32_t tm_full = smem_u32(&S.tmem_full[buf]);
-            bool l1_pending = tl + 1 < my_tiles;
-#pragma unroll 1
-            for (uint32_t ks = 0; ks < (uint32_t)KSTEPS; ++ks) {
+            uint32_t l1_next = tl + 1 < my_tiles ? 0u : 2u;             // next half of tile tl + 1's layer 1 to issue
+            uint32_t have = 0;                                          // the barrier about to be waited for was already seen complete
+            // One K-step; the loop around it is fully unrolled: the issuing warp is a chain of latencies (barrier poll,
+            // fence, three MMAs and a commit from one thread) and rolled up, with the layer-1 poll in every trip, it took
+            // ~520 cycles per K-step against ~360 of tensor work (profiles/exp_tc16_trace.cu).
+            auto kstep = [&](const uint32_t ks) {
                 const uint32_t it = tl * KSTEPS + ks, s = it % STAGES;
+                // everything the elected lane needs is computed BEFORE the wait, in ordinary registers
                 uint32_t lo_ah = a_hi0 + s * (A_STEP >> 4), lo_al = a_lo0 + s * (A_STEP >> 4);
                 uint32_t lo_bh = w2_hi0 + ks * (W2_STEP >> 4), lo_bl = lo_bh + ((W2_STEP / 2) >> 4);
                 uint32_t done_bar = smem_u32(&S.empty[s]);
-                asm volatile("" : "+r"(lo_ah), "+r"(lo_al), "+r"(lo_bh), "+r"(lo_bl), "+r"(done_bar));   // computed before the wait
-                mbar_wait(&S.full[s], (it / STAGES) & 1u);
+                asm volatile("" : "+r"(lo_ah), "+r"(lo_al), "+r"(lo_bh), "+r"(lo_bl), "+r"(done_bar));   // pin the values here
+                const uint32_t last = ks + 1 == (uint32_t)KSTEPS ? 1u : 0u;
+                MG_TRACE16(g_trace_mma, it, 0);
+                if (!have) mbar_wait(&S.full[s], (it / STAGES) & 1u);
+                // poll the NEXT K-step now: the answer arrives while the MMAs below are being issued
+                have = last ? 0u : mbar_test(&S.full[(it + 1) % STAGES], ((it + 1) / STAGES) & 1u);
+                MG_TRACE16(g_trace_mma, it, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 asm volatile(
                     "{\n\t.reg .pred E, L, P;\n\t.reg .b64 dah, dal, dbh, dbl;\n\t"
@@ -258,18 +320,26 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
                     "@E tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %6, 1;\n\t"
                     "@E tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
                     "@L tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t}\n"
-                    :: "r"(d), "r"(lo_ah), "r"(lo_al), "r"(lo_bh), "r"(lo_bl), "r"(deschi), "r"(kIdesc112), "r"(ks),
-                       "r"(ks + 1 == (uint32_t)KSTEPS ? 1u : 0u), "r"(done_bar), "r"(tm_full)
+                    :: "r"(d), "r"(lo_ah), "r"(lo_al), "r"(lo_bh), "r"(lo_bl), "r"(deschi), "r"(kIdesc112), "r"(ks), "r"(last),
+                       "r"(done_bar), "r"(tm_full)
                     : "memory");
-                // Layer 1 of the next tile goes in as soon as the converters have read the last of this tile's layer-1 columns
-                // (they run up to a ring ahead of these MMAs) — polled, so that the K loop never stalls on it; after the last
-                // K-step it has to be waited for.
-                if (l1_pending && ks >= (uint32_t)L1_ISSUE_AT &&
-                    (ks + 1 == (uint32_t)KSTEPS || __all_sync(0xFFFFFFFFu, mbar_test(&S.l1_empty, tl & 1u) != 0u))) {
-                    layer1(tl + 1);
-                    l1_pending = false;
+                MG_TRACE16(g_trace_mma, it, 2);
+                // The next tile's layer 1: its first half as soon as the converters have read this tile's first half (polled at
+                // the K-steps around which that happens — they run a K-step or two ahead of these MMAs), its second half
+                // behind this tile's last K-step (the converters have stored that K-step, so they have read everything).
+                if (ks >= (uint32_t)L1_POLL_FROM && l1_next == 0u &&
+                    (ks + 1 == (uint32_t)KSTEPS || __all_sync(0xFFFFFFFFu, mbar_test(&S.l1_empty[0], tl & 1u) != 0u))) {
+                    layer1(tl + 1, 0u);
+                    l1_next = L1_NB ? 1u : 2u;
                 }
-            }
+                if (ks + 1 == (uint32_t)KSTEPS && l1_next == 1u) {
+                    layer1(tl + 1, 1u);
+                    l1_next = 2u;
+                }
+                MG_TRACE16(g_trace_mma, it, 3);
+            };
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) kstep((uint32_t)ks);
         }
     } else {
         // =================================== EPILOGUE: layer 3 + arg-max ============================================
@@ -282,7 +352,9 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
         for (uint32_t tl = 0; tl < my_tiles; ++tl) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)tl * gridDim.x;
             const uint32_t buf = tl & 1u;
+            if (q4 == 0) MG_TRACE16(g_trace_epi, tl, 0);
             mbar_wait(&S.tmem_full[buf], (tl >> 1) & 1u);
+            if (q4 == 0) MG_TRACE16(g_trace_epi, tl, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + (buf ? (uint32_t)L2_COL1 : (uint32_t)L2_COL0) + ((uint32_t)(q4 * 32) << 16);
             float q[4][OUT];                                            // rows t1 + 8 * {0, 1, 2, 3}: partial sums over this thread's neurons
@@ -290,24 +362,28 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int o = 0; o < OUT; ++o) q[r][o] = 0.f;
+            // 32 columns per trip (tcgen05.ld .x4: four 8-column blocks for rows t1 / t1 + 8 of both 16-lane halves): every trip
+            // exposes one tensor-memory load latency, and the epilogue paces the kernel (profiles/exp_tc16_trace.cu: with 16
+            // columns per trip it was busy 5 800 of a tile's 6 000 cycles).  Rolled up: the body stays in the instruction cache.
 #pragma unroll 1
-            for (int cb = 0; cb < UN / 16; ++cb) {                      // rolled up: the body stays in the instruction cache
-                uint32_t a[2][8];
+            for (int cb = 0; cb < (UN + 31) / 32; ++cb) {
+                uint32_t a[2][16];
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                                  : "=r"(a[h][0]), "=r"(a[h][1]), "=r"(a[h][2]), "=r"(a[h][3]), "=r"(a[h][4]), "=r"(a[h][5]),
-                                   "=r"(a[h][6]), "=r"(a[h][7])
-                                 : "r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(16 * cb)));
+                                   "=r"(a[h][6]), "=r"(a[h][7]), "=r"(a[h][8]), "=r"(a[h][9]), "=r"(a[h][10]), "=r"(a[h][11]),
+                                   "=r"(a[h][12]), "=r"(a[h][13]), "=r"(a[h][14]), "=r"(a[h][15])
+                                 : "r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(32 * cb)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cb == UN / 16 - 1) {                                // everything read: the MMAs of tile tl + 2 may overwrite it
+                if (cb == (UN + 31) / 32 - 1) {                         // everything read: the MMAs of tile tl + 2 may overwrite it
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&S.tmem_empty[buf]);
                 }
 #pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                    if (16 * cb + 8 * blk < H2P) {                      // blocks 0..12 hold the 100 neurons (+4 zero-weight pads)
-                        const int c = 16 * cb + 8 * blk + 2 * t0;
+                for (int blk = 0; blk < 4; ++blk) {
+                    if (32 * cb + 8 * blk < H2P) {                      // blocks 0..12 hold the 100 neurons (+4 zero-weight pads)
+                        const int c = 32 * cb + 8 * blk + 2 * t0;
                         const float2 bias = *reinterpret_cast<const float2 *>(&S.b2[c]);
                         float2 w[OUT];
 #pragma unroll
@@ -339,6 +415,7 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
                 }
                 mine[o] = (t0 == 0 ? q[0][o] : t0 == 1 ? q[1][o] : t0 == 2 ? q[2][o] : q[3][o]) + S.b3[o];
             }
+            if (q4 == 0) MG_TRACE16(g_trace_epi, tl, 2);
             const int64_t e = tile * TM + q4 * 32 + t1 + 8 * t0;
             int best = 0;
             float bv = mine[0];

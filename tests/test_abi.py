@@ -154,7 +154,7 @@ def test_python_constants_match_the_header():
              "MG_POLICY_BACKEND_FP32": nat.POLICY_BACKEND_FP32, "MG_POLICY_BACKEND_TF32X3": nat.POLICY_BACKEND_TF32X3,
              "MG_MLP_FLAG_MIRROR": nat.MLP_FLAG_MIRROR, "MG_MLP_FLAG_PDL": nat.MLP_FLAG_PDL,
              "MG_MLP_FLAG_OBS_SOA": nat.MLP_FLAG_OBS_SOA, "MG_MLP_FLAG_OBS_GOAL_SLOT": nat.MLP_FLAG_OBS_GOAL_SLOT,
-             "MG_MLP_FLAG_WRITE_GOAL": nat.MLP_FLAG_WRITE_GOAL,
+             "MG_MLP_FLAG_WRITE_GOAL": nat.MLP_FLAG_WRITE_GOAL, "MG_MLP_FLAG_F16X3": nat.MLP_FLAG_F16X3,
              "MG_FIELD_OBS": nat.FIELD_OBS, "MG_FIELD_REW": nat.FIELD_REW, "MG_FIELD_DONE": nat.FIELD_DONE,
              "MG_FIELD_INFO": nat.FIELD_INFO, "MG_FIELD_ALL": nat.FIELD_ALL,
              "MG_INFO_COLLISION": nat.INFO_COLLISION, "MG_INFO_WINNER_SHIFT": nat.INFO_WINNER_SHIFT,
@@ -185,6 +185,11 @@ def test_policy_step_and_layout_argument_errors_without_a_gpu(lib):
     assert lib.mg_reset(C.byref(st), 8, None, None, nat.FLAG_AUTO_RESET, None, None) == -4       # not a layout flag
     assert lib.mg_mlp_act(vp(16), None, 8, 10, 5, *[vp(16)] * 6, vp(16), None, nat.MLP_FLAG_WRITE_GOAL, None) == -4   # needs the goal-slot layout
     assert lib.mg_mlp_act(vp(16), None, 8, 11, 5, *[vp(16)] * 6, vp(16), None, 0, None) == -2                         # 11-float rows need the layout flag
+    # MG_MLP_FLAG_F16X3: a flag of mg_mlp_act_tc only (w1t / b1 may then be NULL: they travel inside the operand blob)
+    assert lib.mg_mlp_act(vp(16), None, 8, 10, 5, *[vp(16)] * 6, vp(16), None, nat.MLP_FLAG_F16X3, None) == -4
+    assert lib.mg_mlp_act_tc(vp(16), None, 8, 10, 5, None, None, None, vp(16), vp(16), vp(16), vp(16), None, nat.MLP_FLAG_F16X3, None) == -1
+    assert lib.mg_mlp_act_tc(vp(16), None, 8, 10, 5, None, None, vp(24), vp(16), vp(16), vp(16), vp(16), None, nat.MLP_FLAG_F16X3, None) == -3
+    assert lib.mg_mlp_act_tc(vp(16), None, 8, 10, 5, None, None, vp(16), vp(16), vp(16), vp(16), vp(16), None, 0, None) == -1
     assert lib.mg_explore(None, 8, 5, None, None, 0, 0, None) == -1 and lib.mg_explore(None, 0, 5, None, None, 0, 0, None) == 0
     assert lib.mg_option_update(None, None, None, None, None, 8, None, None, None, None, None) == -1
     assert b"NULL" in lib.mg_last_error()

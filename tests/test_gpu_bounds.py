@@ -86,6 +86,10 @@ def test_no_kernel_writes_out_of_bounds(n, random_reset):
     for flags in (0, 1):
         nat.check(lib.mg_mlp_act_tc(p(obs), None, n, 10, 5, p(w1t), p(b1), p(w2tc), p(b2), p(w3), p(b3), p(act_out),
                                     p(q_out), flags, s), "mlp tc")
+    blob = ar.take(64 + 13312 + 93184, 0)                        # the packed fp16 operands of MG_MLP_FLAG_F16X3 (all zero)
+    for flags in (0, 1):
+        nat.check(lib.mg_mlp_act_tc(p(obs), None, n, 10, 5, None, None, p(blob), p(b2), p(w3), p(b3), p(act_out),
+                                    p(q_out), flags | nat.MLP_FLAG_F16X3, s), "mlp tc f16x3")
     torch.cuda.synchronize()
     ar.check()
     assert int(counter.view(torch.int64)[0]) > 0

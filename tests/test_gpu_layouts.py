@@ -49,7 +49,7 @@ def test_step_and_reset_write_the_same_values_in_every_layout(mg, layout, mode, 
         assert bool((eb.obs_buf[:, :, 0] == 7.0).all())
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("layout", ["soa", "goal_slot"])
 def test_policy_kernels_read_every_layout(mg, backend, layout):
     n = 3001
@@ -90,8 +90,7 @@ def test_policy_step_in_every_layout(mg, backend, layout):
     assert torch.equal(ea.pos1, eb.pos1) and torch.equal(ea.meta, eb.meta)
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
-@pytest.mark.parametrize("fused_step", [False, True])
+@pytest.mark.parametrize("backend,fused_step", [("fused", False), ("fused", True), ("tf32x3", False), ("tf32x3", True), ("f16x3", False)])
 def test_hdqn_on_goal_slot_rows(mg, backend, fused_step):
     """`[goal] + state` rows: the goal network stores its choice into slot 0 (MG_MLP_FLAG_WRITE_GOAL) and the controller
     reads the 11-float row as it is == the loop with a separate goal array on the default rows."""

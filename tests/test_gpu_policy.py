@@ -64,20 +64,22 @@ def test_fused_mlp_matches_torch_reference(mg, in_dim, out_dim, n):
     assert torch.equal(ref.act(obs, goal=goal).cpu()[clear], a.cpu()[clear])
 
 
-@pytest.mark.parametrize("in_dim,out_dim,n", [(10, 5, 5000), (10, 3, 129), (11, 5, 1031), (11, 3, 4096), (10, 5, 1)])
-def test_tensor_core_backend_matches_fp32(mg, in_dim, out_dim, n):
-    """`backend="tf32x3"` (tcgen05 + TMEM, error-compensated 3xTF32 for the 200x100 layer): Q-values
-    within fp32-level error of the fp64 reference and the same actions wherever the margin is clear."""
+@pytest.mark.parametrize("tc_backend", ["tf32x3", "f16x3"])
+@pytest.mark.parametrize("in_dim,out_dim,n", [(10, 5, 5000), (10, 3, 129), (11, 5, 1031), (11, 3, 4096), (10, 5, 1), (10, 5, 148 * 128 * 3 + 77)])
+def test_tensor_core_backend_matches_fp32(mg, in_dim, out_dim, n, tc_backend):
+    """`backend="tf32x3"` (tcgen05 + TMEM, error-compensated 3xTF32 for the 200x100 layer) and `backend="f16x3"` (both
+    hidden layers on the tensor cores as three-product sums of fp16 hi / lo operands): Q-values within fp32-level error
+    of the fp64 reference and the same actions wherever the margin is clear."""
     obs = mid_episode_obs(mg, n, seed=in_dim + n)
     goal = torch.randint(0, 3, (n,), dtype=torch.uint8, device="cuda") if in_dim == 11 else None
     f = mg.MLPPolicy(in_dim, out_dim, seed=3 * in_dim + out_dim)
-    tc = mg.MLPPolicy(in_dim, out_dim, state_dict=f.state_dict(), backend="tf32x3")
+    tc = mg.MLPPolicy(in_dim, out_dim, state_dict=f.state_dict(), backend=tc_backend)
     qf = torch.empty(n, out_dim, device="cuda"); qt = torch.empty(n, out_dim, device="cuda")
     af, at = f.act(obs, goal=goal, q_out=qf), tc.act(obs, goal=goal, q_out=qt)
     x = obs if goal is None else torch.cat([goal.float().unsqueeze(1), obs], 1)
     q64 = q_fp64(f, x.double().cpu())
     scale = q64.abs().max().item()
-    assert (qt.double().cpu() - q64).abs().max().item() <= 2e-5 * scale      # measured 5e-6; fp32 FFMA: 2e-7
+    assert (qt.double().cpu() - q64).abs().max().item() <= 2e-5 * scale      # measured 3e-6 (both); fp32 FFMA: 2e-7
     top2 = q64.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 1e-4 * scale
     assert torch.equal(at.cpu()[clear].long(), q64.argmax(1)[clear])
@@ -85,7 +87,7 @@ def test_tensor_core_backend_matches_fp32(mg, in_dim, out_dim, n):
     assert (af == at).float().mean().item() > 0.999
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("in_dim,out_dim", [(10, 5), (11, 5), (10, 3)])
 def test_mirrored_read_equals_opponent_view(mg, backend, in_dim, out_dim):
     """`mirror=True` (MG_MLP_FLAG_MIRROR): the kernels read every row as the opponent sees it, `state[5:] + state[:5]`
@@ -104,7 +106,8 @@ def test_mirrored_read_equals_opponent_view(mg, backend, in_dim, out_dim):
     assert not torch.equal(q1, q2)                                              # and it differs from the unmirrored read
 
 
-def test_tensor_core_backend_is_stable_under_repetition(mg):
+@pytest.mark.parametrize("tc_backend", ["tf32x3", "f16x3"])
+def test_tensor_core_backend_is_stable_under_repetition(mg, tc_backend):
     """The tensor-core kernel is a multi-role pipeline (8 producer warps, an MMA-issuing warp, 4 epilogue warps
     that hand the accumulator buffers back zeroed, 20 mbarriers).  A protocol race would show up as an occasional lost
     update or a stale tile: 150 launches over many tiles per SM (2^17 envs = 1024 tiles on 148 SMs) on changing
@@ -113,7 +116,7 @@ def test_tensor_core_backend_is_stable_under_repetition(mg):
     n = 1 << 17
     env = mg.MergeVecEnv(n, seed=11)
     f = mg.MLPPolicy(10, 5, seed=5)
-    tc = mg.MLPPolicy(10, 5, state_dict=f.state_dict(), backend="tf32x3")
+    tc = mg.MLPPolicy(10, 5, state_dict=f.state_dict(), backend=tc_backend)
     qf = torch.empty(n, 5, device="cuda"); qt = torch.empty(n, 5, device="cuda")
     worst = torch.zeros((), device="cuda")
     for t in range(150):
@@ -126,7 +129,7 @@ def test_tensor_core_backend_is_stable_under_repetition(mg):
     assert worst.item() < 5e-5                                               # measured 3e-6
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("tag", ["L1_1445", "L0_2037"])
 def test_shipped_dqn_checkpoint_greedy_vs_L0(mg, ckpt, tag, backend):
     """Greedy DQN (test_params/dqn/*/eval.pth) vs the constant-speed opponent: 225 steps, P1 wins,
@@ -154,7 +157,7 @@ def test_shipped_dqn_checkpoint_greedy_vs_L0(mg, ckpt, tag, backend):
     assert abs(R1 - 0.5899968243808502) < 1e-12 and R2 == 1.0
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 def test_two_shipped_checkpoints_play_each_other(mg, ckpt, backend):
     """pvp with a policy on both sides, the opponent acting on the mirrored observation
     `state[5:] + state[:5]` (main.py:196-199 = `env.opponent_view`): the "OP:L2" checkpoint against the
@@ -235,7 +238,7 @@ def test_explore_rule_and_goal_status(mg):
     assert np.array_equal(got[~knife], exact[~knife]) and knife.mean() < 0.01 and len(set(exact.tolist())) == 3
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("seed,mode", [(7, "L0"), (7, "selfplay"), (36, "L0"), (36, "selfplay")])
 def test_hdqn_against_the_reference_classes(mg, seed, mode, backend):
     """tests/golden/hdqn_policies.npz: episodes played by the reference's OWN h-DQN classes (scripts/hdqn.py
