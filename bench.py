@@ -734,7 +734,7 @@ def run_b200(args):
             import bench_policy
             policy = {"note": "BASELINE configs[4]: pve, policy forward + arg-max -> mg_step on the device, random starts; "
                               "graph-timed (bench_policy.measure); rank 0 only"}
-            for be in ("fused", "tf32x3"):
+            for be in ("fused", "tf32x3", "f16x3"):
                 try:
                     policy[be] = bench_policy.measure(args.policy_envs, "dqn", be, device=dev)
                 except Exception as e:  # noqa
