@@ -26,7 +26,8 @@
 //                          scale + ReLU + split, four 16-byte stores into ring slot (K-step % 8), arrive on full[slot]
 //   warps 8-11  epilogue : tcgen05.ld the 128 x 112 fp32 accumulator, scale + bias + ReLU, the 100 x {5,3} layer, arg-max
 // Every mbarrier wait is bounded and traps instead of hanging.  Accumulation order is the issue order of one thread: the
-// kernel is bitwise reproducible.
+// kernel is bitwise reproducible.  Measured: 43 us per 2^18 envs inside a CUDA graph with PDL (3xTF32: 64), a tile takes
+// ~5 500 cycles against 5 355 for its 45 operand-fetch-bound MMAs (profiles/exp_tc16_trace.cu).
 #include <cuda_fp16.h>
 
 #include "abi_common.h"
@@ -197,6 +198,11 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                          : "r"(tl1 + 16u * ks));
+            // the ring slot is waited for HERE, under the tensor-memory load's latency: it is almost always free already (the
+            // converters run a K-step or two ahead of the MMAs, the ring holds eight), and a barrier poll is ~100 cycles anyway
+            const uint32_t s = it % STAGES;
+            mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);          // the MMAs that read this slot last have completed
+            if (q == 0) MG_TRACE16(g_trace_conv, it, 4);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (q == 0) MG_TRACE16(g_trace_conv, it, 2);
             if (ks + CONV_GROUPS >= ((half || !L1_NB) ? (uint32_t)KSTEPS : (uint32_t)KS_HALF)) {   // this warp's last K-step of the half:
@@ -208,9 +214,6 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
             for (int p = 0; p < 8; ++p)
                 split2_relu(__uint_as_float(v[2 * p]) * c1, __uint_as_float(v[2 * p + 1]) * c1, hi[p], lo[p]);
             if (q == 0) MG_TRACE16(g_trace_conv, it, 3);
-            const uint32_t s = it % STAGES;
-            mbar_wait(&S.empty[s], ((it / STAGES) & 1u) ^ 1u);          // the MMAs that read this slot last have completed
-            if (q == 0) MG_TRACE16(g_trace_conv, it, 4);
             *reinterpret_cast<uint4 *>(S.a_hi[s] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);          // units 0-7
             *reinterpret_cast<uint4 *>(S.a_hi[s] + off + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);    // units 8-15
             *reinterpret_cast<uint4 *>(S.a_lo[s] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -362,12 +365,11 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int o = 0; o < OUT; ++o) q[r][o] = 0.f;
-            // 32 columns per trip (tcgen05.ld .x4: four 8-column blocks for rows t1 / t1 + 8 of both 16-lane halves): every trip
-            // exposes one tensor-memory load latency, and the epilogue paces the kernel (profiles/exp_tc16_trace.cu: with 16
-            // columns per trip it was busy 5 800 of a tile's 6 000 cycles).  Rolled up: the body stays in the instruction cache.
-#pragma unroll 1
-            for (int cb = 0; cb < (UN + 31) / 32; ++cb) {
-                uint32_t a[2][16];
+            // 32 columns per trip (tcgen05.ld .x4: four 8-column blocks for rows t1 / t1 + 8 of both 16-lane halves), and the
+            // NEXT trip's columns are requested before this trip's arithmetic starts (two register sets, A and B, two trips
+            // per loop pass): the epilogue paces the kernel, and every tensor-memory load latency it exposes is tile time
+            // (profiles/exp_tc16_trace.cu: 16 columns per trip, nothing in flight: busy 5 800 of a tile's 6 000 cycles).
+            auto request = [&](uint32_t (&a)[2][16], const int cb) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
                     asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -375,11 +377,8 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
                                    "=r"(a[h][6]), "=r"(a[h][7]), "=r"(a[h][8]), "=r"(a[h][9]), "=r"(a[h][10]), "=r"(a[h][11]),
                                    "=r"(a[h][12]), "=r"(a[h][13]), "=r"(a[h][14]), "=r"(a[h][15])
                                  : "r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(32 * cb)));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cb == (UN + 31) / 32 - 1) {                         // everything read: the MMAs of tile tl + 2 may overwrite it
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&S.tmem_empty[buf]);
-                }
+            };
+            auto layer3 = [&](const uint32_t (&a)[2][16], const int cb) {
 #pragma unroll
                 for (int blk = 0; blk < 4; ++blk) {
                     if (32 * cb + 8 * blk < H2P) {                      // blocks 0..12 hold the 100 neurons (+4 zero-weight pads)
@@ -403,6 +402,23 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
                             }
                     }
                 }
+            };
+            static_assert((UN + 31) / 32 == 4, "two loop passes of two 32-column trips");
+            uint32_t ra[2][16], rb[2][16];
+            request(ra, 0);
+#pragma unroll 1
+            for (int p = 0; p < 2; ++p) {                               // rolled up: the body stays in the instruction cache
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                request(rb, 2 * p + 1);
+                layer3(ra, 2 * p);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p == 0) {
+                    request(ra, 2);
+                } else {                                                // everything read: the MMAs of tile tl + 2 may overwrite it
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&S.tmem_empty[buf]);
+                }
+                layer3(rb, 2 * p + 1);
             }
             // sum the 4 lanes that share a row group, then lane t0 finishes row t1 + 8 * t0
             float mine[OUT];
