@@ -45,7 +45,7 @@ using mgtc::mbar_wait;
 using mgtc::smem_u32;
 using mgtc::TM;
 
-constexpr int H1 = 200, H1P = 208, H2 = 100;
+constexpr int H1P = 208, H2 = 100;            // hidden widths: 200 (padded to whole 16-unit K-steps) and 100
 constexpr int UN = 112;                       // layer-2 UMMA N (100 neurons + zero pad; multiple of 16 for M = 128)
 constexpr int H2P = 104;                      // layer-3 weights padded to whole 8-column blocks
 constexpr int KSTEPS = H1P / 16;              // 13 layer-2 K-steps of 16 hidden units

@@ -15,7 +15,7 @@
 //            (counter + offset) % capacity
 // The write pass is launched as a programmatic dependent of the scan: its blocks request their observation rows and take
 // their ballots while the single scan CTA is still running, and only then wait for the offsets (47 -> 44 us per 2^20 rows
-// inside a CUDA graph).  A one-launch variant (tiles by ticket, decoupled look-back over per-tile words) was measured and
+// inside a CUDA graph; 37.6 us with the aliased staging buffer of RowSmem = 4.9 TB/s, 0.75 of the HBM copy peak).  A one-launch variant (tiles by ticket, decoupled look-back over per-tile words) was measured and
 // dropped: 57 us against 47 (profiles/r02_record_onepass_experiment.patch, r02_record_onepass_vs_three_pass.jsonl) — the
 // ticket, publication and look-back round trips put ~5 us of latency in front of every block's first store.
 #include "abi_common.h"
@@ -139,11 +139,15 @@ template <int FORMAT> struct RowFmt {
 };
 constexpr int kWarps = kBlock / 32;
 
+// Per warp ONE staging buffer: first the 32 observation rows s (and s' behind them), then — once every selected lane holds
+// its assembled row in registers — the rows at their ranks (22.5 KB per block instead of 43: eight resident blocks per SM).
 template <int FORMAT>
 struct RowSmem {
-    float prev[kWarps][32 * kObs];
-    float next[kWarps][FORMAT != 1 ? 32 * kObs : 4];
-    float out[kWarps][32 * RowFmt<FORMAT>::WIDTH];
+    static constexpr int IN_FLOATS = (FORMAT != 1 ? 2 : 1) * 32 * kObs, OUT_FLOATS = 32 * RowFmt<FORMAT>::WIDTH;
+    float buf[kWarps][IN_FLOATS > OUT_FLOATS ? IN_FLOATS : OUT_FLOATS];
+    __device__ __forceinline__ float *prev(int w) { return buf[w]; }
+    __device__ __forceinline__ float *next(int w) { return buf[w] + 32 * kObs; }
+    __device__ __forceinline__ float *out(int w) { return buf[w]; }
 };
 
 struct RowArgs {
@@ -196,33 +200,32 @@ __device__ __forceinline__ void assemble_rows(const RowArgs &A, RowSmem<FORMAT> 
         if (FORMAT == 2) { g = (float)A.goal_prev[e]; gn = (float)A.goal_next[e]; }
     }
     if (full) {
-        float4 *sp = reinterpret_cast<float4 *>(sm.prev[warp]);
+        float4 *sp = reinterpret_cast<float4 *>(sm.prev(warp));
         sp[lane] = R.p[0]; sp[lane + 32] = R.p[1];
         if (lane < 16) sp[lane + 64] = R.p[2];
         if (FORMAT != 1) {
-            float4 *sn = reinterpret_cast<float4 *>(sm.next[warp]);
+            float4 *sn = reinterpret_cast<float4 *>(sm.next(warp));
             sn[lane] = R.q[0]; sn[lane + 32] = R.q[1];
             if (lane < 16) sn[lane + 64] = R.q[2];
         }
     } else {
         const int rows = (int)(A.n - w0);
         const float4 *gp = reinterpret_cast<const float4 *>(A.obs_prev + w0 * kObs);
-        float4 *sp = reinterpret_cast<float4 *>(sm.prev[warp]);
+        float4 *sp = reinterpret_cast<float4 *>(sm.prev(warp));
         for (int i = lane; i < rows * kObs / 4; i += 32) sp[i] = __ldg(gp + i);
-        for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) sm.prev[warp][i] = A.obs_prev[w0 * kObs + i];
+        for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) sm.prev(warp)[i] = A.obs_prev[w0 * kObs + i];
         if (FORMAT != 1) {
             const float4 *gq = reinterpret_cast<const float4 *>(A.obs_next + w0 * kObs);
-            float4 *sn = reinterpret_cast<float4 *>(sm.next[warp]);
+            float4 *sn = reinterpret_cast<float4 *>(sm.next(warp));
             for (int i = lane; i < rows * kObs / 4; i += 32) sn[i] = __ldg(gq + i);
-            for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) sm.next[warp][i] = A.obs_next[w0 * kObs + i];
+            for (int i = (rows * kObs / 4) * 4 + lane; i < rows * kObs; i += 32) sm.next(warp)[i] = A.obs_next[w0 * kObs + i];
         }
     }
     __syncwarp();
+    float row[WIDTH];                                                    // assembled in registers: the rows overwrite the staging buffer
     if (sel) {
-        const int r = __popc(b & ((1u << lane) - 1u));
-        float *row = sm.out[warp] + r * WIDTH;
-        const float *sp = sm.prev[warp] + lane * kObs;
-        const float *sn = use_term ? A.term_obs + e * kObs : sm.next[warp] + lane * kObs;
+        const float *sp = sm.prev(warp) + lane * kObs;
+        const float *sn = use_term ? A.term_obs + e * kObs : sm.next(warp) + lane * kObs;
         if (FORMAT == 2) {
             const float dx1 = sp[0], v2 = sp[9];                                  // goal_status, hdqn.py:223-236
             const float status = dx1 < -0.5f * v2 ? 0.f : dx1 < 0.5f * v2 ? 1.f : 2.f;
@@ -248,6 +251,12 @@ __device__ __forceinline__ void assemble_rows(const RowArgs &A, RowSmem<FORMAT> 
             }
         }
     }
+    __syncwarp();                                                        // every lane has read its s / s' row
+    if (sel) {
+        float *dst = sm.out(warp) + __popc(b & ((1u << lane) - 1u)) * WIDTH;
+#pragma unroll
+        for (int k = 0; k < WIDTH; ++k) dst[k] = row[k];
+    }
     __syncwarp();
 }
 
@@ -266,7 +275,7 @@ __device__ __forceinline__ void store_rows(const RowArgs &A, RowSmem<FORMAT> &sm
     }
     if (total <= cap && slot0 + (unsigned long long)cnt <= cap) {
         // common case: one contiguous span, 8-byte aligned (row width 88, 56 or 96 bytes) -> 64-bit stores
-        const float2 *src = reinterpret_cast<const float2 *>(sm.out[warp]);
+        const float2 *src = reinterpret_cast<const float2 *>(sm.out(warp));
         float2 *dst = reinterpret_cast<float2 *>(A.ring + slot0 * WIDTH);
         for (int i = lane; i < cnt * WIDTH / 2; i += 32) dst[i] = src[i];
     } else {
@@ -274,7 +283,7 @@ __device__ __forceinline__ void store_rows(const RowArgs &A, RowSmem<FORMAT> &sm
             const int r = i / WIDTH, c = i - r * WIDTH;
             if (rank0 + r + cap < total) continue;                         // overwritten later in this call
             const unsigned long long slot = (slot0 + (unsigned long long)r) % cap;
-            A.ring[slot * WIDTH + c] = sm.out[warp][i];
+            A.ring[slot * WIDTH + c] = sm.out(warp)[i];
         }
     }
 }
@@ -287,6 +296,7 @@ __device__ __forceinline__ void store_rows(const RowArgs &A, RowSmem<FORMAT> &sm
 // One warp handles 32 consecutive envs: their observation rows are one contiguous 1280-byte span, loaded
 // with coalesced 128-bit loads into shared memory; the selected lanes assemble their rows in shared memory
 // at consecutive ranks; the warp then writes that contiguous piece of the ring with coalesced stores.
+// (40 registers, 22.5 KB: six resident blocks per SM; forcing eight by a 32-register cap spills and is slower: 42 vs 37.6 us)
 template <int FORMAT>
 __global__ void __launch_bounds__(kBlock)
 write_kernel(const RowArgs A, const uint32_t *block_offsets, const unsigned long long *base, const unsigned long long *counter) {
