@@ -15,9 +15,10 @@
 //            (counter + offset) % capacity
 // The write pass is launched as a programmatic dependent of the scan: its blocks request their observation rows and take
 // their ballots while the single scan CTA is still running, and only then wait for the offsets (47 -> 44 us per 2^20 rows
-// inside a CUDA graph; 37.6 us with the aliased staging buffer of RowSmem = 4.9 TB/s, 0.75 of the HBM copy peak).  A one-launch variant (tiles by ticket, decoupled look-back over per-tile words) was measured and
-// dropped: 57 us against 47 (profiles/r02_record_onepass_experiment.patch, r02_record_onepass_vs_three_pass.jsonl) — the
-// ticket, publication and look-back round trips put ~5 us of latency in front of every block's first store.
+// inside a CUDA graph; 37.6 us with the aliased staging buffer of RowSmem = 4.9 TB/s, 0.75 of the HBM copy peak).
+// A one-launch variant (tiles by ticket, decoupled look-back over per-tile words) was measured and dropped: 57 us against
+// 47 (profiles/r02_record_onepass_experiment.patch, r02_record_onepass_vs_three_pass.jsonl) — the ticket, publication and
+// look-back round trips put ~5 us of latency in front of every block's first store.
 #include "abi_common.h"
 
 namespace mgrec {
