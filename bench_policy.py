@@ -92,7 +92,7 @@ def measure(n=1 << 18, policy="dqn", backend="fused", k=50, replays=4, device="c
     st = env.stats()
     ms_pol = graph_ms(policy_only, k, replays)
     fused = None
-    if backend in ("fused", "tf32x3"):             # f16x3 has no fused variant: act() + step() only
+    if backend in ("fused", "tf32x3", "f16x3"):
         for _ in range(3):
             one_step_fused()
         ms_f = graph_ms(one_step_fused, k, replays)

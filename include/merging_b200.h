@@ -306,13 +306,13 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
  *     action = dqn.choose_action(state)                     # Net forward + torch.max, or a random action
  *     next_state, rewards, done, info = env.step(action, action_op)
  * for n envs in ONE kernel: the Q-network forward + arg-max of mg_mlp_act (backend 0, fp32 FFMA: the reference's
- * arithmetic) or mg_mlp_act_tc (backend 1, tcgen05 3xTF32) with MergeEnv.step as its epilogue — the thread that
+ * arithmetic) or mg_mlp_act_tc (backend 1, tcgen05 3xTF32; backend 2, tcgen05 3xF16 = MG_MLP_FLAG_F16X3) with MergeEnv.step as its epilogue — the thread that
  * finishes env e's arg-max also owns env e's state, applies the exploration rule, steps the env and writes the next
  * observation row where the next launch's layer-1 read expects it.  Bit-identical to mg_mlp_act[_tc] followed by
  * mg_step on the same inputs.
  *   obs_in          float[n,10]: the observation the policy acts on (observe() of `state`); out->obs may alias it
  *   goal_or_null    uint8[n]: the h-DQN controller's `[goal] + state` input column (hdqn.py:291); network input 11
- *   w1t..b3         as mg_mlp_act (backend 0: w2 = w2p) or mg_mlp_act_tc (backend 1: w2 = w2_tc); out_dim is 5
+ *   w1t..b3         as mg_mlp_act (backend 0: w2 = w2p) or mg_mlp_act_tc (backend 1: w2 = w2_tc, backend 2: w2 = the fp16 operand blob); out_dim is 5
  *   a2_or_null      uint8[n] actions of player 2 (pvp), NULL = `action_op = None` (pve)
  *   flags           MG_FLAG_AUTO_RESET | MG_POLICY_FLAG_EXPLORE | MG_POLICY_FLAG_PDL | MG_FLAG_OBS_SOA | MG_FLAG_OBS_GOAL_SLOT
  *                   (the layout of obs_in AND out->obs) | MG_POLICY_FLAG_GOAL_IN_SLOT (MG_FLAG_NO_RETURNS is implied by
@@ -330,6 +330,8 @@ MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t 
 #define MG_POLICY_FLAG_PDL 0x200u     /* as MG_MLP_FLAG_PDL: the previous kernel of the stream does not write the weights */
 #define MG_POLICY_BACKEND_FP32 0
 #define MG_POLICY_BACKEND_TF32X3 1
+#define MG_POLICY_BACKEND_F16X3 2 /* mg_mlp_act_tc with MG_MLP_FLAG_F16X3: w2 = the packed fp16 operand blob (w1t / b1 are
+                                     validated but not read) */
 typedef struct MgExplore {
     uint64_t seed, step;
     uint32_t keep_u32, reserved;

@@ -34,7 +34,7 @@ MLP_LAYOUT_FLAG = {"aos": 0, "soa": MLP_FLAG_OBS_SOA, "goal_slot": MLP_FLAG_OBS_
 def soa_stride(n: int) -> int:
     """MG_OBS_SOA_STRIDE: elements per column of the [10][stride] observation layout."""
     return (int(n) + 15) & ~15
-POLICY_BACKEND_FP32, POLICY_BACKEND_TF32X3 = 0, 1
+POLICY_BACKEND_FP32, POLICY_BACKEND_TF32X3, POLICY_BACKEND_F16X3 = 0, 1, 2
 FIELD_OBS, FIELD_REW, FIELD_DONE, FIELD_INFO, FIELD_ALL = 0x1, 0x2, 0x4, 0x8, 0xF
 FIELD_BITS = {"obs": FIELD_OBS, "rew": FIELD_REW, "done": FIELD_DONE, "info": FIELD_INFO}
 

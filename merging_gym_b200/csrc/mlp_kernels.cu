@@ -366,6 +366,8 @@ extern "C" MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, 
 cudaError_t mg_policy_step_tc_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const float *w1t,
                                      const float *b1, const float *w2_tc, const float *b2, const float *w3, const float *b3,
                                      float *q_out, cudaStream_t st, const mgpe::Args &P);
+cudaError_t mg_policy_step_tc16_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const void *blob, const float *b2,
+                                       const float *w3, const float *b3, float *q_out, cudaStream_t st, const mgpe::Args &P);
 
 namespace mgmlp {
 __global__ void __launch_bounds__(256)
@@ -391,8 +393,8 @@ extern "C" MG_API int mg_policy_step(const MgState *state, int64_t n, const floa
         return fail(MG_ERR_BAD_FLAGS, "MG_POLICY_FLAG_GOAL_IN_SLOT needs MG_FLAG_OBS_GOAL_SLOT and no goal array");
     if ((flags & MG_FLAG_OBS_SOA) && (flags & MG_FLAG_OBS_GOAL_SLOT)) return fail(MG_ERR_BAD_FLAGS, "MG_FLAG_OBS_SOA and MG_FLAG_OBS_GOAL_SLOT exclude each other");
     const bool pdl = (flags & MG_POLICY_FLAG_PDL) != 0u;
-    if (backend != MG_POLICY_BACKEND_FP32 && backend != MG_POLICY_BACKEND_TF32X3)
-        return fail(MG_ERR_BAD_FLAGS, "backend must be MG_POLICY_BACKEND_FP32 or MG_POLICY_BACKEND_TF32X3");
+    if (backend != MG_POLICY_BACKEND_FP32 && backend != MG_POLICY_BACKEND_TF32X3 && backend != MG_POLICY_BACKEND_F16X3)
+        return fail(MG_ERR_BAD_FLAGS, "backend must be MG_POLICY_BACKEND_FP32, MG_POLICY_BACKEND_TF32X3 or MG_POLICY_BACKEND_F16X3");
     if ((flags & MG_POLICY_FLAG_EXPLORE) && !explore_or_null) return fail(MG_ERR_NULL_POINTER, "MG_POLICY_FLAG_EXPLORE without an MgExplore");
     if (reset_or_null && reset_or_null->mode > MG_RESET_RANDOM) return fail(MG_ERR_BAD_FLAGS, "MgResetSpec.mode must be MG_RESET_FIXED or MG_RESET_RANDOM");
     if (n == 0) return MG_OK;
@@ -424,6 +426,8 @@ extern "C" MG_API int mg_policy_step(const MgState *state, int64_t n, const floa
     cudaError_t e;
     if (backend == MG_POLICY_BACKEND_TF32X3)
         e = mg_policy_step_tc_launch(in_dim, obs_in, goal_or_null, n, w1t, b1, w2, b2, w3, b3, q_out_or_null, st, P);
+    else if (backend == MG_POLICY_BACKEND_F16X3)        // w2 = the packed fp16 operand blob (w1t / b1 travel inside it)
+        e = mg_policy_step_tc16_launch(in_dim, obs_in, goal_or_null, n, w2, b2, w3, b3, q_out_or_null, st, P);
     else if (in_dim == 10)
         e = a2_or_null ? mgmlp::launch<10, 5, false, 2>(obs_in, goal_or_null, n, obs_mode, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl)
                        : mgmlp::launch<10, 5, false, 1>(obs_in, goal_or_null, n, obs_mode, w1t, b1, w2, b2, w3, b3, nullptr, q_out_or_null, st, P, pdl);

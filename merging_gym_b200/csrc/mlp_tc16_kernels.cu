@@ -18,19 +18,21 @@
 //
 // One persistent CTA per SM, tile = 128 envs (UMMA M = 128), 14 warps:
 //   warp 13     X loader : the tile's observation rows -> hi / lo fp16 operand [128 x 16] (K slot 15 = 1.0), double-buffered
-//   warp 12     MMA issue: per tile 3 MMAs N = 208, K = 16 (layer 1, into TMEM columns [256, 464)) and 13 K-steps x 3 MMAs
-//                          N = 112 (layer 2, accumulator buffer tile & 1); the first MMA of an accumulator overwrites it, so
-//                          nobody zeroes tensor memory.  Layer 1 of the NEXT tile is issued in the middle of this tile's
-//                          K loop, as soon as the converters have read the last of this tile's layer-1 columns.
+//   warp 12     MMA issue: per tile 2 x 3 MMAs N = 112 / 96, K = 16 (layer 1 in two halves, into TMEM columns [256, 464)) and
+//                          13 K-steps x 3 MMAs N = 112 (layer 2, accumulator buffer tile & 1); the first MMA of an accumulator
+//                          overwrites it, so nobody zeroes tensor memory.  The halves of the NEXT tile's layer 1 are issued
+//                          inside this tile's K loop, as soon as the converters have read this tile's.
 //   warps 0-7   converters: warp w owns TMEM lane quarter w % 4 and every second K-step (w / 4): tcgen05.ld 16 columns,
 //                          scale + ReLU + split, four 16-byte stores into ring slot (K-step % 8), arrive on full[slot]
 //   warps 8-11  epilogue : tcgen05.ld the 128 x 112 fp32 accumulator, scale + bias + ReLU, the 100 x {5,3} layer, arg-max
+//   (mg_policy_step: + 4 env warps that step the finished tiles' envs, see ENV below)
 // Every mbarrier wait is bounded and traps instead of hanging.  Accumulation order is the issue order of one thread: the
 // kernel is bitwise reproducible.  Measured: 43 us per 2^18 envs inside a CUDA graph with PDL (3xTF32: 64), a tile takes
 // ~5 500 cycles against 5 355 for its 45 operand-fetch-bound MMAs (profiles/exp_tc16_trace.cu).
 #include <cuda_fp16.h>
 
 #include "abi_common.h"
+#include "policy_env.cuh"
 #include "tc_common.cuh"
 
 namespace mgtc16 {
@@ -67,6 +69,14 @@ constexpr int L2_COL0 = 0, L2_COL1 = 128, L1_COL = 256, TMEM_COLS = 512;
 constexpr int CONV_GROUPS = MG_TC16_CONV_GROUPS;                 // converter warps per TMEM lane quarter: K-steps interleaved over them
 constexpr int CONV_WARPS = 4 * CONV_GROUPS, EPI_WARP0 = CONV_WARPS, MMA_WARP = CONV_WARPS + 4, X_WARP = CONV_WARPS + 5;
 constexpr int NUM_THREADS = 32 * (CONV_WARPS + 6);
+// mg_policy_step only: four more warps own the env step of the tiles the epilogue has finished (policy_env.cuh), one 32-env
+// round of a tile each: 18 warps = 576 threads at 96 registers (52 bytes of spills).  Two env warps keep all 128 registers
+// but take two rounds per tile in sequence: 10.0 instead of 9.2 us per step at 4096 envs, 24.2 instead of 21.1 at 65 536.
+#ifndef MG_TC16_ENV_WARPS
+#define MG_TC16_ENV_WARPS 4
+#endif
+constexpr int ENV_WARP0 = CONV_WARPS + 6, ENV_WARPS = MG_TC16_ENV_WARPS, ENV_BUFS = 4;
+constexpr int NUM_THREADS_ENV = 32 * (ENV_WARP0 + ENV_WARPS);
 #ifndef MG_TC16_TRACE
 #define MG_TC16_TRACE 0                       // 1: CTA 0 records clock64() at the hand-over points (profiles/exp_tc16_trace.cu)
 #endif
@@ -105,6 +115,7 @@ struct Smem {
     float c1, c2;
     unsigned long long full[STAGES], empty[STAGES], x_full[2], x_empty[2], l1_full[2], l1_empty[2], tmem_full[2], tmem_empty[2], w_ready;
     uint32_t tmem_base;
+    mgpe::Handoff<TM, ENV_BUFS> env;          // ENV: the tile's actions, epilogue warps -> env warps
 };
 
 // kind::f16 with fp16 operands (format fields 0), D = f32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
@@ -127,11 +138,15 @@ __device__ __forceinline__ void split2_relu(float v0, float v1, uint32_t &hi, ui
     asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - back.y), "f"(v0 - back.x));
 }
 
-template <int IN, int OUT, bool MIRROR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// ENV: 0 = policy only; 1 / 2 = `mg_policy_step`: MergeEnv.step (pve / pvp) of every finished tile on two extra warps — the
+// epilogue threads drop the tile's arg-max into shared memory (mgpe::Handoff) instead of the action array, the env warps
+// apply the exploration rule, step the envs and write the next observation rows (possibly into the buffer being read:
+// the rows are then read with coherent loads).
+template <int IN, int OUT, bool MIRROR, int ENV>
+__global__ void __launch_bounds__(ENV ? NUM_THREADS_ENV : NUM_THREADS, 1)
 mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const int64_t n, const int obs_mode,
                     const unsigned char *__restrict__ blob, const float *__restrict__ b2, const float *__restrict__ w3,
-                    const float *__restrict__ b3, uint8_t *__restrict__ act, float *__restrict__ q_out) {
+                    const float *__restrict__ b3, uint8_t *__restrict__ act, float *__restrict__ q_out, const mgpe::Args P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem<OUT> &S = *reinterpret_cast<Smem<OUT> *>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -147,6 +162,7 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
         }
         for (int h = 0; h < 2; ++h) { mbar_init(&S.l1_full[h], 1); mbar_init(&S.l1_empty[h], 32 * CONV_WARPS); }
         mbar_init(&S.w_ready, 1);
+        if (ENV) mgpe::handoff_init(S.env, TM, TM / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.w_ready)), "r"((uint32_t)W_BYTES) : "memory");
         for (uint32_t c = 0; c < 8; ++c)
@@ -156,11 +172,11 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
         S.c1 = __ldg(reinterpret_cast<const float *>(blob));
         S.c2 = __ldg(reinterpret_cast<const float *>(blob) + 1);
     }
-    for (int i = t; i < OUT * H2P; i += NUM_THREADS) {
+    for (int i = t; i < OUT * H2P; i += (int)blockDim.x) {
         const int o = i / H2P, c = i - o * H2P;
         S.w3[o][c] = c < H2 ? w3[o * H2 + c] : 0.f;
     }
-    for (int i = t; i < H2 + 12; i += NUM_THREADS) S.b2[i] = i < H2 ? b2[i] : 0.f;
+    for (int i = t; i < H2 + 12; i += (int)blockDim.x) S.b2[i] = i < H2 ? b2[i] : 0.f;
     if (t < OUT) S.b3[t] = b3[t];
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
@@ -173,8 +189,13 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
     const uint32_t tmem_base = S.tmem_base;
     // From here on observations are read: wait for the previous kernel of the stream (a no-op without the PDL attribute)
     cudaGridDependencySynchronize();
+    if (ENV) cudaTriggerProgrammaticLaunchCompletion();        // as in mlp_tc_kernels.cu: the next fused launch may start its prologue
 
-    if (warp < CONV_WARPS) {
+    if (ENV && warp >= ENV_WARP0) {
+        // =================================== ENV WARPS: MergeEnv.step of the tiles the epilogue has finished ==========
+        mgpe::env_warp_loop<TM, ENV_BUFS, ENV_WARPS, ENV == 2>(P, S.env, warp - ENV_WARP0, blockIdx.x, gridDim.x, n_tiles, n, lane,
+                                                               (int)(blockIdx.x % MG_STATS_ROWS));
+    } else if (warp < CONV_WARPS) {
         // =================================== CONVERTERS: layer-1 accumulator -> layer-2 A operand ===================
         const int q = warp & 3, grp = warp >> 2;                        // TMEM lane quarter, K-step residue
         const uint32_t total = my_tiles * KSTEPS;
@@ -230,7 +251,7 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
             const int64_t e0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * TM + lane;
             float x[4][IN];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR>(obs, goal, e0 + 32 * j, n, obs_mode, x[j]);
+            for (int j = 0; j < 4; ++j) load_row<IN, MIRROR, ENV != 0>(obs, goal, e0 + 32 * j, n, obs_mode, x[j]);
             mbar_wait(&S.x_empty[b], ((tl >> 1) & 1u) ^ 1u);            // layer 1 of tile tl - 2 has read this buffer
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -439,12 +460,17 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
             for (int o = 1; o < OUT; ++o)
                 if (mine[o] > bv) { bv = mine[o]; best = o; }           // first maximum, like torch.max
             if (e < n) {
-                act[e] = (uint8_t)best;
-                if (obs_mode & 0x100) const_cast<float *>(obs)[e * (MG_OBS_DIM + 1)] = (float)best;   // MG_MLP_FLAG_WRITE_GOAL
+                if (!ENV) act[e] = (uint8_t)best;
+                if (!ENV && (obs_mode & 0x100)) const_cast<float *>(obs)[e * (MG_OBS_DIM + 1)] = (float)best;   // MG_MLP_FLAG_WRITE_GOAL
                 if (q_out) {
 #pragma unroll
                     for (int o = 0; o < OUT; ++o) q_out[e * OUT + o] = mine[o];
                 }
+            }
+            if (ENV) {                                                  // hand the action to the env warps
+                uint8_t *tile_act = mgpe::handoff_acquire(S.env, tl);
+                tile_act[q4 * 32 + t1 + 8 * t0] = (uint8_t)best;
+                mgpe::handoff_publish(S.env, tl);
             }
         }
     }
@@ -455,10 +481,11 @@ mlp_act_tc16_kernel(const float *obs, const uint8_t *__restrict__ goal, const in
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
 }
 
-template <int IN, int OUT, bool MIRROR>
+template <int IN, int OUT, bool MIRROR, int ENV = 0>
 cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_mode, const unsigned char *blob, const float *b2,
-                   const float *w3, const float *b3, uint8_t *act, float *q_out, cudaStream_t st, bool pdl) {
-    auto kern = mlp_act_tc16_kernel<IN, OUT, MIRROR>;
+                   const float *w3, const float *b3, uint8_t *act, float *q_out, cudaStream_t st, bool pdl,
+                   const mgpe::Args &P = mgpe::Args{}) {
+    auto kern = mlp_act_tc16_kernel<IN, OUT, MIRROR, ENV>;
     const size_t smem = sizeof(Smem<OUT>) + 1024;               // slack for the 1024-byte alignment of the base
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
@@ -467,12 +494,12 @@ cudaError_t launch(const float *obs, const uint8_t *goal, int64_t n, int obs_mod
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + TM - 1) / TM;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms)); cfg.blockDim = dim3(ENV ? NUM_THREADS_ENV : NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_mode, blob, b2, w3, b3, act, q_out);
+    e = cudaLaunchKernelEx(&cfg, kern, obs, goal, n, obs_mode, blob, b2, w3, b3, act, q_out, P);
     return e ? e : cudaGetLastError();
 }
 
@@ -489,5 +516,19 @@ cudaError_t mg_mlp_act_tc16_launch(int in_dim, int out_dim, bool mirror, const f
                       : mgtc16::launch<I, O, false>(obs, goal, n, obs_mode, bl, b2, w3, b3, act, q_out, st, pdl);
     MG_TC16_CASE(10, 5) MG_TC16_CASE(10, 3) MG_TC16_CASE(11, 5) MG_TC16_CASE(11, 3)
 #undef MG_TC16_CASE
+    return cudaErrorInvalidValue;
+}
+
+// the fused policy + env step on the f16x3 backend (called by mg_policy_step in mlp_kernels.cu; `blob` as above)
+cudaError_t mg_policy_step_tc16_launch(int in_dim, const float *obs, const uint8_t *goal, int64_t n, const void *blob, const float *b2,
+                                       const float *w3, const float *b3, float *q_out, cudaStream_t st, const mgpe::Args &P) {
+    const bool pvp = P.a2 != nullptr, pdl = (P.flags & MG_POLICY_FLAG_PDL) != 0u;
+    const int obs_mode = (int)mg::obs_layout_of(P.flags);
+    const auto *bl = static_cast<const unsigned char *>(blob);
+#define MG_TC16_ENV(I) (pvp ? mgtc16::launch<I, 5, false, 2>(obs, goal, n, obs_mode, bl, b2, w3, b3, nullptr, q_out, st, pdl, P) \
+                            : mgtc16::launch<I, 5, false, 1>(obs, goal, n, obs_mode, bl, b2, w3, b3, nullptr, q_out, st, pdl, P))
+    if (in_dim == 10) return MG_TC16_ENV(10);
+    if (in_dim == 11) return MG_TC16_ENV(11);
+#undef MG_TC16_ENV
     return cudaErrorInvalidValue;
 }

@@ -15,7 +15,7 @@ bias, ReLU, arg-max, exactly the reference's fp32 arithmetic on FFMA2); `backend
 error-compensated 3xTF32 product (fp32-level accuracy, not bit-identical); `backend="f16x3"`
 (`MG_MLP_FLAG_F16X3`, csrc/mlp_tc16_kernels.cu) puts BOTH hidden layers on the tensor cores as three-product sums of
 fp16 hi / lo operands (the same ~22 significant bits per product; activations limited to fp16's range after scaling —
-the fastest policy kernel; not available fused with the env step); `backend="torch"` is the
+the fastest policy kernel); `backend="torch"` is the
 plain PyTorch fp32 reference of the same op (cuBLAS), kept for the numerics tests.
 """
 from __future__ import annotations
@@ -30,7 +30,7 @@ from . import _native as nat
 
 EPISILO = 0.7          # scripts/main.py:16, hdqn.py:20
 HIDDEN1, HIDDEN2 = 200, 100
-POLICY_BACKENDS = {"fused": nat.POLICY_BACKEND_FP32, "tf32x3": nat.POLICY_BACKEND_TF32X3}    # mg_policy_step (fused with the env step)
+POLICY_BACKENDS = {"fused": nat.POLICY_BACKEND_FP32, "tf32x3": nat.POLICY_BACKEND_TF32X3, "f16x3": nat.POLICY_BACKEND_F16X3}   # mg_policy_step
 TC_BACKENDS = ("tf32x3", "f16x3")
 
 

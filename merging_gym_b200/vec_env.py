@@ -474,7 +474,7 @@ class MergeVecEnv:
         policy reads the env's current observation buffer; the next observation goes into the next output slot
         (with `out_slots=1`: in place).  Bit-identical to `policy.act(obs)` followed by `step(...)`.
 
-        policy       an `MLPPolicy` with 5 outputs and backend "fused" (fp32) or "tf32x3" (tensor cores)
+        policy       an `MLPPolicy` with 5 outputs and backend "fused" (fp32), "tf32x3" or "f16x3" (tensor cores)
         goal         uint8[N]: the h-DQN controller's `[goal] + state` column (`MLPPolicy(11, 5)`, hdqn.py:291)
         a2           uint8[N] actions of player 2, None = pve (the constant-speed opponent, merging_env.py:152)
         explore      None = greedy; a `policy.Exploration` = the scripts' `randn() <= EPISILO` rule (main.py:103-110)
@@ -484,7 +484,7 @@ class MergeVecEnv:
         """
         from .policy import POLICY_BACKENDS
         if policy.out_dim != nat.NUM_ACTIONS or policy.backend not in POLICY_BACKENDS:
-            raise ValueError("policy_step needs an MLPPolicy with 5 outputs and backend 'fused' or 'tf32x3' (use act() + step() with 'f16x3')")
+            raise ValueError("policy_step needs an MLPPolicy with 5 outputs and backend 'fused', 'tf32x3' or 'f16x3'")
         goal_in_slot = goal is None and self.obs_layout == "goal_slot" and policy.in_dim == nat.OBS_DIM + 1
         if policy.in_dim != nat.OBS_DIM + (0 if goal is None else 1) and not goal_in_slot:
             raise ValueError("policy input width does not match obs (+ goal)")

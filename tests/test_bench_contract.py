@@ -94,5 +94,5 @@ def test_gpu_arm_contract_line():
     assert st["total_envs"] == 65536 and st["steps"] == 256 and len(st["stats_digest"]) == 16 and st["stats_totals"][0] > 0
     assert d["policy_in_loop"]["fused"]["value"] > 0 and 0 < d["policy_in_loop"]["tf32x3"]["env_share"] < 1
     assert d["policy_in_loop"]["tf32x3"]["fused_step"]["value"] > 0 and d["policy_in_loop"]["tf32x3_4096_envs"]["value"] > 0
-    assert d["policy_in_loop"]["f16x3"]["value"] > 0 and d["policy_in_loop"]["f16x3"]["fused_step"] is None   # act + step only
+    assert d["policy_in_loop"]["f16x3"]["value"] > 0 and d["policy_in_loop"]["f16x3"]["fused_step"]["value"] > 0
     assert cb["reference_python_value"] > 0

@@ -33,7 +33,7 @@ def state_of(env):
     return [getattr(env, k).clone() for k in ("pos1", "vel1", "pos2", "vel2", "ret1", "ret2", "meta")]
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("mode,n,reset_mode", [("pve", 5000, "random"), ("pvp", 4099, "fixed"), ("pve", 130, "fixed"),
                                                ("pvp", 1, "random"), ("pve", 66000, "random")])
 def test_policy_step_equals_act_then_step(mg, backend, mode, n, reset_mode):
@@ -64,7 +64,7 @@ def test_policy_step_equals_act_then_step(mg, backend, mode, n, reset_mode):
         assert torch.equal(ea._extras[k], eb._extras[k])
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 def test_policy_step_in_place_without_returns_and_sticky_done(mg, backend):
     """out_slots=1 (the next observation overwrites the rows the policy read), track_returns=False, auto_reset=False."""
     sd, _ = shipped()
@@ -81,7 +81,7 @@ def test_policy_step_in_place_without_returns_and_sticky_done(mg, backend):
     assert torch.equal(ea.stats_tensor(), eb.stats_tensor())
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 def test_policy_step_hdqn_controller_input(mg, backend):
     """`[goal] + state` (hdqn.py:291): HDQNPolicy.step = goal launch + fused controller/env launch."""
     n = 2100
@@ -98,7 +98,7 @@ def test_policy_step_hdqn_controller_input(mg, backend):
     assert torch.equal(ea.pos2, eb.pos2)
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 def test_policy_step_reproduces_reference_episode(mg, backend):
     """The shipped DQN checkpoint played greedily against the L0 opponent through the fused launch reproduces the
     episode recorded in the unmodified reference env (tests/golden/dqn_policies.npz) action for action."""
@@ -148,7 +148,7 @@ def test_device_exploration_rule(mg):
     assert (d != c).float().mean().item() > 0.2
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 def test_fused_exploration_equals_unfused(mg, backend):
     """policy_step(explore=...) == act -> mg_explore -> step, and the actions it reports are the ones it took."""
     sd, _ = shipped()
@@ -170,7 +170,7 @@ def test_fused_exploration_equals_unfused(mg, backend):
     assert torch.equal(ea.pos1, eb.pos1)
 
 
-@pytest.mark.parametrize("backend,hdqn", [("fused", False), ("tf32x3", False), ("tf32x3", True)])
+@pytest.mark.parametrize("backend,hdqn", [("fused", False), ("tf32x3", False), ("tf32x3", True), ("f16x3", False), ("f16x3", True)])
 def test_graphed_fused_rollout_equals_eager(mg, backend, hdqn):
     """GraphedPolicyRollout(fused=True): K fused launches in one CUDA graph == the eager unfused loop, including the
     replay rows the recorder stores and exploration (fresh draws on every replay)."""

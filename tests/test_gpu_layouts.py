@@ -73,7 +73,7 @@ def test_policy_kernels_read_every_layout(mg, backend, layout):
         assert torch.equal(ctrl.act(ea.obs_buf[0], goal=goal), ctrl.act(eb.obs_buf[0], obs_layout=layout))
 
 
-@pytest.mark.parametrize("backend", ["fused", "tf32x3"])
+@pytest.mark.parametrize("backend", ["fused", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("layout", ["soa", "goal_slot"])
 def test_policy_step_in_every_layout(mg, backend, layout):
     n = 2500
@@ -90,7 +90,7 @@ def test_policy_step_in_every_layout(mg, backend, layout):
     assert torch.equal(ea.pos1, eb.pos1) and torch.equal(ea.meta, eb.meta)
 
 
-@pytest.mark.parametrize("backend,fused_step", [("fused", False), ("fused", True), ("tf32x3", False), ("tf32x3", True), ("f16x3", False)])
+@pytest.mark.parametrize("backend,fused_step", [("fused", False), ("fused", True), ("tf32x3", False), ("tf32x3", True), ("f16x3", False), ("f16x3", True)])
 def test_hdqn_on_goal_slot_rows(mg, backend, fused_step):
     """`[goal] + state` rows: the goal network stores its choice into slot 0 (MG_MLP_FLAG_WRITE_GOAL) and the controller
     reads the 11-float row as it is == the loop with a separate goal array on the default rows."""
