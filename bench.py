@@ -739,11 +739,12 @@ def run_b200(args):
                     policy[be] = bench_policy.measure(args.policy_envs, "dqn", be, device=dev)
                 except Exception as e:  # noqa
                     policy[be] = {"error": repr(e)}
-            try:        # the launch-bound end of the same loop: 4096 envs, where one launch per step (mg_policy_step) pays
-                small = bench_policy.measure(4096, "dqn", "tf32x3", device=dev, k=32, replays=8)
-                policy["tf32x3_4096_envs"] = {k_: small[k_] for k_ in ("value", "ms_per_step", "fused_step", "envs")}
-            except Exception as e:  # noqa
-                policy["tf32x3_4096_envs"] = {"error": repr(e)}
+            for be in ("tf32x3", "f16x3"):   # the launch-bound end of the same loop: 4096 envs, where one launch per step (mg_policy_step) pays
+                try:
+                    small = bench_policy.measure(4096, "dqn", be, device=dev, k=32, replays=8)
+                    policy[be + "_4096_envs"] = {k_: small[k_] for k_ in ("value", "ms_per_step", "fused_step", "envs")}
+                except Exception as e:  # noqa
+                    policy[be + "_4096_envs"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:

@@ -3,7 +3,7 @@
 the opponent its mirror image (`state[5:] + state[:5]`, scripts/main.py:196-199), both explore with the scripts'
 `randn() <= 0.7` rule, everything stays on the GPU.  Weights come from tests/golden/dqn_policies.npz.
 
-    python examples/dqn_vs_dqn.py [--backend fused|tf32x3]
+    python examples/dqn_vs_dqn.py [--backend fused|tf32x3|f16x3]
 """
 import argparse
 import os
@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 import merging_gym_b200 as mg  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--backend", default="fused", choices=["fused", "tf32x3"])
+ap.add_argument("--backend", default="fused", choices=["fused", "tf32x3", "f16x3"])
 ap.add_argument("--envs", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=1000)
 args = ap.parse_args()

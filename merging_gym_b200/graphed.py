@@ -22,7 +22,7 @@ class GraphedPolicyRollout:
 
     fused=True: player 1's step is ONE launch, `MergeVecEnv.policy_step` (`mg_policy_step`: forward + arg-max +
     exploration + env step), instead of policy launch + action copy + `mg_step`; `policy1` must then be an `MLPPolicy`
-    (backend "fused" or "tf32x3") or an `HDQNPolicy` (two launches: goal, then controller + env).  `explore` (an
+    (backend "fused", "tf32x3" or "f16x3") or an `HDQNPolicy` (two launches: goal, then controller + env).  `explore` (an
     `Exploration`) applies the scripts' `randn() <= EPISILO` rule on the device.  With `after_step` the env needs
     `out_slots >= 2`, so that the observation the actions were chosen from is still intact when the recorder reads it.
 

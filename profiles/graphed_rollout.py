@@ -22,7 +22,7 @@ def timed(roll, reps=10):
 
 
 for n in (4096, 1 << 16, 1 << 18):
-    for backend in ("fused", "tf32x3"):
+    for backend in ("fused", "tf32x3", "f16x3"):
         for with_rec in (False, True):
             pol = mg.MLPPolicy(10, 5, state_dict=sd, backend=backend)
             env = mg.MergeVecEnv(n, mode="pve", out_slots=1, reset_mode="random")

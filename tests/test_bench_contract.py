@@ -95,4 +95,5 @@ def test_gpu_arm_contract_line():
     assert d["policy_in_loop"]["fused"]["value"] > 0 and 0 < d["policy_in_loop"]["tf32x3"]["env_share"] < 1
     assert d["policy_in_loop"]["tf32x3"]["fused_step"]["value"] > 0 and d["policy_in_loop"]["tf32x3_4096_envs"]["value"] > 0
     assert d["policy_in_loop"]["f16x3"]["value"] > 0 and d["policy_in_loop"]["f16x3"]["fused_step"]["value"] > 0
+    assert d["policy_in_loop"]["f16x3_4096_envs"]["fused_step"]["value"] > 0
     assert cb["reference_python_value"] > 0

@@ -284,7 +284,8 @@ def test_hdqn_policy_fused_equals_torch(mg):
 
 
 @pytest.mark.parametrize("script,args", [("random_rollout.py", ["--envs", "65536", "--steps", "300"]),
-                                         ("dqn_vs_dqn.py", ["--steps", "400"]), ("dqn_vs_dqn.py", ["--steps", "400", "--backend", "tf32x3"])])
+                                         ("dqn_vs_dqn.py", ["--steps", "400"]), ("dqn_vs_dqn.py", ["--steps", "400", "--backend", "tf32x3"]),
+                                         ("dqn_vs_dqn.py", ["--steps", "400", "--backend", "f16x3"])])
 def test_examples_run(script, args):
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
