@@ -293,7 +293,9 @@ MG_API int mg_mlp_act(const float *obs, const uint8_t *goal_or_null, int64_t n, 
  *   bytes [13376,106560) __half [13][28][2][8][8]: layer-2 operand, fc2.weight zero-padded to 112 rows x 208 columns, times
  *                       2^s2; per K-step of 16: row groups 0-13 hi, 14-27 lo
  *   with c1 = 2^-s1 / 8 and c2 = 8 * 2^-s2; s1, s2 chosen so that the largest scaled entry lies in [256, 512).
- * Same ~22 significant bits per product as 3xTF32; hidden-layer-1 activations saturate at 5.2e5 (fp16 range). */
+ * Same ~22 significant bits per product as 3xTF32.  fp16's range is the price: network inputs saturate at +-65504 and
+ * hidden-layer-1 activations at 5.2e5 (finite, wrong); the reference's observations (metres, m/s) and its checkpoints
+ * stay orders of magnitude below both — backend 1 has no such bound. */
 #define MG_MLP_FLAG_F16X3 0x20u
 MG_API int mg_mlp_act_tc(const float *obs, const uint8_t *goal_or_null, int64_t n, int32_t obs_dim,
                          int32_t out_dim, const float *w1t, const float *b1, const float *w2_tc,

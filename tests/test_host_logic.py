@@ -103,3 +103,32 @@ def test_nvtx_ranges_are_off_by_default():
     tracing.enable(True)
     assert tracing.enabled() and tracing.nvtx_range("x").name == "x"
     tracing.enable(False)
+
+
+def test_f16x3_operand_blob_round_trips_the_weights():
+    """`MLPPolicy(backend="f16x3")` packs fc1 (+ its bias in K slot 15) and fc2 as fp16 hi / lo operands, each scaled by a
+    power of two, behind the two constants the kernel multiplies back with (include/merging_b200.h, MG_MLP_FLAG_F16X3).
+    Unpacked on the CPU, hi + lo must give the weights back to 2^-22 of the largest entry, the scaled operands must sit in
+    fp16's comfortable range, and the padding must be zero.  (Built on the CPU: packing needs no GPU.)"""
+    import torch
+    from merging_gym_b200.policy import MLPPolicy
+    for in_dim, out_dim, seed in ((10, 5, 3), (11, 3, 4)):
+        p = MLPPolicy(in_dim, out_dim, device="cpu", seed=seed, backend="f16x3")
+        blob = p.w2_f16
+        assert blob.dtype == torch.uint8 and blob.numel() == 64 + 13312 + 93184
+        c1, c2 = (float(v) for v in blob[:64].view(torch.float32)[:2])
+        s1, s2 = -3 - np.log2(c1), 3 - np.log2(c2)
+        assert s1 == round(s1) and s2 == round(s2)                          # exact powers of two
+        op1 = blob[64:64 + 13312].view(torch.float16).view(52, 2, 8, 8).permute(0, 2, 1, 3).reshape(416, 16).float()
+        hi1, lo1 = op1[:208], op1[208:]
+        assert 256 <= float(hi1.abs().max()) <= 512 and float(lo1.abs().max()) <= 0.26
+        w1op = (hi1 + lo1) / 2.0 ** s1
+        tol1 = 2.0 ** -22 * max(float(p.w1.abs().max()), float(p.b1.abs().max()))
+        assert float((w1op[:200, :in_dim] - p.w1).abs().max()) <= tol1 and float((w1op[:200, 15] - p.b1).abs().max()) <= tol1
+        assert float(w1op[200:].abs().max()) == 0 and float(w1op[:, in_dim:15].abs().max()) == 0
+        op2 = blob[64 + 13312:].view(torch.float16).view(13, 28, 2, 8, 8).permute(1, 3, 0, 2, 4).reshape(224, 208).float()
+        hi2, lo2 = op2[:112], op2[112:]
+        assert 256 <= float(hi2.abs().max()) <= 512
+        w2 = (hi2 + lo2) / 2.0 ** s2
+        assert float((w2[:100, :200] - p.w2).abs().max()) <= 2.0 ** -22 * float(p.w2.abs().max())
+        assert float(w2[100:].abs().max()) == 0 and float(w2[:, 200:].abs().max()) == 0
