@@ -97,7 +97,9 @@ def test_writer_wraps_and_replays_in_a_graph(mg, n, extra, density):
     nxt = torch.where(done.bool().unsqueeze(1), info["terminal_observation"], obs)
     all_rows = torch.cat([obs_prev, a1.float().unsqueeze(1), rew[:, 0:1], nxt], 1)
     gen = torch.Generator(device="cuda").manual_seed(n)
-    select = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    # odd sizes: the mask starts one byte into its allocation — the count pass then takes its byte-by-byte path instead of
+    # the 16-byte loads
+    select = torch.zeros(n + 1, dtype=torch.uint8, device="cuda")[1:] if n % 2 else torch.zeros(n, dtype=torch.uint8, device="cuda")
     want_ring = torch.zeros(cap, 22, device="cuda"); want_ids = torch.full((cap,), -1, dtype=torch.int32, device="cuda")
     counter = 0
 
