@@ -23,7 +23,9 @@ class GraphedPolicyRollout:
     fused=True: player 1's step is ONE launch, `MergeVecEnv.policy_step` (`mg_policy_step`: forward + arg-max +
     exploration + env step), instead of policy launch + action copy + `mg_step`; `policy1` must then be an `MLPPolicy`
     (backend "fused", "tf32x3" or "f16x3") or an `HDQNPolicy` (two launches: goal, then controller + env).  `explore` (an
-    `Exploration`) applies the scripts' `randn() <= EPISILO` rule on the device.  With `after_step` the env needs
+    `Exploration`) applies the scripts' `randn() <= EPISILO` rule on the device.  The single launch pays off where launches
+    dominate — up to roughly 65 536 envs (f16x3: 9.1 vs 12.3 us per step at 4096 envs); from there up the two-launch loop is
+    as fast or faster (profiles/r02_policy_small_batches.jsonl).  With `after_step` the env needs
     `out_slots >= 2`, so that the observation the actions were chosen from is still intact when the recorder reads it.
 
     policy1(obs) -> uint8[N] actions of player 1; policy2 (pvp only) receives the same observation buffer and must
