@@ -368,7 +368,8 @@ MG_API int mg_explore(uint8_t *choices, int64_t n, int32_t num_choices, const Mg
  * counter: device uint64, total rows ever appended (caller zero-initialises).
  * scratch: device uint32[mg_record_scratch_words(n)] (= (n+31)/32 + 4), 8-byte aligned; the library's work area for the
  *          block counts / offsets of the call (count -> scan -> write, three launches; the write pass is a programmatic
- *          dependent of the scan).  env_ids_or_null: int32[capacity], env of each row. */
+ *          dependent of the scan; mask_mode 0 needs no count and no scan: one thread advances the counter).
+ * env_ids_or_null: int32[capacity], env of each row. */
 MG_API int64_t mg_record_scratch_words(int64_t n);
 MG_API int mg_record_transitions(const float *obs_prev, const float *obs_next,
                                  const float *term_obs_or_null, const uint8_t *a1,

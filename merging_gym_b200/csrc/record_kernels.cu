@@ -289,14 +289,14 @@ __device__ __forceinline__ void store_rows(const RowArgs &A, RowSmem<FORMAT> &sm
     }
 }
 
-// format 0 (replay, main.py:115-119): [s(10), a_p, r_p, s'(10)]              22 floats, player p
-// format 1 (log, human_player.py:111) : [s(10), a1, a2, r1, r2]               14 floats
-// format 2 (h-DQN controller, hdqn.py:180-184,291-316): [g, s(10), a, r_int, g', s'(10)]   24 floats, with
-//          r_int = 1 if g' == goal_status(s) else 0 (hdqn.py:314; goal_status :223-236 on the state the action was
-//          chosen from, g' the goal re-chosen from the next state)
-// One warp handles 32 consecutive envs: their observation rows are one contiguous 1280-byte span, loaded
-// with coalesced 128-bit loads into shared memory; the selected lanes assemble their rows in shared memory
-// at consecutive ranks; the warp then writes that contiguous piece of the ring with coalesced stores.
+// mask_mode 0 (every env is stored; the h-DQN controller's rows): the count and the scan reduce to this
+__global__ void advance_kernel(unsigned long long rows, unsigned long long *__restrict__ counter, unsigned long long *__restrict__ base) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    *base = *counter;
+    *counter += rows;
+}
+
+// The write pass (row formats and the warp's staging: see RowFmt / RowSmem above).
 // (40 registers, 22.5 KB: six resident blocks per SM; forcing eight by a 32-register cap spills and is slower: 42 vs 37.6 us)
 template <int FORMAT>
 __global__ void __launch_bounds__(kBlock)
@@ -324,7 +324,8 @@ write_kernel(const RowArgs A, const uint32_t *block_offsets, const unsigned long
     // the compiler and was hoisted above the wait (stale offsets once the scan took several passes).
     cudaGridDependencySynchronize();
     const unsigned long long base_v = __ldcg(base), total_v = __ldcg(counter) - base_v;
-    store_rows<FORMAT>(A, sm, warp, lane, w0, sel, b, base_v, (uint64_t)__ldcg(block_offsets + blockIdx.x) + before, total_v);
+    const uint64_t block_rank = block_offsets ? (uint64_t)__ldcg(block_offsets + blockIdx.x) : (uint64_t)blockIdx.x * kBlock;   // NULL: mask_mode 0
+    store_rows<FORMAT>(A, sm, warp, lane, w0, sel, b, base_v, block_rank + before, total_v);
 }
 
 }  // namespace mgrec
@@ -365,8 +366,15 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
                            goal_next_or_null, n, mask_mode, player, ring, capacity, env_ids_or_null};
     const unsigned count_grid = (unsigned)((n + (int64_t)mgrec::kBlock * mgrec::kCountPerThread - 1) /
                                            ((int64_t)mgrec::kBlock * mgrec::kCountPerThread));
-    mgrec::count_kernel<<<count_grid, mgrec::kBlock, 0, st>>>(info, n, mask_mode, block_counts);
-    mgrec::scan_kernel<<<1, 1024, 0, st>>>(block_counts, (int64_t)grid, ctr, base);
+    const uint32_t *offs = block_counts;
+    if (mask_mode == 0) {
+        // every env is stored: a block's offset is its first env — no count, no scan; one thread advances the counter
+        mgrec::advance_kernel<<<1, 1, 0, st>>>((unsigned long long)n, ctr, base);
+        offs = nullptr;
+    } else {
+        mgrec::count_kernel<<<count_grid, mgrec::kBlock, 0, st>>>(info, n, mask_mode, block_counts);
+        mgrec::scan_kernel<<<1, 1024, 0, st>>>(block_counts, (int64_t)grid, ctr, base);
+    }
     // the write pass starts under the scan (programmatic dependent launch): see write_kernel
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(mgrec::kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -374,7 +382,6 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const uint32_t *offs = block_counts;
     const unsigned long long *cbase = base, *cctr = ctr;
     cudaError_t le;
     if (format == 0) le = cudaLaunchKernelEx(&cfg, mgrec::write_kernel<0>, A, offs, cbase, cctr);
