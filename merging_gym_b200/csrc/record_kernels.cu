@@ -297,8 +297,9 @@ __global__ void advance_kernel(unsigned long long rows, unsigned long long *__re
 }
 
 // The write pass (row formats and the warp's staging: see RowFmt / RowSmem above).
-// (40 registers, 22.5 KB: six resident blocks per SM; forcing eight by a 32-register cap spills and is slower: 42 vs 37.6 us)
-template <int FORMAT>
+// (40 registers, 22.5 KB: six resident blocks per SM; forcing eight by a 32-register cap spills and is slower: 42 vs 37.6 us;
+// ALL = mask_mode 0 is its own instantiation: as a run-time branch it cost the main path 8 registers and a resident block)
+template <int FORMAT, bool ALL>
 __global__ void __launch_bounds__(kBlock)
 write_kernel(const RowArgs A, const uint32_t *block_offsets, const unsigned long long *base, const unsigned long long *counter) {
     __shared__ __align__(16) RowSmem<FORMAT> sm;
@@ -324,7 +325,7 @@ write_kernel(const RowArgs A, const uint32_t *block_offsets, const unsigned long
     // the compiler and was hoisted above the wait (stale offsets once the scan took several passes).
     cudaGridDependencySynchronize();
     const unsigned long long base_v = __ldcg(base), total_v = __ldcg(counter) - base_v;
-    const uint64_t block_rank = block_offsets ? (uint64_t)__ldcg(block_offsets + blockIdx.x) : (uint64_t)blockIdx.x * kBlock;   // NULL: mask_mode 0
+    const uint64_t block_rank = ALL ? (uint64_t)blockIdx.x * kBlock : (uint64_t)__ldcg(block_offsets + blockIdx.x);
     store_rows<FORMAT>(A, sm, warp, lane, w0, sel, b, base_v, block_rank + before, total_v);
 }
 
@@ -384,9 +385,12 @@ extern "C" MG_API int mg_record_transitions(const float *obs_prev, const float *
     cfg.attrs = attr; cfg.numAttrs = 1;
     const unsigned long long *cbase = base, *cctr = ctr;
     cudaError_t le;
-    if (format == 0) le = cudaLaunchKernelEx(&cfg, mgrec::write_kernel<0>, A, offs, cbase, cctr);
-    else if (format == 1) le = cudaLaunchKernelEx(&cfg, mgrec::write_kernel<1>, A, offs, cbase, cctr);
-    else le = cudaLaunchKernelEx(&cfg, mgrec::write_kernel<2>, A, offs, cbase, cctr);
+#define MG_REC_WRITE(F) (offs ? cudaLaunchKernelEx(&cfg, mgrec::write_kernel<F, false>, A, offs, cbase, cctr) \
+                              : cudaLaunchKernelEx(&cfg, mgrec::write_kernel<F, true>, A, offs, cbase, cctr))
+    if (format == 0) le = MG_REC_WRITE(0);
+    else if (format == 1) le = MG_REC_WRITE(1);
+    else le = MG_REC_WRITE(2);
+#undef MG_REC_WRITE
     if (le) return cuda_fail(le, "mg_record_transitions launch");
     if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "mg_record_transitions launch");
     return MG_OK;
